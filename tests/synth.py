@@ -1,0 +1,66 @@
+"""Seeded synthetic clips shared by the tests, the golden generator and bench.py
+(SURVEY.md section 8d): white noise + a tone + periodic full-scale bursts so the
+clippers and the gate both switch.  float32, frame-major (N, C)."""
+from __future__ import annotations
+
+import numpy as np
+
+FS = 48000
+
+
+def clip_channel(seed: int, n: int, tone_idx: int, fs: int = FS) -> np.ndarray:
+    rng = np.random.default_rng(seed)
+    t = np.arange(n, dtype=np.float64) / fs
+    f = 110.0 * 2.0 ** ((tone_idx % 48) / 12.0)
+    x = 0.25 * rng.uniform(-1.0, 1.0, n) + 0.35 * np.sin(2.0 * np.pi * f * t)
+    burst = (np.arange(n) % (2 * fs)) < int(0.05 * fs)          # 50 ms every 2 s
+    x = np.where(burst, 0.95 * np.sign(np.sin(2.0 * np.pi * 997.0 * t) + 1e-12), x)
+    return x.astype(np.float32)
+
+
+def clip(i: int, n: int, channels: int = 2, fs: int = FS) -> np.ndarray:
+    """Clip `i` of the synthetic set: (n, channels) f32; R uses seed + 500000."""
+    cols = [clip_channel(1000 + i + 500000 * c, n, i, fs) for c in range(channels)]
+    return np.ascontiguousarray(np.stack(cols, axis=1))
+
+
+def batch(first: int, count: int, n: int, channels: int = 2, fs: int = FS) -> np.ndarray:
+    return np.stack([clip(first + k, n, channels, fs) for k in range(count)], axis=0)
+
+
+# app.py:41-71 DEFAULT_PRESETS, as data (parameters verbatim).
+PRESETS = {
+    "Robot Voice": [
+        {"type": "gate", "params": {"threshold_db": -30, "attack_ms": 10, "release_ms": 100}},
+        {"type": "octaver", "params": {"semitones": -12, "mix": 1.0}},
+        {"type": "delay", "params": {"delay_ms": 120, "feedback": 0.3, "mix_wet": 0.3, "mix_dry": 1.0, "offset_ms": 10}},
+    ],
+    "Cathedral": [
+        {"type": "reverb", "params": {"rt60_s": 4.0, "mix_wet": 0.6, "mix_dry": 0.6, "damp": 0.2, "pre_delay_ms": 20}},
+    ],
+    "Slapback Echo": [
+        {"type": "delay", "params": {"delay_ms": 100, "feedback": 0.0, "mix_wet": 0.5, "mix_dry": 1.0, "offset_ms": 0}},
+    ],
+    "Clean Noise Removal": [
+        {"type": "spectral", "params": {"threshold_db": -50, "reduction": 0.1}},
+        {"type": "gate", "params": {"threshold_db": -40, "attack_ms": 5, "release_ms": 200}},
+    ],
+    "Guitar Filter": [
+        {"type": "filter", "params": {"filter_type": 2, "cutoff_hz": 800, "q": 0.8}},
+        {"type": "reverb", "params": {"mix_wet": 0.2, "rt60_s": 1.0}},
+    ],
+    "Rain Delay": [
+        {"type": "delay", "params": {"feedback": 0.2, "delay_ms": 375, "mix_dry": 1, "mix_wet": 1, "offset_ms": 0}},
+        {"type": "reverb", "params": {"rt60_s": 2.1, "mix_wet": 0.4, "mix_dry": 0.8, "damp": 0.05, "pre_delay_ms": 0}},
+    ],
+}
+
+
+def err_stats(got: np.ndarray, want: np.ndarray):
+    """(max-abs error, SNR in dB) of `got` against `want`."""
+    d = got.astype(np.float64) - want.astype(np.float64)
+    mx = float(np.max(np.abs(d))) if d.size else 0.0
+    p_sig = float(np.sum(want.astype(np.float64) ** 2))
+    p_err = float(np.sum(d ** 2))
+    snr = float("inf") if p_err == 0.0 else 10.0 * np.log10(max(p_sig, 1e-300) / p_err)
+    return mx, snr
