@@ -1,0 +1,146 @@
+"""ctypes binding of libaesim.so (the C ABI declared in include/aesim.h).
+
+There is no CPU fallback: if the CUDA library is missing or no device is present,
+the first call that needs it raises.  Importing the package stays possible on a
+GPU-less machine so that parameter resolution (pure host logic) can be tested.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("AESIM_LIB", os.path.join(os.path.dirname(_PKG), "lib", "libaesim.so"))
+
+# aes_stage_kind / aes_format (include/aesim.h)
+DELAY, REVERB, BIQUAD, GATE, OCTAVER, DISTORTION = 1, 2, 3, 4, 5, 6
+FMT_F32_STEREO, FMT_F32_MONO, FMT_I16_DOWNMIX, FMT_I16_STEREO = 0, 1, 2, 3
+
+
+class StageDesc(C.Structure):
+    """aes_stage_desc"""
+    _fields_ = [("kind", C.c_int32), ("flags", C.c_int32), ("p", C.c_double * 32), ("q", C.c_int64 * 32)]
+
+    def key(self):
+        return (self.kind, tuple(self.p), tuple(self.q))
+
+
+class AesimError(RuntimeError):
+    pass
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib() -> C.CDLL:
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise AesimError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  audioblocks has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        vp, i64, ci = C.c_void_p, C.c_int64, C.c_int
+        L.aes_last_error.restype = C.c_char_p
+        L.aes_launch_count.restype = i64
+        L.aes_chain_plan_create.argtypes = [C.POINTER(StageDesc), ci, ci, C.POINTER(vp)]
+        L.aes_chain_plan_destroy.argtypes = [vp]
+        L.aes_chain_run.argtypes = [vp, vp, ci, vp, ci, i64, i64, vp]
+        L.aes_chain_process_host.argtypes = [vp, vp, ci, vp, ci, i64, i64]
+        L.aes_chain_plan_info.argtypes = [vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci), C.POINTER(i64)]
+        L.aes_malloc.argtypes = [C.POINTER(vp), C.c_size_t]
+        L.aes_free.argtypes = [vp]
+        L.aes_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
+        L.aes_host_free.argtypes = [vp]
+        L.aes_memcpy_h2d.argtypes = [vp, vp, C.c_size_t, vp]
+        L.aes_memcpy_d2h.argtypes = [vp, vp, C.c_size_t, vp]
+        L.aes_memset.argtypes = [vp, ci, C.c_size_t, vp]
+        L.aes_stream_create.argtypes = [C.POINTER(vp)]
+        L.aes_stream_destroy.argtypes = [vp]
+        L.aes_stream_sync.argtypes = [vp]
+        L.aes_device_count.argtypes = [C.POINTER(ci)]
+        L.aes_set_device.argtypes = [ci]
+        L.aes_device_sm_count.argtypes = [C.POINTER(ci)]
+        L.aes_delay_f32.argtypes = [vp, vp, i64, i64, i64, i64, C.c_double, C.c_double, C.c_double, vp]
+        L.aes_biquad_cascade_f32.argtypes = [vp, vp, i64, i64, ci, C.POINTER(C.c_double), vp]
+        L.aes_quantize_i16.argtypes = [vp, vp, i64, vp]
+        if L.aes_abi_version() != 1:
+            raise AesimError("libaesim.so ABI version mismatch")
+        _lib = L
+        return L
+
+
+def check(rc: int):
+    if rc != 0:
+        raise AesimError(f"aesim error {rc}: {lib().aes_last_error().decode(errors='replace')}")
+
+
+def desc_array(descs):
+    arr = (StageDesc * max(1, len(descs)))()
+    for i, d in enumerate(descs):
+        arr[i] = d
+    return arr
+
+
+class ChainPlan:
+    """RAII wrapper of aes_chain_plan."""
+
+    def __init__(self, descs, sample_rate: int):
+        self._h = C.c_void_p()
+        self._descs = desc_array(descs)
+        check(lib().aes_chain_plan_create(self._descs, len(descs), int(sample_rate), C.byref(self._h)))
+
+    def info(self):
+        t, s, o, sc = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
+        check(lib().aes_chain_plan_info(self._h, C.byref(t), C.byref(s), C.byref(o), C.byref(sc)))
+        return {"tile_frames": t.value, "smem_bytes": s.value, "ctas_per_sm": o.value,
+                "scratch_bytes_per_cta": sc.value}
+
+    def run_device(self, x_ptr: int, in_fmt: int, y_ptr: int, out_fmt: int, n_clips: int, n_frames: int,
+                   stream: int = 0):
+        """x_ptr / y_ptr: CUDA device pointers (e.g. torch tensor .data_ptr())."""
+        check(lib().aes_chain_run(self._h, C.c_void_p(x_ptr), in_fmt, C.c_void_p(y_ptr), out_fmt,
+                                  n_clips, n_frames, C.c_void_p(stream)))
+
+    def run_host(self, x: np.ndarray, in_fmt: int, y: np.ndarray, out_fmt: int, n_clips: int, n_frames: int):
+        assert x.flags.c_contiguous and y.flags.c_contiguous
+        check(lib().aes_chain_process_host(self._h, C.c_void_p(x.ctypes.data), in_fmt,
+                                           C.c_void_p(y.ctypes.data), out_fmt, n_clips, n_frames))
+
+    def close(self):
+        if self._h:
+            lib().aes_chain_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """A numpy array over page-locked host memory (freed with the array)."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    p = C.c_void_p()
+    check(lib().aes_host_alloc(C.byref(p), max(n, 1)))
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    class _Owner:
+        def __init__(self, ptr): self.ptr = ptr
+        def __del__(self):
+            try: lib().aes_host_free(self.ptr)
+            except Exception: pass
+    _OWNERS[arr.ctypes.data] = _Owner(p)
+    return arr
+
+
+_OWNERS: dict = {}

@@ -1,0 +1,283 @@
+"""Chain driver of the drop-in `audioblocks` package.
+
+Same public surface as the reference's src/audioblocks/core.py (SmoothParam
+core.py:56-78, Effect :81-86, PlotDataTap :89-106, EffectsChain :109-161,
+pick_devices :12-53); the signal path is the fused sm_100a kernel behind
+libaesim.so instead of per-effect numpy/numba passes.
+"""
+from __future__ import annotations
+
+import queue
+import threading
+
+import numpy as np
+
+from . import _native
+
+try:                                    # optional, exactly as in the reference (core.py:6-9)
+    import sounddevice as sd
+except (ImportError, OSError):
+    sd = None
+
+
+def pick_devices(ch_in=1, ch_out=2, in_hint=("usb", "mic"), out_hint=("system",)):
+    """(in_idx, out_idx) preferring JACK, else Pulse, else PortAudio defaults
+    (reference core.py:12-53).  Without sounddevice there is nothing to pick."""
+    if sd is None:
+        return None, None
+    try:
+        apis, devices = sd.query_hostapis(), sd.query_devices()
+    except Exception:
+        return None, None
+
+    def api_id(tag):
+        return next((i for i, a in enumerate(apis) if tag in a["name"]), None)
+
+    def find(api, need_in, need_out, tokens):
+        for i, d in enumerate(devices):
+            name = d["name"].lower()
+            if d["hostapi"] != api or not all(t.lower() in name for t in tokens):
+                continue
+            if need_in and d["max_input_channels"] < ch_in:
+                continue
+            if need_out and d["max_output_channels"] < ch_out:
+                continue
+            return i
+        return None
+
+    jack, pulse = api_id("JACK"), api_id("Pulse")
+    if jack is not None:
+        i, o = find(jack, True, False, in_hint), find(jack, False, True, out_hint)
+        if i is not None and o is not None:
+            return i, o
+    if pulse is not None:
+        p = next((i for i, d in enumerate(devices) if d["hostapi"] == pulse), None)
+        if p is not None:
+            return p, p
+    return None, None
+
+
+class SmoothParam:
+    """A clamped target that `current` slews towards, one bounded step per block.
+    The constructor does not clamp (reference core.py:57-59); set_target/nudge do."""
+
+    def __init__(self, value, lo=-np.inf, hi=np.inf):
+        self.current = float(value)
+        self.target = float(value)
+        self.lo = float(lo)
+        self.hi = float(hi)
+        self._lock = threading.Lock()
+
+    def _clamped(self, v):
+        return min(max(float(v), self.lo), self.hi)
+
+    def set_target(self, v):
+        with self._lock:
+            self.target = self._clamped(v)
+
+    def nudge(self, dv):
+        with self._lock:
+            self.target = self._clamped(self.target + float(dv))
+
+    def step_towards(self, max_step=1.0):
+        if max_step < 0:
+            raise ValueError("max_step must be >= 0")
+        with self._lock:
+            gap = self.target - self.current
+            self.current += min(max(gap, -max_step), max_step)
+            return self.current
+
+
+class Effect:
+    """Base effect: prepare() (re)allocates, process_into() writes `out`."""
+
+    def prepare(self, sample_rate: int, channels_in: int, channels_out: int, blocksize: int):
+        pass
+
+    def process_into(self, x_in: np.ndarray, out: np.ndarray) -> None:
+        raise NotImplementedError
+
+
+class NativeEffect(Effect):
+    """An effect executed by the CUDA library.  Subclasses resolve their parameters
+    into aes_stage_desc records (`_stages`) and advance their host-visible state
+    (`_advance`); the signal never touches a CPU implementation."""
+
+    _sr = 48000
+    _dirty = False          # True once a non-silent block went through the delay lines
+
+    def _stages(self, frames: int) -> list:
+        raise NotImplementedError
+
+    def _advance(self, frames: int, silent: bool):
+        if not silent:
+            self._dirty = True
+
+    def _require_fresh(self):
+        if self._dirty:
+            raise _native.AesimError(
+                f"{type(self).__name__}: the whole-clip CUDA path starts every call from freshly "
+                "prepared delay lines; call prepare() (the chain does so whenever the frame count "
+                "changes) before processing another block")
+
+    def process_into(self, x_in: np.ndarray, out: np.ndarray) -> None:
+        run_native([self], self._sr, x_in, out)
+
+
+def run_native(effects, sample_rate, x_in: np.ndarray, out: np.ndarray):
+    """One fused launch over (frames, channels) host arrays for a run of native effects."""
+    frames = x_in.shape[0]
+    descs = []
+    for fx in effects:
+        fx._require_fresh()
+        descs.extend(fx._stages(frames))
+    x = np.ascontiguousarray(x_in, np.float32)
+    if x.shape[1] == 1:
+        fmt_in = _native.FMT_F32_MONO
+    elif x.shape[1] == 2:
+        fmt_in = _native.FMT_F32_STEREO
+    else:
+        raise ValueError("audioblocks (B200) processes mono or stereo blocks")
+    if out.shape != (frames, 2):
+        raise ValueError("output block must be (frames, 2)")
+    y = out if (out.dtype == np.float32 and out.flags.c_contiguous) else np.empty((frames, 2), np.float32)
+    if frames > 0:
+        plan = _native.ChainPlan(descs, sample_rate)
+        try:
+            plan.run_host(x, fmt_in, y, _native.FMT_F32_STEREO, 1, frames)
+        finally:
+            plan.close()
+    if y is not out:
+        out[:, :] = y
+    silent = not x.any()
+    for fx in effects:
+        fx._advance(frames, silent)
+
+
+class PlotDataTap(Effect):
+    """Transparent tap that copies blocks into a queue for the UI (reference core.py:89-106)."""
+
+    def __init__(self, data_queue: queue.Queue):
+        self.queue = data_queue
+
+    def process_into(self, x_in: np.ndarray, out: np.ndarray) -> None:
+        out[:] = x_in
+        try:
+            self.queue.put_nowait(x_in.copy())
+        except queue.Full:
+            pass
+
+
+class EffectsChain:
+    """Ping-pong driver with the reference's protocol (core.py:109-161): effects are
+    prepared on add(); a frame-count change re-prepares all of them; warmup() pushes
+    two silent blocks.  Consecutive native effects run as ONE fused kernel launch."""
+
+    def __init__(self, sample_rate: int, channels_in: int, channels_out: int, blocksize: int):
+        self.sr, self.ci, self.co, self.bs = sample_rate, channels_in, channels_out, blocksize
+        self.effects: list[Effect] = []
+
+    def add(self, effect: Effect):
+        effect.prepare(self.sr, self.ci, self.co, self.bs)
+        self.effects.append(effect)
+
+    def _ensure_blocksize(self, frames: int):
+        if frames != self.bs:
+            self.bs = frames
+            for e in self.effects:
+                e.prepare(self.sr, self.ci, self.co, frames)
+
+    def warmup(self):
+        zi = np.zeros((self.bs, self.ci), np.float32)
+        zo = np.zeros((self.bs, self.co), np.float32)
+        for _ in range(2):
+            self.process(zi, zo)
+
+    def _segments(self):
+        seg = []
+        for e in self.effects:
+            if isinstance(e, NativeEffect):
+                seg.append(e)
+            else:
+                if seg:
+                    yield seg
+                    seg = []
+                yield e
+        if seg:
+            yield seg
+
+    def process(self, in_block: np.ndarray, out_block: np.ndarray):
+        """in_block (frames, ci) float32 -> out_block (frames, co) float32."""
+        frames = in_block.shape[0]
+        self._ensure_blocksize(frames)
+        if self.co != 2:
+            raise ValueError("audioblocks (B200) chains are stereo-out, like the reference engine")
+        src = in_block
+        fanned = False
+        for seg in self._segments():
+            if isinstance(seg, list):
+                # the native path fans mono out to L=R itself (core.py:147-149)
+                dst = np.empty((frames, self.co), np.float32)
+                run_native(seg, self.sr, src if src.shape[1] in (1, 2) else src[:, :2], dst)
+                fanned = True
+            else:
+                if not fanned:
+                    src = self._fan(src, frames)
+                    fanned = True
+                dst = np.empty((frames, self.co), np.float32)
+                seg.process_into(src, dst)
+            src = dst
+        if not fanned:
+            src = self._fan(src, frames)
+        out_block[:, :] = src
+
+    def _fan(self, x, frames):
+        buf = np.zeros((frames, self.co), np.float32)
+        if self.ci == 1 and self.co == 2:
+            buf[:, 0] = x[:, 0]
+            buf[:, 1] = x[:, 0]
+        else:
+            k = min(self.ci, self.co)
+            buf[:, :k] = x[:, :k]
+        return buf
+
+    # ---- batched entry (new; the reference is strictly one clip per call) -------------
+    def stage_descs(self, frames: int):
+        """Resolved aes_stage_desc list for the whole chain at its current state."""
+        descs = []
+        for e in self.effects:
+            if isinstance(e, PlotDataTap):
+                continue
+            if not isinstance(e, NativeEffect):
+                raise TypeError(f"{type(e).__name__} has no CUDA implementation; cannot batch")
+            e._require_fresh()
+            descs.extend(e._stages(frames))
+        return descs
+
+    def prepare_batch(self, frames: int):
+        """Bring the chain to the state it has when a file of `frames` frames arrives
+        (engine.py:99-102: after warm-up, re-prepared at the file's frame count) and
+        return the compiled plan."""
+        self._ensure_blocksize(frames)
+        return _native.ChainPlan(self.stage_descs(frames), self.sr)
+
+    def process_batch(self, x: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """x: (B, frames, 1|2) float32 host array (or (B, frames, 2) int16 PCM, which is
+        down-mixed like engine.py:78-84) -> (B, frames, 2) float32 or int16 (if `out`
+        is int16: clip, *32767, truncate, engine.py:104-105).  Every clip starts from
+        the same freshly prepared state."""
+        B, frames, ch = x.shape
+        if x.dtype == np.int16:
+            fmt_in = _native.FMT_I16_DOWNMIX
+        else:
+            x = np.ascontiguousarray(x, np.float32)
+            fmt_in = _native.FMT_F32_MONO if ch == 1 else _native.FMT_F32_STEREO
+        if out is None:
+            out = np.empty((B, frames, 2), np.float32)
+        fmt_out = _native.FMT_I16_STEREO if out.dtype == np.int16 else _native.FMT_F32_STEREO
+        plan = self.prepare_batch(frames)
+        try:
+            plan.run_host(np.ascontiguousarray(x), fmt_in, out, fmt_out, B, frames)
+        finally:
+            plan.close()
+        return out

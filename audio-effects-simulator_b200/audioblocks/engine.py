@@ -1,0 +1,195 @@
+"""AudioEngine of the drop-in package: same commands and replies as the reference's
+src/audioblocks/engine.py (build_chain :38-65, process_wav_file :67-129,
+update_param :131-145, start_mic_stream :147-183, stop_stream :185-190), with the
+offline WAV path running on the fused CUDA chain."""
+from __future__ import annotations
+
+import base64
+import io
+import json
+import queue
+
+import numpy as np
+import scipy.io.wavfile
+
+import audioblocks as ab
+
+try:
+    import soundfile as sf
+except (ImportError, OSError):          # decode 16/32-bit PCM and float WAVs ourselves
+    sf = None
+
+try:
+    import sounddevice as sd
+except (ImportError, OSError):
+    sd = None
+
+SAMPLE_RATE = 48000
+BLOCKSIZE = 256
+CHANNELS_IN = 1
+CHANNELS_OUT = 2
+
+_EFFECT_TYPES = {
+    "delay": lambda p: ab.StereoDelayEffect(**p),
+    "reverb": lambda p: ab.ReverbEffect(**p),
+    "gate": lambda p: ab.NoiseGateEffect(**p),
+    "spectral": lambda p: ab.SpectralFilter(**p),
+    "octaver": lambda p: ab.OctaverEffect(**p),
+    "filter": lambda p: ab.FilterEffect(**p),
+    "distortion": lambda p: ab.DistortionEffect(**p),     # extension (no reference block)
+}
+
+
+def make_effect(config: dict):
+    """Effect instance for one chain-config entry, or None for an unknown type
+    (the reference skips those silently, engine.py:56,97)."""
+    factory = _EFFECT_TYPES.get(config.get("type"))
+    return factory(config.get("params", {})) if factory else None
+
+
+def read_wav(blob: bytes):
+    """(float32 audio in [-1,1), sample_rate); libsndfile's int16 scale is 1/32768."""
+    with io.BytesIO(blob) as fh:
+        if sf is not None:
+            return sf.read(fh, dtype="float32")
+        fs, pcm = scipy.io.wavfile.read(fh)
+    if pcm.dtype == np.int16:
+        audio = pcm.astype(np.float32) / np.float32(32768.0)
+    elif pcm.dtype == np.int32:
+        audio = (pcm.astype(np.float64) / 2147483648.0).astype(np.float32)
+    elif pcm.dtype == np.uint8:
+        audio = (pcm.astype(np.float32) - 128.0) / np.float32(128.0)
+    else:
+        audio = pcm.astype(np.float32)
+    return audio, fs
+
+
+def file_chain(chain_config, fs, channels_in=1, blocksize=1024):
+    """The offline chain exactly as the reference builds it (engine.py:86-99):
+    blocksize 1024, every known effect added in order, then warmed up."""
+    chain = ab.EffectsChain(fs, channels_in, CHANNELS_OUT, blocksize)
+    for cfg in chain_config:
+        fx = make_effect(cfg)
+        if fx is not None:
+            chain.add(fx)
+    chain.warmup()
+    return chain
+
+
+class AudioEngine:
+    def __init__(self, data_queues: dict[str, queue.Queue]):
+        self.stream = None
+        self.effects_chain = None
+        self.data_queues = data_queues
+        self.is_running = False
+        self.effects_map = {}
+        self.last_chain_config = []
+        self.is_processing_file = False
+        self.status_count = 0
+        self.current_sample_rate = SAMPLE_RATE
+        self.build_chain([])
+
+    def build_chain(self, effects_config: list[dict]):
+        self.last_chain_config = effects_config
+        chain = ab.EffectsChain(self.current_sample_rate, CHANNELS_IN, CHANNELS_OUT, BLOCKSIZE)
+        self.effects_map.clear()
+        chain.add(ab.PlotDataTap(self.data_queues["input"]))
+        for config in effects_config:
+            fx = make_effect(config)
+            if fx is None:
+                continue
+            chain.add(fx)
+            if config.get("effect_id"):
+                self.effects_map[config["effect_id"]] = fx
+        chain.add(ab.PlotDataTap(self.data_queues["output"]))
+        chain.warmup()
+        self.effects_chain = chain
+
+    def process_file_arrays(self, audio: np.ndarray, fs: int):
+        """The numeric core of process_wav_file: (mono float32 (N,1), processed
+        float32 (N,2) already clipped, int16 (N,2))."""
+        mono = audio.mean(axis=1, keepdims=True) if audio.ndim > 1 else audio.reshape(-1, 1)
+        chain = file_chain(self.last_chain_config, fs, 1)
+        processed = np.zeros((len(mono), CHANNELS_OUT), dtype=np.float32)
+        chain.process(np.ascontiguousarray(mono, np.float32), processed)
+        processed = np.clip(processed, -1.0, 1.0)
+        return mono, processed, (processed * 32767).astype(np.int16)
+
+    async def process_wav_file(self, contents, websocket):
+        if self.is_processing_file:
+            print("Warning. A file is already being process. Ignoring new request")
+            return
+        self.is_processing_file = True
+        try:
+            print("Info: Processing WAV")
+            _, payload = contents.split(",")
+            audio, fs = read_wav(base64.b64decode(payload))
+            mono, processed, pcm = self.process_file_arrays(audio, fs)
+            with io.BytesIO() as out_io:
+                scipy.io.wavfile.write(out_io, fs, pcm)
+                processed_url = "data:audio/wav;base64," + base64.b64encode(out_io.getvalue()).decode("ascii")
+            await websocket.send(json.dumps({
+                "type": "file_processed",
+                "original_b64": contents,
+                "processed_b64": processed_url,
+                "sample_rate": fs,
+                "original_samples": mono.flatten().tolist(),
+                "processed_samples": processed.mean(axis=1).flatten().tolist(),
+            }))
+        except Exception as e:
+            print(f"Error processing WAV file: {e}")
+        finally:
+            print("Success: Finished processing WAV file")
+            self.is_processing_file = False
+
+    def update_param(self, effect_id: str, param_name: str, value: float):
+        effect = self.effects_map.get(effect_id)
+        if effect is None:
+            print(f"Error: effect ID '{effect_id}' not found")
+            return
+        setter = getattr(effect, f"set_{param_name}", None)
+        attr = getattr(effect, param_name, None)
+        if setter is not None:
+            setter(value)
+        elif isinstance(attr, ab.SmoothParam):
+            attr.set_target(value)
+        else:
+            print(f"Warning: parameter '{param_name}' in effect '{effect_id}' could not be updated")
+
+    def start_mic_stream(self):
+        if self.is_running:
+            print("Warning: stream is already running")
+            return
+        if sd is None:
+            print("Server Mode: Microphone hardware not available. Stream ignored.")
+            return
+
+        def callback(indata, outdata, frames, time, status):
+            if status:
+                self.status_count += 1
+            if self.effects_chain:
+                self.effects_chain.process(indata, outdata)
+            else:
+                outdata.fill(0)
+
+        try:
+            self.stream = sd.Stream(samplerate=self.current_sample_rate, blocksize=BLOCKSIZE,
+                                    dtype="float32", latency="low",
+                                    channels=(CHANNELS_IN, CHANNELS_OUT), callback=callback,
+                                    prime_output_buffers_using_stream_callback=True)
+            self.stream.start()
+            self.is_running = True
+            actual = self.stream.samplerate
+            if actual != self.current_sample_rate:
+                self.current_sample_rate = int(actual)
+                print(f"Rebuilding effects chain for {self.current_sample_rate} Hz...")
+                self.build_chain(self.last_chain_config)
+        except Exception as e:
+            print(f"Error on stream start: {e}")
+
+    def stop_stream(self):
+        if self.stream:
+            self.stream.stop()
+            self.stream.close()
+            self.stream = None
+            self.is_running = False

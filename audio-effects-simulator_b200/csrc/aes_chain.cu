@@ -1,0 +1,245 @@
+// aes_chain.cu -- host side of the fused effect chain: plan objects, kernel launch,
+// and the host-buffer entry that pipelines H2D / kernel / D2H over internal streams.
+#include <algorithm>
+#include <new>
+#include <string.h>
+#include <vector>
+
+#include "aes_common.h"
+#include "aes_plan_build.h"
+#include "aes_chain_kernel.cuh"
+
+#define AES_HOST_SLOTS 3
+
+struct HostSlot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    void *d_in = nullptr, *d_out = nullptr;     // device staging for one sub-batch
+    void *h_in = nullptr, *h_out = nullptr;     // pinned staging (only for pageable user buffers)
+    float *scratch = nullptr;
+    size_t in_cap = 0, out_cap = 0, hin_cap = 0, hout_cap = 0;
+    // pending copy-out of a finished sub-batch from pinned staging to the user's buffer
+    void *pend_dst = nullptr;
+    size_t pend_bytes = 0;
+};
+
+struct aes_chain_plan {
+    DevPlan host;
+    DevPlan *dev = nullptr;
+    int fs = 0, device = 0, sm_count = 0, ctas_per_sm = 0, grid_max = 0;
+    size_t smem_bytes = 0;
+    float *scratch = nullptr;                   // grid_max * scratch_floats, for aes_chain_run
+    HostSlot slot[AES_HOST_SLOTS];
+    bool slots_ready = false;
+};
+
+template <int K>
+static int configure_kernel(aes_chain_plan *pl)
+{
+    AES_CUDA(cudaFuncSetAttribute(aes_chain_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)pl->smem_bytes));
+    int occ = 0;
+    AES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, aes_chain_kernel<K>, AES_NT, pl->smem_bytes));
+    if (occ < 1) { aes_set_error("chain kernel does not fit on an SM"); return AES_ERR_UNSUPPORTED; }
+    pl->ctas_per_sm = occ;
+    return 0;
+}
+
+static int launch_chain(aes_chain_plan *pl, const void *x, int in_fmt, void *y, int out_fmt,
+                        long long B, long long N, float *scratch, cudaStream_t st)
+{
+    if (B <= 0 || N <= 0) return 0;
+    ChainArgs a{ pl->dev, x, y, B, N, scratch, in_fmt, out_fmt };
+    const unsigned grid = (unsigned)std::min<long long>(B, pl->grid_max);
+    switch (pl->host.K) {
+    case 8: aes_chain_kernel<8><<<grid, AES_NT, pl->smem_bytes, st>>>(a); break;
+    case 4: aes_chain_kernel<4><<<grid, AES_NT, pl->smem_bytes, st>>>(a); break;
+    default: aes_chain_kernel<2><<<grid, AES_NT, pl->smem_bytes, st>>>(a); break;
+    }
+    aes_count_launch();
+    AES_CUDA(cudaGetLastError());
+    return 0;
+}
+
+static size_t in_frame_bytes(int fmt)
+{
+    return fmt == AES_FMT_F32_STEREO ? 8 : 4;       // f32 mono and i16 stereo are both 4 bytes/frame
+}
+static size_t out_frame_bytes(int fmt) { return fmt == AES_FMT_I16_STEREO ? 4 : 8; }
+
+static int check_formats(int in_fmt, int out_fmt)
+{
+    AES_REQUIRE(in_fmt == AES_FMT_F32_STEREO || in_fmt == AES_FMT_F32_MONO || in_fmt == AES_FMT_I16_STEREO_DOWNMIX,
+                "unsupported input format %d", in_fmt);
+    AES_REQUIRE(out_fmt == AES_FMT_F32_STEREO || out_fmt == AES_FMT_I16_STEREO, "unsupported output format %d", out_fmt);
+    return 0;
+}
+
+AES_EXPORT int aes_chain_plan_create(const aes_stage_desc *stages, int n_stages, int sample_rate,
+                                     aes_chain_plan **out)
+{
+    AES_REQUIRE(out != nullptr, "plan out-pointer is NULL");
+    AES_REQUIRE(n_stages == 0 || stages != nullptr, "stages is NULL");
+    aes_chain_plan *pl = new (std::nothrow) aes_chain_plan();
+    if (!pl) { aes_set_error("out of host memory"); return AES_ERR_NOMEM; }
+    char err[512];
+    int rc = aes_build_devplan(stages, n_stages, sample_rate, &pl->host, err, sizeof err);
+    if (rc) { aes_set_error("%s", err); delete pl; return rc; }
+    pl->fs = sample_rate;
+    pl->smem_bytes = aes_plan_smem_bytes(pl->host);
+    rc = [&]() -> int {
+        AES_CUDA(cudaGetDevice(&pl->device));
+        AES_CUDA(cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, pl->device));
+        int r2;
+        switch (pl->host.K) {
+        case 8: r2 = configure_kernel<8>(pl); break;
+        case 4: r2 = configure_kernel<4>(pl); break;
+        default: r2 = configure_kernel<2>(pl); break;
+        }
+        if (r2) return r2;
+        pl->grid_max = pl->sm_count * pl->ctas_per_sm;
+        AES_CUDA(cudaMalloc(&pl->dev, sizeof(DevPlan)));
+        AES_CUDA(cudaMemcpy(pl->dev, &pl->host, sizeof(DevPlan), cudaMemcpyHostToDevice));
+        AES_CUDA(cudaMalloc(&pl->scratch, (size_t)pl->grid_max * pl->host.scratch_floats * sizeof(float)));
+        return 0;
+    }();
+    if (rc) { aes_chain_plan_destroy(pl); return rc; }
+    *out = pl;
+    return 0;
+}
+
+AES_EXPORT int aes_chain_plan_destroy(aes_chain_plan *pl)
+{
+    if (!pl) return 0;
+    for (HostSlot &s : pl->slot) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.h_in) cudaFreeHost(s.h_in);
+        if (s.h_out) cudaFreeHost(s.h_out);
+        if (s.scratch) cudaFree(s.scratch);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    if (pl->dev) cudaFree(pl->dev);
+    if (pl->scratch) cudaFree(pl->scratch);
+    delete pl;
+    return 0;
+}
+
+AES_EXPORT int aes_chain_plan_info(const aes_chain_plan *pl, int *tile_frames, int *smem_bytes,
+                                   int *ctas_per_sm, int64_t *scratch_bytes_per_cta)
+{
+    AES_REQUIRE(pl != nullptr, "plan is NULL");
+    if (tile_frames) *tile_frames = pl->host.T;
+    if (smem_bytes) *smem_bytes = (int)pl->smem_bytes;
+    if (ctas_per_sm) *ctas_per_sm = pl->ctas_per_sm;
+    if (scratch_bytes_per_cta) *scratch_bytes_per_cta = (int64_t)pl->host.scratch_floats * 4;
+    return 0;
+}
+
+AES_EXPORT int aes_chain_run(aes_chain_plan *pl, const void *x, int in_fmt, void *y, int out_fmt,
+                             int64_t n_clips, int64_t n_frames, void *stream)
+{
+    AES_REQUIRE(pl != nullptr, "plan is NULL");
+    AES_REQUIRE(n_clips >= 0 && n_frames >= 0, "negative size");
+    if (n_clips == 0 || n_frames == 0) return 0;
+    AES_REQUIRE(x != nullptr && y != nullptr, "NULL device buffer");
+    AES_REQUIRE(((uintptr_t)x & 7) == 0 && ((uintptr_t)y & 3) == 0, "buffers must be 8-byte aligned");
+    int rc = check_formats(in_fmt, out_fmt);
+    if (rc) return rc;
+    return launch_chain(pl, x, in_fmt, y, out_fmt, n_clips, n_frames, pl->scratch, (cudaStream_t)stream);
+}
+
+static int ensure_slots(aes_chain_plan *pl)
+{
+    if (pl->slots_ready) return 0;
+    for (HostSlot &s : pl->slot) {
+        AES_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        AES_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        AES_CUDA(cudaMalloc(&s.scratch, (size_t)pl->grid_max * pl->host.scratch_floats * sizeof(float)));
+    }
+    pl->slots_ready = true;
+    return 0;
+}
+
+static int grow(void **p, size_t *cap, size_t need, bool host)
+{
+    if (*cap >= need) return 0;
+    if (*p) { if (host) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *cap = 0; }
+    if (host) AES_CUDA(cudaMallocHost(p, need)); else AES_CUDA(cudaMalloc(p, need));
+    *cap = need;
+    return 0;
+}
+
+static bool is_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+static int drain_slot(HostSlot &s)
+{
+    AES_CUDA(cudaEventSynchronize(s.done));
+    if (s.pend_dst) { memcpy(s.pend_dst, s.h_out, s.pend_bytes); s.pend_dst = nullptr; }
+    return 0;
+}
+
+// Host buffers in, host buffers out.  The batch is cut into sub-batches of whole clips
+// (about one full grid of CTAs each); sub-batch k runs on stream k mod 3 as
+// H2D -> chain kernel -> D2H, so both copy engines and the SMs overlap.
+AES_EXPORT int aes_chain_process_host(aes_chain_plan *pl, const void *x_host, int in_fmt, void *y_host,
+                                      int out_fmt, int64_t n_clips, int64_t n_frames)
+{
+    AES_REQUIRE(pl != nullptr, "plan is NULL");
+    AES_REQUIRE(n_clips >= 0 && n_frames >= 0, "negative size");
+    if (n_clips == 0 || n_frames == 0) return 0;
+    AES_REQUIRE(x_host != nullptr && y_host != nullptr, "NULL host buffer");
+    int rc = check_formats(in_fmt, out_fmt);
+    if (rc) return rc;
+    if ((rc = ensure_slots(pl))) return rc;
+
+    const size_t in_clip = (size_t)n_frames * in_frame_bytes(in_fmt);
+    const size_t out_clip = (size_t)n_frames * out_frame_bytes(out_fmt);
+    // sub-batch: one grid's worth of clips, capped at ~1 GiB of input per slot
+    int64_t per = std::max<int64_t>(1, pl->grid_max);
+    const size_t cap_bytes = (size_t)1 << 30;
+    if ((size_t)per * in_clip > cap_bytes) per = std::max<int64_t>(1, (int64_t)(cap_bytes / in_clip));
+    per = std::min<int64_t>(per, n_clips);
+    // keep at least AES_HOST_SLOTS sub-batches in flight when the batch allows it
+    if (n_clips >= 2 * AES_HOST_SLOTS && per * AES_HOST_SLOTS > n_clips)
+        per = (n_clips + AES_HOST_SLOTS - 1) / AES_HOST_SLOTS;
+    const bool pin_in = is_pinned(x_host), pin_out = is_pinned(y_host);
+
+    int k = 0;
+    for (int64_t b0 = 0; b0 < n_clips; b0 += per, ++k) {
+        const int64_t nb = std::min<int64_t>(per, n_clips - b0);
+        HostSlot &s = pl->slot[k % AES_HOST_SLOTS];
+        if (k >= AES_HOST_SLOTS && (rc = drain_slot(s))) return rc;
+        if ((rc = grow(&s.d_in, &s.in_cap, (size_t)per * in_clip, false))) return rc;
+        if ((rc = grow(&s.d_out, &s.out_cap, (size_t)per * out_clip, false))) return rc;
+        const char *src = (const char *)x_host + (size_t)b0 * in_clip;
+        char *dst = (char *)y_host + (size_t)b0 * out_clip;
+        if (!pin_in) {
+            if ((rc = grow(&s.h_in, &s.hin_cap, (size_t)per * in_clip, true))) return rc;
+            memcpy(s.h_in, src, (size_t)nb * in_clip);
+            src = (const char *)s.h_in;
+        }
+        AES_CUDA(cudaMemcpyAsync(s.d_in, src, (size_t)nb * in_clip, cudaMemcpyHostToDevice, s.stream));
+        if ((rc = launch_chain(pl, s.d_in, in_fmt, s.d_out, out_fmt, nb, n_frames, s.scratch, s.stream))) return rc;
+        if (!pin_out) {
+            if ((rc = grow(&s.h_out, &s.hout_cap, (size_t)per * out_clip, true))) return rc;
+            AES_CUDA(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)nb * out_clip, cudaMemcpyDeviceToHost, s.stream));
+            s.pend_dst = dst;
+            s.pend_bytes = (size_t)nb * out_clip;
+        } else {
+            AES_CUDA(cudaMemcpyAsync(dst, s.d_out, (size_t)nb * out_clip, cudaMemcpyDeviceToHost, s.stream));
+        }
+        AES_CUDA(cudaEventRecord(s.done, s.stream));
+    }
+    const int used = std::min(k, AES_HOST_SLOTS);
+    for (int i = 0; i < used; ++i)
+        if ((rc = drain_slot(pl->slot[i]))) return rc;
+    return 0;
+}

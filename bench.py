@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the offline effect-chain hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # B200 arm (this repo)
+    python bench.py --impl reference --gpus N --steps K ...  # reference arm: the CPU algorithm on host cores
+
+A "step" is one pass of the fused preset chain over one batch of synthetic 48 kHz
+stereo clips that is already resident in HBM (`value`), and the same batch pushed
+through the reference-facing host-buffer call with H2D/D2H inside the timed region
+(`e2e`).  1 sample = one float32 value of one channel of output;
+algorithmic traffic is 8 bytes per sample (read once, write once).
+
+Under torchrun (N>1) every rank processes its own shard of clips (no data-path
+collective: clips are independent), times it with CUDA events, and rank 0 reports
+total samples / max-over-ranks time ("scaling": "weak").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "audio-effects-simulator_b200"), os.path.join(ROOT, "tests")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+FS = 48000
+METRIC = "Msamples/s through preset chain"
+UNIT = "Msamples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--preset", default="Rain Delay")
+    ap.add_argument("--clips", type=int, default=1024, help="clips per GPU")
+    ap.add_argument("--seconds", type=float, default=10.0, help="clip length")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-clips", type=int, default=0, help="clips in the CPU baseline sample (0 = auto)")
+    return ap.parse_args()
+
+
+def workload(args):
+    return {"workload": f"'{args.preset}' preset chain (app.py:41-71) on {args.clips} synthetic "
+                        f"{args.seconds:g} s 48 kHz stereo float32 clips per GPU (BASELINE configs[4] shard)",
+            "preset": args.preset, "clips_per_gpu": args.clips, "frames_per_clip": int(args.seconds * FS),
+            "sample_rate": FS, "l2": "inputs larger than L2 (no flush needed)", "parallelism": "clip-sharded"}
+
+
+# ------------------------------------------------------------------ reference arm / CPU baseline
+def cpu_run(preset, n_clips, n_frames, threads, reps=1):
+    """Time the CPU port of the reference algorithm (oracle, fast build) on `n_clips` clips."""
+    import numpy as np
+    import synth
+    from oracle import oracle as orc
+    x = np.stack([synth.clip(i % 16, n_frames, 2) for i in range(min(n_clips, 16))])
+    if n_clips > x.shape[0]:
+        x = np.concatenate([x] * ((n_clips + x.shape[0] - 1) // x.shape[0]))[:n_clips]
+    x = np.ascontiguousarray(x)
+    cfg = synth.PRESETS[preset]
+    orc.run_batch_c(cfg, x[:threads], FS, threads=threads, fast=True)      # page in / warm caches
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        orc.run_batch_c(cfg, x, FS, threads=threads, fast=True)
+        best = min(best, time.perf_counter() - t0)
+    return x.size / best / 1e6, best
+
+
+def reference_arm(args):
+    """The reference's own algorithm on the box's host cores.  The reference is pure
+    Python+numba and cannot travel to the GPU box, so this times the C port under
+    oracle/ (kind "port"), one clip per thread like the reference's single-threaded
+    kernels, on all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_frames = int(args.seconds * FS)
+    n_clips = args.cpu_clips or max(cores, min(4 * cores, 256))
+    cpu_run(args.preset, cores, n_frames, cores)
+    times = []
+    for _ in range(args.warmup):
+        cpu_run(args.preset, n_clips, n_frames, cores)
+    for _ in range(args.steps):
+        _, dt = cpu_run(args.preset, n_clips, n_frames, cores)
+        times.append(dt)
+    total = sum(times)
+    value = n_clips * n_frames * 2 * len(times) / total / 1e6
+    sample = f"{n_clips} clips x {args.seconds:g} s per step on {cores} threads (one clip per thread)"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, len(times)),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------ B200 arm
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def synth_device(torch, n_clips, n_frames, first_clip, device):
+    """Synthetic batch on the device with the shape of SURVEY 8d: white noise + a per-clip
+    tone + a 50 ms full-scale burst every 2 s; (B, N, 2) float32."""
+    g = torch.Generator(device=device)
+    g.manual_seed(1000 + first_clip)
+    x = torch.empty((n_clips, n_frames, 2), dtype=torch.float32, device=device)
+    t = torch.arange(n_frames, device=device, dtype=torch.float32) / FS
+    burst = ((torch.arange(n_frames, device=device) % (2 * FS)) < int(0.05 * FS))
+    sq = 0.95 * torch.sign(torch.sin(2 * torch.pi * 997.0 * t) + 1e-12)
+    step = 64
+    for b0 in range(0, n_clips, step):
+        nb = min(step, n_clips - b0)
+        idx = torch.arange(first_clip + b0, first_clip + b0 + nb, device=device) % 48
+        f = 110.0 * torch.pow(torch.tensor(2.0, device=device), idx.float() / 12.0)
+        tone = 0.35 * torch.sin(2 * torch.pi * f[:, None] * t[None, :])
+        noise = 0.25 * (2.0 * torch.rand((nb, n_frames, 2), generator=g, device=device) - 1.0)
+        blk = noise + tone[:, :, None]
+        blk = torch.where(burst[None, :, None], sq[None, :, None], blk)
+        x[b0:b0 + nb] = blk
+    return x
+
+
+def b200_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import audioblocks  # noqa: F401
+    from audioblocks import _native
+    from audioblocks.engine import file_chain
+    import synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the B200 arm has no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _native.lib()
+    _native.check(L.aes_set_device(local))
+
+    n_frames = int(args.seconds * FS)
+    B = args.clips
+    cfg = synth.PRESETS[args.preset]
+    chain = file_chain(cfg, FS, channels_in=2)            # build@1024 + warm-up, as engine.py:86-99
+    plan = chain.prepare_batch(n_frames)                  # re-prepared at the file's frame count
+    info = plan.info()
+
+    x = synth_device(torch, B, n_frames, rank * B, dev)
+    y = torch.empty_like(x)
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+
+    def step():
+        plan.run_device(x.data_ptr(), _native.FMT_F32_STEREO, y.data_ptr(), _native.FMT_F32_STEREO, B, n_frames, sptr)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = L.aes_launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    barrier()
+    ev[0].record(stream)
+    for k in range(args.steps):
+        step()
+        ev[k + 1].record(stream)
+    barrier()
+    launches = L.aes_launch_count() - launches0
+    total_ms = ev[0].elapsed_time(ev[-1])
+    per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    clk = clocks.stop() if rank == 0 else None
+
+    # parity spot check of the timed buffers (first clip of this rank) against the oracle
+    parity = None
+    if rank == 0 and not args.no_cpu:
+        from oracle import oracle as orc
+        n_chk = min(n_frames, 96000)
+        xs = x[0, :n_chk].cpu().numpy()
+        want = orc.run_file_path(cfg, np.ascontiguousarray(xs), FS)
+        got = y[0, :n_chk].cpu().numpy()
+        mx, snr = synth.err_stats(got, want)
+        parity = {"max_abs_err": mx, "snr_db": snr, "frames": n_chk}
+
+    # ---- end to end through the host-buffer call (pinned host memory, H2D + D2H timed)
+    e2e = None
+    if not args.no_e2e:
+        Be = B
+        xh = _native.pinned_empty((Be, n_frames, 2), np.float32)
+        yh = _native.pinned_empty((Be, n_frames, 2), np.float32)
+        torch.from_numpy(xh).copy_(x[:Be])
+        torch.cuda.synchronize()
+        fmt = _native.FMT_F32_STEREO
+        plan.run_host(xh, fmt, yh, fmt, Be, n_frames)     # warm-up: allocates the staging slots
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            plan.run_host(xh, fmt, yh, fmt, Be, n_frames)
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        e2e_ok = bool(np.array_equal(yh[0, :4096], y[0, :4096].cpu().numpy()))
+        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * Be * n_frames * 2 * args.e2e_steps / float(t.item()) / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": int(xh.nbytes), "d2h_bytes_per_step": int(yh.nbytes),
+               "steps": args.e2e_steps, "matches_device_path": e2e_ok,
+               "api": "EffectsChain.prepare_batch(...).run_host -> aes_chain_process_host (pinned host buffers)"}
+        del xh, yh
+
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+
+    if rank == 0:
+        samples_per_step = world * B * n_frames * 2
+        value = samples_per_step * args.steps / (total_ms * 1e-3) / 1e6
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        else:
+            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+        k_ms = sum(per_launch_ms) / len(per_launch_ms)
+        achieved = B * n_frames * 2 * 8 / (k_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {**workload(args), "tile_frames": info["tile_frames"], "smem_bytes_per_cta": info["smem_bytes"],
+                       "ctas_per_sm": info["ctas_per_sm"]},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "kernel": "aes_chain_kernel<8>", "algorithmic_bytes_per_launch": B * n_frames * 16,
+                         "launch_ms": k_ms},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "parity": parity,
+        }
+        if not args.no_cpu:
+            cores = os.cpu_count() or 1
+            n_cpu = args.cpu_clips or max(cores, min(2 * cores, 128))
+            v, dt = cpu_run(args.preset, n_cpu, n_frames, cores)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": f"{n_cpu} clips x {args.seconds:g} s, {cores} threads, {dt:.2f} s"}
+        print(json.dumps(line))
+    plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

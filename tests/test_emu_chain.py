@@ -1,0 +1,102 @@
+"""Kernel-logic tests without a GPU: the product's chain kernel SOURCE
+(csrc/aes_chain_kernel.cuh) and plan compiler run on the CPU emulator in
+tests/cpu_emu and are held to the reference's golden vectors and to the oracle.
+The same cases run on the real sm_100a build in tests/test_gpu_parity.py."""
+import numpy as np
+import pytest
+
+import emu
+import goldens
+import synth
+from oracle import oracle as orc
+
+FP_TOL = 1e-5      # north_star: max-abs 1e-5 of full scale, SNR > 100 dB
+NATIVE = [n for n in synth.PRESETS if n != "Clean Noise Removal"]      # spectral: no CUDA block yet
+
+
+def check(got, want, exact=False, what=""):
+    mx, snr = synth.err_stats(got, want)
+    if exact:
+        assert np.array_equal(got, want), (what, mx)
+    scale = max(1.0, float(np.max(np.abs(want))))
+    assert mx <= FP_TOL * scale and snr >= 100.0, (what, mx, snr)
+
+
+def test_golden_blocks_through_emulated_kernel():
+    z, meta = goldens.load("blocks")
+    for name, m in meta.items():
+        if name.startswith("spectral"):
+            continue
+        x = goldens.block_input(m)
+        d = emu.resolved_descs(m["config"], m["fs"], m["n"], m["ci"])
+        y = emu.run(d, m["fs"], x[None])[0]
+        check(y, z[name + "_y"], exact=(name == "delay_fb0"), what=name)
+
+
+def test_golden_presets_through_emulated_kernel():
+    z, meta = goldens.load("presets")
+    mono = np.ascontiguousarray(z["rain_mono"], np.float32)
+    syn = goldens.syn_input(meta["syn"])
+    for name in NATIVE:
+        key = meta["presets"][name]
+        cfg = synth.PRESETS[name]
+        y = emu.run(emu.resolved_descs(cfg, meta["rain"]["fs"], mono.shape[0], 1), meta["rain"]["fs"], mono[None])[0]
+        check(y, z[f"rain_{key}"], exact=(name == "Slapback Echo"), what=("rain", name))
+        y = emu.run(emu.resolved_descs(cfg, 48000, syn.shape[0], 2), 48000, syn[None])[0]
+        check(y, z[f"syn_{key}"], exact=(name == "Slapback Echo"), what=("syn", name))
+
+
+@pytest.mark.parametrize("n", [1, 2, 255, 1024, 1025, 2999])
+def test_ragged_lengths(n):
+    cfg = synth.PRESETS["Robot Voice"] + synth.PRESETS["Guitar Filter"]
+    x = synth.clip(11, n, 2)
+    y = emu.run(emu.resolved_descs(cfg, 48000, n, 2), 48000, x[None])[0]
+    check(y, orc.run_file_path(cfg, x, 48000), what=n)
+
+
+def test_batch_striding_and_fresh_state_per_clip():
+    cfg = synth.PRESETS["Rain Delay"]
+    n = 21000
+    x = synth.batch(20, 3, n)
+    y = emu.run(emu.resolved_descs(cfg, 48000, n, 2), 48000, x, grid=2)      # CTA 0 takes clips 0 and 2
+    for b in range(3):
+        check(y[b], orc.run_file_path(cfg, x[b], 48000), what=b)
+
+
+@pytest.mark.parametrize("fs,tile", [(44100, 1024), (22050, 512), (11025, 256)])
+def test_smaller_tiles_at_lower_sample_rates(fs, tile):
+    cfg = synth.PRESETS["Cathedral"]
+    n = 9000
+    x = synth.clip(5, n, 2, fs)
+    d = emu.resolved_descs(cfg, fs, n, 2)
+    y = emu.run(d, fs, x[None])[0]
+    check(y, orc.run_file_path(cfg, x, fs), what=fs)
+
+
+def test_int16_file_path_formats():
+    """engine.py:78-84 down-mix on the way in, engine.py:104-105 quantise on the way out."""
+    cfg = synth.PRESETS["Slapback Echo"]
+    n = 12000
+    rng = np.random.default_rng(5)
+    pcm = rng.integers(-32768, 32767, (1, n, 2), dtype=np.int16)
+    d = emu.resolved_descs(cfg, 48000, n, 1)
+    q = emu.run(d, 48000, pcm, out_dtype=np.int16)[0]
+    audio = pcm[0].astype(np.float32) / np.float32(32768.0)
+    mono = orc.mono_downmix(audio)
+    want = orc.quantize_i16(np.clip(orc.run_file_path(cfg, mono, 48000), -1.0, 1.0))
+    assert np.array_equal(q, want)                       # index-only chain: bit-exact end to end
+
+
+def test_distortion_and_peaking_extensions():
+    cfg = [{"type": "distortion", "params": {"drive": 4.0, "mix": 0.7}},
+           {"type": "filter", "params": {"filter_type": 3, "cutoff_hz": 1000, "q": 1.0, "gain_db": 6.0}}]
+    n = 6000
+    x = synth.clip(2, n, 2)
+    y = emu.run(emu.resolved_descs(cfg, 48000, n, 2), 48000, x[None])[0]
+    check(y, orc.run_file_path(cfg, x, 48000))
+
+
+def test_unsupported_short_comb_is_refused():
+    cfg = [{"type": "reverb", "params": {"comb_times_ms": (1.0, 2.0)}}]
+    with pytest.raises(RuntimeError, match="shorter than the smallest tile"):
+        emu.run(emu.resolved_descs(cfg, 48000, 4096, 2), 48000, synth.clip(0, 4096, 2)[None])

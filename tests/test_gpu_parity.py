@@ -1,0 +1,197 @@
+"""Parity tests proper: the sm_100a build behind the C ABI (through the drop-in
+`audioblocks` API) against the reference's golden vectors and the CPU oracle."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import goldens
+import synth
+
+pytestmark = pytest.mark.gpu
+
+FP_TOL = 1e-5      # north_star: max-abs 1e-5 of full scale, SNR > 100 dB
+NATIVE = [n for n in synth.PRESETS if n != "Clean Noise Removal"]
+
+
+@pytest.fixture(scope="module")
+def ab():
+    import audioblocks
+    from audioblocks import _native
+    _native.lib()                                  # fail loudly if the CUDA library is missing
+    return audioblocks
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+def check(got, want, exact=False, what=""):
+    mx, snr = synth.err_stats(got, want)
+    if exact:
+        assert np.array_equal(got, want), (what, mx)
+    scale = max(1.0, float(np.max(np.abs(want))))
+    assert mx <= FP_TOL * scale and snr >= 100.0, (what, mx, snr)
+
+
+def run_file(ab, config, x, fs):
+    """engine.py:86-102 through the drop-in package: build@1024, warm-up, one whole call."""
+    from audioblocks.engine import file_chain
+    chain = file_chain(config, fs, channels_in=x.shape[1])
+    out = np.zeros((x.shape[0], 2), np.float32)
+    chain.process(x, out)
+    return out
+
+
+def test_golden_blocks(ab):
+    z, meta = goldens.load("blocks")
+    for name, m in meta.items():
+        if name.startswith("spectral"):
+            continue
+        y = run_file(ab, m["config"], goldens.block_input(m), m["fs"])
+        check(y, z[name + "_y"], exact=(name == "delay_fb0"), what=name)
+
+
+def test_golden_presets_rain_and_synthetic(ab):
+    z, meta = goldens.load("presets")
+    mono = np.ascontiguousarray(z["rain_mono"], np.float32)
+    syn = goldens.syn_input(meta["syn"])
+    for name in NATIVE:
+        key = meta["presets"][name]
+        y = run_file(ab, synth.PRESETS[name], mono, meta["rain"]["fs"])
+        check(y, z[f"rain_{key}"], exact=(name == "Slapback Echo"), what=("rain", name))
+        q = (np.clip(y, -1.0, 1.0) * 32767).astype(np.int16)
+        assert np.max(np.abs(q.astype(np.int32) - z[f"rain_{key}_i16"].astype(np.int32))) <= 1
+        y = run_file(ab, synth.PRESETS[name], syn, 48000)
+        check(y, z[f"syn_{key}"], exact=(name == "Slapback Echo"), what=("syn", name))
+
+
+@pytest.mark.parametrize("n", [1, 2, 255, 1024, 1025, 2999, 70001])
+def test_ragged_lengths(ab, orc, n):
+    cfg = synth.PRESETS["Robot Voice"] + synth.PRESETS["Guitar Filter"]
+    x = synth.clip(11, n, 2)
+    check(run_file(ab, cfg, x, 48000), orc.run_file_path(cfg, x, 48000), what=n)
+
+
+@pytest.mark.parametrize("name", NATIVE)
+def test_batch_matches_oracle_per_clip(ab, orc, name):
+    from audioblocks.engine import file_chain
+    cfg = synth.PRESETS[name]
+    n, B = 100000, 6
+    x = synth.batch(40, B, n)
+    y = file_chain(cfg, 48000, channels_in=2).process_batch(x)
+    for b in range(B):
+        check(y[b], orc.run_file_path(cfg, x[b], 48000), exact=(name == "Slapback Echo"), what=(name, b))
+
+
+def test_many_clips_fresh_state_and_grid_striding(ab, orc):
+    """More clips than resident CTAs: every clip must start from fresh lines."""
+    from audioblocks.engine import file_chain
+    cfg = synth.PRESETS["Rain Delay"]
+    n, B = 20000, 700
+    base = synth.batch(60, 4, n)
+    x = np.ascontiguousarray(np.tile(base, (B // 4, 1, 1)))
+    y = file_chain(cfg, 48000, channels_in=2).process_batch(x)
+    want = [orc.run_file_path(cfg, base[k], 48000) for k in range(4)]
+    for b in range(B):
+        assert np.array_equal(y[b], y[b % 4]), b              # identical inputs -> identical outputs
+    for k in range(4):
+        check(y[k], want[k], what=k)
+
+
+@pytest.mark.parametrize("fs", [44100, 22050, 11025])
+def test_lower_sample_rates_use_smaller_tiles(ab, orc, fs):
+    cfg = synth.PRESETS["Cathedral"]
+    x = synth.clip(5, 30000, 2, fs)
+    check(run_file(ab, cfg, x, fs), orc.run_file_path(cfg, x, fs), what=fs)
+
+
+def test_int16_file_path_bit_exact(ab, orc):
+    """engine.py:78-84 down-mix in, engine.py:104-105 quantise out; index-only chain."""
+    from audioblocks.engine import file_chain
+    cfg = synth.PRESETS["Slapback Echo"]
+    n = 50000
+    rng = np.random.default_rng(5)
+    pcm = rng.integers(-32768, 32767, (3, n, 2), dtype=np.int16)
+    out = np.empty((3, n, 2), np.int16)
+    file_chain(cfg, 48000, channels_in=1).process_batch(pcm, out)
+    for b in range(3):
+        mono = orc.mono_downmix(pcm[b].astype(np.float32) / np.float32(32768.0))
+        want = orc.quantize_i16(np.clip(orc.run_file_path(cfg, mono, 48000), -1.0, 1.0))
+        assert np.array_equal(out[b], want)
+
+
+def test_extensions_distortion_peaking(ab, orc):
+    cfg = [{"type": "distortion", "params": {"drive": 4.0, "mix": 0.7}},
+           {"type": "filter", "params": {"filter_type": 3, "cutoff_hz": 1000, "q": 1.0, "gain_db": 6.0}},
+           {"type": "octaver", "params": {"semitones": -12, "mix": 0.5}},
+           {"type": "delay", "params": {"delay_ms": 120, "feedback": 0.3, "offset_ms": 10}}]
+    x = synth.clip(2, 60000, 2)
+    check(run_file(ab, cfg, x, 48000), orc.run_file_path(cfg, x, 48000))
+
+
+def test_c2_biquad_cascade_long_clip(ab, orc):
+    """BASELINE configs[1]: one long stereo clip through LP/HP/BP/peaking, plus the low-fc stress."""
+    n = 48000 * 20
+    x = synth.clip(1, n, 2)
+    cfg = [{"type": "filter", "params": {"filter_type": 0, "cutoff_hz": 8000, "q": 0.707}},
+           {"type": "filter", "params": {"filter_type": 1, "cutoff_hz": 80, "q": 0.707}},
+           {"type": "filter", "params": {"filter_type": 2, "cutoff_hz": 1000, "q": 0.8}},
+           {"type": "filter", "params": {"filter_type": 3, "cutoff_hz": 1000, "q": 1.0, "gain_db": 6.0}}]
+    check(run_file(ab, cfg, x, 48000), orc.run_file_path(cfg, x, 48000), what="cascade")
+    cfg = [{"type": "filter", "params": {"filter_type": 0, "cutoff_hz": 40, "q": 5.0}}]
+    check(run_file(ab, cfg, x, 48000), orc.run_file_path(cfg, x, 48000), what="lp40q5")
+
+
+def test_full_size_properties(ab):
+    """BASELINE-size clip (10 s): size-independent properties instead of a CPU run.
+    Slapback (fb=0): out[n] = clip(x[n] + 0.5*x[n-4800]) exactly; and linearity of the
+    un-clipped reverb: reverb(a*x) == a*reverb(x) for a power-of-two gain."""
+    from audioblocks.engine import file_chain
+    n = 480000
+    x = synth.batch(80, 2, n) * np.float32(0.25)
+    y = file_chain(synth.PRESETS["Slapback Echo"], 48000, channels_in=2).process_batch(x)
+    d = np.zeros_like(x)
+    d[:, 4800:] = x[:, :-4800]
+    want = np.clip(np.float32(1.0) * x + np.float32(0.5) * d, -1.0, 1.0)
+    assert np.array_equal(y, want)
+    cfg = [{"type": "reverb", "params": {"rt60_s": 1.0, "mix_wet": 0.25, "mix_dry": 0.25}}]
+    x = x * np.float32(0.25)
+    y1 = file_chain(cfg, 48000, channels_in=2).process_batch(x)
+    y2 = file_chain(cfg, 48000, channels_in=2).process_batch(x * np.float32(0.5))
+    assert np.max(np.abs(y1)) < 1.0
+    assert np.array_equal(y1 * np.float32(0.5), y2)          # scaling by 2^-1 commutes with every rounding
+
+
+def test_engine_process_file_arrays(ab, orc):
+    import queue
+    eng = ab.AudioEngine({"input": queue.Queue(10), "output": queue.Queue(10)})
+    eng.last_chain_config = synth.PRESETS["Rain Delay"]
+    z, meta = goldens.load("presets")
+    mono = np.ascontiguousarray(z["rain_mono"], np.float32)
+    stereo = np.repeat(mono, 2, axis=1)
+    m, processed, pcm = eng.process_file_arrays(stereo, meta["rain"]["fs"])
+    assert np.array_equal(m, mono)
+    check(processed, np.clip(z["rain_Rain_Delay"], -1, 1))
+    assert np.max(np.abs(pcm.astype(np.int32) - z["rain_Rain_Delay_i16"].astype(np.int32))) <= 1
+
+
+def test_single_block_c_abi_entries(ab, orc):
+    import torch
+    from audioblocks import _native
+    L = _native.lib()
+    n, B = 30000, 3
+    x = synth.batch(90, B, n)
+    xd = torch.from_numpy(x).cuda()
+    yd = torch.empty_like(xd)
+    _native.check(L.aes_delay_f32(xd.data_ptr(), yd.data_ptr(), B, n, 4800, 5280, 0.3, 1.0, 0.3, None))
+    cfg = [{"type": "delay", "params": {"delay_ms": 100, "feedback": 0.3, "mix_wet": 0.3, "mix_dry": 1.0, "offset_ms": 10}}]
+    for b in range(B):
+        check(yd[b].cpu().numpy(), orc.run_file_path(cfg, x[b], 48000))
+    qd = torch.empty((B, n, 2), dtype=torch.int16, device="cuda")
+    _native.check(L.aes_quantize_i16(yd.data_ptr(), qd.data_ptr(), B * n * 2, None))
+    torch.cuda.synchronize()
+    assert np.array_equal(qd.cpu().numpy(), (np.clip(yd.cpu().numpy(), -1, 1) * 32767).astype(np.int16))
+    assert L.aes_launch_count() > 0
