@@ -12,3 +12,4 @@ from .octaver import OctaverEffect
 from .filter import FilterEffect
 from .distortion import DistortionEffect
 from .engine import AudioEngine, SAMPLE_RATE
+from . import sharding

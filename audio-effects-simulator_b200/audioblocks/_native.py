@@ -53,6 +53,7 @@ def lib() -> C.CDLL:
         L.aes_chain_plan_destroy.argtypes = [vp]
         L.aes_chain_run.argtypes = [vp, vp, ci, vp, ci, i64, i64, vp]
         L.aes_chain_process_host.argtypes = [vp, vp, ci, vp, ci, i64, i64]
+        L.aes_chain_final_state.argtypes = [vp, ci, C.POINTER(C.c_double)]
         L.aes_chain_plan_info.argtypes = [vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci), C.POINTER(i64)]
         L.aes_malloc.argtypes = [C.POINTER(vp), C.c_size_t]
         L.aes_free.argtypes = [vp]
@@ -112,6 +113,12 @@ class ChainPlan:
         assert x.flags.c_contiguous and y.flags.c_contiguous
         check(lib().aes_chain_process_host(self._h, C.c_void_p(x.ctypes.data), in_fmt,
                                            C.c_void_p(y.ctypes.data), out_fmt, n_clips, n_frames))
+
+    def final_state(self, stage: int):
+        """Carried scalars (16 doubles) of `stage` after a single-clip run_host."""
+        out = (C.c_double * 16)()
+        check(lib().aes_chain_final_state(self._h, stage, out))
+        return list(out)
 
     def close(self):
         if self._h:

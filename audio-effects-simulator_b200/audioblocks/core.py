@@ -109,7 +109,9 @@ class NativeEffect(Effect):
     def _stages(self, frames: int) -> list:
         raise NotImplementedError
 
-    def _advance(self, frames: int, silent: bool):
+    def _advance(self, frames: int, silent: bool, final=None):
+        """Host-visible state after a block of `frames`; `final` holds the stage's carried
+        scalars read back from the device (None when nothing was run)."""
         if not silent:
             self._dirty = True
 
@@ -141,17 +143,19 @@ def run_native(effects, sample_rate, x_in: np.ndarray, out: np.ndarray):
     if out.shape != (frames, 2):
         raise ValueError("output block must be (frames, 2)")
     y = out if (out.dtype == np.float32 and out.flags.c_contiguous) else np.empty((frames, 2), np.float32)
+    finals = [None] * len(descs)
     if frames > 0:
         plan = _native.ChainPlan(descs, sample_rate)
         try:
             plan.run_host(x, fmt_in, y, _native.FMT_F32_STEREO, 1, frames)
+            finals = [plan.final_state(s) for s in range(len(descs))]
         finally:
             plan.close()
     if y is not out:
         out[:, :] = y
     silent = not x.any()
-    for fx in effects:
-        fx._advance(frames, silent)
+    for fx, final in zip(effects, finals):          # one stage per effect
+        fx._advance(frames, silent, final)
 
 
 class PlotDataTap(Effect):

@@ -25,5 +25,5 @@ class DistortionEffect(NativeEffect):
         d.p[1] = self.mix.step_towards(0.05)
         return [d]
 
-    def _advance(self, frames, silent):
+    def _advance(self, frames, silent, final=None):
         pass                      # memoryless

@@ -72,8 +72,9 @@ class FilterEffect(NativeEffect):
                 d.p[8 + 4 * c + k] = float(row[k])
         return [d]
 
-    def _advance(self, frames, silent):
-        # The filter keeps no delay line; its 4 scalars are re-seeded from _state on
-        # every call.  The whole-clip path does not read the final state back.
-        if not silent:
-            self._dirty = True
+    def _advance(self, frames, silent, final=None):
+        # The filter keeps no delay line: its DF-I scalars come back from the device and
+        # are stored as float32 between calls, like the reference's state array (filter.py:35-40).
+        if final is not None:
+            for c in range(self._state.shape[0]):
+                self._state[c, :] = final[4 * c:4 * c + 4]

@@ -41,9 +41,6 @@ class NoiseGateEffect(NativeEffect):
         self._rel_now = d.p[2]
         return [d]
 
-    def _advance(self, frames, silent):
-        if silent:
-            # silence keeps the detector below any threshold: pure release decay
-            self._gain_state *= (1.0 - self._rel_now) ** frames
-        else:
-            self._dirty = True
+    def _advance(self, frames, silent, final=None):
+        if final is not None:
+            self._gain_state = float(final[0])      # gain after the block's last frame (gate.py:42)

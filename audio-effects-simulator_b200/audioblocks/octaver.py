@@ -43,7 +43,7 @@ class OctaverEffect(NativeEffect):
         d.p[0], d.p[1], d.p[2] = self.phasor, self._step_now, mix_now
         return [d]
 
-    def _advance(self, frames, silent):
+    def _advance(self, frames, silent, final=None):
         self.w = (self.w + frames) % self.size
         step, ph = self._step_now, self.phasor
         if frames <= 8192:            # the reference's running sum, bit for bit (octaver.py:77-80)

@@ -1,0 +1,62 @@
+"""Batch sharding across the GPUs of one box (one process per GPU, torch.distributed).
+
+Clips and (clip, preset) pairs are independent: rank r processes a
+contiguous slice of the batch with no exchange during compute.  The only
+collective is the optional gather of results over NCCL/NVLink (gloo on CPU in the
+tests); it is never inside the timed compute region -- gathering full float32
+audio onto one GPU costs ~25x the compute at roofline, so callers gather int16 or
+per-clip statistics when they can."""
+from __future__ import annotations
+
+
+def shard_range(total: int, rank: int, world: int) -> tuple[int, int]:
+    """Contiguous, balanced [start, stop) of `total` items for `rank` of `world`:
+    the first total % world ranks take one extra item."""
+    if world < 1 or not 0 <= rank < world or total < 0:
+        raise ValueError("bad shard request")
+    base, extra = divmod(total, world)
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_sizes(total: int, world: int) -> list[int]:
+    return [shard_range(total, r, world)[1] - shard_range(total, r, world)[0] for r in range(world)]
+
+
+def gather_clips(y_local, total: int, dst: int | None = 0, group=None):
+    """Gather per-rank results (n_local, frames, 2) into (total, frames, 2).
+
+    dst=None -> every rank gets the full batch (all_gather); otherwise only `dst`
+    does (others return None).  Works for CUDA tensors over NCCL and CPU tensors
+    over gloo; ragged shards are padded to the largest one for the collective."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    sizes = shard_sizes(total, world)
+    if y_local.shape[0] != sizes[rank]:
+        raise ValueError(f"rank {rank}: expected {sizes[rank]} clips, got {y_local.shape[0]}")
+    cap = max(sizes)
+    pad = y_local
+    if y_local.shape[0] < cap:
+        pad = torch.zeros((cap,) + tuple(y_local.shape[1:]), dtype=y_local.dtype, device=y_local.device)
+        pad[: y_local.shape[0]] = y_local
+    pad = pad.contiguous()
+    if dst is None:
+        bufs = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(bufs, pad, group=group)
+    else:
+        bufs = [torch.empty_like(pad) for _ in range(world)] if rank == dst else None
+        dist.gather(pad, bufs, dst=dst, group=group)
+        if rank != dst:
+            return None
+    return torch.cat([b[:n] for b, n in zip(bufs, sizes)], dim=0)
+
+
+def max_over_ranks(seconds: float, device=None, group=None) -> float:
+    """Timing reduction used by bench.py: the slowest rank defines the step."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([seconds], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())

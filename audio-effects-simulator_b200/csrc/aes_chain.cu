@@ -29,6 +29,9 @@ struct aes_chain_plan {
     int fs = 0, device = 0, sm_count = 0, ctas_per_sm = 0, grid_max = 0;
     size_t smem_bytes = 0;
     float *scratch = nullptr;                   // grid_max * scratch_floats, for aes_chain_run
+    double *d_state = nullptr;                  // final carried scalars of a single-clip host call
+    double h_state[16 * AES_MAX_STAGES];
+    bool state_valid = false;
     HostSlot slot[AES_HOST_SLOTS];
     bool slots_ready = false;
 };
@@ -46,10 +49,10 @@ static int configure_kernel(aes_chain_plan *pl)
 }
 
 static int launch_chain(aes_chain_plan *pl, const void *x, int in_fmt, void *y, int out_fmt,
-                        long long B, long long N, float *scratch, cudaStream_t st)
+                        long long B, long long N, float *scratch, cudaStream_t st, double *state_out = nullptr)
 {
     if (B <= 0 || N <= 0) return 0;
-    ChainArgs a{ pl->dev, x, y, B, N, scratch, in_fmt, out_fmt };
+    ChainArgs a{ pl->dev, x, y, B, N, scratch, in_fmt, out_fmt, state_out };
     const unsigned grid = (unsigned)std::min<long long>(B, pl->grid_max);
     switch (pl->host.K) {
     case 8: aes_chain_kernel<8><<<grid, AES_NT, pl->smem_bytes, st>>>(a); break;
@@ -101,6 +104,7 @@ AES_EXPORT int aes_chain_plan_create(const aes_stage_desc *stages, int n_stages,
         AES_CUDA(cudaMalloc(&pl->dev, sizeof(DevPlan)));
         AES_CUDA(cudaMemcpy(pl->dev, &pl->host, sizeof(DevPlan), cudaMemcpyHostToDevice));
         AES_CUDA(cudaMalloc(&pl->scratch, (size_t)pl->grid_max * pl->host.scratch_floats * sizeof(float)));
+        AES_CUDA(cudaMalloc(&pl->d_state, sizeof pl->h_state));
         return 0;
     }();
     if (rc) { aes_chain_plan_destroy(pl); return rc; }
@@ -123,6 +127,7 @@ AES_EXPORT int aes_chain_plan_destroy(aes_chain_plan *pl)
     }
     if (pl->dev) cudaFree(pl->dev);
     if (pl->scratch) cudaFree(pl->scratch);
+    if (pl->d_state) cudaFree(pl->d_state);
     delete pl;
     return 0;
 }
@@ -227,7 +232,11 @@ AES_EXPORT int aes_chain_process_host(aes_chain_plan *pl, const void *x_host, in
             src = (const char *)s.h_in;
         }
         AES_CUDA(cudaMemcpyAsync(s.d_in, src, (size_t)nb * in_clip, cudaMemcpyHostToDevice, s.stream));
-        if ((rc = launch_chain(pl, s.d_in, in_fmt, s.d_out, out_fmt, nb, n_frames, s.scratch, s.stream))) return rc;
+        double *st_out = n_clips == 1 ? pl->d_state : nullptr;
+        if ((rc = launch_chain(pl, s.d_in, in_fmt, s.d_out, out_fmt, nb, n_frames, s.scratch, s.stream, st_out))) return rc;
+        if (st_out)
+            AES_CUDA(cudaMemcpyAsync(pl->h_state, pl->d_state, (size_t)pl->host.n_state * sizeof(double),
+                                     cudaMemcpyDeviceToHost, s.stream));
         if (!pin_out) {
             if ((rc = grow(&s.h_out, &s.hout_cap, (size_t)per * out_clip, true))) return rc;
             AES_CUDA(cudaMemcpyAsync(s.h_out, s.d_out, (size_t)nb * out_clip, cudaMemcpyDeviceToHost, s.stream));
@@ -241,5 +250,17 @@ AES_EXPORT int aes_chain_process_host(aes_chain_plan *pl, const void *x_host, in
     const int used = std::min(k, AES_HOST_SLOTS);
     for (int i = 0; i < used; ++i)
         if ((rc = drain_slot(pl->slot[i]))) return rc;
+    pl->state_valid = (n_clips == 1);
+    return 0;
+}
+
+// Carried scalars of stage `stage` after the last single-clip aes_chain_process_host call:
+// BIQUAD out[4*c+{0..3}] = x1,x2,y1,y2 of channel c; GATE out[0] = gain.
+AES_EXPORT int aes_chain_final_state(aes_chain_plan *pl, int stage, double *out16)
+{
+    AES_REQUIRE(pl != nullptr && out16 != nullptr, "NULL argument");
+    AES_REQUIRE(stage >= 0 && stage < pl->host.n_stages, "stage index out of range");
+    AES_REQUIRE(pl->state_valid, "final state is only kept for single-clip host calls");
+    memcpy(out16, pl->h_state + 16 * stage, 16 * sizeof(double));
     return 0;
 }

@@ -57,6 +57,7 @@ struct ChainArgs {
     long long B, N;
     float *scratch;          // gridDim.x * plan->scratch_floats
     int in_fmt, out_fmt;
+    double *state_out;       // optional: [B][plan->n_state] carried scalars at the end of each clip
 };
 
 struct TileCtx {
@@ -343,10 +344,10 @@ __device__ void aes_stage_biquad(const DevStage &st, const TileCtx &c, const dou
         const double y = b0 * xs[j] + b1 * p1 + b2 * p2 - a1 * y1 - a2 * y2;
         xc[i0 + j] = (float)y;
         y2 = y1; y1 = y; p2 = p1; p1 = xs[j];
-    }
-    if (q == 127) {
-        sout[4 * ch + 0] = xs[K - 1]; sout[4 * ch + 1] = xs[K - 2];
-        sout[4 * ch + 2] = y1; sout[4 * ch + 3] = y2;
+        if (i0 + j == c.len - 1) {                               // DF-I state after the tile's last frame
+            sout[4 * ch + 0] = p1; sout[4 * ch + 1] = p2;
+            sout[4 * ch + 2] = y1; sout[4 * ch + 3] = y2;
+        }
     }
     __syncthreads();
 }
@@ -388,8 +389,8 @@ __device__ void aes_stage_gate(const DevStage &st, const TileCtx &c, const doubl
         const float gf = (float)g;
         c.cur[i0 + f] *= gf;
         c.cur[T + i0 + f] *= gf;
+        if (i0 + f == c.len - 1) sout[0] = g;                    // gain after the tile's last frame
     }
-    if (tid == AES_NT - 1) sout[0] = g;
     __syncthreads();
 }
 
@@ -529,6 +530,8 @@ __device__ void aes_chain_body(const ChainArgs &a)
             }
             __syncthreads();
         }
+        if (a.state_out != nullptr)
+            for (int i = c.tid; i < nstate; i += AES_NT) a.state_out[b * nstate + i] = state[par * nstate + i];
     }
 }
 

@@ -116,6 +116,11 @@ int aes_chain_run(aes_chain_plan *plan, const void *x, int in_fmt, void *y, int 
  * internal streams (H2D, kernel, D2H overlapped) and returns when y is complete. */
 int aes_chain_process_host(aes_chain_plan *plan, const void *x_host, int in_fmt, void *y_host,
                            int out_fmt, int64_t n_clips, int64_t n_frames);
+/* Carried scalars of stage `stage` at the end of the clip, after the last
+ * aes_chain_process_host call with n_clips == 1 (what the reference keeps in the
+ * effect object between calls): BIQUAD out16[4*c+{0,1,2,3}] = x1,x2,y1,y2 of channel c
+ * (filter.py:35-40); GATE out16[0] = gain (gate.py:42). */
+int aes_chain_final_state(aes_chain_plan *plan, int stage, double *out16);
 /* Introspection for the benchmark / tests. */
 int aes_chain_plan_info(const aes_chain_plan *plan, int *tile_frames, int *smem_bytes,
                         int *ctas_per_sm, int64_t *scratch_bytes_per_cta);

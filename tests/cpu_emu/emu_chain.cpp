@@ -15,14 +15,14 @@ const char *emu_last_error() { return g_err; }
 
 extern "C" __attribute__((visibility("default")))
 int emu_chain_run(const aes_stage_desc *stages, int n, int fs, const void *x, int in_fmt, void *y,
-                  int out_fmt, long long B, long long N, int grid)
+                  int out_fmt, long long B, long long N, int grid, double *state_out)
 {
     static DevPlan plan;
     int rc = aes_build_devplan(stages, n, fs, &plan, g_err, sizeof g_err);
     if (rc) return rc;
     if (grid < 1) grid = 1;
     std::vector<float> scratch((size_t)grid * plan.scratch_floats, 1e30f);   // poison
-    ChainArgs a{ &plan, x, y, B, N, scratch.data(), in_fmt, out_fmt };
+    ChainArgs a{ &plan, x, y, B, N, scratch.data(), in_fmt, out_fmt, state_out };
     size_t smem = aes_plan_smem_bytes(plan);
     switch (plan.K) {
     case 8: emu::launch(entry<8>, &a, grid, AES_NT, smem); break;

@@ -24,7 +24,7 @@ def lib():
         L = C.CDLL(os.path.join(_DIR, "libaes_emu.so"))
         L.emu_last_error.restype = C.c_char_p
         L.emu_chain_run.argtypes = [C.POINTER(_native.StageDesc), C.c_int, C.c_int, C.c_void_p, C.c_int,
-                                    C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_int]
+                                    C.c_void_p, C.c_int, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -41,13 +41,13 @@ def resolved_descs(config, fs, frames, channels_in=1, blocksize=1024):
     for _ in range(2):
         for fx in chain.effects:
             fx._stages(blocksize)
-            fx._advance(blocksize, True)
+            fx._advance(blocksize, True, None)
     chain._ensure_blocksize(frames)
     return chain.stage_descs(frames)
 
 
-def run(descs, fs, x, out_dtype=np.float32, grid=1):
-    """x: (B, N, 1|2) f32 or (B, N, 2) int16."""
+def run(descs, fs, x, out_dtype=np.float32, grid=1, state_out=None):
+    """x: (B, N, 1|2) f32 or (B, N, 2) int16.  state_out: optional (B, 16*len(descs)) f64."""
     B, N, ch = x.shape
     if x.dtype == np.int16:
         fmt_in = _native.FMT_I16_DOWNMIX
@@ -57,7 +57,8 @@ def run(descs, fs, x, out_dtype=np.float32, grid=1):
     y = np.full((B, N, 2), 77, out_dtype)
     fmt_out = _native.FMT_I16_STEREO if out_dtype == np.int16 else _native.FMT_F32_STEREO
     arr = _native.desc_array(descs)
-    rc = lib().emu_chain_run(arr, len(descs), fs, x.ctypes.data, fmt_in, y.ctypes.data, fmt_out, B, N, grid)
+    sp = state_out.ctypes.data if state_out is not None else None
+    rc = lib().emu_chain_run(arr, len(descs), fs, x.ctypes.data, fmt_in, y.ctypes.data, fmt_out, B, N, grid, sp)
     if rc != 0:
         raise RuntimeError(lib().emu_last_error().decode())
     return y

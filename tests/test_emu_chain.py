@@ -100,3 +100,21 @@ def test_unsupported_short_comb_is_refused():
     cfg = [{"type": "reverb", "params": {"comb_times_ms": (1.0, 2.0)}}]
     with pytest.raises(RuntimeError, match="shorter than the smallest tile"):
         emu.run(emu.resolved_descs(cfg, 48000, 4096, 2), 48000, synth.clip(0, 4096, 2)[None])
+
+
+def test_final_state_of_filter_and_gate_matches_oracle():
+    """What the reference keeps in the effect objects between calls (filter.py:35-40,
+    gate.py:42) is read back from the device, also for a ragged last tile."""
+    cfg = [{"type": "gate", "params": {"threshold_db": -25}},
+           {"type": "filter", "params": {"filter_type": 0, "cutoff_hz": 300, "q": 2.0}}]
+    for n in (1024, 3333):
+        x = synth.clip(4, n, 2)
+        st = np.zeros((1, 32), np.float64)
+        emu.run(emu.resolved_descs(cfg, 48000, n, 2), 48000, x[None], state_out=st)
+        ch = orc.build_chain(cfg, 48000, ci=2)
+        ch.warmup()
+        ch.process(x, np.zeros((n, 2), np.float32))
+        gate, filt = ch.fx
+        assert abs(st[0, 0] - gate.gain) < 1e-12
+        got = st[0, 16:24].reshape(2, 4)
+        assert np.max(np.abs(got - filt.state.astype(np.float64))) < 1e-6 * max(1.0, np.abs(filt.state).max())
