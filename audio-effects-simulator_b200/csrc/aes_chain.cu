@@ -2,12 +2,14 @@
 // and the host-buffer entry that pipelines H2D / kernel / D2H over internal streams.
 #include <algorithm>
 #include <new>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
 #include "aes_common.h"
 #include "aes_plan_build.h"
 #include "aes_chain_kernel.cuh"
+#include "aes_fast_build.h"
 
 #define AES_HOST_SLOTS 3
 
@@ -23,8 +25,18 @@ struct HostSlot {
     size_t pend_bytes = 0;
 };
 
+// ---- shape-specialised kernels (aes_fast_kernel.cuh): launch table -----------------------
+typedef void (*fast_kernel_t)(const FastArgs);
+struct FastShape { int c[AESF_MAX_STAGES]; fast_kernel_t fn; };
+#define X(c0, c1, c2, c3) { { c0, c1, c2, c3 }, aes_fast_kernel<4, c0, c1, c2, c3> },
+static const FastShape g_fast_shapes[] = { AESF_SHAPES(X) };
+#undef X
+
 struct aes_chain_plan {
     DevPlan host;
+    FastArgs fast;                              // flattened descriptors when a specialised kernel fits
+    fast_kernel_t fast_fn = nullptr;
+    float *d_lane_tab = nullptr;
     DevPlan *dev = nullptr;
     int fs = 0, device = 0, sm_count = 0, ctas_per_sm = 0, grid_max = 0;
     size_t smem_bytes = 0;
@@ -54,10 +66,19 @@ static int launch_chain(aes_chain_plan *pl, const void *x, int in_fmt, void *y, 
     if (B <= 0 || N <= 0) return 0;
     ChainArgs a{ pl->dev, x, y, B, N, scratch, in_fmt, out_fmt, state_out };
     const unsigned grid = (unsigned)std::min<long long>(B, pl->grid_max);
-    switch (pl->host.K) {
-    case 8: aes_chain_kernel<8><<<grid, AES_NT, pl->smem_bytes, st>>>(a); break;
+    if (pl->fast_fn) {
+        FastArgs fa = pl->fast;
+        fa.x = x; fa.y = y; fa.B = B; fa.N = N; fa.scratch = scratch; fa.lane_tab = pl->d_lane_tab;
+        fa.state_out = state_out; fa.in_fmt = in_fmt; fa.out_fmt = out_fmt;
+        pl->fast_fn<<<grid, AES_NT, pl->smem_bytes, st>>>(fa);
+        aes_count_launch();
+        AES_CUDA(cudaGetLastError());
+        return 0;
+    }
+    switch (pl->host.FR) {
     case 4: aes_chain_kernel<4><<<grid, AES_NT, pl->smem_bytes, st>>>(a); break;
-    default: aes_chain_kernel<2><<<grid, AES_NT, pl->smem_bytes, st>>>(a); break;
+    case 2: aes_chain_kernel<2><<<grid, AES_NT, pl->smem_bytes, st>>>(a); break;
+    default: aes_chain_kernel<1><<<grid, AES_NT, pl->smem_bytes, st>>>(a); break;
     }
     aes_count_launch();
     AES_CUDA(cudaGetLastError());
@@ -93,11 +114,29 @@ AES_EXPORT int aes_chain_plan_create(const aes_stage_desc *stages, int n_stages,
     rc = [&]() -> int {
         AES_CUDA(cudaGetDevice(&pl->device));
         AES_CUDA(cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, pl->device));
-        int r2;
-        switch (pl->host.K) {
-        case 8: r2 = configure_kernel<8>(pl); break;
+        // a specialised kernel, when the chain's shape is one of the pre-instantiated ones
+        static float lane_tab[AESF_MAX_STAGES * 32 * FAST_LANE_STRIDE];
+        int codes[AESF_MAX_STAGES];
+        if (!getenv("AES_NO_FAST") && aes_fast_build(pl->host, &pl->fast, codes, lane_tab)) {
+            for (const FastShape &sh : g_fast_shapes) {
+                if (memcmp(sh.c, codes, sizeof codes) != 0) continue;
+                AES_CUDA(cudaFuncSetAttribute(sh.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
+                int occ = 0;
+                AES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sh.fn, AES_NT, pl->smem_bytes));
+                if (occ < 1) break;
+                AES_CUDA(cudaMalloc(&pl->d_lane_tab, sizeof lane_tab));
+                AES_CUDA(cudaMemcpy(pl->d_lane_tab, lane_tab, sizeof lane_tab, cudaMemcpyHostToDevice));
+                pl->fast_fn = sh.fn;
+                pl->ctas_per_sm = occ;
+                break;
+            }
+        }
+        int r2 = 0;
+        if (!pl->fast_fn)
+        switch (pl->host.FR) {
         case 4: r2 = configure_kernel<4>(pl); break;
-        default: r2 = configure_kernel<2>(pl); break;
+        case 2: r2 = configure_kernel<2>(pl); break;
+        default: r2 = configure_kernel<1>(pl); break;
         }
         if (r2) return r2;
         pl->grid_max = pl->sm_count * pl->ctas_per_sm;
@@ -105,6 +144,7 @@ AES_EXPORT int aes_chain_plan_create(const aes_stage_desc *stages, int n_stages,
         AES_CUDA(cudaMemcpy(pl->dev, &pl->host, sizeof(DevPlan), cudaMemcpyHostToDevice));
         AES_CUDA(cudaMalloc(&pl->scratch, (size_t)pl->grid_max * pl->host.scratch_floats * sizeof(float)));
         AES_CUDA(cudaMalloc(&pl->d_state, sizeof pl->h_state));
+        AES_CUDA(cudaMemset(pl->d_state, 0, sizeof pl->h_state));
         return 0;
     }();
     if (rc) { aes_chain_plan_destroy(pl); return rc; }
@@ -128,6 +168,7 @@ AES_EXPORT int aes_chain_plan_destroy(aes_chain_plan *pl)
     if (pl->dev) cudaFree(pl->dev);
     if (pl->scratch) cudaFree(pl->scratch);
     if (pl->d_state) cudaFree(pl->d_state);
+    if (pl->d_lane_tab) cudaFree(pl->d_lane_tab);
     delete pl;
     return 0;
 }
@@ -150,7 +191,7 @@ AES_EXPORT int aes_chain_run(aes_chain_plan *pl, const void *x, int in_fmt, void
     AES_REQUIRE(n_clips >= 0 && n_frames >= 0, "negative size");
     if (n_clips == 0 || n_frames == 0) return 0;
     AES_REQUIRE(x != nullptr && y != nullptr, "NULL device buffer");
-    AES_REQUIRE(((uintptr_t)x & 7) == 0 && ((uintptr_t)y & 3) == 0, "buffers must be 8-byte aligned");
+    AES_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "buffers must be 16-byte aligned");
     int rc = check_formats(in_fmt, out_fmt);
     if (rc) return rc;
     return launch_chain(pl, x, in_fmt, y, out_fmt, n_clips, n_frames, pl->scratch, (cudaStream_t)stream);

@@ -1,32 +1,31 @@
-// aes_chain_kernel.cuh -- the fused effect-chain kernel (device code).
+// aes_chain_kernel.cuh -- the fused effect-chain kernel (device code), revision 2.
 //
 // One CTA owns one clip at a time (persistent grid, clips strided over CTAs) and
-// walks it in time tiles of T = 128*K stereo frames.  A tile is read from HBM
-// once, pushed through every block of the chain while it sits in shared memory,
-// and written once: 8 algorithmic bytes per output sample whatever the chain
-// length.  All recurrences of the reference are kept exactly, only
-// re-associated so that a tile is parallel:
+// walks it in time tiles of T = 256*FR stereo frames.  Every thread keeps FR
+// consecutive frames x 2 channels of the tile IN REGISTERS from the HBM load to the
+// HBM store; a tile is read once and written once: 8 algorithmic bytes per output
+// sample whatever the chain length.  The next tile (and the long delay
+// line it needs) is prefetched into registers while the current one is computed.
 //
-//   * lag-L feedback lines (delay.py:7-22, reverb.py:48-67 all-pass, pre-delay
-//     reverb.py:11-31): thread j walks the samples j, j+L, j+2L.. of the tile with
-//     the line value in a register ("phase walk"); the ring (length exactly L,
-//     slot = n mod L) is touched once per thread per tile.  L >= T degenerates to
-//     one read-modify-write per sample, fully parallel.
-//   * damped comb (reverb.py:33-46): lag L >= T, so every delayed sample of the
-//     tile is already in the ring; the one-pole that runs along time inside the
-//     feedback path is a constant-coefficient first-order scan: K samples per
-//     thread serially, warp-shuffle Kogge-Stone across lanes (truncated when
-//     h^(K*2^s) < 2^-32), 4-entry carry chain across warps through shared memory.
-//   * biquad DF-I (filter.py:8-40): same shape with 2x2 companion-matrix powers,
-//     everything in f64 like the reference's promoted arithmetic.
-//   * gate (gate.py:6-42): the branch depends only on the input (gain stays in
-//     [0,1], target in {0,1}), so the gain is an affine scan with per-sample
-//     coefficients; f64.
-//   * octaver (octaver.py:17-82): no feedback; a gather from the mono history with
-//     the phasor in closed form, frac(ph0 + n*step).
+// All recurrences of the reference are kept, only re-associated so a tile is parallel:
 //
-// The file is also compiled by g++ against tests/cpu_emu/cuda_emu.h (AES_CPU_EMU)
-// so the logic can be exercised without a GPU; the product build is nvcc only.
+//   * lag-L lines with L >= T (feedback delay delay.py:7-22, pre-delay reverb.py:11-31):
+//     every delayed sample of the tile predates the tile, so the line is elementwise;
+//     "aligned" rings (period a multiple of 4) make the 4 frames of a thread one float4.
+//   * damped comb (reverb.py:33-46): L >= T as well; the one-pole inside the feedback
+//     path is a constant-coefficient first-order scan: FR samples serially per thread,
+//     warp-shuffle Kogge-Stone across lanes (steps with h^(FR*2^s) < 2^-32 are skipped),
+//     carry chain across the 8 warps through shared memory (truncated the same way).
+//   * short lines (all-pass reverb.py:48-67, any lag < T): "phase walk" on the tile in
+//     shared memory: thread j walks samples j, j+L, j+2L.. with the line in a register.
+//   * biquad DF-I (filter.py:8-40): scan with 2x2 companion-matrix powers, all f64.
+//   * gate (gate.py:6-42): the branch depends only on the input (gain in [0,1], target in
+//     {0,1}), so the gain is an affine scan with per-sample coefficients; f64.
+//   * octaver (octaver.py:17-82): no feedback; gather from the mono history, phasor in
+//     closed form frac(ph0 + n*step).
+//
+// The file is also compiled by g++ against tests/cpu_emu/cuda_emu.h (AES_CPU_EMU) so the
+// logic can be exercised without a GPU; the product build is nvcc only.
 #pragma once
 #include "aes_plan.h"
 
@@ -60,13 +59,13 @@ struct ChainArgs {
     double *state_out;       // optional: [B][plan->n_state] carried scalars at the end of each clip
 };
 
-struct TileCtx {
+struct KCtx {
     const DevPlan *P;
-    float *cur, *aux, *rings, *gscr;
+    float *tile, *rings, *gscr;
     double *wtot;
     int *rpos;
     long long n0;
-    int len, tid;
+    int len, tid, lane, warp;
 };
 
 __device__ __forceinline__ float aes_clip1(float v) { return fminf(fmaxf(v, -1.0f), 1.0f); }
@@ -78,294 +77,440 @@ __device__ __forceinline__ float aes_mix_clip(float dry, float x, float wet, flo
     return aes_clip1(__fadd_rn(__fmul_rn(dry, x), __fmul_rn(wet, w)));
 }
 
-__device__ __forceinline__ float *aes_ring_base(const TileCtx &c, const DevRing &r)
+__device__ __forceinline__ float *aes_ring_base(const KCtx &c, const DevRing &r)
 {
     return (r.space == AES_SPACE_GLOBAL ? c.gscr : c.rings) + r.off;
 }
 
-// ---- tile I/O ------------------------------------------------------------------
-template <int K>
-__device__ __forceinline__ void aes_load_tile(const ChainArgs &a, long long b, const TileCtx &c)
+// ---- FR-wide vector access (p aligned to 4*FR bytes) -----------------------------------
+template <int FR> __device__ __forceinline__ void aes_ldv(const float *p, float (&o)[FR])
 {
-    constexpr int T = 128 * K;
-    const long long base = b * a.N + c.n0;
+    if (FR == 4) { const float4 t = *reinterpret_cast<const float4 *>(p); o[0] = t.x; o[1] = t.y; o[2 % FR] = t.z; o[3 % FR] = t.w; }
+    else if (FR == 2) { const float2 t = *reinterpret_cast<const float2 *>(p); o[0] = t.x; o[1 % FR] = t.y; }
+    else o[0] = p[0];
+}
+template <int FR> __device__ __forceinline__ void aes_stv(float *p, const float (&o)[FR])
+{
+    if (FR == 4) *reinterpret_cast<float4 *>(p) = make_float4(o[0], o[1], o[2 % FR], o[3 % FR]);
+    else if (FR == 2) *reinterpret_cast<float2 *>(p) = make_float2(o[0], o[1 % FR]);
+    else p[0] = o[0];
+}
+
+// FR consecutive ring elements starting at r (0 <= r < len, len a multiple of 4).  The
+// misalignment m = r mod FR is the same for every thread (it is -lag mod FR), so the
+// branch is uniform: one aligned vector load when m == 0, two plus a static select else.
+template <int FR> __device__ __forceinline__ void aes_ring_read(const float *rb, int r, int len, float (&o)[FR])
+{
+    const int m = r & (FR - 1);
+    const int a0 = r - m;
+    float A[FR];
+    aes_ldv<FR>(rb + a0, A);
+    if (m == 0) {
 #pragma unroll
-    for (int m = 0; m < T / AES_NT; ++m) {
-        const int i = c.tid + AES_NT * m;
+        for (int j = 0; j < FR; ++j) o[j] = A[j];
+        return;
+    }
+    int b0 = a0 + FR;
+    if (b0 >= len) b0 -= len;
+    float Bv[FR];
+    aes_ldv<FR>(rb + b0, Bv);
+    if (m == 1) {
+#pragma unroll
+        for (int j = 0; j < FR; ++j) o[j] = (j + 1 < FR) ? A[(j + 1) % FR] : Bv[(j + 1) % FR];
+    } else if (m == 2) {
+#pragma unroll
+        for (int j = 0; j < FR; ++j) o[j] = (j + 2 < FR) ? A[(j + 2) % FR] : Bv[(j + 2) % FR];
+    } else {
+#pragma unroll
+        for (int j = 0; j < FR; ++j) o[j] = (j + 3 < FR) ? A[(j + 3) % FR] : Bv[(j + 3) % FR];
+    }
+}
+
+// first read / write slot of this thread in a REG ring whose tile-start slot is `wpos`
+__device__ __forceinline__ int aes_rslot(int wpos, int i0, const DevRing &rg)
+{
+    int r = wpos + i0 - rg.lag;            // > -len because i0 >= 0, wpos >= 0, lag <= len
+    if (r < 0) r += rg.len;
+    return r;                              // < len because wpos + i0 < len + lag (i0 < T <= lag)
+}
+__device__ __forceinline__ int aes_wslot(int wpos, int i0, const DevRing &rg)
+{
+    int w = wpos + i0;
+    if (w >= rg.len) w -= rg.len;
+    return w;
+}
+
+// ---- tile I/O: FR frames x 2 channels per thread, registers <-> HBM ----------------------
+template <int FR>
+__device__ __forceinline__ void aes_load_frames(const ChainArgs &a, long long b, long long n0, int len,
+                                                int tid, float (&x)[2][FR])
+{
+    const int i0 = FR * tid;
+    const long long base = b * a.N + n0 + i0;
+    if (a.in_fmt == AESK_F32_STEREO && FR >= 2 && i0 + FR <= len && ((b * a.N) & 1) == 0) {
+        const float4 *p = reinterpret_cast<const float4 *>(reinterpret_cast<const float *>(a.x) + 2 * base);
+#pragma unroll
+        for (int j = 0; j < FR / 2; ++j) {
+            const float4 t = __ldcs(p + j);
+            x[0][2 * j] = t.x; x[1][2 * j] = t.y; x[0][(2 * j + 1) % FR] = t.z; x[1][(2 * j + 1) % FR] = t.w;
+        }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < FR; ++j) {
         float l = 0.f, r = 0.f;
-        if (i < c.len) {
+        if (i0 + j < len) {
             if (a.in_fmt == AESK_F32_STEREO) {
-                const float2 v = reinterpret_cast<const float2 *>(a.x)[base + i];
-                l = v.x; r = v.y;
+                const float2 t = __ldcs(reinterpret_cast<const float2 *>(a.x) + base + j);
+                l = t.x; r = t.y;
             } else if (a.in_fmt == AESK_F32_MONO) {
-                l = r = reinterpret_cast<const float *>(a.x)[base + i];   // core.py:147-149
+                l = r = __ldcs(reinterpret_cast<const float *>(a.x) + base + j);     // core.py:147-149
             } else {
                 // engine.py:78-84: int16 -> /32768 -> mean over channels (exact in f32)
-                const short2 v = reinterpret_cast<const short2 *>(a.x)[base + i];
-                l = r = (float)((int)v.x + (int)v.y) * (1.0f / 65536.0f);
+                const short2 t = reinterpret_cast<const short2 *>(a.x)[base + j];
+                l = r = (float)((int)t.x + (int)t.y) * (1.0f / 65536.0f);
             }
         }
-        c.cur[i] = l;
-        c.cur[T + i] = r;
+        x[0][j] = l; x[1][j] = r;
     }
 }
 
-template <int K>
-__device__ __forceinline__ void aes_store_tile(const ChainArgs &a, long long b, const TileCtx &c)
+template <int FR>
+__device__ __forceinline__ void aes_store_frames(const ChainArgs &a, long long b, long long n0, int len,
+                                                 int tid, const float (&v)[2][FR])
 {
-    constexpr int T = 128 * K;
-    const long long base = b * a.N + c.n0;
+    const int i0 = FR * tid;
+    const long long base = b * a.N + n0 + i0;
+    if (a.out_fmt == AESK_F32_STEREO && FR >= 2 && i0 + FR <= len && ((b * a.N) & 1) == 0) {
+        float4 *p = reinterpret_cast<float4 *>(reinterpret_cast<float *>(a.y) + 2 * base);
 #pragma unroll
-    for (int m = 0; m < T / AES_NT; ++m) {
-        const int i = c.tid + AES_NT * m;
-        if (i < c.len) {
-            const float l = c.cur[i], r = c.cur[T + i];
+        for (int j = 0; j < FR / 2; ++j)
+            __stcs(p + j, make_float4(v[0][2 * j], v[1][2 * j], v[0][(2 * j + 1) % FR], v[1][(2 * j + 1) % FR]));
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < FR; ++j) {
+        if (i0 + j < len) {
             if (a.out_fmt == AESK_F32_STEREO) {
-                reinterpret_cast<float2 *>(a.y)[base + i] = make_float2(l, r);
+                __stcs(reinterpret_cast<float2 *>(a.y) + base + j, make_float2(v[0][j], v[1][j]));
             } else {
                 // engine.py:104-105: clip, *32767, astype(int16) truncates toward zero
-                const short ql = (short)__float2int_rz(__fmul_rn(aes_clip1(l), 32767.0f));
-                const short qr = (short)__float2int_rz(__fmul_rn(aes_clip1(r), 32767.0f));
-                reinterpret_cast<short2 *>(a.y)[base + i] = make_short2(ql, qr);
+                const short ql = (short)__float2int_rz(__fmul_rn(aes_clip1(v[0][j]), 32767.0f));
+                const short qr = (short)__float2int_rz(__fmul_rn(aes_clip1(v[1][j]), 32767.0f));
+                reinterpret_cast<short2 *>(a.y)[base + j] = make_short2(ql, qr);
             }
         }
     }
 }
 
-// ---- feedback delay (delay.py:7-22 + mix/clip delay.py:94-96), in place on cur ------
-template <int K>
-__device__ void aes_stage_delay(const DevStage &st, const TileCtx &c)
+// registers <-> the planar tile buffer in shared memory (own entries only)
+template <int FR> __device__ __forceinline__ void aes_spill(const KCtx &c, const float (&v)[2][FR])
 {
-    constexpr int T = 128 * K;
+    constexpr int T = AES_NT * FR;
+    aes_stv<FR>(c.tile + FR * c.tid, v[0]);
+    aes_stv<FR>(c.tile + T + FR * c.tid, v[1]);
+}
+template <int FR> __device__ __forceinline__ void aes_reload(const KCtx &c, float (&v)[2][FR])
+{
+    constexpr int T = AES_NT * FR;
+    aes_ldv<FR>(c.tile + FR * c.tid, v[0]);
+    aes_ldv<FR>(c.tile + T + FR * c.tid, v[1]);
+}
+
+// ---- phase walk over the tile in shared memory (any lag >= 1) ---------------------------
+// Threads 0..127 take channel 0, 128..255 channel 1; thread j walks samples j, j+L, j+2L..
+// of the tile with the line value in a register.  OP 0: feedback delay + mix/clip
+// (delay.py:7-22,94-96); OP 1: pure delay (reverb.py:11-31); OP 2: all-pass (reverb.py:48-67).
+template <int FR, int OP>
+__device__ void aes_walk(const KCtx &c, int ring_id, float p0, float p1, float p2)
+{
+    constexpr int T = AES_NT * FR;
     const int ch = c.tid >> 7, j0 = c.tid & 127;
-    const DevRing rg = c.P->ring[st.ring[ch][0]];
+    const DevRing rg = c.P->ring[ring_id];
     float *rb = aes_ring_base(c, rg);
-    const int L = rg.len, pos = c.rpos[st.ring[ch][0]];
+    const int L = rg.len, pos = c.rpos[ring_id];
     const int W = L < T ? L : T;
-    float *xc = c.cur + ch * T;
-    const float fb = st.fb, dry = st.dry, wet = st.wet;
+    float *s = c.tile + ch * T;
     for (int j = j0; j < W && j < c.len; j += 128) {
         int slot = pos + j;
         if (slot >= L) slot -= L;
-        float line = (c.n0 + j >= L) ? rb[slot] : 0.0f;        // buf[n-L]; zero history on a fresh clip
-        for (int i = j; i < c.len; i += L) {
-            const float x = xc[i];
-            const float nb = fmaf(line, fb, x);                // buf[n] = x + buf[n-L]*fb
-            xc[i] = aes_mix_clip(dry, x, wet, line);
-            line = nb;
+        float line = (c.n0 + j >= L) ? rb[slot] : 0.0f;       // zero history on a fresh clip
+        for (int i = j; i < c.len; i += 4 * L) {
+            float xs[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {                       // loads first: the walk is a serial chain
+                const long long ii = (long long)i + (long long)u * L;
+                xs[u] = ii < c.len ? s[ii] : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long ii = (long long)i + (long long)u * L;
+                if (ii < c.len) {
+                    const float x = xs[u];
+                    if (OP == 0) {                              // buf[n] = x + fb*buf[n-L]; out = clip(dry*x + wet*buf[n-L])
+                        s[ii] = aes_mix_clip(p1, x, p2, line);
+                        line = fmaf(line, p0, x);
+                    } else if (OP == 1) {                       // y[n] = x[n-L]
+                        s[ii] = line;
+                        line = x;
+                    } else {                                    // y = d - a*x ; buf = x + a*y
+                        const float yo = fmaf(-p0, x, line);
+                        s[ii] = yo;
+                        line = fmaf(p0, yo, x);
+                    }
+                }
+            }
         }
         rb[slot] = line;
     }
-    __syncthreads();
 }
 
-// ---- Schroeder/Moorer reverb (reverb.py:208-277): cur -> cur, aux as scratch ----------
-template <int K>
-__device__ void aes_stage_reverb(const DevStage &st, const TileCtx &c, const double *sin, double *sout)
+// ---- feedback delay, lag >= T: elementwise on registers ------------------------------------
+template <int FR>
+__device__ __forceinline__ void aes_delay_fetch(const DevStage &st, const KCtx &c, int tile_ahead, float (&ln)[2][FR])
 {
-    constexpr int T = 128 * K;
-    const int tid = c.tid;
-    const int ch = tid >> 7, q = tid & 127, lane = tid & 31, wq = q >> 5;
-    const float *in = c.cur;
+    const int i0 = FR * c.tid;
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+        const int rid = st.ring[ch][0];
+        const DevRing rg = c.P->ring[rid];
+        int wpos = c.rpos[rid];
+        if (tile_ahead) { wpos += rg.tinc; if (wpos >= rg.len) wpos -= rg.len; }
+        aes_ring_read<FR>(aes_ring_base(c, rg), aes_rslot(wpos, i0, rg), rg.len, ln[ch]);
+    }
+}
 
-    // pre-delay (reverb.py:11-31): pure shift into aux
-    if (st.pre_ring[0] >= 0) {
-        const DevRing rg = c.P->ring[st.pre_ring[ch]];
-        float *rb = aes_ring_base(c, rg);
-        const int L = rg.len, pos = c.rpos[st.pre_ring[ch]];
-        const int W = L < T ? L : T;
-        for (int j = q; j < W && j < c.len; j += 128) {
-            int slot = pos + j;
-            if (slot >= L) slot -= L;
-            float line = (c.n0 + j >= L) ? rb[slot] : 0.0f;
-            for (int i = j; i < c.len; i += L) {
-                const float x = c.cur[ch * T + i];
-                c.aux[ch * T + i] = line;
-                line = x;
-            }
-            rb[slot] = line;
+template <int FR>
+__device__ __forceinline__ void aes_stage_delay_reg(const DevStage &st, const KCtx &c, float (&v)[2][FR],
+                                                    const float (&ln)[2][FR])
+{
+    const int i0 = FR * c.tid;
+    const float fb = st.fb, dry = st.dry, wet = st.wet;
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+        const int rid = st.ring[ch][0];
+        const DevRing rg = c.P->ring[rid];
+        float nb[FR];
+#pragma unroll
+        for (int j = 0; j < FR; ++j) {
+            const float line = (c.n0 + i0 + j >= rg.lag) ? ln[ch][j] : 0.0f;   // zero history on a fresh clip
+            const float x = v[ch][j];
+            nb[j] = fmaf(line, fb, x);                           // buf[n] = x + buf[n-L]*fb
+            v[ch][j] = aes_mix_clip(dry, x, wet, line);
         }
+        aes_stv<FR>(aes_ring_base(c, rg) + aes_wslot(c.rpos[rid], i0, rg), nb);
+    }
+}
+
+// ---- Schroeder/Moorer reverb (reverb.py:208-277) ---------------------------------------------
+template <int FR>
+__device__ void aes_stage_reverb(const DevStage &st, const KCtx &c, float (&v)[2][FR], const double *sin,
+                                 double *sout)
+{
+    const int i0 = FR * c.tid, lane = c.lane, warp = c.warp;
+    float pre[2][FR];
+
+    // pre-delay (reverb.py:11-31)
+    if (st.pre_ring[0] < 0) {
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+            for (int j = 0; j < FR; ++j) pre[ch][j] = v[ch][j];
+    } else if (st.mode == AES_MODE_REG) {
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const int rid = st.pre_ring[ch];
+            const DevRing rg = c.P->ring[rid];
+            float *rb = aes_ring_base(c, rg);
+            aes_ring_read<FR>(rb, aes_rslot(c.rpos[rid], i0, rg), rg.len, pre[ch]);
+#pragma unroll
+            for (int j = 0; j < FR; ++j)
+                if (c.n0 + i0 + j < rg.lag) pre[ch][j] = 0.0f;
+            aes_stv<FR>(rb + aes_wslot(c.rpos[rid], i0, rg), v[ch]);
+        }
+    } else {
+        aes_spill<FR>(c, v);
         __syncthreads();
-        in = c.aux;
+        aes_walk<FR, 1>(c, st.pre_ring[c.tid >> 7], 0.f, 0.f, 0.f);
+        __syncthreads();
+        aes_reload<FR>(c, pre);
     }
 
-    // damped combs (reverb.py:33-46), 4 at a time; sum accumulated in comb order in f32
-    const int i0 = q * K;
-    float x[K], sum[K];
+    // damped combs (reverb.py:33-46), 4 per side at a time; sum in comb order in f32
+    float sum[2][FR];
 #pragma unroll
-    for (int j = 0; j < K; ++j) { x[j] = in[ch * T + i0 + j]; sum[j] = 0.0f; }
-    const float h = st.h, omh = st.omh, hl = st.hlane[lane];
-    float *wt = reinterpret_cast<float *>(c.wtot);            // [2 ch][4 warps][4 combs]
-    for (int gi = 0; gi < st.nc; gi += 4) {
-        float y[4][K], e[4];
+    for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            e[cc] = 0.0f;
-            if (gi + cc < st.nc) {
-                const int rid = st.ring[ch][gi + cc];
-                const DevRing rg = c.P->ring[rid];
-                const float *rb = c.rings + rg.off;
-                int idx = c.rpos[rid] + i0;                     // i0 < T <= len of every comb ring
-                if (idx >= rg.len) idx -= rg.len;
-                float lp = 0.0f;
+        for (int j = 0; j < FR; ++j) sum[ch][j] = 0.0f;
+    const float h = st.h, omh = st.omh, hl = st.hlane[lane], hw = st.hp[5];
+    const int nc = st.nc, nscan = st.nscan;
+    float *wt = reinterpret_cast<float *>(c.wtot);              // [8 warps][2 ch][4 combs]
+    for (int gi = 0; gi < nc; gi += 4) {
+        float y[2][4][FR], e[2][4];
 #pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    y[cc][j] = rb[idx];
-                    if (++idx == rg.len) idx = 0;
-                    lp = fmaf(h, lp, omh * y[cc][j]);           // zero-state one-pole over the chunk
-                }
-                e[cc] = lp;
-            }
-        }
-        // inclusive warp scan of the chunk end values, multiplier h^(K*2^s)
-        for (int s = 0; s < st.nscan; ++s) {
-            const float m = st.hp[s];
+        for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
-                const float v = __shfl_up_sync(0xffffffffu, e[cc], 1 << s);
-                if (lane >= (1 << s)) e[cc] = fmaf(m, v, e[cc]);
+                e[ch][cc] = 0.0f;
+                if (gi + cc < nc) {
+                    const int rid = st.ring[ch][gi + cc];
+                    const DevRing rg = c.P->ring[rid];
+                    aes_ring_read<FR>(c.rings + rg.off, aes_rslot(c.rpos[rid], i0, rg), rg.len, y[ch][cc]);
+                    float lp = 0.0f;
+#pragma unroll
+                    for (int j = 0; j < FR; ++j) lp = fmaf(h, lp, omh * y[ch][cc][j]);   // zero-state one-pole
+                    e[ch][cc] = lp;
+                }
             }
+        // inclusive warp scan of the chunk end values, multiplier h^(FR*2^s)
+        for (int s = 0; s < nscan; ++s) {
+            const float m = st.hp[s];
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const float u = __shfl_up_sync(0xffffffffu, e[ch][cc], 1 << s);
+                    if (lane >= (1 << s)) e[ch][cc] = fmaf(m, u, e[ch][cc]);
+                }
         }
         if (lane == 31) {
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) wt[(ch * 4 + wq) * 4 + cc] = e[cc];
+            for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) wt[(warp * 2 + ch) * 4 + cc] = e[ch][cc];
         }
         __syncthreads();
+        const int u0 = warp > st.nxw ? warp - st.nxw : 0;       // older warps' carries are below 2^-32
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const float ex = __shfl_up_sync(0xffffffffu, e[cc], 1);
-            if (gi + cc < st.nc) {
-                float C = (float)sin[ch * 8 + gi + cc];         // lp at the end of the previous tile
-                for (int w = 0; w < wq; ++w) C = fmaf(st.hp[5], C, wt[(ch * 4 + w) * 4 + cc]);
-                float lp = fmaf(hl, C, lane == 0 ? 0.0f : ex);  // lp just before this thread's chunk
-                const int rid = st.ring[ch][gi + cc];
-                const DevRing rg = c.P->ring[rid];
-                float *rb = c.rings + rg.off;
-                const float g = st.g[ch][gi + cc];
-                int idx = c.rpos[rid] + i0;
-                if (idx >= rg.len) idx -= rg.len;
+        for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
-                for (int j = 0; j < K; ++j) {
-                    lp = fmaf(h, lp, omh * y[cc][j]);           // damped = (1-h)*y + h*lp
-                    rb[idx] = fmaf(g, lp, x[j]);                // buf[n] = x + g*damped
-                    if (++idx == rg.len) idx = 0;
-                    sum[j] = __fadd_rn(sum[j], y[cc][j]);       // comb output is the delayed sample
+            for (int cc = 0; cc < 4; ++cc) {
+                const float ex = __shfl_up_sync(0xffffffffu, e[ch][cc], 1);
+                if (gi + cc < nc) {
+                    float C = u0 == 0 ? (float)sin[ch * 8 + gi + cc] : 0.0f;     // lp at the end of the previous tile
+                    for (int u = u0; u < warp; ++u) C = fmaf(hw, C, wt[(u * 2 + ch) * 4 + cc]);
+                    float lp = fmaf(hl, C, lane == 0 ? 0.0f : ex);               // lp just before this thread's chunk
+                    const int rid = st.ring[ch][gi + cc];
+                    const DevRing rg = c.P->ring[rid];
+                    const float g = st.g[ch][gi + cc];
+                    float nb[FR];
+#pragma unroll
+                    for (int j = 0; j < FR; ++j) {
+                        lp = fmaf(h, lp, omh * y[ch][cc][j]);                    // damped = (1-h)*y + h*lp
+                        nb[j] = fmaf(g, lp, pre[ch][j]);                         // buf[n] = x + g*damped
+                        sum[ch][j] = __fadd_rn(sum[ch][j], y[ch][cc][j]);        // comb output = delayed sample
+                    }
+                    aes_stv<FR>(c.rings + rg.off + aes_wslot(c.rpos[rid], i0, rg), nb);
+                    if (c.tid == AES_NT - 1) sout[ch * 8 + gi + cc] = (double)lp;
                 }
-                if (q == 127) sout[ch * 8 + gi + cc] = (double)lp;
             }
-        }
-        __syncthreads();                                        // wt is reused by the next group
+        if (gi + 4 < nc) __syncthreads();                       // wt is reused by the next group
     }
-#pragma unroll
-    for (int j = 0; j < K; ++j) c.aux[ch * T + i0 + j] = sum[j];
-    __syncthreads();
 
-    // series all-passes (reverb.py:48-67), in place on aux
-    const float a = st.a;
+    // series all-passes (reverb.py:48-67): phase walk on the tile
+    aes_spill<FR>(c, sum);
+    __syncthreads();
     for (int k = 0; k < st.na; ++k) {
-        const DevRing rg = c.P->ring[st.apring[ch][k]];
-        float *rb = aes_ring_base(c, rg);
-        const int L = rg.len, pos = c.rpos[st.apring[ch][k]];
-        const int W = L < T ? L : T;
-        float *s = c.aux + ch * T;
-        for (int j = q; j < W && j < c.len; j += 128) {
-            int slot = pos + j;
-            if (slot >= L) slot -= L;
-            float line = (c.n0 + j >= L) ? rb[slot] : 0.0f;
-            for (int i = j; i < c.len; i += L) {
-                const float xi = s[i];
-                const float yo = fmaf(-a, xi, line);            // y = delayed - a*x
-                s[i] = yo;
-                line = fmaf(a, yo, xi);                         // buf = x + a*y
-            }
-            rb[slot] = line;
-        }
+        aes_walk<FR, 2>(c, st.apring[c.tid >> 7][k], st.a, 0.f, 0.f);
         __syncthreads();
     }
+    aes_reload<FR>(c, sum);
 
     // mix + clip (reverb.py:275-277)
     const float dry = st.dry, wet = st.wet;
 #pragma unroll
-    for (int m = 0; m < 2 * T / AES_NT; ++m) {
-        const int e = tid + AES_NT * m;
-        c.cur[e] = aes_mix_clip(dry, c.cur[e], wet, c.aux[e]);
-    }
-    __syncthreads();
+    for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+        for (int j = 0; j < FR; ++j) v[ch][j] = aes_mix_clip(dry, v[ch][j], wet, sum[ch][j]);
 }
 
-// ---- biquad, Direct Form I in f64 (filter.py:8-40), in place on cur ---------------------
-template <int K>
-__device__ void aes_stage_biquad(const DevStage &st, const TileCtx &c, const double *sin, double *sout)
+// ---- biquad, Direct Form I in f64 (filter.py:8-40) ---------------------------------------------
+template <int FR>
+__device__ void aes_stage_biquad(const DevStage &st, const KCtx &c, float (&v)[2][FR], const double *sin,
+                                 double *sout)
 {
-    constexpr int T = 128 * K;
-    const int tid = c.tid;
-    const int ch = tid >> 7, q = tid & 127, lane = tid & 31, wq = q >> 5;
-    const int i0 = q * K;
-    float *xc = c.cur + ch * T;
+    constexpr int T = AES_NT * FR;
+    const int i0 = FR * c.tid, lane = c.lane, warp = c.warp;
     const double b0 = st.bq[0], b1 = st.bq[1], b2 = st.bq[2], a1 = st.bq[3], a2 = st.bq[4];
-    double xs[K];
+    aes_spill<FR>(c, v);                                        // neighbours' x[n-1], x[n-2]
+    __syncthreads();
+    double xm1[2], xm2[2], e1[2], e2[2];
 #pragma unroll
-    for (int j = 0; j < K; ++j) xs[j] = (double)xc[i0 + j];
-    double xm1, xm2;
-    if (q == 0) { xm1 = sin[4 * ch + 0]; xm2 = sin[4 * ch + 1]; }
-    else        { xm1 = (double)xc[i0 - 1]; xm2 = (double)xc[i0 - 2]; }
-
-    // zero-state response of the chunk: end state (y[K-1], y[K-2])
-    double y1 = 0.0, y2 = 0.0, p1 = xm1, p2 = xm2;
+    for (int ch = 0; ch < 2; ++ch) {
+        const float *xc = c.tile + ch * T;
+        xm1[ch] = i0 >= 1 ? (double)xc[i0 - 1] : sin[4 * ch + 0];
+        xm2[ch] = i0 >= 2 ? (double)xc[i0 - 2] : (i0 == 1 ? sin[4 * ch + 0] : sin[4 * ch + 1]);
+        // zero-state response of the chunk: end state (y[FR-1], y[FR-2])
+        double y1 = 0.0, y2 = 0.0, p1 = xm1[ch], p2 = xm2[ch];
 #pragma unroll
-    for (int j = 0; j < K; ++j) {
-        const double y = b0 * xs[j] + b1 * p1 + b2 * p2 - a1 * y1 - a2 * y2;
-        y2 = y1; y1 = y; p2 = p1; p1 = xs[j];
+        for (int j = 0; j < FR; ++j) {
+            const double xj = (double)v[ch][j];
+            const double y = b0 * xj + b1 * p1 + b2 * p2 - a1 * y1 - a2 * y2;
+            y2 = y1; y1 = y; p2 = p1; p1 = xj;
+        }
+        e1[ch] = y1; e2[ch] = y2;
     }
-    double e1 = y1, e2 = y2;
     for (int s = 0; s < 5; ++s) {
-        const double u1 = __shfl_up_sync(0xffffffffu, e1, 1 << s);
-        const double u2 = __shfl_up_sync(0xffffffffu, e2, 1 << s);
-        if (lane >= (1 << s)) {
-            e1 += st.bq_pow[s][0] * u1 + st.bq_pow[s][1] * u2;
-            e2 += st.bq_pow[s][2] * u1 + st.bq_pow[s][3] * u2;
-        }
-    }
-    if (lane == 31) { c.wtot[(ch * 4 + wq) * 2] = e1; c.wtot[(ch * 4 + wq) * 2 + 1] = e2; }
-    __syncthreads();
-    double C1 = sin[4 * ch + 2], C2 = sin[4 * ch + 3];           // (y[n0-1], y[n0-2])
-    for (int w = 0; w < wq; ++w) {
-        const double t1 = st.bq_pow[5][0] * C1 + st.bq_pow[5][1] * C2 + c.wtot[(ch * 4 + w) * 2];
-        const double t2 = st.bq_pow[5][2] * C1 + st.bq_pow[5][3] * C2 + c.wtot[(ch * 4 + w) * 2 + 1];
-        C1 = t1; C2 = t2;
-    }
-    double x1 = __shfl_up_sync(0xffffffffu, e1, 1), x2 = __shfl_up_sync(0xffffffffu, e2, 1);
-    if (lane == 0) { x1 = 0.0; x2 = 0.0; }
-    y1 = x1 + st.bq_lane[lane][0] * C1 + st.bq_lane[lane][1] * C2;
-    y2 = x2 + st.bq_lane[lane][2] * C1 + st.bq_lane[lane][3] * C2;
-    p1 = xm1; p2 = xm2;
+        const double m0 = st.bq_pow[s][0], m1 = st.bq_pow[s][1], m2 = st.bq_pow[s][2], m3 = st.bq_pow[s][3];
 #pragma unroll
-    for (int j = 0; j < K; ++j) {
-        const double y = b0 * xs[j] + b1 * p1 + b2 * p2 - a1 * y1 - a2 * y2;
-        xc[i0 + j] = (float)y;
-        y2 = y1; y1 = y; p2 = p1; p1 = xs[j];
-        if (i0 + j == c.len - 1) {                               // DF-I state after the tile's last frame
-            sout[4 * ch + 0] = p1; sout[4 * ch + 1] = p2;
-            sout[4 * ch + 2] = y1; sout[4 * ch + 3] = y2;
+        for (int ch = 0; ch < 2; ++ch) {
+            const double u1 = __shfl_up_sync(0xffffffffu, e1[ch], 1 << s);
+            const double u2 = __shfl_up_sync(0xffffffffu, e2[ch], 1 << s);
+            if (lane >= (1 << s)) {
+                e1[ch] += m0 * u1 + m1 * u2;
+                e2[ch] += m2 * u1 + m3 * u2;
+            }
+        }
+    }
+    if (lane == 31) {
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            c.wtot[(warp * 2 + ch) * 2] = e1[ch];
+            c.wtot[(warp * 2 + ch) * 2 + 1] = e2[ch];
         }
     }
     __syncthreads();
+    const double w0 = st.bq_pow[5][0], w1 = st.bq_pow[5][1], w2 = st.bq_pow[5][2], w3 = st.bq_pow[5][3];
+    const double l0 = st.bq_lane[lane][0], l1 = st.bq_lane[lane][1], l2 = st.bq_lane[lane][2], l3 = st.bq_lane[lane][3];
+#pragma unroll
+    for (int ch = 0; ch < 2; ++ch) {
+        double C1 = sin[4 * ch + 2], C2 = sin[4 * ch + 3];       // (y[n0-1], y[n0-2])
+        for (int u = 0; u < warp; ++u) {
+            const double t1 = w0 * C1 + w1 * C2 + c.wtot[(u * 2 + ch) * 2];
+            const double t2 = w2 * C1 + w3 * C2 + c.wtot[(u * 2 + ch) * 2 + 1];
+            C1 = t1; C2 = t2;
+        }
+        double x1 = __shfl_up_sync(0xffffffffu, e1[ch], 1), x2 = __shfl_up_sync(0xffffffffu, e2[ch], 1);
+        if (lane == 0) { x1 = 0.0; x2 = 0.0; }
+        double y1 = x1 + l0 * C1 + l1 * C2;
+        double y2 = x2 + l2 * C1 + l3 * C2;
+        double p1 = xm1[ch], p2 = xm2[ch];
+#pragma unroll
+        for (int j = 0; j < FR; ++j) {
+            const double xj = (double)v[ch][j];
+            const double y = b0 * xj + b1 * p1 + b2 * p2 - a1 * y1 - a2 * y2;
+            v[ch][j] = (float)y;
+            y2 = y1; y1 = y; p2 = p1; p1 = xj;
+            if (i0 + j == c.len - 1) {                           // DF-I state after the tile's last frame
+                sout[4 * ch + 0] = p1; sout[4 * ch + 1] = p2;
+                sout[4 * ch + 2] = y1; sout[4 * ch + 3] = y2;
+            }
+        }
+    }
+    __syncthreads();                                             // wtot / tile are free again
 }
 
-// ---- noise gate (gate.py:6-42), in place on cur ---------------------------------------
-template <int K>
-__device__ void aes_stage_gate(const DevStage &st, const TileCtx &c, const double *sin, double *sout)
+// ---- noise gate (gate.py:6-42) -------------------------------------------------------------------
+template <int FR>
+__device__ void aes_stage_gate(const DevStage &st, const KCtx &c, float (&v)[2][FR], const double *sin, double *sout)
 {
-    constexpr int T = 128 * K;
-    constexpr int F = T / AES_NT;                                // consecutive frames per thread
-    const int tid = c.tid, lane = tid & 31, w = tid >> 5;
-    const int i0 = tid * F;
+    const int i0 = FR * c.tid, lane = c.lane, w = c.warp;
     const double thr = st.thr, ka = 1.0 - st.att, kr = 1.0 - st.rel, att = st.att;
-    bool open[F];
+    bool open[FR];
     double A = 1.0, Bv = 0.0;
 #pragma unroll
-    for (int f = 0; f < F; ++f) {
-        const float lvl = fmaxf(fabsf(c.cur[i0 + f]), fabsf(c.cur[T + i0 + f]));   // stereo-linked level
+    for (int f = 0; f < FR; ++f) {
+        const float lvl = fmaxf(fabsf(v[0][f]), fabsf(v[1][f]));     // stereo-linked level
         open[f] = (double)lvl > thr;
         const double am = open[f] ? ka : kr, bm = open[f] ? att : 0.0;
         Bv = am * Bv + bm;                                       // compose g -> am*g + bm
@@ -379,22 +524,22 @@ __device__ void aes_stage_gate(const DevStage &st, const TileCtx &c, const doubl
     if (lane == 31) { c.wtot[2 * w] = A; c.wtot[2 * w + 1] = Bv; }
     __syncthreads();
     double g = sin[0];
-    for (int v = 0; v < w; ++v) g = c.wtot[2 * v] * g + c.wtot[2 * v + 1];
+    for (int u = 0; u < w; ++u) g = c.wtot[2 * u] * g + c.wtot[2 * u + 1];
     double Ae = __shfl_up_sync(0xffffffffu, A, 1), Be = __shfl_up_sync(0xffffffffu, Bv, 1);
     if (lane == 0) { Ae = 1.0; Be = 0.0; }
     g = Ae * g + Be;
 #pragma unroll
-    for (int f = 0; f < F; ++f) {
+    for (int f = 0; f < FR; ++f) {
         g = (open[f] ? ka : kr) * g + (open[f] ? att : 0.0);
         const float gf = (float)g;
-        c.cur[i0 + f] *= gf;
-        c.cur[T + i0 + f] *= gf;
+        v[0][f] *= gf;
+        v[1][f] *= gf;
         if (i0 + f == c.len - 1) sout[0] = g;                    // gain after the tile's last frame
     }
-    __syncthreads();
+    __syncthreads();                                             // wtot is free again
 }
 
-// ---- octaver (octaver.py:17-82 + wrapper 116-150), in place on cur ------------------------
+// ---- octaver (octaver.py:17-82 + wrapper 116-150) ---------------------------------------------------
 __device__ __forceinline__ float aes_hermite(float t, float y0, float y1, float y2, float y3)
 {
     const float c1 = 0.5f * (y2 - y0);
@@ -411,122 +556,152 @@ __device__ __forceinline__ float aes_octaver_tap(const float *rb, int mask, long
     const double raw = fsize - p * fsize;
     const int m = (int)raw;
     const float frac = (float)(raw - (double)m);
-    int d0 = size - m + 1;                                       // tap k=-1 .. k=2 -> d0, d0-1, d0-2, d0-3 (mod size)
-    float v[4];
+    const int d0 = size - m + 1;                                 // taps k=-1..2 -> d0, d0-1, d0-2, d0-3 (mod size)
+    float t[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         int d = d0 - k;
         if (d < 0) d += size;
         if (d >= size) d -= size;
-        v[k] = rb[(int)((n - d) & mask)];
+        t[k] = rb[(int)((n - d) & mask)];
     }
-    return aes_hermite(frac, v[0], v[1], v[2], v[3]);
+    return aes_hermite(frac, t[0], t[1], t[2], t[3]);
 }
 
-template <int K>
-__device__ void aes_stage_octaver(const DevStage &st, const TileCtx &c)
+template <int FR>
+__device__ void aes_stage_octaver(const DevStage &st, const KCtx &c, float (&v)[2][FR])
 {
-    constexpr int T = 128 * K;
+    const int i0 = FR * c.tid;
     const DevRing rg = c.P->ring[st.ring[0][0]];
     float *rb = c.rings + rg.off;
     const int mask = st.oct_mask, size = st.oct_size;
+    float mono[FR];
 #pragma unroll
-    for (int m = 0; m < T / AES_NT; ++m) {
-        const int i = c.tid + AES_NT * m;
-        // np.mean over the 2 channels in f32 (octaver.py:124-126)
-        rb[(int)((c.n0 + i) & mask)] = __fmul_rn(__fadd_rn(c.cur[i], c.cur[T + i]), 0.5f);
-    }
+    for (int j = 0; j < FR; ++j) mono[j] = __fmul_rn(__fadd_rn(v[0][j], v[1][j]), 0.5f);   // np.mean, octaver.py:124-126
+    aes_stv<FR>(rb + (int)((c.n0 + i0) & mask), mono);
     __syncthreads();
     const float wet_g = st.mix, dry_g = (float)(1.0 - (double)st.mix);
+    const double ph0 = st.ph0, step = st.step, fsize = st.fsize;
 #pragma unroll
-    for (int m = 0; m < T / AES_NT; ++m) {
-        const int i = c.tid + AES_NT * m;
-        const long long n = c.n0 + i;
-        double ph = st.ph0 + (double)n * st.step;                // phasor in closed form
+    for (int j = 0; j < FR; ++j) {
+        const long long n = c.n0 + i0 + j;
+        double ph = ph0 + (double)n * step;                      // phasor in closed form
         ph -= floor(ph);
         double p2 = ph + 0.5;
         if (p2 >= 1.0) p2 -= 1.0;
-        const float s1 = aes_octaver_tap(rb, mask, n, size, st.fsize, ph);
-        const float s2 = aes_octaver_tap(rb, mask, n, size, st.fsize, p2);
+        const float s1 = aes_octaver_tap(rb, mask, n, size, fsize, ph);
+        const float s2 = aes_octaver_tap(rb, mask, n, size, fsize, p2);
         const float sn = sinpif((float)ph);
         const float g1 = sn * sn;                                // 0.5*(1-cos(2*pi*p))
         const float g2 = 1.0f - g1;                              // p2 = p + 1/2
-        const float wet = s1 * g1 + s2 * g2;
-        c.cur[i] = __fadd_rn(__fmul_rn(c.cur[i], dry_g), __fmul_rn(wet, wet_g));
-        c.cur[T + i] = __fadd_rn(__fmul_rn(c.cur[T + i], dry_g), __fmul_rn(wet, wet_g));
+        const float wet = __fmul_rn(s1 * g1 + s2 * g2, wet_g);
+        v[0][j] = __fadd_rn(__fmul_rn(v[0][j], dry_g), wet);
+        v[1][j] = __fadd_rn(__fmul_rn(v[1][j], dry_g), wet);
     }
-    __syncthreads();
 }
 
-// ---- distortion (our definition, no reference block) -----------------------------------------
-template <int K>
-__device__ void aes_stage_distortion(const DevStage &st, const TileCtx &c)
+// ---- distortion (our definition, no reference block) ---------------------------------------------
+template <int FR>
+__device__ __forceinline__ void aes_stage_distortion(const DevStage &st, float (&v)[2][FR])
 {
-    constexpr int T = 128 * K;
     const float drive = st.drive, mix = st.mix, dry = 1.0f - st.mix;
 #pragma unroll
-    for (int m = 0; m < 2 * T / AES_NT; ++m) {
-        const int e = c.tid + AES_NT * m;
-        const float v = c.cur[e];
-        const float t = tanhf(__fmul_rn(drive, v));
-        c.cur[e] = aes_clip1(__fadd_rn(__fmul_rn(dry, v), __fmul_rn(mix, t)));
-    }
-    __syncthreads();
+    for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+        for (int j = 0; j < FR; ++j) {
+            const float x = v[ch][j];
+            const float t = tanhf(__fmul_rn(drive, x));
+            v[ch][j] = aes_clip1(__fadd_rn(__fmul_rn(dry, x), __fmul_rn(mix, t)));
+        }
 }
 
-// ---- the kernel body ------------------------------------------------------------------------
-template <int K>
+// ---- the kernel body ------------------------------------------------------------------------------
+template <int FR>
 __device__ void aes_chain_body(const ChainArgs &a)
 {
-    constexpr int T = 128 * K;
+    constexpr int T = AES_NT * FR;
     AES_DYN_SMEM(float, smem);
     const DevPlan *P = a.plan;
-    TileCtx c;
+    KCtx c;
     c.P = P;
     c.tid = threadIdx.x;
-    c.cur = smem;
-    c.aux = smem + 2 * T;
-    c.rings = smem + 4 * T;
-    const int foff = (4 * T + P->smem_floats + 1) & ~1;
+    c.lane = c.tid & 31;
+    c.warp = c.tid >> 5;
+    c.tile = smem;
+    c.rings = smem + 2 * T;
+    const int foff = (2 * T + P->smem_floats + 3) & ~3;
     c.wtot = reinterpret_cast<double *>(smem + foff);
     double *state = c.wtot + 64;
     const int nstate = P->n_state;
-    c.rpos = reinterpret_cast<int *>(state + 2 * nstate);
+    int *rpos2 = reinterpret_cast<int *>(state + 2 * nstate);   // [2][n_rings], ping-pong by tile parity
     c.gscr = a.scratch + (long long)blockIdx.x * P->scratch_floats;
-    const int nst = P->n_stages, nr = P->n_rings;
+    const int nst = P->n_stages, nr = P->n_rings, pf_stage = P->pf_stage;
 
     for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
         // fresh block state for every clip (the chain's re-prepare, core.py:123-129)
         for (int i = c.tid; i < P->smem_floats; i += AES_NT) c.rings[i] = 0.0f;
-        for (int i = c.tid; i < nr; i += AES_NT) c.rpos[i] = 0;
+        for (int i = c.tid; i < nr; i += AES_NT) rpos2[i] = 0;
+        c.rpos = rpos2;
         for (int i = c.tid; i < nstate; i += AES_NT) state[i] = P->stage[i >> 4].init[i & 15];
         __syncthreads();
+
+        float xn[2][FR], pf[2][FR];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+            for (int j = 0; j < FR; ++j) pf[ch][j] = 0.0f;
+        c.n0 = 0;
+        c.len = a.N < (long long)T ? (int)a.N : T;
+        aes_load_frames<FR>(a, b, 0, c.len, c.tid, xn);
+        if (pf_stage >= 0) aes_delay_fetch<FR>(P->stage[pf_stage], c, 0, pf);
         int par = 0;
         for (long long n0 = 0; n0 < a.N; n0 += T, par ^= 1) {
             c.n0 = n0;
             c.len = (a.N - n0 < (long long)T) ? (int)(a.N - n0) : T;
-            aes_load_tile<K>(a, b, c);
-            __syncthreads();
+            c.rpos = rpos2 + par * nr;
+            float v[2][FR], ln[2][FR];
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+                for (int j = 0; j < FR; ++j) { v[ch][j] = xn[ch][j]; ln[ch][j] = pf[ch][j]; }
+            // software pipeline: next tile's frames and the long delay line it needs
+            const bool more = n0 + T < a.N;
+            if (more) {
+                const long long rem = a.N - n0 - T;
+                aes_load_frames<FR>(a, b, n0 + T, rem < (long long)T ? (int)rem : T, c.tid, xn);
+                if (pf_stage >= 0) aes_delay_fetch<FR>(P->stage[pf_stage], c, 1, pf);
+            }
             for (int s = 0; s < nst; ++s) {
                 const DevStage &st = P->stage[s];
                 const double *sin = state + par * nstate + 16 * s;
                 double *sout = state + (par ^ 1) * nstate + 16 * s;
                 switch (st.kind) {
-                case AESK_DELAY:      aes_stage_delay<K>(st, c); break;
-                case AESK_REVERB:     aes_stage_reverb<K>(st, c, sin, sout); break;
-                case AESK_BIQUAD:     aes_stage_biquad<K>(st, c, sin, sout); break;
-                case AESK_GATE:       aes_stage_gate<K>(st, c, sin, sout); break;
-                case AESK_OCTAVER:    aes_stage_octaver<K>(st, c); break;
-                case AESK_DISTORTION: aes_stage_distortion<K>(st, c); break;
+                case AESK_DELAY:
+                    if (st.mode == AES_MODE_REG) {
+                        if (s != pf_stage) aes_delay_fetch<FR>(st, c, 0, ln);
+                        aes_stage_delay_reg<FR>(st, c, v, ln);
+                    } else {
+                        aes_spill<FR>(c, v);
+                        __syncthreads();
+                        aes_walk<FR, 0>(c, st.ring[c.tid >> 7][0], st.fb, st.dry, st.wet);
+                        __syncthreads();
+                        aes_reload<FR>(c, v);
+                    }
+                    break;
+                case AESK_REVERB:     aes_stage_reverb<FR>(st, c, v, sin, sout); break;
+                case AESK_BIQUAD:     aes_stage_biquad<FR>(st, c, v, sin, sout); break;
+                case AESK_GATE:       aes_stage_gate<FR>(st, c, v, sin, sout); break;
+                case AESK_OCTAVER:    aes_stage_octaver<FR>(st, c, v); break;
+                case AESK_DISTORTION: aes_stage_distortion<FR>(st, v); break;
                 default: break;
                 }
             }
-            aes_store_tile<K>(a, b, c);
-            if (c.tid < nr) {
-                const DevRing rg = P->ring[c.tid];
+            aes_store_frames<FR>(a, b, n0, c.len, c.tid, v);
+            if (c.tid < nr) {                                    // next tile's slots go to the other parity:
+                const DevRing rg = P->ring[c.tid];               // slower threads may still read this tile's
                 int p = c.rpos[c.tid] + rg.tinc;
                 if (p >= rg.len) p -= rg.len;
-                c.rpos[c.tid] = p;
+                rpos2[(par ^ 1) * nr + c.tid] = p;
             }
             __syncthreads();
         }
@@ -536,9 +711,9 @@ __device__ void aes_chain_body(const ChainArgs &a)
 }
 
 #ifndef AES_CPU_EMU
-template <int K>
+template <int FR>
 __global__ void __launch_bounds__(AES_NT, 2) aes_chain_kernel(const ChainArgs a)
 {
-    aes_chain_body<K>(a);
+    aes_chain_body<FR>(a);
 }
 #endif

@@ -1,0 +1,647 @@
+// aes_fast_kernel.cuh -- shape-specialised variant of the fused chain kernel.
+//
+// Same algorithm and thread mapping as aes_chain_kernel.cuh (thread = FR consecutive
+// frames x 2 channels in registers, one CTA per clip, tiles of T = 256*FR frames), but
+// the chain SHAPE (stage kinds, comb/all-pass counts, line modes) is a template
+// parameter and every descriptor lives in the kernel-parameter constant bank:
+//   * no plan loads from global memory (the generic interpreter spends ~100 LDG per
+//     thread per tile on them), stage loop and comb loops fully unrolled;
+//   * ring slots of the register-path lines are per-thread registers advanced by one
+//     add + wrap per tile;  for a comb whose ring period is roundup4(L) the aligned read
+//     base EQUALS the write slot (r = w - L = w + m  (mod len), m = len - L), so one
+//     register per ring serves both;
+//   * the comb one-pole is run on u = lp/(1-h):  u[n] = y[n] + h*u[n-1],
+//     buf[n] = x[n] + (g*(1-h))*u[n]  -- one FFMA per sample per pass instead of FMUL+FFMA.
+// The host (aes_chain.cu) picks an instantiation whose shape matches the plan, else runs
+// the generic interpreter.  Also compiled for the CPU emulator (AES_CPU_EMU).
+#pragma once
+#include "aes_chain_kernel.cuh"
+
+#define AESF_MAX_STAGES 4
+#define AESF_MAX_WALK 12
+
+// shape code of one stage (template parameter)
+#define AESF_CODE(kind, nc, na, mode, premode, pf) \
+    ((kind) | ((nc) << 4) | ((na) << 8) | ((mode) << 12) | ((premode) << 14) | ((pf) << 16))
+#define AESF_KIND(c) ((c) & 15)
+#define AESF_NC(c) (((c) >> 4) & 15)
+#define AESF_NA(c) (((c) >> 8) & 15)
+#define AESF_MODE(c) (((c) >> 12) & 3)
+#define AESF_PREMODE(c) (((c) >> 14) & 3)      // 0 none, 1 REG, 2 WALK
+#define AESF_PF(c) (((c) >> 16) & 1)
+
+struct FRing {
+    int off;        // float offset in the smem ring area or the CTA's global scratch
+    int len;        // period (floats)
+    int tinc;       // T mod len
+    int lag;
+};
+
+struct FastStage {
+    FRing ring[2][4];       // delay: ring[c][0]; reverb: comb rings
+    FRing pre[2];           // reverb pre-delay line (REG); WALK lines use `walk` ids below
+    int walk_pre[2];        // ids into FastArgs::walk (WALK pre-delay / WALK delay)
+    int walk_ap[2][2];      // ids into FastArgs::walk
+    int glob;               // delay / pre-delay REG rings live in the global scratch
+    int nscan, nxw, pad0;
+    float gs[2][4];         // g * (1 - h)
+    float dry, wet, h, a, fb, mix, drive, pad1;
+    float hp[6];            // h^(FR*2^s), hp[5] = h^(32*FR)
+    int oct_size, oct_mask;
+    double bq[5];
+    double bq_pow[6][4];
+    double thr, att, rel;
+    double ph0, step, fsize;
+};
+
+struct FastArgs {
+    FastStage st[AESF_MAX_STAGES];
+    FRing walk[AESF_MAX_WALK];
+    double init[AESF_MAX_STAGES][8];    // carried scalars at clip start (biquad 8, gate 1)
+    const void *x;
+    void *y;
+    long long B, N;
+    float *scratch;
+    const float *lane_tab;              // global: per stage 32 x {hlane, pad, pad, pad, bq_lane[4] as 8 floats} -> see FAST_LANE_STRIDE
+    double *state_out;
+    long long scratch_floats;
+    int in_fmt, out_fmt;
+    int smem_floats, n_walk, n_stages, pad;
+};
+#define FAST_LANE_STRIDE 12             // floats per lane per stage: [0]=hlane, [4..11]=bq_lane as 4 doubles
+
+struct FCtx {
+    float *tile, *rings, *gscr;
+    double *wtot;
+    int *rpos;              // current parity
+    long long n0;
+    int len, tid, lane, warp;
+};
+
+struct SRegs {              // per-thread, per-stage persistent ring slots (floats)
+    int w[2][4];            // comb rings: write slot == aligned read base
+    int dw[2], da[2];       // delay / pre-delay REG line: write slot, aligned read base
+};
+
+__device__ __forceinline__ int aesf_adv(int s, int inc, int len)
+{
+    s += inc;
+    return s >= len ? s - len : s;
+}
+
+// FR consecutive elements starting m (< FR) past the aligned base a0; the next aligned
+// vector wraps at len.  m is uniform over the CTA.
+template <int FR>
+__device__ __forceinline__ void aesf_read(const float *rb, int a0, int m, int len, float (&o)[FR])
+{
+    if (FR < 4) {                                   // m is given relative to a 4-aligned base
+        a0 += m & ~(FR - 1);
+        if (a0 >= len) a0 -= len;
+        m &= FR - 1;
+    }
+    float A[FR];
+    aes_ldv<FR>(rb + a0, A);
+    if (m == 0 || FR == 1) {
+#pragma unroll
+        for (int j = 0; j < FR; ++j) o[j] = A[j];
+        return;
+    }
+    int b0 = a0 + FR;
+    if (b0 >= len) b0 -= len;
+    float Bv[FR];
+    aes_ldv<FR>(rb + b0, Bv);
+    if (m == 1) {
+#pragma unroll
+        for (int j = 0; j < FR; ++j) o[j] = (j + 1 < FR) ? A[(j + 1) % FR] : Bv[(j + 1) % FR];
+    } else if (m == 2) {
+#pragma unroll
+        for (int j = 0; j < FR; ++j) o[j] = (j + 2 < FR) ? A[(j + 2) % FR] : Bv[(j + 2) % FR];
+    } else {
+#pragma unroll
+        for (int j = 0; j < FR; ++j) o[j] = (j + 3 < FR) ? A[(j + 3) % FR] : Bv[(j + 3) % FR];
+    }
+}
+
+// ---- phase walk on the smem tile for a WALK ring described in the parameter bank --------
+template <int FR, int OP>
+__device__ __forceinline__ void aesf_walk(const FCtx &c, const FRing rg, int ring_id, bool glob, float p0, float p1, float p2)
+{
+    constexpr int T = AES_NT * FR;
+    const int ch = c.tid >> 7, j0 = c.tid & 127;
+    float *rb = (glob ? c.gscr : c.rings) + rg.off;
+    const int L = rg.len, pos = c.rpos[ring_id];
+    const int W = L < T ? L : T;
+    float *s = c.tile + ch * T;
+    for (int j = j0; j < W && j < c.len; j += 128) {
+        int slot = pos + j;
+        if (slot >= L) slot -= L;
+        float line = (c.n0 + j >= L) ? rb[slot] : 0.0f;
+        for (int i = j; i < c.len; i += 4 * L) {
+            float xs[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long ii = (long long)i + (long long)u * L;
+                xs[u] = ii < c.len ? s[ii] : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long ii = (long long)i + (long long)u * L;
+                if (ii < c.len) {
+                    const float x = xs[u];
+                    if (OP == 0) {
+                        s[ii] = aes_mix_clip(p1, x, p2, line);
+                        line = fmaf(line, p0, x);
+                    } else if (OP == 1) {
+                        s[ii] = line;
+                        line = x;
+                    } else {
+                        const float yo = fmaf(-p0, x, line);
+                        s[ii] = yo;
+                        line = fmaf(p0, yo, x);
+                    }
+                }
+            }
+        }
+        rb[slot] = line;
+    }
+}
+
+template <int FR> __device__ __forceinline__ void aesf_spill(const FCtx &c, const float (&v)[2][FR])
+{
+    constexpr int T = AES_NT * FR;
+    aes_stv<FR>(c.tile + FR * c.tid, v[0]);
+    aes_stv<FR>(c.tile + T + FR * c.tid, v[1]);
+}
+template <int FR> __device__ __forceinline__ void aesf_reload(const FCtx &c, float (&v)[2][FR])
+{
+    constexpr int T = AES_NT * FR;
+    aes_ldv<FR>(c.tile + FR * c.tid, v[0]);
+    aes_ldv<FR>(c.tile + T + FR * c.tid, v[1]);
+}
+
+// ---- register-path line (feedback delay / pre-delay with lag >= T) ------------------------
+template <int FR>
+__device__ __forceinline__ void aesf_line_init(const FRing rg, int i0, int &w, int &a0)
+{
+    w = i0;                                         // slot of sample n0 + i0 at n0 = 0
+    const int lag4 = (rg.lag + 3) & ~3;
+    a0 = i0 - lag4;
+    if (a0 < 0) a0 += rg.len;                       // len = lag4 + T > lag4
+}
+template <int FR>
+__device__ __forceinline__ void aesf_line_read(const FCtx &c, const FRing rg, bool glob, int a0, float (&o)[FR])
+{
+    const float *rb = (glob ? c.gscr : c.rings) + rg.off;
+    aesf_read<FR>(rb, a0, ((rg.lag + 3) & ~3) - rg.lag, rg.len, o);
+}
+
+// ---- one stage, specialised on its shape code ------------------------------------------------
+template <int FR, int CODE, int S>
+__device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRegs &sr, float (&v)[2][FR],
+                                           const float (&ln)[2][FR], const double *sin, double *sout)
+{
+    constexpr int KIND = AESF_KIND(CODE);
+    const FastStage &st = a.st[S];
+    const int i0 = FR * c.tid, lane = c.lane, warp = c.warp;
+
+    if constexpr (KIND == AESK_DELAY) {
+        if (AESF_MODE(CODE) == AES_MODE_REG) {
+            const float fb = st.fb, dry = st.dry, wet = st.wet;
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const FRing rg = st.ring[ch][0];
+                float line[FR];
+                if (AESF_PF(CODE)) {
+#pragma unroll
+                    for (int j = 0; j < FR; ++j) line[j] = ln[ch][j];
+                } else {
+                    aesf_line_read<FR>(c, rg, st.glob != 0, sr.da[ch], line);
+                }
+                float nb[FR];
+#pragma unroll
+                for (int j = 0; j < FR; ++j) {
+                    const float l = (c.n0 + i0 + j >= rg.lag) ? line[j] : 0.0f;   // zero history on a fresh clip
+                    const float x = v[ch][j];
+                    nb[j] = fmaf(l, fb, x);
+                    v[ch][j] = aes_mix_clip(dry, x, wet, l);
+                }
+                aes_stv<FR>((st.glob ? c.gscr : c.rings) + rg.off + sr.dw[ch], nb);
+            }
+        } else {
+            aesf_spill<FR>(c, v);
+            __syncthreads();
+            const int ch = c.tid >> 7;
+            aesf_walk<FR, 0>(c, a.walk[st.walk_pre[ch]], st.walk_pre[ch], st.glob != 0, st.fb, st.dry, st.wet);
+            __syncthreads();
+            aesf_reload<FR>(c, v);
+        }
+    } else if constexpr (KIND == AESK_REVERB) {
+        constexpr int NC = AESF_NC(CODE), NA = AESF_NA(CODE), PM = AESF_PREMODE(CODE);
+        float pre[2][FR];
+        if (PM == 0) {
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+                for (int j = 0; j < FR; ++j) pre[ch][j] = v[ch][j];
+        } else if (PM == 1) {
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const FRing rg = st.pre[ch];
+                aesf_line_read<FR>(c, rg, st.glob != 0, sr.da[ch], pre[ch]);
+#pragma unroll
+                for (int j = 0; j < FR; ++j)
+                    if (c.n0 + i0 + j < rg.lag) pre[ch][j] = 0.0f;
+                aes_stv<FR>((st.glob ? c.gscr : c.rings) + rg.off + sr.dw[ch], v[ch]);
+            }
+        } else {
+            aesf_spill<FR>(c, v);
+            __syncthreads();
+            const int ch = c.tid >> 7;
+            aesf_walk<FR, 1>(c, a.walk[st.walk_pre[ch]], st.walk_pre[ch], st.glob != 0, 0.f, 0.f, 0.f);
+            __syncthreads();
+            aesf_reload<FR>(c, pre);
+        }
+
+        // damped combs on u = lp/(1-h)
+        const float h = st.h, hw = st.hp[5];
+        const float hl = a.lane_tab[(S * 32 + lane) * FAST_LANE_STRIDE];
+        float y[2][NC][FR], e[2][NC];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+            for (int cc = 0; cc < NC; ++cc) {
+                const FRing rg = st.ring[ch][cc];
+                aesf_read<FR>(c.rings + rg.off, sr.w[ch][cc], rg.len - rg.lag, rg.len, y[ch][cc]);
+                float u = 0.0f;
+#pragma unroll
+                for (int j = 0; j < FR; ++j) u = fmaf(h, u, y[ch][cc][j]);
+                e[ch][cc] = u;
+            }
+        const int nscan = st.nscan;
+        for (int s = 0; s < nscan; ++s) {
+            const float m = st.hp[s];
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+                for (int cc = 0; cc < NC; ++cc) {
+                    const float t = __shfl_up_sync(0xffffffffu, e[ch][cc], 1 << s);
+                    if (lane >= (1 << s)) e[ch][cc] = fmaf(m, t, e[ch][cc]);
+                }
+        }
+        float *wt = reinterpret_cast<float *>(c.wtot);          // [8 warps][2][4]
+        if (lane == 31) {
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+                for (int cc = 0; cc < NC; ++cc) wt[(warp * 2 + ch) * 4 + cc] = e[ch][cc];
+        }
+        __syncthreads();
+        const int u0 = warp > st.nxw ? warp - st.nxw : 0;
+        float sum[2][FR];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+#pragma unroll
+            for (int j = 0; j < FR; ++j) sum[ch][j] = 0.0f;
+#pragma unroll
+            for (int cc = 0; cc < NC; ++cc) {
+                const float ex = __shfl_up_sync(0xffffffffu, e[ch][cc], 1);
+                float C = u0 == 0 ? (float)sin[ch * 4 + cc] : 0.0f;
+                for (int t = u0; t < warp; ++t) C = fmaf(hw, C, wt[(t * 2 + ch) * 4 + cc]);
+                float u = fmaf(hl, C, lane == 0 ? 0.0f : ex);
+                const FRing rg = st.ring[ch][cc];
+                const float gs = st.gs[ch][cc];
+                float nb[FR];
+#pragma unroll
+                for (int j = 0; j < FR; ++j) {
+                    u = fmaf(h, u, y[ch][cc][j]);
+                    nb[j] = fmaf(gs, u, pre[ch][j]);            // buf[n] = x + g*(1-h)*u
+                    sum[ch][j] = __fadd_rn(sum[ch][j], y[ch][cc][j]);
+                }
+                aes_stv<FR>(c.rings + rg.off + sr.w[ch][cc], nb);
+                if (c.tid == AES_NT - 1) sout[ch * 4 + cc] = (double)u;
+            }
+        }
+        aesf_spill<FR>(c, sum);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < NA; ++k) {
+            const int ch = c.tid >> 7;
+            aesf_walk<FR, 2>(c, a.walk[st.walk_ap[ch][k]], st.walk_ap[ch][k], false, st.a, 0.f, 0.f);
+            __syncthreads();
+        }
+        aesf_reload<FR>(c, sum);
+        const float dry = st.dry, wet = st.wet;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+            for (int j = 0; j < FR; ++j) v[ch][j] = aes_mix_clip(dry, v[ch][j], wet, sum[ch][j]);
+    } else if constexpr (KIND == AESK_BIQUAD) {
+        constexpr int T = AES_NT * FR;
+        const double b0 = st.bq[0], b1 = st.bq[1], b2 = st.bq[2], a1 = st.bq[3], a2 = st.bq[4];
+        aesf_spill<FR>(c, v);
+        __syncthreads();
+        double xm1[2], xm2[2], e1[2], e2[2];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const float *xc = c.tile + ch * T;
+            xm1[ch] = i0 >= 1 ? (double)xc[i0 - 1] : sin[4 * ch + 0];
+            xm2[ch] = i0 >= 2 ? (double)xc[i0 - 2] : (i0 == 1 ? sin[4 * ch + 0] : sin[4 * ch + 1]);
+            double y1 = 0.0, y2 = 0.0, p1 = xm1[ch], p2 = xm2[ch];
+#pragma unroll
+            for (int j = 0; j < FR; ++j) {
+                const double xj = (double)v[ch][j];
+                const double y = b0 * xj + b1 * p1 + b2 * p2 - a1 * y1 - a2 * y2;
+                y2 = y1; y1 = y; p2 = p1; p1 = xj;
+            }
+            e1[ch] = y1; e2[ch] = y2;
+        }
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            const double m0 = st.bq_pow[s][0], m1 = st.bq_pow[s][1], m2 = st.bq_pow[s][2], m3 = st.bq_pow[s][3];
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const double u1 = __shfl_up_sync(0xffffffffu, e1[ch], 1 << s);
+                const double u2 = __shfl_up_sync(0xffffffffu, e2[ch], 1 << s);
+                if (lane >= (1 << s)) {
+                    e1[ch] += m0 * u1 + m1 * u2;
+                    e2[ch] += m2 * u1 + m3 * u2;
+                }
+            }
+        }
+        if (lane == 31) {
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                c.wtot[(warp * 2 + ch) * 2] = e1[ch];
+                c.wtot[(warp * 2 + ch) * 2 + 1] = e2[ch];
+            }
+        }
+        __syncthreads();
+        const double w0 = st.bq_pow[5][0], w1 = st.bq_pow[5][1], w2 = st.bq_pow[5][2], w3 = st.bq_pow[5][3];
+        const double *lt = reinterpret_cast<const double *>(a.lane_tab + (S * 32 + lane) * FAST_LANE_STRIDE + 4);
+        const double l0 = lt[0], l1 = lt[1], l2 = lt[2], l3 = lt[3];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            double C1 = sin[4 * ch + 2], C2 = sin[4 * ch + 3];
+            for (int t = 0; t < warp; ++t) {
+                const double t1 = w0 * C1 + w1 * C2 + c.wtot[(t * 2 + ch) * 2];
+                const double t2 = w2 * C1 + w3 * C2 + c.wtot[(t * 2 + ch) * 2 + 1];
+                C1 = t1; C2 = t2;
+            }
+            double x1 = __shfl_up_sync(0xffffffffu, e1[ch], 1), x2 = __shfl_up_sync(0xffffffffu, e2[ch], 1);
+            if (lane == 0) { x1 = 0.0; x2 = 0.0; }
+            double y1 = x1 + l0 * C1 + l1 * C2;
+            double y2 = x2 + l2 * C1 + l3 * C2;
+            double p1 = xm1[ch], p2 = xm2[ch];
+#pragma unroll
+            for (int j = 0; j < FR; ++j) {
+                const double xj = (double)v[ch][j];
+                const double y = b0 * xj + b1 * p1 + b2 * p2 - a1 * y1 - a2 * y2;
+                v[ch][j] = (float)y;
+                y2 = y1; y1 = y; p2 = p1; p1 = xj;
+                if (i0 + j == c.len - 1) {
+                    sout[4 * ch + 0] = p1; sout[4 * ch + 1] = p2;
+                    sout[4 * ch + 2] = y1; sout[4 * ch + 3] = y2;
+                }
+            }
+        }
+        __syncthreads();
+    } else if constexpr (KIND == AESK_GATE) {
+        const double thr = st.thr, ka = 1.0 - st.att, kr = 1.0 - st.rel, att = st.att;
+        bool open[FR];
+        double A = 1.0, Bv = 0.0;
+#pragma unroll
+        for (int f = 0; f < FR; ++f) {
+            const float lvl = fmaxf(fabsf(v[0][f]), fabsf(v[1][f]));
+            open[f] = (double)lvl > thr;
+            const double am = open[f] ? ka : kr, bm = open[f] ? att : 0.0;
+            Bv = am * Bv + bm;
+            A = am * A;
+        }
+#pragma unroll
+        for (int s = 0; s < 5; ++s) {
+            const double Au = __shfl_up_sync(0xffffffffu, A, 1 << s);
+            const double Bu = __shfl_up_sync(0xffffffffu, Bv, 1 << s);
+            if (lane >= (1 << s)) { Bv = A * Bu + Bv; A = A * Au; }
+        }
+        if (lane == 31) { c.wtot[2 * warp] = A; c.wtot[2 * warp + 1] = Bv; }
+        __syncthreads();
+        double g = sin[0];
+        for (int t = 0; t < warp; ++t) g = c.wtot[2 * t] * g + c.wtot[2 * t + 1];
+        double Ae = __shfl_up_sync(0xffffffffu, A, 1), Be = __shfl_up_sync(0xffffffffu, Bv, 1);
+        if (lane == 0) { Ae = 1.0; Be = 0.0; }
+        g = Ae * g + Be;
+#pragma unroll
+        for (int f = 0; f < FR; ++f) {
+            g = (open[f] ? ka : kr) * g + (open[f] ? att : 0.0);
+            const float gf = (float)g;
+            v[0][f] *= gf;
+            v[1][f] *= gf;
+            if (i0 + f == c.len - 1) sout[0] = g;
+        }
+        __syncthreads();
+    } else if constexpr (KIND == AESK_OCTAVER) {
+        float *rb = c.rings + st.ring[0][0].off;
+        const int mask = st.oct_mask, size = st.oct_size;
+        float mono[FR];
+#pragma unroll
+        for (int j = 0; j < FR; ++j) mono[j] = __fmul_rn(__fadd_rn(v[0][j], v[1][j]), 0.5f);
+        aes_stv<FR>(rb + (int)((c.n0 + i0) & mask), mono);
+        __syncthreads();
+        const float wet_g = st.mix, dry_g = (float)(1.0 - (double)st.mix);
+        const double ph0 = st.ph0, step = st.step, fsize = st.fsize;
+#pragma unroll
+        for (int j = 0; j < FR; ++j) {
+            const long long n = c.n0 + i0 + j;
+            double ph = ph0 + (double)n * step;
+            ph -= floor(ph);
+            double p2 = ph + 0.5;
+            if (p2 >= 1.0) p2 -= 1.0;
+            const float s1 = aes_octaver_tap(rb, mask, n, size, fsize, ph);
+            const float s2 = aes_octaver_tap(rb, mask, n, size, fsize, p2);
+            const float sn = sinpif((float)ph);
+            const float g1 = sn * sn;
+            const float g2 = 1.0f - g1;
+            const float wet = __fmul_rn(s1 * g1 + s2 * g2, wet_g);
+            v[0][j] = __fadd_rn(__fmul_rn(v[0][j], dry_g), wet);
+            v[1][j] = __fadd_rn(__fmul_rn(v[1][j], dry_g), wet);
+        }
+    } else if constexpr (KIND == AESK_DISTORTION) {
+        const float drive = st.drive, mix = st.mix, dry = 1.0f - st.mix;
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+            for (int j = 0; j < FR; ++j) {
+                const float x = v[ch][j];
+                const float t = tanhf(__fmul_rn(drive, x));
+                v[ch][j] = aes_clip1(__fadd_rn(__fmul_rn(dry, x), __fmul_rn(mix, t)));
+            }
+    }
+}
+
+// per-clip initialisation / per-tile advance of a stage's register slots
+template <int FR, int CODE, int S>
+__device__ __forceinline__ void aesf_slots_init(const FastArgs &a, int i0, SRegs &sr)
+{
+    constexpr int KIND = AESF_KIND(CODE);
+    const FastStage &st = a.st[S];
+    if (KIND == AESK_DELAY && AESF_MODE(CODE) == AES_MODE_REG) {
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) aesf_line_init<FR>(st.ring[ch][0], i0, sr.dw[ch], sr.da[ch]);
+    }
+    if constexpr (KIND == AESK_REVERB) {
+        if (AESF_PREMODE(CODE) == 1) {
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) aesf_line_init<FR>(st.pre[ch], i0, sr.dw[ch], sr.da[ch]);
+        }
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+            for (int cc = 0; cc < AESF_NC(CODE); ++cc) sr.w[ch][cc] = i0;
+    }
+}
+
+template <int FR, int CODE, int S>
+__device__ __forceinline__ void aesf_slots_advance(const FastArgs &a, SRegs &sr)
+{
+    constexpr int KIND = AESF_KIND(CODE);
+    const FastStage &st = a.st[S];
+    if (KIND == AESK_DELAY && AESF_MODE(CODE) == AES_MODE_REG) {
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const FRing rg = st.ring[ch][0];
+            sr.dw[ch] = aesf_adv(sr.dw[ch], rg.tinc, rg.len);
+            sr.da[ch] = aesf_adv(sr.da[ch], rg.tinc, rg.len);
+        }
+    }
+    if constexpr (KIND == AESK_REVERB) {
+        if (AESF_PREMODE(CODE) == 1) {
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const FRing rg = st.pre[ch];
+                sr.dw[ch] = aesf_adv(sr.dw[ch], rg.tinc, rg.len);
+                sr.da[ch] = aesf_adv(sr.da[ch], rg.tinc, rg.len);
+            }
+        }
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+            for (int cc = 0; cc < AESF_NC(CODE); ++cc) {
+                const FRing rg = st.ring[ch][cc];
+                sr.w[ch][cc] = aesf_adv(sr.w[ch][cc], rg.tinc, rg.len);
+            }
+    }
+}
+
+// prefetch of the long feedback-delay line one tile ahead (lag >= 2T): issued at the top
+// of tile i for tile i+1, consumed a full tile of work later.
+template <int FR, int CODE, int S>
+__device__ __forceinline__ void aesf_prefetch(const FastArgs &a, const FCtx &c, const SRegs &sr, int ahead,
+                                              float (&pf)[2][FR])
+{
+    if (AESF_KIND(CODE) == AESK_DELAY && AESF_PF(CODE)) {
+        const FastStage &st = a.st[S];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const FRing rg = st.ring[ch][0];
+            const int a0 = ahead ? aesf_adv(sr.da[ch], rg.tinc, rg.len) : sr.da[ch];
+            aesf_line_read<FR>(c, rg, st.glob != 0, a0, pf[ch]);
+        }
+    }
+}
+
+template <int FR, int C0, int C1, int C2, int C3>
+__device__ void aes_fast_body(const FastArgs &a)
+{
+    constexpr int T = AES_NT * FR;
+    constexpr int NS = (C0 != 0) + (C1 != 0) + (C2 != 0) + (C3 != 0);
+    AES_DYN_SMEM(float, smem);
+    FCtx c;
+    c.tid = threadIdx.x;
+    c.lane = c.tid & 31;
+    c.warp = c.tid >> 5;
+    c.tile = smem;
+    c.rings = smem + 2 * T;
+    const int foff = (2 * T + a.smem_floats + 3) & ~3;
+    c.wtot = reinterpret_cast<double *>(smem + foff);
+    double *state = c.wtot + 64;                    // [2][NS*8]
+    constexpr int NST = NS * 8;
+    int *rpos2 = reinterpret_cast<int *>(state + 2 * NST);
+    c.gscr = a.scratch + (long long)blockIdx.x * a.scratch_floats;
+    const int nw = a.n_walk, i0 = FR * c.tid;
+
+    for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
+        for (int i = c.tid; i < a.smem_floats; i += AES_NT) c.rings[i] = 0.0f;
+        for (int i = c.tid; i < nw; i += AES_NT) rpos2[i] = 0;
+        for (int i = c.tid; i < NST; i += AES_NT) state[i] = a.init[i >> 3][i & 7];
+        SRegs sr0, sr1, sr2, sr3;
+        if (C0) aesf_slots_init<FR, C0, 0>(a, i0, sr0);
+        if (C1) aesf_slots_init<FR, C1, 1>(a, i0, sr1);
+        if (C2) aesf_slots_init<FR, C2, 2>(a, i0, sr2);
+        if (C3) aesf_slots_init<FR, C3, 3>(a, i0, sr3);
+        __syncthreads();
+
+        float xn[2][FR], pf[2][FR];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+            for (int j = 0; j < FR; ++j) pf[ch][j] = 0.0f;
+        c.n0 = 0;
+        c.len = a.N < (long long)T ? (int)a.N : T;
+        c.rpos = rpos2;
+        ChainArgs io;                                // tile I/O helpers are shared with the generic kernel
+        io.x = a.x; io.y = a.y; io.N = a.N; io.in_fmt = a.in_fmt; io.out_fmt = a.out_fmt;
+        aes_load_frames<FR>(io, b, 0, c.len, c.tid, xn);
+        if (C0) aesf_prefetch<FR, C0, 0>(a, c, sr0, 0, pf);
+        if (C1) aesf_prefetch<FR, C1, 1>(a, c, sr1, 0, pf);
+        if (C2) aesf_prefetch<FR, C2, 2>(a, c, sr2, 0, pf);
+        if (C3) aesf_prefetch<FR, C3, 3>(a, c, sr3, 0, pf);
+        int par = 0;
+        for (long long n0 = 0; n0 < a.N; n0 += T, par ^= 1) {
+            c.n0 = n0;
+            c.len = (a.N - n0 < (long long)T) ? (int)(a.N - n0) : T;
+            c.rpos = rpos2 + par * nw;
+            float v[2][FR], ln[2][FR];
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+                for (int j = 0; j < FR; ++j) { v[ch][j] = xn[ch][j]; ln[ch][j] = pf[ch][j]; }
+            if (n0 + T < a.N) {
+                const long long rem = a.N - n0 - T;
+                aes_load_frames<FR>(io, b, n0 + T, rem < (long long)T ? (int)rem : T, c.tid, xn);
+                if (C0) aesf_prefetch<FR, C0, 0>(a, c, sr0, 1, pf);
+                if (C1) aesf_prefetch<FR, C1, 1>(a, c, sr1, 1, pf);
+                if (C2) aesf_prefetch<FR, C2, 2>(a, c, sr2, 1, pf);
+                if (C3) aesf_prefetch<FR, C3, 3>(a, c, sr3, 1, pf);
+            }
+            const double *sin = state + par * NST;
+            double *sout = state + (par ^ 1) * NST;
+            if (C0) aesf_stage<FR, C0, 0>(a, c, sr0, v, ln, sin, sout);
+            if (C1) aesf_stage<FR, C1, 1>(a, c, sr1, v, ln, sin + 8, sout + 8);
+            if (C2) aesf_stage<FR, C2, 2>(a, c, sr2, v, ln, sin + 16, sout + 16);
+            if (C3) aesf_stage<FR, C3, 3>(a, c, sr3, v, ln, sin + 24, sout + 24);
+            aes_store_frames<FR>(io, b, n0, c.len, c.tid, v);
+            if (C0) aesf_slots_advance<FR, C0, 0>(a, sr0);
+            if (C1) aesf_slots_advance<FR, C1, 1>(a, sr1);
+            if (C2) aesf_slots_advance<FR, C2, 2>(a, sr2);
+            if (C3) aesf_slots_advance<FR, C3, 3>(a, sr3);
+            if (c.tid < nw) {
+                const FRing rg = a.walk[c.tid];
+                int p = c.rpos[c.tid] + rg.tinc;
+                if (p >= rg.len) p -= rg.len;
+                rpos2[(par ^ 1) * nw + c.tid] = p;
+            }
+            __syncthreads();
+        }
+        if (a.state_out != nullptr)
+            for (int i = c.tid; i < NST; i += AES_NT)
+                a.state_out[b * (16 * NS) + (i >> 3) * 16 + (i & 7)] = state[par * NST + i];
+    }
+}
+
+#ifndef AES_CPU_EMU
+template <int FR, int C0, int C1, int C2, int C3>
+__global__ void __launch_bounds__(AES_NT, 2) aes_fast_kernel(const __grid_constant__ FastArgs a)
+{
+    aes_fast_body<FR, C0, C1, C2, C3>(a);
+}
+#endif

@@ -5,6 +5,7 @@
 #pragma once
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "../../include/aesim.h"
 #include "aes_plan.h"
@@ -39,27 +40,35 @@ struct AesPlanBuilder {
 
     int fail(const char *msg) { snprintf(err, errlen, "%s", msg); return AES_ERR_INVALID; }
 
-    int add_ring(long long len, bool allow_global, int *id)
+    // WALK ring: period == lag.  REG ring: period = roundup4(lag) (+ extra), see aes_plan.h.
+    int add_ring(long long lag, long long period, bool allow_global, int *id)
     {
-        if (len < 1) return fail("ring length must be >= 1");
-        if (len > 0x3fffffff) return fail("ring too long");
+        if (lag < 1) return fail("delay line length must be >= 1");
+        if (period > 0x3fffffff) return fail("delay line too long");
         if (p->n_rings >= AES_MAX_RINGS) return fail("too many delay lines in one chain");
         DevRing &r = p->ring[p->n_rings];
-        r.len = (int)len;
-        r.tinc = (int)(p->T % len);
-        if (allow_global && len > AES_SMEM_RING_MAX_LEN) {
+        r.len = (int)period;
+        r.lag = (int)lag;
+        r.tinc = (int)(p->T % period);
+        if (allow_global && period > AES_SMEM_RING_MAX_LEN) {
             r.space = AES_SPACE_GLOBAL;
             r.off = glob_off;
-            glob_off += (len + 31) & ~31LL;           // 128-byte aligned lines
+            glob_off += (period + 31) & ~31LL;        // 128-byte aligned lines
         } else {
             r.space = AES_SPACE_SMEM;
             r.off = smem_off;
-            smem_off += (len + 3) & ~3LL;
+            smem_off += (period + 3) & ~3LL;
         }
         *id = p->n_rings++;
         return 0;
     }
+    int add_walk(long long lag, bool allow_global, int *id) { return add_ring(lag, lag, allow_global, id); }
+    // register-path line without a barrier between its reads and writes: the period
+    // must cover lag + T so a tile's writes never land on samples the tile still reads
+    int add_reg_line(long long lag, int *id) { return add_ring(lag, ((lag + 3) & ~3LL) + p->T, true, id); }
 };
+
+static inline long long aes_roundup4(long long v) { return (v + 3) & ~3LL; }
 
 // Returns 0 or a negative aes_status; on failure `err` holds the reason.
 static inline int aes_build_devplan(const aes_stage_desc *stages, int n, int fs, DevPlan *p,
@@ -81,17 +90,19 @@ static inline int aes_build_devplan(const aes_stage_desc *stages, int n, int fs,
             for (int c = 0; c < d.q[0]; ++c)
                 if (d.q[4 + 8 * side + c] < min_comb) min_comb = d.q[4 + 8 * side + c];
     }
-    int K = 8;
-    while (K > 2 && 128LL * K > min_comb) K >>= 1;
-    if (128LL * K > min_comb) {
+    int FR = 4;
+    while (FR > 1 && (long long)AES_NT * FR > min_comb) FR >>= 1;
+    if ((long long)AES_NT * FR > min_comb) {
         snprintf(err, errlen, "reverb comb line of %lld samples is shorter than the smallest tile (256)",
                  min_comb);
         return AES_ERR_UNSUPPORTED;
     }
-    p->K = K;
-    p->T = 128 * K;
+    p->FR = FR;
+    p->T = AES_NT * FR;
     p->n_stages = n;
     p->n_state = 16 * n;
+    p->pf_stage = -1;
+    const int T = p->T;
 
     for (int s = 0; s < n; ++s) {
         const aes_stage_desc &d = stages[s];
@@ -100,13 +111,23 @@ static inline int aes_build_devplan(const aes_stage_desc *stages, int n, int fs,
         st.pre_ring[0] = st.pre_ring[1] = -1;
         int rc;
         switch (d.kind) {
-        case AES_STAGE_DELAY:
+        case AES_STAGE_DELAY: {
+            if (d.q[0] < 1 || d.q[1] < 1) return B.fail("delay: lag must be >= 1 sample");
+            st.mode = (d.q[0] >= T && d.q[1] >= T) ? AES_MODE_REG : AES_MODE_WALK;
             for (int c = 0; c < 2; ++c) {
-                if (d.q[c] < 1) return B.fail("delay: lag must be >= 1 sample");
-                if ((rc = B.add_ring(d.q[c], true, &st.ring[c][0]))) return rc;
+                rc = st.mode == AES_MODE_REG ? B.add_reg_line(d.q[c], &st.ring[c][0])
+                                             : B.add_walk(d.q[c], true, &st.ring[c][0]);
+                if (rc) return rc;
             }
             st.fb = (float)d.p[0]; st.dry = (float)d.p[1]; st.wet = (float)d.p[2];
+            const bool glob = p->ring[st.ring[0][0]].space == AES_SPACE_GLOBAL &&
+                              p->ring[st.ring[1][0]].space == AES_SPACE_GLOBAL;
+            if (st.mode == AES_MODE_REG && glob && d.q[0] >= 2 * T && d.q[1] >= 2 * T && p->pf_stage < 0 && !getenv("AES_NO_PF")) {
+                st.pf = 1;
+                p->pf_stage = s;
+            }
             break;
+        }
         case AES_STAGE_REVERB: {
             st.nc = (int)d.q[0]; st.na = (int)d.q[1];
             st.dry = (float)d.p[0]; st.wet = (float)d.p[1];
@@ -114,31 +135,42 @@ static inline int aes_build_devplan(const aes_stage_desc *stages, int n, int fs,
             if (!(h >= 0.0 && h < 1.0)) return B.fail("reverb: damp must be in [0,1)");
             st.h = (float)h; st.omh = (float)(1.0 - h); st.a = (float)d.p[3];
             st.nscan = 0;
+            const double eps = ldexp(1.0, -32);
             for (int i = 0; i < 5; ++i) {
-                const double v = pow(h, (double)K * (double)(1 << i));
+                const double v = pow(h, (double)FR * (double)(1 << i));
                 st.hp[i] = (float)v;
-                if (v >= ldexp(1.0, -32)) st.nscan = i + 1;
+                if (v >= eps) st.nscan = i + 1;
             }
-            st.hp[5] = (float)pow(h, 32.0 * K);
-            for (int l = 0; l < 32; ++l) st.hlane[l] = (float)pow(h, (double)K * l);
+            const double hw = pow(h, 32.0 * FR);
+            st.hp[5] = (float)hw;
+            st.nxw = 1;
+            for (double v = hw; v >= eps && st.nxw < 8; v *= hw) ++st.nxw;
+            for (int l = 0; l < 32; ++l) st.hlane[l] = (float)pow(h, (double)FR * l);
             if (d.q[2] < 0) return B.fail("reverb: negative pre-delay");
+            st.mode = d.q[2] >= T ? AES_MODE_REG : AES_MODE_WALK;
             for (int side = 0; side < 2; ++side) {
-                if (d.q[2] > 0 && (rc = B.add_ring(d.q[2], true, &st.pre_ring[side]))) return rc;
+                if (d.q[2] > 0) {
+                    rc = st.mode == AES_MODE_REG ? B.add_reg_line(d.q[2], &st.pre_ring[side])
+                                                 : B.add_walk(d.q[2], true, &st.pre_ring[side]);
+                    if (rc) return rc;
+                }
                 for (int c = 0; c < st.nc; ++c) {
-                    if ((rc = B.add_ring(d.q[4 + 8 * side + c], false, &st.ring[side][c]))) return rc;
+                    const long long L = d.q[4 + 8 * side + c];
+                    // reads and writes of a comb are separated by the scan barrier: period roundup4(L) suffices
+                    if ((rc = B.add_ring(L, aes_roundup4(L), false, &st.ring[side][c]))) return rc;
                     st.g[side][c] = (float)d.p[4 + 8 * side + c];
                 }
                 for (int k = 0; k < st.na; ++k)
-                    if ((rc = B.add_ring(d.q[20 + 4 * side + k], true, &st.apring[side][k]))) return rc;
+                    if ((rc = B.add_walk(d.q[20 + 4 * side + k], true, &st.apring[side][k]))) return rc;
             }
             break;
         }
         case AES_STAGE_BIQUAD: {
             for (int i = 0; i < 5; ++i) st.bq[i] = d.p[i];
             const double A[4] = { -d.p[3], -d.p[4], 1.0, 0.0 };
-            for (int i = 0; i < 5; ++i) aes_mat2_pow(A, (long long)K << i, st.bq_pow[i]);
-            aes_mat2_pow(A, 32LL * K, st.bq_pow[5]);
-            for (int l = 0; l < 32; ++l) aes_mat2_pow(A, (long long)K * l, st.bq_lane[l]);
+            for (int i = 0; i < 5; ++i) aes_mat2_pow(A, (long long)FR << i, st.bq_pow[i]);
+            aes_mat2_pow(A, 32LL * FR, st.bq_pow[5]);
+            for (int l = 0; l < 32; ++l) aes_mat2_pow(A, (long long)FR * l, st.bq_lane[l]);
             for (int i = 0; i < 8; ++i) st.init[i] = d.p[8 + i];
             break;
         }
@@ -149,10 +181,10 @@ static inline int aes_build_devplan(const aes_stage_desc *stages, int n, int fs,
         case AES_STAGE_OCTAVER: {
             if (d.q[0] < 4 || d.q[0] > (1 << 20)) return B.fail("octaver: ring size out of range");
             st.oct_size = (int)d.q[0];
-            int R = 1;
-            while (R < st.oct_size + p->T + 4) R <<= 1;
+            int R = 4;
+            while (R < st.oct_size + T + 4) R <<= 1;
             st.oct_mask = R - 1;
-            if ((rc = B.add_ring(R, false, &st.ring[0][0]))) return rc;
+            if ((rc = B.add_ring(R, R, false, &st.ring[0][0]))) return rc;
             st.ph0 = d.p[0]; st.step = d.p[1]; st.mix = (float)d.p[2];
             st.fsize = (double)st.oct_size;
             break;

@@ -29,6 +29,7 @@
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
+#define __grid_constant__
 
 struct emu_dim3 { unsigned x = 1, y = 1, z = 1; };
 struct float2 { float x, y; };
@@ -126,3 +127,5 @@ char *dyn_smem();
 
 #define AES_DYN_SMEM(type, name) type *name = reinterpret_cast<type *>(emu::dyn_smem())
 static inline int __float2int_rz(float f) { return (int)f; }
+template <typename T> static inline T __ldcs(const T *p) { return *p; }
+template <typename T> static inline void __stcs(T *p, T v) { *p = v; }

@@ -5,10 +5,21 @@
 #include "cuda_emu.h"
 #include "../../audio-effects-simulator_b200/csrc/aes_plan_build.h"
 #include "../../audio-effects-simulator_b200/csrc/aes_chain_kernel.cuh"
+#include "../../audio-effects-simulator_b200/csrc/aes_fast_build.h"
 
 static char g_err[512];
 
 template <int K> static void entry(void *p) { aes_chain_body<K>(*reinterpret_cast<ChainArgs *>(p)); }
+template <int C0, int C1, int C2, int C3> static void fentry(void *p)
+{
+    aes_fast_body<4, C0, C1, C2, C3>(*reinterpret_cast<FastArgs *>(p));
+}
+struct FastShape { int c[4]; void (*fn)(void *); };
+#define X(c0, c1, c2, c3) { { c0, c1, c2, c3 }, fentry<c0, c1, c2, c3> },
+static const FastShape g_shapes[] = { AESF_SHAPES(X) };
+#undef X
+static int g_last_fast = 0;
+extern "C" __attribute__((visibility("default"))) int emu_last_was_fast() { return g_last_fast; }
 
 extern "C" __attribute__((visibility("default")))
 const char *emu_last_error() { return g_err; }
@@ -24,11 +35,25 @@ int emu_chain_run(const aes_stage_desc *stages, int n, int fs, const void *x, in
     std::vector<float> scratch((size_t)grid * plan.scratch_floats, 1e30f);   // poison
     ChainArgs a{ &plan, x, y, B, N, scratch.data(), in_fmt, out_fmt, state_out };
     size_t smem = aes_plan_smem_bytes(plan);
-    switch (plan.K) {
-    case 8: emu::launch(entry<8>, &a, grid, AES_NT, smem); break;
+    g_last_fast = 0;
+    static FastArgs fa;
+    static float lane_tab[AESF_MAX_STAGES * 32 * FAST_LANE_STRIDE];
+    int codes[4];
+    if (!getenv("AES_NO_FAST") && aes_fast_build(plan, &fa, codes, lane_tab)) {
+        for (const FastShape &sh : g_shapes) {
+            if (memcmp(sh.c, codes, sizeof codes) != 0) continue;
+            fa.x = x; fa.y = y; fa.B = B; fa.N = N; fa.scratch = scratch.data(); fa.lane_tab = lane_tab;
+            fa.state_out = state_out; fa.in_fmt = in_fmt; fa.out_fmt = out_fmt;
+            emu::launch(sh.fn, &fa, grid, AES_NT, smem);
+            g_last_fast = 1;
+            return 0;
+        }
+    }
+    switch (plan.FR) {
     case 4: emu::launch(entry<4>, &a, grid, AES_NT, smem); break;
     case 2: emu::launch(entry<2>, &a, grid, AES_NT, smem); break;
-    default: snprintf(g_err, sizeof g_err, "bad K"); return -1;
+    case 1: emu::launch(entry<1>, &a, grid, AES_NT, smem); break;
+    default: snprintf(g_err, sizeof g_err, "bad FR"); return -1;
     }
     return 0;
 }
