@@ -118,3 +118,22 @@ def test_final_state_of_filter_and_gate_matches_oracle():
         assert abs(st[0, 0] - gate.gain) < 1e-12
         got = st[0, 16:24].reshape(2, 4)
         assert np.max(np.abs(got - filt.state.astype(np.float64))) < 1e-6 * max(1.0, np.abs(filt.state).max())
+
+
+@pytest.mark.parametrize("name", NATIVE)
+def test_specialised_and_generic_kernels_agree_with_oracle(name, monkeypatch):
+    """Every preset has a shape-specialised kernel (aes_fast_kernel.cuh); the generic
+    interpreter (aes_chain_kernel.cuh) must give the same answer when forced."""
+    cfg = synth.PRESETS[name]
+    n = 26000
+    x = synth.batch(30, 2, n)
+    want = [orc.run_file_path(cfg, x[b], 48000) for b in range(2)]
+    d = emu.resolved_descs(cfg, 48000, n, 2)
+    y_fast = emu.run(d, 48000, x)
+    assert emu.lib().emu_last_was_fast() == 1, name
+    monkeypatch.setenv("AES_NO_FAST", "1")
+    y_gen = emu.run(d, 48000, x)
+    assert emu.lib().emu_last_was_fast() == 0
+    for b in range(2):
+        check(y_fast[b], want[b], exact=(name == "Slapback Echo"), what=(name, "fast", b))
+        check(y_gen[b], want[b], exact=(name == "Slapback Echo"), what=(name, "generic", b))
