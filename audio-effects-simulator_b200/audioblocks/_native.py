@@ -54,6 +54,8 @@ def lib() -> C.CDLL:
         L.aes_chain_run.argtypes = [vp, vp, ci, vp, ci, i64, i64, vp]
         L.aes_chain_process_host.argtypes = [vp, vp, ci, vp, ci, i64, i64]
         L.aes_chain_final_state.argtypes = [vp, ci, C.POINTER(C.c_double)]
+        L.aes_chain_plan_kernel_name.restype = C.c_char_p
+        L.aes_chain_plan_kernel_name.argtypes = [vp]
         L.aes_chain_plan_info.argtypes = [vp, C.POINTER(ci), C.POINTER(ci), C.POINTER(ci), C.POINTER(i64)]
         L.aes_malloc.argtypes = [C.POINTER(vp), C.c_size_t]
         L.aes_free.argtypes = [vp]
@@ -101,7 +103,8 @@ class ChainPlan:
         t, s, o, sc = C.c_int(), C.c_int(), C.c_int(), C.c_int64()
         check(lib().aes_chain_plan_info(self._h, C.byref(t), C.byref(s), C.byref(o), C.byref(sc)))
         return {"tile_frames": t.value, "smem_bytes": s.value, "ctas_per_sm": o.value,
-                "scratch_bytes_per_cta": sc.value}
+                "scratch_bytes_per_cta": sc.value,
+                "kernel": lib().aes_chain_plan_kernel_name(self._h).decode()}
 
     def run_device(self, x_ptr: int, in_fmt: int, y_ptr: int, out_fmt: int, n_clips: int, n_frames: int,
                    stream: int = 0):

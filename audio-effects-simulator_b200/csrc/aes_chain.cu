@@ -184,6 +184,12 @@ AES_EXPORT int aes_chain_plan_info(const aes_chain_plan *pl, int *tile_frames, i
     return 0;
 }
 
+AES_EXPORT const char *aes_chain_plan_kernel_name(const aes_chain_plan *pl)
+{
+    if (!pl) return "";
+    return pl->fast_fn ? "aes_fast_kernel<FR=4, shape-specialised>" : "aes_chain_kernel<generic interpreter>";
+}
+
 AES_EXPORT int aes_chain_run(aes_chain_plan *pl, const void *x, int in_fmt, void *y, int out_fmt,
                              int64_t n_clips, int64_t n_frames, void *stream)
 {

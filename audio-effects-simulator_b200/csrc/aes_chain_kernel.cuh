@@ -82,7 +82,39 @@ __device__ __forceinline__ float *aes_ring_base(const KCtx &c, const DevRing &r)
     return (r.space == AES_SPACE_GLOBAL ? c.gscr : c.rings) + r.off;
 }
 
+// 128-bit loads that the optimiser may not split: NVVM otherwise scalarises a float4 load
+// whose elements are consumed in different branches of the misalignment switch (ncu showed
+// 141 LDS.32 + 33 LDS.64 with 2-way bank conflicts instead of ~30 LDS.128).
+#ifndef AES_CPU_EMU
+__device__ __forceinline__ float4 aes_lds_v4(const float *p)
+{
+    float4 r;
+    const unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ float4 aes_ldg_v4(const float *p)
+{
+    float4 r;
+    asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+#else
+static inline float4 aes_lds_v4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+static inline float4 aes_ldg_v4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
+#endif
+
 // ---- FR-wide vector access (p aligned to 4*FR bytes) -----------------------------------
+// SP: 0 = shared memory, 1 = global memory, 2 = unknown (generic load)
+template <int FR, int SP> __device__ __forceinline__ void aes_ldv_sp(const float *p, float (&o)[FR])
+{
+    if (FR == 4 && SP != 2) {
+        const float4 t = SP == 0 ? aes_lds_v4(p) : aes_ldg_v4(p);
+        o[0] = t.x; o[1 % FR] = t.y; o[2 % FR] = t.z; o[3 % FR] = t.w;
+    } else if (FR == 4) { const float4 t = *reinterpret_cast<const float4 *>(p); o[0] = t.x; o[1 % FR] = t.y; o[2 % FR] = t.z; o[3 % FR] = t.w; }
+    else if (FR == 2) { const float2 t = *reinterpret_cast<const float2 *>(p); o[0] = t.x; o[1 % FR] = t.y; }
+    else o[0] = p[0];
+}
 template <int FR> __device__ __forceinline__ void aes_ldv(const float *p, float (&o)[FR])
 {
     if (FR == 4) { const float4 t = *reinterpret_cast<const float4 *>(p); o[0] = t.x; o[1] = t.y; o[2 % FR] = t.z; o[3 % FR] = t.w; }

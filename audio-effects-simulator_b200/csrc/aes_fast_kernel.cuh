@@ -91,7 +91,7 @@ __device__ __forceinline__ int aesf_adv(int s, int inc, int len)
 
 // FR consecutive elements starting m (< FR) past the aligned base a0; the next aligned
 // vector wraps at len.  m is uniform over the CTA.
-template <int FR>
+template <int FR, int SP>
 __device__ __forceinline__ void aesf_read(const float *rb, int a0, int m, int len, float (&o)[FR])
 {
     if (FR < 4) {                                   // m is given relative to a 4-aligned base
@@ -100,7 +100,7 @@ __device__ __forceinline__ void aesf_read(const float *rb, int a0, int m, int le
         m &= FR - 1;
     }
     float A[FR];
-    aes_ldv<FR>(rb + a0, A);
+    aes_ldv_sp<FR, SP>(rb + a0, A);
     if (m == 0 || FR == 1) {
 #pragma unroll
         for (int j = 0; j < FR; ++j) o[j] = A[j];
@@ -109,7 +109,7 @@ __device__ __forceinline__ void aesf_read(const float *rb, int a0, int m, int le
     int b0 = a0 + FR;
     if (b0 >= len) b0 -= len;
     float Bv[FR];
-    aes_ldv<FR>(rb + b0, Bv);
+    aes_ldv_sp<FR, SP>(rb + b0, Bv);
     if (m == 1) {
 #pragma unroll
         for (int j = 0; j < FR; ++j) o[j] = (j + 1 < FR) ? A[(j + 1) % FR] : Bv[(j + 1) % FR];
@@ -132,34 +132,44 @@ __device__ __forceinline__ void aesf_walk(const FCtx &c, const FRing rg, int rin
     const int L = rg.len, pos = c.rpos[ring_id];
     const int W = L < T ? L : T;
     float *s = c.tile + ch * T;
-    for (int j = j0; j < W && j < c.len; j += 128) {
+    const int len = c.len;
+    for (int j = j0; j < W && j < len; j += 128) {
         int slot = pos + j;
         if (slot >= L) slot -= L;
         float line = (c.n0 + j >= L) ? rb[slot] : 0.0f;
-        for (int i = j; i < c.len; i += 4 * L) {
+        int i = j;
+        for (; i + 3 * L < len; i += 4 * L) {           // 4 steps per trip: loads first, the walk is a serial chain
             float xs[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const long long ii = (long long)i + (long long)u * L;
-                xs[u] = ii < c.len ? s[ii] : 0.0f;
-            }
+            for (int u = 0; u < 4; ++u) xs[u] = s[i + u * L];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                const long long ii = (long long)i + (long long)u * L;
-                if (ii < c.len) {
-                    const float x = xs[u];
-                    if (OP == 0) {
-                        s[ii] = aes_mix_clip(p1, x, p2, line);
-                        line = fmaf(line, p0, x);
-                    } else if (OP == 1) {
-                        s[ii] = line;
-                        line = x;
-                    } else {
-                        const float yo = fmaf(-p0, x, line);
-                        s[ii] = yo;
-                        line = fmaf(p0, yo, x);
-                    }
+                const float x = xs[u];
+                if (OP == 0) {
+                    s[i + u * L] = aes_mix_clip(p1, x, p2, line);
+                    line = fmaf(line, p0, x);
+                } else if (OP == 1) {
+                    s[i + u * L] = line;
+                    line = x;
+                } else {
+                    const float yo = fmaf(-p0, x, line);
+                    s[i + u * L] = yo;
+                    line = fmaf(p0, yo, x);
                 }
+            }
+        }
+        for (; i < len; i += L) {
+            const float x = s[i];
+            if (OP == 0) {
+                s[i] = aes_mix_clip(p1, x, p2, line);
+                line = fmaf(line, p0, x);
+            } else if (OP == 1) {
+                s[i] = line;
+                line = x;
+            } else {
+                const float yo = fmaf(-p0, x, line);
+                s[i] = yo;
+                line = fmaf(p0, yo, x);
             }
         }
         rb[slot] = line;
@@ -175,8 +185,8 @@ template <int FR> __device__ __forceinline__ void aesf_spill(const FCtx &c, cons
 template <int FR> __device__ __forceinline__ void aesf_reload(const FCtx &c, float (&v)[2][FR])
 {
     constexpr int T = AES_NT * FR;
-    aes_ldv<FR>(c.tile + FR * c.tid, v[0]);
-    aes_ldv<FR>(c.tile + T + FR * c.tid, v[1]);
+    aes_ldv_sp<FR, 0>(c.tile + FR * c.tid, v[0]);
+    aes_ldv_sp<FR, 0>(c.tile + T + FR * c.tid, v[1]);
 }
 
 // ---- register-path line (feedback delay / pre-delay with lag >= T) ------------------------
@@ -191,14 +201,35 @@ __device__ __forceinline__ void aesf_line_init(const FRing rg, int i0, int &w, i
 template <int FR>
 __device__ __forceinline__ void aesf_line_read(const FCtx &c, const FRing rg, bool glob, int a0, float (&o)[FR])
 {
-    const float *rb = (glob ? c.gscr : c.rings) + rg.off;
-    aesf_read<FR>(rb, a0, ((rg.lag + 3) & ~3) - rg.lag, rg.len, o);
+    const int m = ((rg.lag + 3) & ~3) - rg.lag;
+    if (glob) aesf_read<FR, 1>(c.gscr + rg.off, a0, m, rg.len, o);
+    else      aesf_read<FR, 0>(c.rings + rg.off, a0, m, rg.len, o);
+}
+
+template <int FR>
+__device__ __forceinline__ void aesf_select4(const float4 A, const float4 B, int m, float (&o)[FR])
+{
+    static_assert(FR == 4 || FR == 2 || FR == 1, "");
+    const float w[8] = { A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w };
+    if (m == 0) {
+#pragma unroll
+        for (int j = 0; j < FR; ++j) o[j] = w[j];
+    } else if (m == 1) {
+#pragma unroll
+        for (int j = 0; j < FR; ++j) o[j] = w[j + 1];
+    } else if (m == 2) {
+#pragma unroll
+        for (int j = 0; j < FR; ++j) o[j] = w[j + 2];
+    } else {
+#pragma unroll
+        for (int j = 0; j < FR; ++j) o[j] = w[j + 3];
+    }
 }
 
 // ---- one stage, specialised on its shape code ------------------------------------------------
 template <int FR, int CODE, int S>
 __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRegs &sr, float (&v)[2][FR],
-                                           const float (&ln)[2][FR], const double *sin, double *sout)
+                                           const float4 (&lnA)[2], const float4 (&lnB)[2], const double *sin, double *sout)
 {
     constexpr int KIND = AESF_KIND(CODE);
     const FastStage &st = a.st[S];
@@ -212,20 +243,26 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
                 const FRing rg = st.ring[ch][0];
                 float line[FR];
                 if (AESF_PF(CODE)) {
-#pragma unroll
-                    for (int j = 0; j < FR; ++j) line[j] = ln[ch][j];
+                    // raw vectors fetched a tile ago; the (uniform) misalignment select happens only now,
+                    // so nothing touched the load's destination registers while it was in flight
+                    aesf_select4<FR>(lnA[ch], lnB[ch], ((rg.lag + 3) & ~3) - rg.lag, line);
                 } else {
                     aesf_line_read<FR>(c, rg, st.glob != 0, sr.da[ch], line);
+                }
+                if (c.n0 < (long long)rg.lag) {                     // only the first tiles of a clip: zero history
+#pragma unroll
+                    for (int j = 0; j < FR; ++j)
+                        if (c.n0 + i0 + j < rg.lag) line[j] = 0.0f;
                 }
                 float nb[FR];
 #pragma unroll
                 for (int j = 0; j < FR; ++j) {
-                    const float l = (c.n0 + i0 + j >= rg.lag) ? line[j] : 0.0f;   // zero history on a fresh clip
                     const float x = v[ch][j];
-                    nb[j] = fmaf(l, fb, x);
-                    v[ch][j] = aes_mix_clip(dry, x, wet, l);
+                    nb[j] = fmaf(line[j], fb, x);
+                    v[ch][j] = aes_mix_clip(dry, x, wet, line[j]);
                 }
-                aes_stv<FR>((st.glob ? c.gscr : c.rings) + rg.off + sr.dw[ch], nb);
+                if (st.glob) aes_stv<FR>(c.gscr + rg.off + sr.dw[ch], nb);
+                else         aes_stv<FR>(c.rings + rg.off + sr.dw[ch], nb);
             }
         } else {
             aesf_spill<FR>(c, v);
@@ -248,10 +285,13 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
             for (int ch = 0; ch < 2; ++ch) {
                 const FRing rg = st.pre[ch];
                 aesf_line_read<FR>(c, rg, st.glob != 0, sr.da[ch], pre[ch]);
+                if (c.n0 < (long long)rg.lag) {
 #pragma unroll
-                for (int j = 0; j < FR; ++j)
-                    if (c.n0 + i0 + j < rg.lag) pre[ch][j] = 0.0f;
-                aes_stv<FR>((st.glob ? c.gscr : c.rings) + rg.off + sr.dw[ch], v[ch]);
+                    for (int j = 0; j < FR; ++j)
+                        if (c.n0 + i0 + j < rg.lag) pre[ch][j] = 0.0f;
+                }
+                if (st.glob) aes_stv<FR>(c.gscr + rg.off + sr.dw[ch], v[ch]);
+                else         aes_stv<FR>(c.rings + rg.off + sr.dw[ch], v[ch]);
             }
         } else {
             aesf_spill<FR>(c, v);
@@ -271,7 +311,7 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
 #pragma unroll
             for (int cc = 0; cc < NC; ++cc) {
                 const FRing rg = st.ring[ch][cc];
-                aesf_read<FR>(c.rings + rg.off, sr.w[ch][cc], rg.len - rg.lag, rg.len, y[ch][cc]);
+                aesf_read<FR, 0>(c.rings + rg.off, sr.w[ch][cc], rg.len - rg.lag, rg.len, y[ch][cc]);
                 float u = 0.0f;
 #pragma unroll
                 for (int j = 0; j < FR; ++j) u = fmaf(h, u, y[ch][cc][j]);
@@ -296,7 +336,10 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
                 for (int cc = 0; cc < NC; ++cc) wt[(warp * 2 + ch) * 4 + cc] = e[ch][cc];
         }
         __syncthreads();
-        const int u0 = warp > st.nxw ? warp - st.nxw : 0;
+        const int nxw = st.nxw;
+        const int u0 = warp > nxw ? warp - nxw : 0;
+        const float *fsin = reinterpret_cast<const float *>(sin);   // comb carries are kept as f32
+        float *fsout = reinterpret_cast<float *>(sout);
         float sum[2][FR];
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
@@ -305,8 +348,13 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
 #pragma unroll
             for (int cc = 0; cc < NC; ++cc) {
                 const float ex = __shfl_up_sync(0xffffffffu, e[ch][cc], 1);
-                float C = u0 == 0 ? (float)sin[ch * 4 + cc] : 0.0f;
-                for (int t = u0; t < warp; ++t) C = fmaf(hw, C, wt[(t * 2 + ch) * 4 + cc]);
+                float C;
+                if (nxw == 1) {                                  // usual case: h^(32*FR) < 2^-32
+                    C = warp == 0 ? fsin[ch * 4 + cc] : wt[((warp - 1) * 2 + ch) * 4 + cc];
+                } else {
+                    C = u0 == 0 ? fsin[ch * 4 + cc] : 0.0f;
+                    for (int t = u0; t < warp; ++t) C = fmaf(hw, C, wt[(t * 2 + ch) * 4 + cc]);
+                }
                 float u = fmaf(hl, C, lane == 0 ? 0.0f : ex);
                 const FRing rg = st.ring[ch][cc];
                 const float gs = st.gs[ch][cc];
@@ -318,7 +366,7 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
                     sum[ch][j] = __fadd_rn(sum[ch][j], y[ch][cc][j]);
                 }
                 aes_stv<FR>(c.rings + rg.off + sr.w[ch][cc], nb);
-                if (c.tid == AES_NT - 1) sout[ch * 4 + cc] = (double)u;
+                if (c.tid == AES_NT - 1) fsout[ch * 4 + cc] = u;
             }
         }
         aesf_spill<FR>(c, sum);
@@ -536,15 +584,20 @@ __device__ __forceinline__ void aesf_slots_advance(const FastArgs &a, SRegs &sr)
 // of tile i for tile i+1, consumed a full tile of work later.
 template <int FR, int CODE, int S>
 __device__ __forceinline__ void aesf_prefetch(const FastArgs &a, const FCtx &c, const SRegs &sr, int ahead,
-                                              float (&pf)[2][FR])
+                                              float4 (&pfA)[2], float4 (&pfB)[2])
 {
     if (AESF_KIND(CODE) == AESK_DELAY && AESF_PF(CODE)) {
-        const FastStage &st = a.st[S];
+        static_assert(!(AESF_KIND(CODE) == AESK_DELAY && AESF_PF(CODE)) || FR == 4, "prefetch path is FR=4 only");
+        const FastStage &st = a.st[S];                  // PF lines always live in the global scratch
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
             const FRing rg = st.ring[ch][0];
             const int a0 = ahead ? aesf_adv(sr.da[ch], rg.tinc, rg.len) : sr.da[ch];
-            aesf_line_read<FR>(c, rg, st.glob != 0, a0, pf[ch]);
+            int b0 = a0 + 4;
+            b0 = b0 >= rg.len ? b0 - rg.len : b0;
+            const float *rb = c.gscr + rg.off;
+            pfA[ch] = aes_ldg_v4(rb + a0);              // straight-line: no branch, no copy of the results
+            pfB[ch] = aes_ldg_v4(rb + b0);
         }
     }
 }
@@ -580,45 +633,46 @@ __device__ void aes_fast_body(const FastArgs &a)
         if (C3) aesf_slots_init<FR, C3, 3>(a, i0, sr3);
         __syncthreads();
 
-        float xn[2][FR], pf[2][FR];
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch)
-#pragma unroll
-            for (int j = 0; j < FR; ++j) pf[ch][j] = 0.0f;
+        float xn[2][FR];
+        float4 pfA[2], pfB[2];
+        pfA[0] = pfA[1] = pfB[0] = pfB[1] = make_float4(0.f, 0.f, 0.f, 0.f);
         c.n0 = 0;
         c.len = a.N < (long long)T ? (int)a.N : T;
         c.rpos = rpos2;
         ChainArgs io;                                // tile I/O helpers are shared with the generic kernel
         io.x = a.x; io.y = a.y; io.N = a.N; io.in_fmt = a.in_fmt; io.out_fmt = a.out_fmt;
         aes_load_frames<FR>(io, b, 0, c.len, c.tid, xn);
-        if (C0) aesf_prefetch<FR, C0, 0>(a, c, sr0, 0, pf);
-        if (C1) aesf_prefetch<FR, C1, 1>(a, c, sr1, 0, pf);
-        if (C2) aesf_prefetch<FR, C2, 2>(a, c, sr2, 0, pf);
-        if (C3) aesf_prefetch<FR, C3, 3>(a, c, sr3, 0, pf);
+        if (C0) aesf_prefetch<FR, C0, 0>(a, c, sr0, 0, pfA, pfB);
+        if (C1) aesf_prefetch<FR, C1, 1>(a, c, sr1, 0, pfA, pfB);
+        if (C2) aesf_prefetch<FR, C2, 2>(a, c, sr2, 0, pfA, pfB);
+        if (C3) aesf_prefetch<FR, C3, 3>(a, c, sr3, 0, pfA, pfB);
         int par = 0;
         for (long long n0 = 0; n0 < a.N; n0 += T, par ^= 1) {
             c.n0 = n0;
             c.len = (a.N - n0 < (long long)T) ? (int)(a.N - n0) : T;
             c.rpos = rpos2 + par * nw;
-            float v[2][FR], ln[2][FR];
+            float v[2][FR];
+            float4 lnA[2], lnB[2];
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch)
+            for (int ch = 0; ch < 2; ++ch) {
+                lnA[ch] = pfA[ch]; lnB[ch] = pfB[ch];
 #pragma unroll
-                for (int j = 0; j < FR; ++j) { v[ch][j] = xn[ch][j]; ln[ch][j] = pf[ch][j]; }
+                for (int j = 0; j < FR; ++j) v[ch][j] = xn[ch][j];
+            }
             if (n0 + T < a.N) {
                 const long long rem = a.N - n0 - T;
                 aes_load_frames<FR>(io, b, n0 + T, rem < (long long)T ? (int)rem : T, c.tid, xn);
-                if (C0) aesf_prefetch<FR, C0, 0>(a, c, sr0, 1, pf);
-                if (C1) aesf_prefetch<FR, C1, 1>(a, c, sr1, 1, pf);
-                if (C2) aesf_prefetch<FR, C2, 2>(a, c, sr2, 1, pf);
-                if (C3) aesf_prefetch<FR, C3, 3>(a, c, sr3, 1, pf);
+                if (C0) aesf_prefetch<FR, C0, 0>(a, c, sr0, 1, pfA, pfB);
+                if (C1) aesf_prefetch<FR, C1, 1>(a, c, sr1, 1, pfA, pfB);
+                if (C2) aesf_prefetch<FR, C2, 2>(a, c, sr2, 1, pfA, pfB);
+                if (C3) aesf_prefetch<FR, C3, 3>(a, c, sr3, 1, pfA, pfB);
             }
             const double *sin = state + par * NST;
             double *sout = state + (par ^ 1) * NST;
-            if (C0) aesf_stage<FR, C0, 0>(a, c, sr0, v, ln, sin, sout);
-            if (C1) aesf_stage<FR, C1, 1>(a, c, sr1, v, ln, sin + 8, sout + 8);
-            if (C2) aesf_stage<FR, C2, 2>(a, c, sr2, v, ln, sin + 16, sout + 16);
-            if (C3) aesf_stage<FR, C3, 3>(a, c, sr3, v, ln, sin + 24, sout + 24);
+            if (C0) aesf_stage<FR, C0, 0>(a, c, sr0, v, lnA, lnB, sin, sout);
+            if (C1) aesf_stage<FR, C1, 1>(a, c, sr1, v, lnA, lnB, sin + 8, sout + 8);
+            if (C2) aesf_stage<FR, C2, 2>(a, c, sr2, v, lnA, lnB, sin + 16, sout + 16);
+            if (C3) aesf_stage<FR, C3, 3>(a, c, sr3, v, lnA, lnB, sin + 24, sout + 24);
             aes_store_frames<FR>(io, b, n0, c.len, c.tid, v);
             if (C0) aesf_slots_advance<FR, C0, 0>(a, sr0);
             if (C1) aesf_slots_advance<FR, C1, 1>(a, sr1);
@@ -638,9 +692,12 @@ __device__ void aes_fast_body(const FastArgs &a)
     }
 }
 
+#ifndef AESF_MIN_CTAS
+#define AESF_MIN_CTAS 2
+#endif
 #ifndef AES_CPU_EMU
 template <int FR, int C0, int C1, int C2, int C3>
-__global__ void __launch_bounds__(AES_NT, 2) aes_fast_kernel(const __grid_constant__ FastArgs a)
+__global__ void __launch_bounds__(AES_NT, AESF_MIN_CTAS) aes_fast_kernel(const __grid_constant__ FastArgs a)
 {
     aes_fast_body<FR, C0, C1, C2, C3>(a);
 }

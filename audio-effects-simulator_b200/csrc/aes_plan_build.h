@@ -44,7 +44,7 @@ struct AesPlanBuilder {
     int add_ring(long long lag, long long period, bool allow_global, int *id)
     {
         if (lag < 1) return fail("delay line length must be >= 1");
-        if (period > 0x3fffffff) return fail("delay line too long");
+        if (period > 0x0fffffff) return fail("delay line too long");
         if (p->n_rings >= AES_MAX_RINGS) return fail("too many delay lines in one chain");
         DevRing &r = p->ring[p->n_rings];
         r.len = (int)period;

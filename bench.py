@@ -37,11 +37,11 @@ UNIT = "Msamples/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--preset", default="Rain Delay")
-    ap.add_argument("--clips", type=int, default=1024, help="clips per GPU")
+    ap.add_argument("--clips", type=int, default=1184, help="clips per GPU (default 8 per SM: whole clips for every resident CTA)")
     ap.add_argument("--seconds", type=float, default=10.0, help="clip length")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
@@ -52,7 +52,7 @@ def parse():
 
 def workload(args):
     return {"workload": f"'{args.preset}' preset chain (app.py:41-71) on {args.clips} synthetic "
-                        f"{args.seconds:g} s 48 kHz stereo float32 clips per GPU (BASELINE configs[4] shard)",
+                        f"{args.seconds:g} s 48 kHz stereo float32 clips per GPU (BASELINE configs[4]-style shard)",
             "preset": args.preset, "clips_per_gpu": args.clips, "frames_per_clip": int(args.seconds * FS),
             "sample_rate": FS, "l2": "inputs larger than L2 (no flush needed)", "parallelism": "clip-sharded"}
 
@@ -111,7 +111,7 @@ def reference_arm(args):
 # ------------------------------------------------------------------ B200 arm
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -121,7 +121,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except OSError:
@@ -131,13 +131,30 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def stop(self, t_from=None, t_to=None):
+        """Median SM clock and throttle reasons over the samples inside [t_from, t_to] (epoch
+        seconds; the load window: warm-up + timed steps), all samples if none fall inside."""
+        import datetime
         if self.proc:
+            time.sleep(0.05)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+        rows = [r for r in self.rows if len(r) > 8]
+        if t_from is not None:
+            inside = []
+            for r in rows:
+                try:
+                    ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except ValueError:
+                    continue
+                if t_from - 0.02 <= ts <= t_to + 0.02:
+                    inside.append(r)
+            if inside:
+                rows = inside
+        self.rows = rows
         sm = sorted(float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit())
         mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
         reasons = set()
@@ -192,6 +209,9 @@ def b200_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     L = _native.lib()
     _native.check(L.aes_set_device(local))
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()              # nvidia-smi takes a while to start: launch it before the data is built
 
     n_frames = int(args.seconds * FS)
     B = args.clips
@@ -213,12 +233,10 @@ def b200_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    t_load0 = time.time()
     for _ in range(max(3, args.warmup)):
         step()
     barrier()
-    clocks = ClockSampler(local)
-    if rank == 0:
-        clocks.start()
     launches0 = L.aes_launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     barrier()
@@ -230,7 +248,7 @@ def b200_arm(args):
     launches = L.aes_launch_count() - launches0
     total_ms = ev[0].elapsed_time(ev[-1])
     per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop(t_load0, time.time()) if rank == 0 else None
 
     # parity spot check of the timed buffers (first clip of this rank) against the oracle
     parity = None
@@ -292,7 +310,7 @@ def b200_arm(args):
                        "ctas_per_sm": info["ctas_per_sm"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "aes_chain_kernel<8>", "algorithmic_bytes_per_launch": B * n_frames * 16,
+                         "kernel": info["kernel"], "algorithmic_bytes_per_launch": B * n_frames * 16,
                          "launch_ms": k_ms},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "parity": parity,
         }

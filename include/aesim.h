@@ -124,6 +124,8 @@ int aes_chain_final_state(aes_chain_plan *plan, int stage, double *out16);
 /* Introspection for the benchmark / tests. */
 int aes_chain_plan_info(const aes_chain_plan *plan, int *tile_frames, int *smem_bytes,
                         int *ctas_per_sm, int64_t *scratch_bytes_per_cta);
+/* Which kernel the plan launches ("aes_fast_kernel<...>" or the generic interpreter). */
+const char *aes_chain_plan_kernel_name(const aes_chain_plan *plan);
 /* Number of kernel launches issued by this library since load (bench "gpu_launches"). */
 int64_t aes_launch_count(void);
 

@@ -195,3 +195,17 @@ def test_single_block_c_abi_entries(ab, orc):
     torch.cuda.synchronize()
     assert np.array_equal(qd.cpu().numpy(), (np.clip(yd.cpu().numpy(), -1, 1) * 32767).astype(np.int16))
     assert L.aes_launch_count() > 0
+
+
+@pytest.mark.parametrize("name", NATIVE)
+def test_generic_interpreter_kernel_matches_too(ab, orc, name, monkeypatch):
+    """The presets normally run on shape-specialised kernels; the generic interpreter
+    (used for arbitrary chains) must agree."""
+    from audioblocks.engine import file_chain
+    monkeypatch.setenv("AES_NO_FAST", "1")
+    cfg = synth.PRESETS[name]
+    n, B = 60000, 3
+    x = synth.batch(50, B, n)
+    y = file_chain(cfg, 48000, channels_in=2).process_batch(x)
+    for b in range(B):
+        check(y[b], orc.run_file_path(cfg, x[b], 48000), exact=(name == "Slapback Echo"), what=(name, b))
