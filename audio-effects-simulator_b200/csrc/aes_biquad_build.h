@@ -1,0 +1,36 @@
+// aes_biquad_build.h -- host tables of the time-parallel biquad cascade (pure host C++,
+// shared with tests/cpu_emu).
+#pragma once
+#include <string.h>
+#include "aes_plan_build.h"
+#include "aes_biquad_scan.cuh"
+
+// coeffs5: n_stages x (b0,b1,b2,a1,a2); dfi_state: optional n_stages x 2 ch x (x1,x2,y1,y2).
+// lane_pw: n_stages x 32 x 4 doubles; tile_pw: n_stages x 256 x 4 doubles.
+static inline void aes_biquad_build(int n_stages, const double *coeffs5, const double *dfi_state,
+                                    BqArgs *a, double *lane_pw, double *tile_pw)
+{
+    memset(a, 0, sizeof *a);
+    a->n_stages = n_stages;
+    for (int s = 0; s < n_stages; ++s) {
+        BqStage &st = a->st[s];
+        const double *c = coeffs5 + 5 * s;
+        st.b0 = c[0]; st.b1 = c[1]; st.b2 = c[2]; st.a1 = c[3]; st.a2 = c[4];
+        const double A[4] = { -c[3], 1.0, -c[4], 0.0 };          // zero-input TDF-II transition
+        for (int k = 0; k < 5; ++k) aes_mat2_pow(A, (long long)AESB_FR << k, st.pw[k]);
+        aes_mat2_pow(A, 32LL * AESB_FR, st.pw[5]);
+        aes_mat2_pow(A, (long long)AESB_T, st.tile);
+        aes_mat2_pow(A, (long long)AES_NT * AESB_T, st.tile256);
+        for (int l = 0; l < 32; ++l) aes_mat2_pow(A, (long long)AESB_FR * l, lane_pw + (s * 32 + l) * 4);
+        for (int l = 0; l < AES_NT; ++l) aes_mat2_pow(A, (long long)AESB_T * l, tile_pw + ((size_t)s * AES_NT + l) * 4);
+        for (int ch = 0; ch < 2; ++ch) {
+            st.init[ch][0] = st.init[ch][1] = 0.0;
+            if (dfi_state) {
+                // DF-I history (x1,x2,y1,y2) -> TDF-II state: s1 = b1*x1 + b2*x2 - a1*y1 - a2*y2, s2 = b2*x1 - a2*y1
+                const double *d = dfi_state + (s * 2 + ch) * 4;
+                st.init[ch][0] = c[1] * d[0] + c[2] * d[1] - c[3] * d[2] - c[4] * d[3];
+                st.init[ch][1] = c[2] * d[0] - c[4] * d[2];
+            }
+        }
+    }
+}

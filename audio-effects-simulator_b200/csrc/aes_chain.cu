@@ -10,6 +10,7 @@
 #include "aes_plan_build.h"
 #include "aes_chain_kernel.cuh"
 #include "aes_fast_build.h"
+#include "aes_biquad_build.h"
 
 #define AES_HOST_SLOTS 3
 
@@ -34,6 +35,12 @@ static const FastShape g_fast_shapes[] = { AESF_SHAPES(X) };
 
 struct aes_chain_plan {
     DevPlan host;
+    // time-parallel biquad cascade (aes_biquad_scan.cuh) for few long clips
+    bool bq_ok = false;
+    BqArgs bq;
+    double *d_bq_tab = nullptr;                 // lane_pw [8][32][4] | tile_pw [8][256][4]
+    void *d_bq_scan = nullptr;                  // agg | inc | flag | ticket, grown on demand
+    size_t bq_scan_cap = 0;
     FastArgs fast;                              // flattened descriptors when a specialised kernel fits
     fast_kernel_t fast_fn = nullptr;
     float *d_lane_tab = nullptr;
@@ -64,6 +71,33 @@ static int launch_chain(aes_chain_plan *pl, const void *x, int in_fmt, void *y, 
                         long long B, long long N, float *scratch, cudaStream_t st, double *state_out = nullptr)
 {
     if (B <= 0 || N <= 0) return 0;
+    if (pl->bq_ok && B < pl->grid_max && in_fmt == AES_FMT_F32_STEREO && out_fmt == AES_FMT_F32_STEREO &&
+        !getenv("AES_NO_SCAN")) {
+        // fewer clips than resident CTAs: go parallel in time (one CTA per 1024-frame tile)
+        const long long nt = (N + AESB_T - 1) / AESB_T;
+        const size_t recs = (size_t)B * pl->bq.n_stages * nt;
+        const size_t need = recs * (8 * sizeof(double) + sizeof(int)) + 64;
+        if (pl->bq_scan_cap < need) {
+            if (pl->d_bq_scan) cudaFree(pl->d_bq_scan);
+            pl->d_bq_scan = nullptr; pl->bq_scan_cap = 0;
+            AES_CUDA(cudaMalloc(&pl->d_bq_scan, need));
+            pl->bq_scan_cap = need;
+        }
+        BqArgs a = pl->bq;
+        a.x = (const float *)x; a.y = (float *)y; a.N = N; a.n_tiles = nt; a.B = B; a.dbg_skip = 0;
+        a.agg = (double *)pl->d_bq_scan;
+        a.inc = a.agg + recs * 4;
+        a.flag = (int *)(a.inc + recs * 4);
+        a.ticket = (unsigned *)(a.flag + recs);
+        a.lane_pw = pl->d_bq_tab;
+        a.tile_pw = pl->d_bq_tab + (size_t)AESB_MAX_STAGES * 128;
+        a.final_state = state_out;
+        AES_CUDA(cudaMemsetAsync(a.flag, 0, (recs + 1) * sizeof(int), st));
+        aes_biquad_scan_kernel<<<(unsigned)(B * nt), AES_NT, 80 * sizeof(double), st>>>(a);
+        aes_count_launch();
+        AES_CUDA(cudaGetLastError());
+        return 0;
+    }
     ChainArgs a{ pl->dev, x, y, B, N, scratch, in_fmt, out_fmt, state_out };
     const unsigned grid = (unsigned)std::min<long long>(B, pl->grid_max);
     if (pl->fast_fn) {
@@ -143,6 +177,21 @@ AES_EXPORT int aes_chain_plan_create(const aes_stage_desc *stages, int n_stages,
         AES_CUDA(cudaMalloc(&pl->dev, sizeof(DevPlan)));
         AES_CUDA(cudaMemcpy(pl->dev, &pl->host, sizeof(DevPlan), cudaMemcpyHostToDevice));
         AES_CUDA(cudaMalloc(&pl->scratch, (size_t)pl->grid_max * pl->host.scratch_floats * sizeof(float)));
+        // all-biquad chains also get the time-parallel scan kernel
+        bool all_bq = n_stages >= 1 && n_stages <= AESB_MAX_STAGES;
+        for (int s2 = 0; s2 < n_stages && all_bq; ++s2) all_bq = stages[s2].kind == AES_STAGE_BIQUAD;
+        if (all_bq) {
+            static double tab[AESB_MAX_STAGES * 128 + AESB_MAX_STAGES * AES_NT * 4];
+            double co[5 * AESB_MAX_STAGES], dfi[AESB_MAX_STAGES * 8];
+            for (int s2 = 0; s2 < n_stages; ++s2) {
+                for (int i = 0; i < 5; ++i) co[5 * s2 + i] = stages[s2].p[i];
+                for (int i = 0; i < 8; ++i) dfi[8 * s2 + i] = stages[s2].p[8 + i];
+            }
+            aes_biquad_build(n_stages, co, dfi, &pl->bq, tab, tab + AESB_MAX_STAGES * 128);
+            AES_CUDA(cudaMalloc(&pl->d_bq_tab, sizeof tab));
+            AES_CUDA(cudaMemcpy(pl->d_bq_tab, tab, sizeof tab, cudaMemcpyHostToDevice));
+            pl->bq_ok = true;
+        }
         AES_CUDA(cudaMalloc(&pl->d_state, sizeof pl->h_state));
         AES_CUDA(cudaMemset(pl->d_state, 0, sizeof pl->h_state));
         return 0;
@@ -169,6 +218,8 @@ AES_EXPORT int aes_chain_plan_destroy(aes_chain_plan *pl)
     if (pl->scratch) cudaFree(pl->scratch);
     if (pl->d_state) cudaFree(pl->d_state);
     if (pl->d_lane_tab) cudaFree(pl->d_lane_tab);
+    if (pl->d_bq_tab) cudaFree(pl->d_bq_tab);
+    if (pl->d_bq_scan) cudaFree(pl->d_bq_scan);
     delete pl;
     return 0;
 }

@@ -50,6 +50,28 @@ def parse():
     return ap.parse_args()
 
 
+EXTRA_CHAINS = {
+    # BASELINE configs[1]: LP / HP / BP / peaking cascade
+    "c2-biquad-cascade": [
+        {"type": "filter", "params": {"filter_type": 0, "cutoff_hz": 8000, "q": 0.707}},
+        {"type": "filter", "params": {"filter_type": 1, "cutoff_hz": 80, "q": 0.707}},
+        {"type": "filter", "params": {"filter_type": 2, "cutoff_hz": 1000, "q": 0.8}},
+        {"type": "filter", "params": {"filter_type": 3, "cutoff_hz": 1000, "q": 1.0, "gain_db": 6.0}}],
+    # BASELINE configs[2]: distortion + octaver + feedback delay
+    "c3-dist-octaver-delay": [
+        {"type": "distortion", "params": {"drive": 4.0}},
+        {"type": "octaver", "params": {"semitones": -12, "mix": 0.5}},
+        {"type": "delay", "params": {"delay_ms": 120, "feedback": 0.3, "offset_ms": 10}}],
+}
+
+
+def chain_config(name):
+    import synth
+    if name in synth.PRESETS:
+        return synth.PRESETS[name]
+    return EXTRA_CHAINS[name]
+
+
 def workload(args):
     return {"workload": f"'{args.preset}' preset chain (app.py:41-71) on {args.clips} synthetic "
                         f"{args.seconds:g} s 48 kHz stereo float32 clips per GPU (BASELINE configs[4]-style shard)",
@@ -67,7 +89,7 @@ def cpu_run(preset, n_clips, n_frames, threads, reps=1):
     if n_clips > x.shape[0]:
         x = np.concatenate([x] * ((n_clips + x.shape[0] - 1) // x.shape[0]))[:n_clips]
     x = np.ascontiguousarray(x)
-    cfg = synth.PRESETS[preset]
+    cfg = chain_config(preset)
     orc.run_batch_c(cfg, x[:threads], FS, threads=threads, fast=True)      # page in / warm caches
     best = float("inf")
     for _ in range(reps):
@@ -215,7 +237,7 @@ def b200_arm(args):
 
     n_frames = int(args.seconds * FS)
     B = args.clips
-    cfg = synth.PRESETS[args.preset]
+    cfg = chain_config(args.preset)
     chain = file_chain(cfg, FS, channels_in=2)            # build@1024 + warm-up, as engine.py:86-99
     plan = chain.prepare_batch(n_frames)                  # re-prepared at the file's frame count
     info = plan.info()

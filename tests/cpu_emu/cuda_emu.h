@@ -102,6 +102,21 @@ template <typename T> static inline T __shfl_down_sync(unsigned, T v, int d) {
     return emu_shfl(v, (int)(emu::g_cta->cur & 31) + d, false, 0);
 }
 
+template <typename T> static inline T __shfl_xor_sync(unsigned, T v, int k) {
+    return emu_shfl(v, (int)(emu::g_cta->cur & 31) ^ k, false, 0);
+}
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    emu::Cta &c = *emu::g_cta;
+    int me = c.cur, base = me & ~31;
+    c.slot[me] = pred ? 1 : 0;
+    emu::warp_barrier();
+    unsigned m = 0;
+    int lanes = std::min(32, c.nthreads - base);
+    for (int l = 0; l < lanes; ++l) if (c.slot[base + l]) m |= 1u << l;
+    emu::warp_barrier();
+    return m;
+}
+static inline int __ffs(int x) { return __builtin_ffs(x); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }

@@ -6,6 +6,7 @@
 #include "../../audio-effects-simulator_b200/csrc/aes_plan_build.h"
 #include "../../audio-effects-simulator_b200/csrc/aes_chain_kernel.cuh"
 #include "../../audio-effects-simulator_b200/csrc/aes_fast_build.h"
+#include "../../audio-effects-simulator_b200/csrc/aes_biquad_build.h"
 
 static char g_err[512];
 
@@ -65,5 +66,28 @@ int emu_plan_info(const aes_stage_desc *stages, int n, int fs, int *T, int *smem
     int rc = aes_build_devplan(stages, n, fs, &plan, g_err, sizeof g_err);
     if (rc) return rc;
     *T = plan.T; *smem_bytes = (int)aes_plan_smem_bytes(plan); *scratch_floats = plan.scratch_floats;
+    return 0;
+}
+
+static void bq_entry(void *p) { aes_biquad_scan_body(*reinterpret_cast<BqArgs *>(p)); }
+
+// time-parallel biquad cascade (aes_biquad_scan.cuh) on the emulator
+extern "C" __attribute__((visibility("default")))
+int emu_biquad_scan(const float *x, float *y, long long B, long long N, int n_stages, const double *coeffs5,
+                    const double *dfi_state, int dbg_skip)
+{
+    if (n_stages < 1 || n_stages > AESB_MAX_STAGES) return -1;
+    static BqArgs a;
+    std::vector<double> lane_pw((size_t)n_stages * 128), tile_pw((size_t)n_stages * AES_NT * 4);
+    aes_biquad_build(n_stages, coeffs5, dfi_state, &a, lane_pw.data(), tile_pw.data());
+    const long long nt = (N + AESB_T - 1) / AESB_T;
+    const size_t recs = (size_t)(B * n_stages * nt);
+    std::vector<double> agg(recs * 4, 1e300), inc(recs * 4, 1e300);
+    std::vector<int> flag(recs, 0);
+    unsigned ticket = 0;
+    a.x = x; a.y = y; a.N = N; a.n_tiles = nt; a.B = B; a.dbg_skip = dbg_skip;
+    a.agg = agg.data(); a.inc = inc.data(); a.flag = flag.data(); a.ticket = &ticket;
+    a.lane_pw = lane_pw.data(); a.tile_pw = tile_pw.data(); a.final_state = nullptr;
+    emu::launch(bq_entry, &a, (unsigned)(B * nt), AES_NT, 80 * sizeof(double));
     return 0;
 }

@@ -209,3 +209,28 @@ def test_generic_interpreter_kernel_matches_too(ab, orc, name, monkeypatch):
     y = file_chain(cfg, 48000, channels_in=2).process_batch(x)
     for b in range(B):
         check(y[b], orc.run_file_path(cfg, x[b], 48000), exact=(name == "Slapback Echo"), what=(name, b))
+
+
+def test_time_parallel_scan_equals_batch_kernel_on_a_single_clip(ab, orc, monkeypatch):
+    """One long clip through biquads takes the decoupled-look-back scan kernel
+    (aes_biquad_scan.cuh); forcing the one-CTA-per-clip kernel must give the same audio,
+    and the carried DF-I state must match the oracle's (filter.py:35-40)."""
+    n = 48000 * 8 + 123
+    x = synth.clip(6, n, 2)
+    cfg = [{"type": "filter", "params": {"filter_type": 0, "cutoff_hz": 300, "q": 2.0}},
+           {"type": "filter", "params": {"filter_type": 1, "cutoff_hz": 50, "q": 0.9}}]
+    from audioblocks.engine import file_chain
+    ch = file_chain(cfg, 48000, channels_in=2)
+    y_scan = np.zeros((n, 2), np.float32)
+    ch.process(x, y_scan)
+    states = [fx._state.copy() for fx in ch.effects]
+    monkeypatch.setenv("AES_NO_SCAN", "1")
+    y_batch = run_file(ab, cfg, x, 48000)
+    want = orc.run_file_path(cfg, x, 48000)
+    check(y_scan, want, what="scan")
+    check(y_batch, want, what="batch")
+    och = orc.build_chain(cfg, 48000, ci=2)
+    och.warmup()
+    och.process(x, np.zeros((n, 2), np.float32))
+    for st, ofx in zip(states, och.fx):
+        assert np.max(np.abs(st - ofx.state)) <= 1e-5 * max(1.0, float(np.abs(ofx.state).max()))
