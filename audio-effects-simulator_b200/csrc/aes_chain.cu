@@ -152,12 +152,14 @@ AES_EXPORT int aes_chain_plan_create(const aes_stage_desc *stages, int n_stages,
         static float lane_tab[AESF_MAX_STAGES * 32 * FAST_LANE_STRIDE];
         int codes[AESF_MAX_STAGES];
         if (!getenv("AES_NO_FAST") && aes_fast_build(pl->host, &pl->fast, codes, lane_tab)) {
+            const size_t fast_smem = aes_fast_smem_bytes(pl->host);
             for (const FastShape &sh : g_fast_shapes) {
-                if (memcmp(sh.c, codes, sizeof codes) != 0) continue;
-                AES_CUDA(cudaFuncSetAttribute(sh.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem_bytes));
+                if (memcmp(sh.c, codes, sizeof codes) != 0 || fast_smem > AES_SMEM_LIMIT) continue;
+                AES_CUDA(cudaFuncSetAttribute(sh.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
                 int occ = 0;
-                AES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sh.fn, AES_NT, pl->smem_bytes));
+                AES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sh.fn, AES_NT, fast_smem));
                 if (occ < 1) break;
+                pl->smem_bytes = fast_smem;
                 AES_CUDA(cudaMalloc(&pl->d_lane_tab, sizeof lane_tab));
                 AES_CUDA(cudaMemcpy(pl->d_lane_tab, lane_tab, sizeof lane_tab, cudaMemcpyHostToDevice));
                 pl->fast_fn = sh.fn;

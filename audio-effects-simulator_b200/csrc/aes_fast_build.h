@@ -33,6 +33,14 @@
     X(AESF_OCTAVER, 0, 0, 0)                                                             \
     X(AESF_DIST, 0, 0, 0)
 
+// dynamic shared memory of a specialised kernel: the generic layout (superset of what the
+// fast kernel carves) + the TMA staging area: 2 input tiles, 2 x [2][T+8] line samples, 2 mbarriers
+static inline size_t aes_fast_smem_bytes(const DevPlan &p)
+{
+    const size_t T = (size_t)p.T;
+    return aes_plan_smem_bytes(p) + 16 + (4 * T + 4 * (T + 8)) * sizeof(float) + 2 * sizeof(unsigned long long) + 16;
+}
+
 static inline FRing aesf_ring(const DevRing &r)
 {
     FRing f;

@@ -70,12 +70,78 @@ struct FastArgs {
 };
 #define FAST_LANE_STRIDE 12             // floats per lane per stage: [0]=hlane, [4..11]=bq_lane as 4 doubles
 
+
+// ---- cp.async.bulk (TMA, 1-D) staging of the next tile ------------------------------------
+// One elected thread arms an mbarrier with the byte count and issues bulk copies
+// global -> shared for the NEXT tile's input frames (8 KB) and, for a prefetched feedback
+// delay, the T+4 line samples per channel it will read.  Nothing is held in registers and no
+// scoreboard slot is occupied while the copies fly; consumers wait on the mbarrier parity
+// at the top of the next tile and read their own 32 bytes with LDS.128.
+#ifndef AES_CPU_EMU
+__device__ __forceinline__ void aes_mbar_init(unsigned long long *bar, unsigned count)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(a), "r"(count) : "memory");
+}
+__device__ __forceinline__ void aes_mbar_init_fence() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void aes_mbar_expect(unsigned long long *bar, unsigned bytes)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(a), "r"(bytes) : "memory");
+}
+// `policy`: an L2 cache policy from createpolicy (streamed input = evict_first, delay line = evict_last)
+__device__ __forceinline__ void aes_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar,
+                                             unsigned long long policy)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                 ::"r"(d), "l"(src), "r"(bytes), "r"(b), "l"(policy) : "memory");
+}
+__device__ __forceinline__ unsigned long long aes_policy_evict_first()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long aes_policy_evict_last()
+{
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ void aes_mbar_wait(unsigned long long *bar, unsigned use_index)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar), parity = use_index & 1u;
+    unsigned done;
+    do {
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(a), "r"(parity) : "memory");
+    } while (!done);
+}
+// generic-proxy global stores -> visible to later async-proxy (TMA) reads.  Executed by the
+// issuing thread only, after the CTA barrier that orders every thread's ring stores before it
+// (fences are cumulative); a per-thread fence after the stores cost 15 % of all stall samples.
+__device__ __forceinline__ void aes_fence_proxy_async() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+#else
+// emulator: the copy completes at issue; the barrier word counts completed uses
+static inline void aes_mbar_init(unsigned long long *bar, unsigned) { *bar = 0; }
+static inline void aes_mbar_init_fence() {}
+static inline void aes_mbar_expect(unsigned long long *, unsigned) {}
+static inline void aes_bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *, unsigned long long) { std::memcpy(dst, src, bytes); }
+static inline unsigned long long aes_policy_evict_first() { return 0; }
+static inline unsigned long long aes_policy_evict_last() { return 0; }
+static inline void aes_mbar_complete_emu(unsigned long long *bar) { *bar += 1; }
+static inline void aes_mbar_wait(unsigned long long *bar, unsigned use_index) { while (*bar <= use_index) emu::yield(); }
+static inline void aes_fence_proxy_async() {}
+#endif
+
 struct FCtx {
     float *tile, *rings, *gscr;
     double *wtot;
     int *rpos;              // current parity
     long long n0;
     int len, tid, lane, warp;
+    const float *ln_stage;  // this tile's staged delay line: [2 ch][T + 8] floats (PF shapes), or null
 };
 
 struct SRegs {              // per-thread, per-stage persistent ring slots (floats)
@@ -242,9 +308,13 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
             for (int ch = 0; ch < 2; ++ch) {
                 const FRing rg = st.ring[ch][0];
                 float line[FR];
-                if (AESF_PF(CODE)) {
-                    // raw vectors fetched a tile ago; the (uniform) misalignment select happens only now,
-                    // so nothing touched the load's destination registers while it was in flight
+                if (AESF_PF(CODE) && c.ln_stage != nullptr) {
+                    // line samples staged by TMA a tile ago: [i0 + m, i0 + m + FR) of the staged span
+                    constexpr int T = AES_NT * FR;
+                    const float *sp = c.ln_stage + ch * (T + 8) + i0;
+                    const float4 A = aes_lds_v4(sp), B = aes_lds_v4(sp + 4);
+                    aesf_select4<FR>(A, B, ((rg.lag + 3) & ~3) - rg.lag, line);
+                } else if (AESF_PF(CODE)) {
                     aesf_select4<FR>(lnA[ch], lnB[ch], ((rg.lag + 3) & ~3) - rg.lag, line);
                 } else {
                     aesf_line_read<FR>(c, rg, st.glob != 0, sr.da[ch], line);
@@ -602,11 +672,49 @@ __device__ __forceinline__ void aesf_prefetch(const FastArgs &a, const FCtx &c, 
     }
 }
 
+// issue the TMA copies for one tile (called by thread 0 only): input frames and, for a PF
+// delay stage PS, the T+4 line samples per channel starting at thread 0's aligned read base
+template <int FR, int PCODE, int PS>
+__device__ __forceinline__ void aesf_issue_tile(const FastArgs &a, const FCtx &c, const SRegs &srp, int ahead,
+                                                long long frame0, float *stage_x, float *stage_ln,
+                                                unsigned long long *bar)
+{
+    constexpr int T = AES_NT * FR;
+    constexpr bool PF = AESF_KIND(PCODE) == AESK_DELAY && AESF_PF(PCODE);
+    aes_mbar_expect(bar, (unsigned)(T * 8 + (PF ? 2 * (T + 4) * 4 : 0)));
+    aes_bulk_g2s(stage_x, reinterpret_cast<const float *>(a.x) + 2 * frame0, T * 8, bar, aes_policy_evict_first());
+    if (PF) {
+        aes_fence_proxy_async();                    // the line was written with ordinary stores >= 1 tile ago
+        const unsigned long long keep = aes_policy_evict_last();
+        const FastStage &st = a.st[PS];
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const FRing rg = st.ring[ch][0];
+            const int a0 = ahead ? aesf_adv(srp.da[ch], rg.tinc, rg.len) : srp.da[ch];   // thread 0: i0 == 0
+            const float *rb = c.gscr + rg.off;
+            float *dst = stage_ln + ch * (T + 8);
+            const int n1 = (rg.len - a0) < (T + 4) ? (rg.len - a0) : (T + 4);
+            aes_bulk_g2s(dst, rb + a0, (unsigned)n1 * 4, bar, keep);
+            if (n1 < T + 4) aes_bulk_g2s(dst + n1, rb, (unsigned)(T + 4 - n1) * 4, bar, keep);   // the ring wraps
+        }
+    }
+#ifdef AES_CPU_EMU
+    aes_mbar_complete_emu(bar);
+#endif
+}
+
 template <int FR, int C0, int C1, int C2, int C3>
 __device__ void aes_fast_body(const FastArgs &a)
 {
     constexpr int T = AES_NT * FR;
     constexpr int NS = (C0 != 0) + (C1 != 0) + (C2 != 0) + (C3 != 0);
+    // the (single) prefetched feedback-delay stage, if the shape has one
+    constexpr int PS = (AESF_KIND(C0) == AESK_DELAY && AESF_PF(C0)) ? 0
+                     : (AESF_KIND(C1) == AESK_DELAY && AESF_PF(C1)) ? 1
+                     : (AESF_KIND(C2) == AESK_DELAY && AESF_PF(C2)) ? 2
+                     : (AESF_KIND(C3) == AESK_DELAY && AESF_PF(C3)) ? 3 : -1;
+    constexpr int PCODE = PS == 0 ? C0 : PS == 1 ? C1 : PS == 2 ? C2 : PS == 3 ? C3 : 0;
+    constexpr bool STAGED = FR == 4;               // TMA staging needs 16-byte granules per thread
     AES_DYN_SMEM(float, smem);
     FCtx c;
     c.tid = threadIdx.x;
@@ -619,8 +727,21 @@ __device__ void aes_fast_body(const FastArgs &a)
     double *state = c.wtot + 64;                    // [2][NS*8]
     constexpr int NST = NS * 8;
     int *rpos2 = reinterpret_cast<int *>(state + 2 * NST);
+    // staging area (16-byte aligned): 2 x input tile, 2 x [2 ch][T+8] line samples, 2 mbarriers
+    float *stg = reinterpret_cast<float *>((reinterpret_cast<size_t>(rpos2 + 2 * AESF_MAX_WALK) + 15) & ~(size_t)15);
+    float *stage_x = stg;                           // [2][2T]
+    float *stage_ln = stg + 4 * T;                  // [2][2][T+8]
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(stage_ln + 4 * (T + 8));
     c.gscr = a.scratch + (long long)blockIdx.x * a.scratch_floats;
+    c.ln_stage = nullptr;
     const int nw = a.n_walk, i0 = FR * c.tid;
+    if (STAGED) {
+        if (c.tid == 0) { aes_mbar_init(bars, 1); aes_mbar_init(bars + 1, 1); aes_mbar_init_fence(); }
+        __syncthreads();
+    }
+    unsigned it_issue = 0, it_wait = 0;             // tiles issued / consumed through the staging ring (CTA-uniform)
+    ChainArgs io;                                   // tile I/O helpers are shared with the generic kernel
+    io.x = a.x; io.y = a.y; io.N = a.N; io.in_fmt = a.in_fmt; io.out_fmt = a.out_fmt;
 
     for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
         for (int i = c.tid; i < a.smem_floats; i += AES_NT) c.rings[i] = 0.0f;
@@ -631,41 +752,53 @@ __device__ void aes_fast_body(const FastArgs &a)
         if (C1) aesf_slots_init<FR, C1, 1>(a, i0, sr1);
         if (C2) aesf_slots_init<FR, C2, 2>(a, i0, sr2);
         if (C3) aesf_slots_init<FR, C3, 3>(a, i0, sr3);
+        SRegs &srp = PS == 0 ? sr0 : PS == 1 ? sr1 : PS == 2 ? sr2 : sr3;
         __syncthreads();
 
-        float xn[2][FR];
-        float4 pfA[2], pfB[2];
-        pfA[0] = pfA[1] = pfB[0] = pfB[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        c.n0 = 0;
-        c.len = a.N < (long long)T ? (int)a.N : T;
-        c.rpos = rpos2;
-        ChainArgs io;                                // tile I/O helpers are shared with the generic kernel
-        io.x = a.x; io.y = a.y; io.N = a.N; io.in_fmt = a.in_fmt; io.out_fmt = a.out_fmt;
-        aes_load_frames<FR>(io, b, 0, c.len, c.tid, xn);
-        if (C0) aesf_prefetch<FR, C0, 0>(a, c, sr0, 0, pfA, pfB);
-        if (C1) aesf_prefetch<FR, C1, 1>(a, c, sr1, 0, pfA, pfB);
-        if (C2) aesf_prefetch<FR, C2, 2>(a, c, sr2, 0, pfA, pfB);
-        if (C3) aesf_prefetch<FR, C3, 3>(a, c, sr3, 0, pfA, pfB);
+        // a tile goes through TMA staging when it is full, 16-byte aligned and plain f32 stereo
+        const bool clip_staged = STAGED && a.in_fmt == AESK_F32_STEREO && ((b * a.N) & 1) == 0;
+        const long long clip_frame0 = b * a.N;
+        if (clip_staged && a.N >= (long long)T && c.tid == 0)
+            aesf_issue_tile<FR, PCODE, PS < 0 ? 0 : PS>(a, c, srp, 0, clip_frame0, stage_x + (it_issue & 1) * 2 * T,
+                                                       stage_ln + (it_issue & 1) * 2 * (T + 8), bars + (it_issue & 1));
+        if (clip_staged && a.N >= (long long)T) ++it_issue;
+        float4 lnA[2], lnB[2];
+        lnA[0] = lnA[1] = lnB[0] = lnB[1] = make_float4(0.f, 0.f, 0.f, 0.f);
         int par = 0;
         for (long long n0 = 0; n0 < a.N; n0 += T, par ^= 1) {
             c.n0 = n0;
             c.len = (a.N - n0 < (long long)T) ? (int)(a.N - n0) : T;
             c.rpos = rpos2 + par * nw;
             float v[2][FR];
-            float4 lnA[2], lnB[2];
+            const bool staged = clip_staged && c.len == T;
+            if (staged) {
+                const unsigned q = it_wait & 1;
+                aes_mbar_wait(bars + q, it_wait >> 1);
+                ++it_wait;
+                const float *sx = stage_x + q * 2 * T + 2 * i0;          // interleaved L R L R ...
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-                lnA[ch] = pfA[ch]; lnB[ch] = pfB[ch];
-#pragma unroll
-                for (int j = 0; j < FR; ++j) v[ch][j] = xn[ch][j];
+                for (int j = 0; j < FR / 2; ++j) {
+                    const float4 t = aes_lds_v4(sx + 4 * j);
+                    v[0][2 * j] = t.x; v[1][2 * j] = t.y; v[0][(2 * j + 1) % FR] = t.z; v[1][(2 * j + 1) % FR] = t.w;
+                }
+                c.ln_stage = PS >= 0 ? stage_ln + q * 2 * (T + 8) : nullptr;
+            } else {
+                aes_load_frames<FR>(io, b, n0, c.len, c.tid, v);         // ragged / unaligned / non-f32 tiles
+                c.ln_stage = nullptr;
+                if (PS >= 0) {
+                    if (C0) aesf_prefetch<FR, C0, 0>(a, c, sr0, 0, lnA, lnB);
+                    if (C1) aesf_prefetch<FR, C1, 1>(a, c, sr1, 0, lnA, lnB);
+                    if (C2) aesf_prefetch<FR, C2, 2>(a, c, sr2, 0, lnA, lnB);
+                    if (C3) aesf_prefetch<FR, C3, 3>(a, c, sr3, 0, lnA, lnB);
+                }
             }
-            if (n0 + T < a.N) {
-                const long long rem = a.N - n0 - T;
-                aes_load_frames<FR>(io, b, n0 + T, rem < (long long)T ? (int)rem : T, c.tid, xn);
-                if (C0) aesf_prefetch<FR, C0, 0>(a, c, sr0, 1, pfA, pfB);
-                if (C1) aesf_prefetch<FR, C1, 1>(a, c, sr1, 1, pfA, pfB);
-                if (C2) aesf_prefetch<FR, C2, 2>(a, c, sr2, 1, pfA, pfB);
-                if (C3) aesf_prefetch<FR, C3, 3>(a, c, sr3, 1, pfA, pfB);
+            // next tile: hand it to the TMA now, a whole tile of work ahead of its use
+            if (clip_staged && a.N - n0 - T >= (long long)T) {
+                if (c.tid == 0)
+                    aesf_issue_tile<FR, PCODE, PS < 0 ? 0 : PS>(a, c, srp, 1, clip_frame0 + n0 + T,
+                                                               stage_x + (it_issue & 1) * 2 * T,
+                                                               stage_ln + (it_issue & 1) * 2 * (T + 8), bars + (it_issue & 1));
+                ++it_issue;
             }
             const double *sin = state + par * NST;
             double *sout = state + (par ^ 1) * NST;

@@ -45,7 +45,7 @@ int emu_chain_run(const aes_stage_desc *stages, int n, int fs, const void *x, in
             if (memcmp(sh.c, codes, sizeof codes) != 0) continue;
             fa.x = x; fa.y = y; fa.B = B; fa.N = N; fa.scratch = scratch.data(); fa.lane_tab = lane_tab;
             fa.state_out = state_out; fa.in_fmt = in_fmt; fa.out_fmt = out_fmt;
-            emu::launch(sh.fn, &fa, grid, AES_NT, smem);
+            emu::launch(sh.fn, &fa, grid, AES_NT, aes_fast_smem_bytes(plan));
             g_last_fast = 1;
             return 0;
         }
