@@ -11,5 +11,6 @@ from .spectral import SpectralFilter
 from .octaver import OctaverEffect
 from .filter import FilterEffect
 from .distortion import DistortionEffect
+from .convreverb import ConvolutionReverbEffect
 from .engine import AudioEngine, SAMPLE_RATE
 from . import sharding

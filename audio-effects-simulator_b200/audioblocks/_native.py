@@ -73,6 +73,11 @@ def lib() -> C.CDLL:
         L.aes_delay_f32.argtypes = [vp, vp, i64, i64, i64, i64, C.c_double, C.c_double, C.c_double, vp]
         L.aes_biquad_cascade_f32.argtypes = [vp, vp, i64, i64, ci, C.POINTER(C.c_double), vp]
         L.aes_quantize_i16.argtypes = [vp, vp, i64, vp]
+        L.aes_convreverb_plan_create.argtypes = [vp, i64, ci, C.POINTER(vp)]
+        L.aes_convreverb_plan_destroy.argtypes = [vp]
+        L.aes_convreverb_run.argtypes = [vp, vp, vp, i64, i64, C.c_double, C.c_double, vp]
+        L.aes_convreverb_process_host.argtypes = [vp, vp, vp, i64, i64, C.c_double, C.c_double]
+        L.aes_convreverb_plan_info.argtypes = [vp, C.POINTER(ci), C.POINTER(ci)]
         if L.aes_abi_version() != 1:
             raise AesimError("libaesim.so ABI version mismatch")
         _lib = L
@@ -126,6 +131,42 @@ class ChainPlan:
     def close(self):
         if self._h:
             lib().aes_chain_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ConvReverbPlan:
+    """RAII wrapper of aes_convreverb_plan (IR partition spectra live on the device)."""
+
+    def __init__(self, ir: np.ndarray, block_log2: int = 0):
+        ir = np.ascontiguousarray(ir, np.float32)
+        if ir.ndim != 2 or ir.shape[1] != 2:
+            raise ValueError("impulse response must be (n_taps, 2)")
+        self._h = C.c_void_p()
+        check(lib().aes_convreverb_plan_create(C.c_void_p(ir.ctypes.data), ir.shape[0], block_log2, C.byref(self._h)))
+
+    def info(self):
+        n, p = C.c_int(), C.c_int()
+        check(lib().aes_convreverb_plan_info(self._h, C.byref(n), C.byref(p)))
+        return {"fft_size": n.value, "partitions": p.value}
+
+    def run_device(self, x_ptr, y_ptr, n_clips, n_frames, dry, wet, stream=0):
+        check(lib().aes_convreverb_run(self._h, C.c_void_p(x_ptr), C.c_void_p(y_ptr), n_clips, n_frames,
+                                       float(dry), float(wet), C.c_void_p(stream)))
+
+    def run_host(self, x: np.ndarray, y: np.ndarray, n_clips, n_frames, dry, wet):
+        assert x.flags.c_contiguous and y.flags.c_contiguous and x.dtype == np.float32 and y.dtype == np.float32
+        check(lib().aes_convreverb_process_host(self._h, C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data),
+                                                n_clips, n_frames, float(dry), float(wet)))
+
+    def close(self):
+        if self._h:
+            lib().aes_convreverb_plan_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

@@ -269,19 +269,61 @@ class EffectsChain:
         """x: (B, frames, 1|2) float32 host array (or (B, frames, 2) int16 PCM, which is
         down-mixed like engine.py:78-84) -> (B, frames, 2) float32 or int16 (if `out`
         is int16: clip, *32767, truncate, engine.py:104-105).  Every clip starts from
-        the same freshly prepared state."""
+        the same freshly prepared state.  Runs of fusable effects are one kernel launch each;
+        whole-clip FFT effects (ConvolutionReverbEffect) run between them."""
+        from .convreverb import ConvolutionReverbEffect
         B, frames, ch = x.shape
-        if x.dtype == np.int16:
-            fmt_in = _native.FMT_I16_DOWNMIX
-        else:
-            x = np.ascontiguousarray(x, np.float32)
-            fmt_in = _native.FMT_F32_MONO if ch == 1 else _native.FMT_F32_STEREO
+        self._ensure_blocksize(frames)
+        segs, cur = [], []
+        for e in self.effects:
+            if isinstance(e, PlotDataTap):
+                continue
+            if isinstance(e, NativeEffect):
+                cur.append(e)
+            elif isinstance(e, ConvolutionReverbEffect):
+                if cur:
+                    segs.append(cur)
+                    cur = []
+                segs.append(e)
+            else:
+                raise TypeError(f"{type(e).__name__} has no CUDA implementation; cannot batch")
+        if cur or not segs:
+            segs.append(cur)
+        want_i16 = out is not None and out.dtype == np.int16
+        data = x if x.dtype == np.int16 else np.ascontiguousarray(x, np.float32)
+        for k, seg in enumerate(segs):
+            last = k == len(segs) - 1
+            if isinstance(seg, list):
+                descs = []
+                for e in seg:
+                    e._require_fresh()
+                    descs.extend(e._stages(frames))
+                if data.dtype == np.int16:
+                    fmt_in = _native.FMT_I16_DOWNMIX
+                else:
+                    fmt_in = _native.FMT_F32_MONO if data.shape[2] == 1 else _native.FMT_F32_STEREO
+                if last and out is not None:
+                    dst = out
+                else:
+                    dst = np.empty((B, frames, 2), np.int16 if (last and want_i16) else np.float32)
+                fmt_out = _native.FMT_I16_STEREO if dst.dtype == np.int16 else _native.FMT_F32_STEREO
+                plan = _native.ChainPlan(descs, self.sr)
+                try:
+                    plan.run_host(np.ascontiguousarray(data), fmt_in, dst, fmt_out, B, frames)
+                finally:
+                    plan.close()
+                data = dst
+            else:
+                if data.dtype == np.int16 or data.shape[2] != 2:      # down-mix / fan out through an empty chain
+                    data = EffectsChain(self.sr, self.ci, self.co, frames).process_batch(data)
+                dst = out if (last and out is not None and out.dtype == np.float32) else None
+                data = seg.process_batch(data, dst)
         if out is None:
-            out = np.empty((B, frames, 2), np.float32)
-        fmt_out = _native.FMT_I16_STEREO if out.dtype == np.int16 else _native.FMT_F32_STEREO
-        plan = self.prepare_batch(frames)
-        try:
-            plan.run_host(np.ascontiguousarray(x), fmt_in, out, fmt_out, B, frames)
-        finally:
-            plan.close()
+            return data
+        if data is not out:
+            if want_i16 and data.dtype != np.int16:
+                tmp = EffectsChain(self.sr, 2, 2, frames)
+                tmp.process_batch(data, out)
+            else:
+                out[...] = data
         return out

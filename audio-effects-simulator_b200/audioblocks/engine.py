@@ -37,6 +37,7 @@ _EFFECT_TYPES = {
     "octaver": lambda p: ab.OctaverEffect(**p),
     "filter": lambda p: ab.FilterEffect(**p),
     "distortion": lambda p: ab.DistortionEffect(**p),     # extension (no reference block)
+    "convreverb": lambda p: ab.ConvolutionReverbEffect(**p),   # extension (BASELINE configs[3])
 }
 
 

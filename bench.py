@@ -65,6 +65,58 @@ EXTRA_CHAINS = {
 }
 
 
+def conv_arm(args, torch, dist, _native, rank, world, local, dev):
+    """BASELINE configs[3]: IR-convolution reverb, 3 s synthetic IR, synthetic 30 s stereo clips."""
+    import numpy as np
+    from oracle import oracle as orc
+    n_frames = int(args.seconds * FS)
+    B = args.clips
+    ir = orc.synthetic_ir(int(3.0 * FS))
+    plan = _native.ConvReverbPlan(ir)
+    x = synth_device(torch, B, n_frames, rank * B, dev)
+    y = torch.empty_like(x)
+    sptr = torch.cuda.current_stream().cuda_stream
+    L = _native.lib()
+    for _ in range(max(3, args.warmup)):
+        plan.run_device(x.data_ptr(), y.data_ptr(), B, n_frames, 0.7, 0.5, sptr)
+    torch.cuda.synchronize()
+    l0 = L.aes_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        plan.run_device(x.data_ptr(), y.data_ptr(), B, n_frames, 0.7, 0.5, sptr)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    n_chk = min(n_frames, 200000)
+    fx = orc.OConvReverb(ir, 0.7, 0.5)
+    xs = x[0, :n_chk].cpu().numpy()
+    want = np.zeros_like(xs)
+    fx.process_into(xs, want)
+    import synth
+    mx, snr = synth.err_stats(y[0, :n_chk].cpu().numpy(), want)
+    info = plan.info()
+    samples = B * n_frames * 2
+    nblk = -(-n_frames // (info["fft_size"] // 2))
+    mac_flops = B * nblk * info["fft_size"] * info["partitions"] * 16.0
+    peak = 6547.8
+    pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pp):
+        peak = float(json.load(open(pp))["hbm_gbs"])
+    ach = samples * 8 / (ms * 1e-3) / 1e9
+    print(json.dumps({
+        "metric": METRIC, "value": samples / (ms * 1e-3) / 1e6, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"IR-convolution reverb, 3 s synthetic IR ({ir.shape[0]} taps), {B} synthetic "
+                               f"{args.seconds:g} s 48 kHz stereo clips (BASELINE configs[3])", **info},
+        "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                     "kernel": "aesc_fft_blocks + aesc_mac + aesc_ifft_mix", "mac_fp32_tflops": mac_flops / (ms * 1e-3) / 1e12},
+        "gpu_launches": int(L.aes_launch_count() - l0), "parity": {"max_abs_err": mx, "snr_db": snr, "frames": n_chk},
+    }))
+    plan.close()
+
+
 def chain_config(name):
     import synth
     if name in synth.PRESETS:
@@ -235,6 +287,8 @@ def b200_arm(args):
     if rank == 0:
         clocks.start()              # nvidia-smi takes a while to start: launch it before the data is built
 
+    if args.preset == "c4-convreverb":
+        return conv_arm(args, torch, dist, _native, rank, world, local, dev)
     n_frames = int(args.seconds * FS)
     B = args.clips
     cfg = chain_config(args.preset)

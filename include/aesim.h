@@ -137,6 +137,18 @@ int aes_biquad_cascade_f32(const float *x, float *y, int64_t n_clips, int64_t n_
                            int n_stages, const double *coeffs5, void *stream);
 int aes_quantize_i16(const float *x, int16_t *q, int64_t n_values, void *stream);
 
+/* ---- IR-convolution reverb (BASELINE configs[3]; no counterpart in the reference, whose
+ *      reverb.py:72-277 is a Schroeder network): out = clip(dry*x + wet*(x (*) ir)) per channel.
+ *      ir_host: (n_taps, 2) float32 host array; block_log2: FFT size 2^14 (0 = default), 2^11, 2^8. */
+typedef struct aes_convreverb_plan aes_convreverb_plan;
+int aes_convreverb_plan_create(const float *ir_host, int64_t n_taps, int block_log2, aes_convreverb_plan **plan);
+int aes_convreverb_plan_destroy(aes_convreverb_plan *plan);
+int aes_convreverb_run(aes_convreverb_plan *plan, const float *x, float *y, int64_t n_clips, int64_t n_frames,
+                       double mix_dry, double mix_wet, void *stream);           /* device pointers */
+int aes_convreverb_process_host(aes_convreverb_plan *plan, const float *x_host, float *y_host, int64_t n_clips,
+                                int64_t n_frames, double mix_dry, double mix_wet);
+int aes_convreverb_plan_info(const aes_convreverb_plan *plan, int *fft_size, int *partitions);
+
 #ifdef __cplusplus
 }
 #endif

@@ -355,7 +355,36 @@ class ODistortion:
         L.orc_distortion(_p(x), _p(out), x.size, np.float32(self.drive), np.float32(self.mix))
 
 
-KINDS = {"delay": ODelay, "reverb": OReverb, "gate": OGate, "spectral": OSpectral,
+class OConvReverb:
+    """OUR definition (no reference implementation; SURVEY 0.2 / BASELINE configs[3]):
+    out[:, c] = clip(f32(dry)*x[:, c] + f32(wet)*f32(conv(x[:, c], ir[:, c])[:N]), -1, 1) with the
+    convolution evaluated in float64 (scipy.signal.fftconvolve).  Parity unpinned by the reference."""
+
+    def __init__(self, ir, mix_dry=0.7, mix_wet=0.5):
+        self.ir = np.asarray(ir, np.float32).reshape(-1, 2)
+        self.mix_dry, self.mix_wet = float(mix_dry), float(mix_wet)
+
+    def prepare(self, fs, ci, co, bs):
+        pass
+
+    def process_into(self, x, out, L=None):
+        from scipy.signal import fftconvolve
+        n = x.shape[0]
+        for c in range(2):
+            wet = fftconvolve(x[:, c].astype(np.float64), self.ir[:, c].astype(np.float64))[:n].astype(np.float32)
+            out[:, c] = np.clip(np.float32(self.mix_dry) * x[:, c] + np.float32(self.mix_wet) * wet, -1.0, 1.0)
+
+
+def synthetic_ir(n_taps, fs=48000, rt60=1.5, seed=7):
+    """rng(7) noise x 10^(-3 t / rt60) envelope, L/R independent, sum|h| = 4 per channel."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n_taps) / fs
+    h = rng.standard_normal((n_taps, 2)) * (10.0 ** (-3.0 * t / rt60))[:, None]
+    h *= 4.0 / np.abs(h).sum(axis=0, keepdims=True)
+    return h.astype(np.float32)
+
+
+KINDS = {"convreverb": OConvReverb, "delay": ODelay, "reverb": OReverb, "gate": OGate, "spectral": OSpectral,
          "octaver": OOctaver, "filter": OFilter, "distortion": ODistortion}
 
 

@@ -32,7 +32,7 @@ void launch(void (*fn)(void *), void *args, unsigned grid, unsigned threads, siz
         blockIdx.x = b;
         for (unsigned t = 0; t < threads; ++t) {
             Thread &th = cta.th[t];
-            th.stack.resize(256 * 1024);
+            th.stack.resize(threads > 256 ? 64 * 1024 : 256 * 1024);
             getcontext(&th.ctx);
             th.ctx.uc_stack.ss_sp = th.stack.data();
             th.ctx.uc_stack.ss_size = th.stack.size();

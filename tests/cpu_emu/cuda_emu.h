@@ -117,6 +117,7 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
     return m;
 }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x); }
 template <typename T> static inline T __ldg(const T *p) { return *p; }
 static inline float __fmul_rn(float a, float b) { volatile float r = a * b; return r; }
 static inline float __fadd_rn(float a, float b) { volatile float r = a + b; return r; }

@@ -7,6 +7,7 @@
 #include "../../audio-effects-simulator_b200/csrc/aes_chain_kernel.cuh"
 #include "../../audio-effects-simulator_b200/csrc/aes_fast_build.h"
 #include "../../audio-effects-simulator_b200/csrc/aes_biquad_build.h"
+#include "../../audio-effects-simulator_b200/csrc/aes_convreverb.cuh"
 
 static char g_err[512];
 
@@ -89,5 +90,33 @@ int emu_biquad_scan(const float *x, float *y, long long B, long long N, int n_st
     a.agg = agg.data(); a.inc = inc.data(); a.flag = flag.data(); a.ticket = &ticket;
     a.lane_pw = lane_pw.data(); a.tile_pw = tile_pw.data(); a.final_state = nullptr;
     emu::launch(bq_entry, &a, (unsigned)(B * nt), AES_NT, 80 * sizeof(double));
+    return 0;
+}
+
+// ---- IR-convolution reverb (aes_convreverb.cuh) on the emulator, FFT size 2^8 -----------------
+struct ConvLaunch { ConvArgs a; int cpc; const float *ir; int n_taps; cpx *A, *B; const cpx *tw; };
+static void conv_k1(void *p) { aesc_fft_blocks_body<8>(reinterpret_cast<ConvLaunch *>(p)->a); }
+static void conv_k2(void *p) { ConvLaunch *l = reinterpret_cast<ConvLaunch *>(p); aesc_mac_body<8>(l->a, l->cpc); }
+static void conv_k3(void *p) { aesc_ifft_mix_body<8>(reinterpret_cast<ConvLaunch *>(p)->a); }
+static void conv_k0(void *p) { ConvLaunch *l = reinterpret_cast<ConvLaunch *>(p); aesc_ir_prep_body<8>(l->ir, l->n_taps, l->A, l->B, l->tw); }
+
+extern "C" __attribute__((visibility("default")))
+int emu_convreverb(const float *ir, long long n_taps, const float *x, float *y, long long B, long long Nf,
+                   float dry, float wet)
+{
+    constexpr int L = 8, N = 1 << L, BK = N / 2;
+    const int P = (int)((n_taps + BK - 1) / BK);
+    const int nblk = (int)((Nf + BK - 1) / BK);
+    std::vector<cpx> tw(N / 2), A((size_t)P * N), Bc((size_t)P * N), Z((size_t)B * nblk * N), W((size_t)B * nblk * N);
+    for (int q = 0; q < N / 2; ++q) { double ang = -2.0 * M_PI * q / N; tw[q].x = (float)cos(ang); tw[q].y = (float)sin(ang); }
+    ConvLaunch l;
+    l.ir = ir; l.n_taps = (int)n_taps; l.A = A.data(); l.B = Bc.data(); l.tw = tw.data(); l.cpc = 2;
+    emu::launch(conv_k0, &l, P, AESC_NT, N * 8);
+    l.a.x = x; l.a.y = y; l.a.Z = Z.data(); l.a.W = W.data(); l.a.A = A.data(); l.a.Bc = Bc.data(); l.a.tw = tw.data();
+    l.a.B = B; l.a.Nf = Nf; l.a.nblk = nblk; l.a.P = P; l.a.dry = dry; l.a.wet = wet;
+    emu::launch(conv_k1, &l, (unsigned)(B * nblk), AESC_NT, N * 8);
+    // N / AESC_KT == 1 tile of 256 bins at this FFT size
+    emu::launch(conv_k2, &l, (unsigned)((N / AESC_KT) * ((B + 1) / 2)), AESC_KT, 2 * P * AESC_KT * 8);
+    emu::launch(conv_k3, &l, (unsigned)(B * nblk), AESC_NT, N * 8);
     return 0;
 }

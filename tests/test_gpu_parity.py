@@ -234,3 +234,40 @@ def test_time_parallel_scan_equals_batch_kernel_on_a_single_clip(ab, orc, monkey
     och.process(x, np.zeros((n, 2), np.float32))
     for st, ofx in zip(states, och.fx):
         assert np.max(np.abs(st - ofx.state)) <= 1e-5 * max(1.0, float(np.abs(ofx.state).max()))
+
+
+def test_convolution_reverb_3s_ir(ab, orc):
+    """BASELINE configs[3] shape at test size: 3 s synthetic IR (144 000 taps, 18 partitions of
+    the 16384-point FFT), 5 s clips; float64 fftconvolve oracle (parity unpinned by the reference)."""
+    ir = orc.synthetic_ir(144000)
+    n, B = 48000 * 5 + 777, 3
+    x = synth.batch(70, B, n)
+    fx = ab.ConvolutionReverbEffect(ir, mix_dry=0.7, mix_wet=0.5)
+    assert fx.plan().info() == {"fft_size": 16384, "partitions": 18}
+    y = fx.process_batch(x)
+    for b in range(B):
+        want = np.zeros_like(x[b])
+        orc.OConvReverb(ir, 0.7, 0.5).process_into(x[b], want)
+        check(y[b], want, what=b)
+    # inside a chain, between fused segments, with a mono file-path input
+    from audioblocks.engine import file_chain
+    cfg = [{"type": "filter", "params": {"filter_type": 1, "cutoff_hz": 120}},
+           {"type": "convreverb", "params": {"ir": ir[:20000], "mix_wet": 0.8}},
+           {"type": "delay", "params": {"delay_ms": 100, "feedback": 0.0, "mix_wet": 0.5, "mix_dry": 1.0, "offset_ms": 0}}]
+    xm = synth.clip(3, 50000, 1)
+    got = np.zeros((50000, 2), np.float32)
+    file_chain(cfg, 48000, channels_in=1).process(xm, got)
+    check(got, orc.run_file_path(cfg, xm, 48000), what="chain")
+    yb = file_chain(cfg, 48000, channels_in=1).process_batch(xm[None])
+    assert np.array_equal(yb[0], got)
+
+
+def test_convolution_reverb_small_fft_sizes(ab, orc):
+    for log2n, taps in ((8, 300), (11, 5000)):
+        ir = orc.synthetic_ir(taps, rt60=0.05)
+        x = synth.batch(75, 2, 30000)
+        y = ab.ConvolutionReverbEffect(ir, 0.5, 0.9, block_log2=log2n).process_batch(x)
+        for b in range(2):
+            want = np.zeros_like(x[b])
+            orc.OConvReverb(ir, 0.5, 0.9).process_into(x[b], want)
+            check(y[b], want, what=(log2n, b))
