@@ -78,6 +78,11 @@ def lib() -> C.CDLL:
         L.aes_convreverb_run.argtypes = [vp, vp, vp, i64, i64, C.c_double, C.c_double, vp]
         L.aes_convreverb_process_host.argtypes = [vp, vp, vp, i64, i64, C.c_double, C.c_double]
         L.aes_convreverb_plan_info.argtypes = [vp, C.POINTER(ci), C.POINTER(ci)]
+        L.aes_spectral_plan_create.argtypes = [i64, C.POINTER(vp)]
+        L.aes_spectral_plan_destroy.argtypes = [vp]
+        L.aes_spectral_frames_host.argtypes = [vp, vp, vp, vp, ci, C.c_double, C.c_double, C.c_double]
+        L.aes_spectral_run.argtypes = [vp, vp, vp, i64, i64, C.c_double, C.c_double, C.c_double, vp]
+        L.aes_spectral_process_host.argtypes = [vp, vp, vp, i64, i64, C.c_double, C.c_double, C.c_double]
         if L.aes_abi_version() != 1:
             raise AesimError("libaesim.so ABI version mismatch")
         _lib = L
@@ -167,6 +172,45 @@ class ConvReverbPlan:
     def close(self):
         if self._h:
             lib().aes_convreverb_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SpectralPlan:
+    """RAII wrapper of aes_spectral_plan for one frame length M = 2 * hop."""
+
+    def __init__(self, frame_len: int):
+        self.frame_len = int(frame_len)
+        self._h = C.c_void_p()
+        check(lib().aes_spectral_plan_create(self.frame_len, C.byref(self._h)))
+
+    def frames_host(self, in_buffers: np.ndarray, mask: np.ndarray, thr: float, red: float, alpha: float) -> np.ndarray:
+        """in_buffers (nb, M) f32 raw analysis buffers, mask (nb, M/2+1) f32 updated in place ->
+        (nb, M) f32 irfft of the gated spectrum."""
+        assert in_buffers.dtype == np.float32 and mask.dtype == np.float32
+        assert in_buffers.flags.c_contiguous and mask.flags.c_contiguous
+        y = np.empty_like(in_buffers)
+        check(lib().aes_spectral_frames_host(self._h, C.c_void_p(in_buffers.ctypes.data), C.c_void_p(mask.ctypes.data),
+                                             C.c_void_p(y.ctypes.data), in_buffers.shape[0], thr, red, alpha))
+        return y
+
+    def process_host(self, x: np.ndarray, y: np.ndarray, thr: float, red: float, alpha: float):
+        """Whole clips from the freshly re-initialised state: x, y (B, N, 2) f32 host arrays, M == 2N."""
+        check(lib().aes_spectral_process_host(self._h, C.c_void_p(x.ctypes.data), C.c_void_p(y.ctypes.data),
+                                              x.shape[0], x.shape[1], thr, red, alpha))
+
+    def run_device(self, x_ptr, y_ptr, n_clips, n_frames, thr, red, alpha, stream=0):
+        check(lib().aes_spectral_run(self._h, C.c_void_p(x_ptr), C.c_void_p(y_ptr), n_clips, n_frames,
+                                     thr, red, alpha, C.c_void_p(stream)))
+
+    def close(self):
+        if self._h:
+            lib().aes_spectral_plan_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

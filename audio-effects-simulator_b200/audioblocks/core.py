@@ -272,6 +272,7 @@ class EffectsChain:
         the same freshly prepared state.  Runs of fusable effects are one kernel launch each;
         whole-clip FFT effects (ConvolutionReverbEffect) run between them."""
         from .convreverb import ConvolutionReverbEffect
+        from .spectral import SpectralFilter
         B, frames, ch = x.shape
         self._ensure_blocksize(frames)
         segs, cur = [], []
@@ -280,7 +281,7 @@ class EffectsChain:
                 continue
             if isinstance(e, NativeEffect):
                 cur.append(e)
-            elif isinstance(e, ConvolutionReverbEffect):
+            elif isinstance(e, (ConvolutionReverbEffect, SpectralFilter)):
                 if cur:
                     segs.append(cur)
                     cur = []

@@ -1,15 +1,19 @@
 """Spectral noise filter (reference src/audioblocks/spectral.py:5-100).
 
-The reference block is a per-block rfft -> magnitude mask -> irfft overlap-add with
-one block of latency; on the whole-file path (hop == N) it degenerates to emitting
-the zero-padded half of a single 2N-point frame.  It is the lowest
-priority row of the scope table (8-a8) and has no CUDA implementation yet: the
-class keeps the reference's constructor and setters so presets can be built, and
-fails loudly when asked to process -- there is no CPU fallback."""
+Per block: shift the analysis buffer, rfft of the Hann-windowed frame of 2*hop samples,
+per-bin magnitude gate with a temporally smoothed mask, irfft, overlap-add with one block of
+latency.  hop follows the chain's block size (spectral.py:30-42), so on the whole-file path the
+frame is 2N samples long and the block emits the zero-padded half of a single frame -- near
+silence; that quirk is reproduced, not fixed.
+
+The transforms run on the GPU (csrc/aes_spectral.cuh: Bluestein chirp-z over power-of-two
+FFTs, any frame length); the buffer shifting and the overlap-add bookkeeping around them are
+the same few numpy lines as in the reference.  There is no CPU fallback for the transforms."""
 from __future__ import annotations
 
 import numpy as np
 
+from . import _native
 from .core import Effect, SmoothParam
 
 
@@ -18,18 +22,60 @@ class SpectralFilter(Effect):
         self.threshold_db = SmoothParam(threshold_db, -80.0, 0.0)
         self.reduction = SmoothParam(reduction, 0.0, 1.0)
         self.alpha_param = smoothing
-        self.blocksize = self.hop = 256
-        self.n_fft = 512
+        self._plans: dict[int, _native.SpectralPlan] = {}
+        self._alloc(256)
+
+    def _alloc(self, hop: int):
+        self.blocksize = self.hop = hop
+        self.n_fft = 2 * hop
+        self.in_buffer = np.zeros(self.n_fft, dtype=np.float32)
+        self.out_accum = np.zeros(self.n_fft, dtype=np.float32)
+        self.mask_smooth = np.ones(self.n_fft // 2 + 1, dtype=np.float32)
 
     def set_threshold_db(self, v): self.threshold_db.set_target(v)
     def set_reduction(self, v): self.reduction.set_target(v)
 
     def prepare(self, sample_rate: int, channels_in: int, channels_out: int, blocksize: int):
-        if blocksize != self.hop:
-            self.blocksize = self.hop = blocksize
-            self.n_fft = 2 * blocksize
+        if blocksize != self.hop:                      # re-initialise when the block size changes
+            self._alloc(blocksize)
+
+    def _plan(self, frame_len: int) -> _native.SpectralPlan:
+        pl = self._plans.get(frame_len)
+        if pl is None:
+            for old in self._plans.values():
+                old.close()
+            self._plans = {frame_len: _native.SpectralPlan(frame_len)}
+            pl = self._plans[frame_len]
+        return pl
+
+    def _params(self):
+        th_db = self.threshold_db.step_towards(1.0)
+        red = self.reduction.step_towards(0.05)
+        return 10.0 ** (th_db / 20.0), red
 
     def process_into(self, x_in: np.ndarray, out: np.ndarray) -> None:
-        raise NotImplementedError(
-            "SpectralFilter has no CUDA implementation yet (scope row 8-a8, lowest priority); "
-            "audioblocks (B200) has no CPU fallback")
+        thr, red = self._params()
+        if x_in.shape[0] != self.hop:
+            self._alloc(x_in.shape[0])
+        hop = self.hop
+        self.in_buffer[:-hop] = self.in_buffer[hop:]
+        self.in_buffer[-hop:] = np.mean(x_in, axis=1)
+        mask = self.mask_smooth[None, :].copy()
+        y = self._plan(self.n_fft).frames_host(self.in_buffer[None, :].copy(), mask, thr, red, float(self.alpha_param))
+        self.mask_smooth = mask[0]
+        self.out_accum += y[0]
+        for c in range(out.shape[1]):
+            out[:, c] = self.out_accum[:hop]
+        self.out_accum[:-hop] = self.out_accum[hop:]
+        self.out_accum[-hop:] = 0.0
+
+    def process_batch(self, x: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
+        """Whole clips, every clip from the state a re-prepare at its frame count leaves:
+        x (B, frames, 2) float32 -> (B, frames, 2) float32."""
+        x = np.ascontiguousarray(x, np.float32)
+        if out is None:
+            out = np.empty_like(x)
+        thr, red = self._params()
+        if x.shape[0] and x.shape[1]:
+            self._plan(2 * x.shape[1]).process_host(x, out, thr, red, float(self.alpha_param))
+        return out

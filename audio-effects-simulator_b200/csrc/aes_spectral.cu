@@ -1,0 +1,264 @@
+// aes_spectral.cu -- host side and kernels of the SpectralFilter block (see aes_spectral.cuh).
+#include <algorithm>
+#include <math.h>
+#include <new>
+#include <string.h>
+#include <vector>
+
+#include "aes_common.h"
+#include "aes_chain_kernel.cuh"      // AES_DYN_SMEM
+#include "aes_spectral.cuh"
+
+__global__ void aess_load_kernel(const __grid_constant__ SpecArgs a) { aess_load_body(a); }
+__global__ void aess_global_stage_kernel(const __grid_constant__ SpecArgs a, int st, int inv) { aess_global_stage_body(a, st, inv); }
+__global__ void __launch_bounds__(AESC_NT) aess_local_kernel(const __grid_constant__ SpecArgs a, int inv, int mul) { aess_local_body(a, inv, mul); }
+__global__ void aess_gate_kernel(const __grid_constant__ SpecArgs a) { aess_gate_body(a); }
+__global__ void aess_zero_pad_kernel(const __grid_constant__ SpecArgs a) { aess_zero_pad_body(a); }
+__global__ void aess_store_kernel(const __grid_constant__ SpecArgs a) { aess_store_body(a); }
+
+// whole-clip, fresh-state helpers (spectral.py:30-42 re-initialises at hop == N):
+// frame = [zeros(N), mono * hanning(2N)[N:]], output = first N samples of the irfft, both channels
+__global__ void aess_frames_from_clips_kernel(const float *x, const float *window, float *frames, long long nb, long long N)
+{
+    const long long M = 2 * N, stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nb * M; e += stride) {
+        const long long b = e / M, n = e % M;
+        float v = 0.f;
+        if (n >= N) {
+            const float2 f = reinterpret_cast<const float2 *>(x)[b * N + (n - N)];
+            v = __fmul_rn(__fmul_rn(__fadd_rn(f.x, f.y), 0.5f), window[n]);      // np.mean then * window, f32
+        }
+        frames[e] = v;
+    }
+}
+__global__ void aess_clips_from_frames_kernel(const float *out, float *y, long long nb, long long N)
+{
+    const long long M = 2 * N, stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < nb * N; e += stride) {
+        const long long b = e / N, n = e % N;
+        const float v = out[b * M + n];
+        reinterpret_cast<float2 *>(y)[e] = make_float2(v, v);
+    }
+}
+__global__ void aess_fill_kernel(float *p, float v, long long n)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += stride) p[e] = v;
+}
+
+struct aes_spectral_plan {
+    long long M = 0, P = 0;
+    int L = 0, sms = 148;
+    cpx *d_vhat = nullptr, *d_chirp = nullptr, *d_twP = nullptr, *d_tw1k = nullptr;
+    float *d_window = nullptr;
+    void *d_work = nullptr;          // buf | frames | mask | out | (x | y for the clip entry)
+    size_t work_cap = 0;
+};
+
+static int spec_grid(const aes_spectral_plan *pl) { return pl->sms * 8; }
+
+static int spec_fft(const aes_spectral_plan *pl, const SpecArgs &a, int inverse, int mul, cudaStream_t st)
+{
+    const int g = spec_grid(pl);
+    const unsigned chunks = (unsigned)((long long)a.nb * a.P / 1024);
+    if (!inverse) {
+        for (int s = 0; s <= a.L - 11; ++s) { aess_global_stage_kernel<<<g, 256, 0, st>>>(a, s, 0); aes_count_launch(); }
+        aess_local_kernel<<<chunks, AESC_NT, 1024 * sizeof(cpx), st>>>(a, 0, mul); aes_count_launch();
+    } else {
+        aess_local_kernel<<<chunks, AESC_NT, 1024 * sizeof(cpx), st>>>(a, 1, 0); aes_count_launch();
+        for (int s = 10; s < a.L; ++s) { aess_global_stage_kernel<<<g, 256, 0, st>>>(a, s, 1); aes_count_launch(); }
+    }
+    AES_CUDA(cudaGetLastError());
+    return 0;
+}
+
+// frames (device, windowed) -> out (device, irfft of the gated spectrum); mask updated in place
+static int spec_process(const aes_spectral_plan *pl, SpecArgs a, cudaStream_t st)
+{
+    const int g = spec_grid(pl);
+    int rc;
+    aess_load_kernel<<<g, 256, 0, st>>>(a); aes_count_launch();
+    if ((rc = spec_fft(pl, a, 0, 1, st))) return rc;
+    if ((rc = spec_fft(pl, a, 1, 0, st))) return rc;
+    aess_gate_kernel<<<g, 256, 0, st>>>(a); aes_count_launch();
+    aess_zero_pad_kernel<<<g, 256, 0, st>>>(a); aes_count_launch();
+    if ((rc = spec_fft(pl, a, 0, 1, st))) return rc;
+    if ((rc = spec_fft(pl, a, 1, 0, st))) return rc;
+    aess_store_kernel<<<g, 256, 0, st>>>(a); aes_count_launch();
+    AES_CUDA(cudaGetLastError());
+    return 0;
+}
+
+AES_EXPORT int aes_spectral_plan_destroy(aes_spectral_plan *pl)
+{
+    if (!pl) return 0;
+    if (pl->d_vhat) cudaFree(pl->d_vhat);
+    if (pl->d_chirp) cudaFree(pl->d_chirp);
+    if (pl->d_twP) cudaFree(pl->d_twP);
+    if (pl->d_tw1k) cudaFree(pl->d_tw1k);
+    if (pl->d_window) cudaFree(pl->d_window);
+    if (pl->d_work) cudaFree(pl->d_work);
+    delete pl;
+    return 0;
+}
+
+AES_EXPORT int aes_spectral_plan_create(int64_t frame_len, aes_spectral_plan **out)
+{
+    AES_REQUIRE(out != nullptr, "NULL argument");
+    AES_REQUIRE(frame_len >= 2 && frame_len % 2 == 0 && frame_len <= (1LL << 26), "frame length: even, 2..2^26");
+    aes_spectral_plan *pl = new (std::nothrow) aes_spectral_plan();
+    if (!pl) { aes_set_error("out of host memory"); return AES_ERR_NOMEM; }
+    const long long M = frame_len;
+    long long P = 1024; int L = 10;
+    while (P < 2 * M - 1) { P <<= 1; ++L; }
+    pl->M = M; pl->P = P; pl->L = L;
+    int rc = [&]() -> int {
+        aes_device_sm_count(&pl->sms);
+        std::vector<cpx> chirp((size_t)M), v((size_t)P), twP((size_t)P / 2), tw1k(512);
+        for (long long n = 0; n < M; ++n) {
+            const long long r = (long long)(((unsigned long long)n * (unsigned long long)n) % (unsigned long long)(2 * M));   // n^2 mod 2M, exact
+            const double ang = -M_PI * (double)r / (double)M;
+            chirp[n].x = (float)cos(ang); chirp[n].y = (float)sin(ang);
+        }
+        memset(v.data(), 0, v.size() * sizeof(cpx));
+        for (long long m = 0; m < M; ++m) {                   // v[m] = conj(c[|m|]) at index m mod P
+            cpx c; c.x = chirp[m].x; c.y = -chirp[m].y;
+            v[m] = c;
+            if (m > 0) v[P - m] = c;
+        }
+        for (long long q = 0; q < P / 2; ++q) { const double ang = -2.0 * M_PI * (double)q / (double)P; twP[q].x = (float)cos(ang); twP[q].y = (float)sin(ang); }
+        for (int q = 0; q < 512; ++q) { const double ang = -2.0 * M_PI * q / 1024.0; tw1k[q].x = (float)cos(ang); tw1k[q].y = (float)sin(ang); }
+        std::vector<float> win((size_t)M);
+        for (long long n = 0; n < M; ++n) win[n] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * (double)n / (double)(M - 1)));   // np.hanning(M).astype(f32)
+        AES_CUDA(cudaMalloc(&pl->d_chirp, chirp.size() * sizeof(cpx)));
+        AES_CUDA(cudaMalloc(&pl->d_vhat, v.size() * sizeof(cpx)));
+        AES_CUDA(cudaMalloc(&pl->d_twP, twP.size() * sizeof(cpx)));
+        AES_CUDA(cudaMalloc(&pl->d_tw1k, tw1k.size() * sizeof(cpx)));
+        AES_CUDA(cudaMalloc(&pl->d_window, win.size() * sizeof(float)));
+        AES_CUDA(cudaMemcpy(pl->d_chirp, chirp.data(), chirp.size() * sizeof(cpx), cudaMemcpyHostToDevice));
+        AES_CUDA(cudaMemcpy(pl->d_twP, twP.data(), twP.size() * sizeof(cpx), cudaMemcpyHostToDevice));
+        AES_CUDA(cudaMemcpy(pl->d_tw1k, tw1k.data(), tw1k.size() * sizeof(cpx), cudaMemcpyHostToDevice));
+        AES_CUDA(cudaMemcpy(pl->d_window, win.data(), win.size() * sizeof(float), cudaMemcpyHostToDevice));
+        AES_CUDA(cudaFuncSetAttribute(aess_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * (int)sizeof(cpx)));
+        // vhat = FFT_P(v) / P, kept in bit-reversed order
+        for (auto &e : v) { e.x /= (float)P; e.y /= (float)P; }
+        AES_CUDA(cudaMemcpy(pl->d_vhat, v.data(), v.size() * sizeof(cpx), cudaMemcpyHostToDevice));
+        SpecArgs a; memset(&a, 0, sizeof a);
+        a.buf = pl->d_vhat; a.twP = pl->d_twP; a.tw1k = pl->d_tw1k; a.M = M; a.P = P; a.L = L; a.nb = 1;
+        int r2 = spec_fft(pl, a, 0, 0, nullptr);
+        if (r2) return r2;
+        AES_CUDA(cudaDeviceSynchronize());
+        return 0;
+    }();
+    if (rc) { aes_spectral_plan_destroy(pl); return rc; }
+    *out = pl;
+    return 0;
+}
+
+static int spec_reserve(aes_spectral_plan *pl, size_t bytes)
+{
+    if (pl->work_cap >= bytes) return 0;
+    if (pl->d_work) cudaFree(pl->d_work);
+    pl->d_work = nullptr; pl->work_cap = 0;
+    AES_CUDA(cudaMalloc(&pl->d_work, bytes));
+    pl->work_cap = bytes;
+    return 0;
+}
+
+static size_t al256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+// General entry (any block size, carried state on the host): in_buffers [nb][M] are the raw
+// analysis buffers (the Hann window is applied here), mask [nb][M/2+1] is updated in place,
+// y [nb][M] receives irfft(processed spectrum).  Host pointers.
+AES_EXPORT int aes_spectral_frames_host(aes_spectral_plan *pl, const float *in_buffers, float *mask, float *y,
+                                        int n_frames, double thresh_lin, double reduction, double alpha)
+{
+    AES_REQUIRE(pl != nullptr && in_buffers != nullptr && mask != nullptr && y != nullptr, "NULL argument");
+    if (n_frames <= 0) return 0;
+    const long long M = pl->M, nbins = M / 2 + 1;
+    const size_t s_buf = al256((size_t)pl->P * sizeof(cpx)), s_fr = al256((size_t)M * 4), s_mk = al256((size_t)nbins * 4);
+    int rc = spec_reserve(pl, s_buf + 2 * s_fr + s_mk);
+    if (rc) return rc;
+    char *w = (char *)pl->d_work;
+    SpecArgs a; memset(&a, 0, sizeof a);
+    a.buf = (cpx *)w; a.frames = (float *)(w + s_buf); a.out = (float *)(w + s_buf + s_fr); a.mask = (float *)(w + s_buf + 2 * s_fr);
+    a.vhat = pl->d_vhat; a.chirp = pl->d_chirp; a.twP = pl->d_twP; a.tw1k = pl->d_tw1k;
+    a.M = M; a.P = pl->P; a.L = pl->L; a.nb = 1;
+    a.thr = (float)thresh_lin; a.red = (float)reduction; a.alpha = (float)alpha;
+    std::vector<float> tmp((size_t)M);
+    std::vector<float> win((size_t)M);
+    AES_CUDA(cudaMemcpy(win.data(), pl->d_window, (size_t)M * 4, cudaMemcpyDeviceToHost));
+    for (int f = 0; f < n_frames; ++f) {
+        const float *src = in_buffers + (size_t)f * M;
+        for (long long n = 0; n < M; ++n) tmp[n] = src[n] * win[n];            // f32 product like numpy
+        AES_CUDA(cudaMemcpy((void *)a.frames, tmp.data(), (size_t)M * 4, cudaMemcpyHostToDevice));
+        AES_CUDA(cudaMemcpy(a.mask, mask + (size_t)f * nbins, (size_t)nbins * 4, cudaMemcpyHostToDevice));
+        if ((rc = spec_process(pl, a, nullptr))) return rc;
+        AES_CUDA(cudaMemcpy(y + (size_t)f * M, a.out, (size_t)M * 4, cudaMemcpyDeviceToHost));
+        AES_CUDA(cudaMemcpy(mask + (size_t)f * nbins, a.mask, (size_t)nbins * 4, cudaMemcpyDeviceToHost));
+    }
+    return 0;
+}
+
+// Whole-clip entry with the fresh state the file path produces (hop == N, M == 2N): x, y are
+// DEVICE pointers (n_clips, n_frames, 2) f32; the plan must have been created with frame_len 2N.
+AES_EXPORT int aes_spectral_run(aes_spectral_plan *pl, const float *x, float *y, int64_t n_clips, int64_t n_frames,
+                                double thresh_lin, double reduction, double alpha, void *stream)
+{
+    AES_REQUIRE(pl != nullptr, "plan is NULL");
+    if (n_clips <= 0 || n_frames <= 0) return 0;
+    AES_REQUIRE(x != nullptr && y != nullptr, "NULL device buffer");
+    AES_REQUIRE(pl->M == 2 * n_frames, "plan frame length %lld != 2 * n_frames", pl->M);
+    const long long M = pl->M, nbins = M / 2 + 1;
+    const size_t per = al256((size_t)pl->P * sizeof(cpx)) + 2 * al256((size_t)M * 4) + al256((size_t)nbins * 4);
+    const size_t budget = (size_t)8 << 30;
+    int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_clips, (int64_t)(budget / per)));
+    int rc = spec_reserve(pl, per * (size_t)chunk);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int g = spec_grid(pl);
+    char *w = (char *)pl->d_work;
+    for (int64_t b0 = 0; b0 < n_clips; b0 += chunk) {
+        const int64_t nb = std::min<int64_t>(chunk, n_clips - b0);
+        SpecArgs a; memset(&a, 0, sizeof a);
+        // packed (unaligned-free) layout for nb frames: buf [nb][P] | frames [nb][M] | out [nb][M] | mask [nb][nbins]
+        a.buf = (cpx *)w;
+        float *frames = (float *)(w + (size_t)chunk * al256((size_t)pl->P * sizeof(cpx)));
+        float *outp = frames + (size_t)chunk * M;
+        float *maskp = outp + (size_t)chunk * M;
+        a.frames = frames; a.out = outp; a.mask = maskp;
+        a.vhat = pl->d_vhat; a.chirp = pl->d_chirp; a.twP = pl->d_twP; a.tw1k = pl->d_tw1k;
+        a.M = M; a.P = pl->P; a.L = pl->L; a.nb = (int)nb;
+        a.thr = (float)thresh_lin; a.red = (float)reduction; a.alpha = (float)alpha;
+        aess_frames_from_clips_kernel<<<g, 256, 0, st>>>(x + (size_t)b0 * n_frames * 2, pl->d_window, frames, nb, n_frames);
+        aess_fill_kernel<<<g, 256, 0, st>>>(maskp, 1.0f, nb * nbins);          // mask_smooth starts at ones
+        aes_count_launch(); aes_count_launch();
+        if ((rc = spec_process(pl, a, st))) return rc;
+        aess_clips_from_frames_kernel<<<g, 256, 0, st>>>(outp, y + (size_t)b0 * n_frames * 2, nb, n_frames);
+        aes_count_launch();
+        AES_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+AES_EXPORT int aes_spectral_process_host(aes_spectral_plan *pl, const float *x_host, float *y_host, int64_t n_clips,
+                                         int64_t n_frames, double thresh_lin, double reduction, double alpha)
+{
+    AES_REQUIRE(pl != nullptr && x_host != nullptr && y_host != nullptr, "NULL argument");
+    if (n_clips <= 0 || n_frames <= 0) return 0;
+    const size_t clip_bytes = (size_t)n_frames * 2 * sizeof(float);
+    const int64_t step = std::max<int64_t>(1, std::min<int64_t>(n_clips, (int64_t)(((size_t)1 << 30) / clip_bytes)));
+    float *dx = nullptr, *dy = nullptr;
+    AES_CUDA(cudaMalloc(&dx, clip_bytes * step));
+    if (cudaMalloc(&dy, clip_bytes * step) != cudaSuccess) { cudaFree(dx); aes_set_error("out of device memory"); return AES_ERR_NOMEM; }
+    int rc = 0;
+    for (int64_t b0 = 0; b0 < n_clips && !rc; b0 += step) {
+        const int64_t nb = std::min<int64_t>(step, n_clips - b0);
+        if (cudaMemcpy(dx, x_host + (size_t)b0 * n_frames * 2, clip_bytes * nb, cudaMemcpyHostToDevice) != cudaSuccess) { rc = AES_ERR_CUDA; break; }
+        rc = aes_spectral_run(pl, dx, dy, nb, n_frames, thresh_lin, reduction, alpha, nullptr);
+        if (!rc && cudaMemcpy(y_host + (size_t)b0 * n_frames * 2, dy, clip_bytes * nb, cudaMemcpyDeviceToHost) != cudaSuccess) rc = AES_ERR_CUDA;
+    }
+    cudaFree(dx); cudaFree(dy);
+    if (rc == AES_ERR_CUDA) aes_set_error("CUDA copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return rc;
+}

@@ -149,6 +149,21 @@ int aes_convreverb_process_host(aes_convreverb_plan *plan, const float *x_host, 
                                 int64_t n_frames, double mix_dry, double mix_wet);
 int aes_convreverb_plan_info(const aes_convreverb_plan *plan, int *fft_size, int *partitions);
 
+/* ---- SpectralFilter (spectral.py:44-100): rfft of a Hann-windowed frame of M = 2*hop samples,
+ *      per-bin magnitude gate with a smoothed mask, irfft.  M is arbitrary (even): Bluestein. */
+typedef struct aes_spectral_plan aes_spectral_plan;
+int aes_spectral_plan_create(int64_t frame_len, aes_spectral_plan **plan);
+int aes_spectral_plan_destroy(aes_spectral_plan *plan);
+/* one call of SpectralFilter.process_into per frame (spectral.py:60-77), host pointers:
+ * in_buffers [n][M] raw analysis buffers, mask [n][M/2+1] in/out, y [n][M] = irfft(processed) */
+int aes_spectral_frames_host(aes_spectral_plan *plan, const float *in_buffers, float *mask, float *y, int n_frames,
+                             double thresh_lin, double reduction, double alpha);
+/* whole clips from the freshly re-initialised state (hop == n_frames, M == 2*n_frames): device pointers */
+int aes_spectral_run(aes_spectral_plan *plan, const float *x, float *y, int64_t n_clips, int64_t n_frames,
+                     double thresh_lin, double reduction, double alpha, void *stream);
+int aes_spectral_process_host(aes_spectral_plan *plan, const float *x_host, float *y_host, int64_t n_clips,
+                              int64_t n_frames, double thresh_lin, double reduction, double alpha);
+
 #ifdef __cplusplus
 }
 #endif

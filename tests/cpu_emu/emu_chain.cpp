@@ -8,6 +8,7 @@
 #include "../../audio-effects-simulator_b200/csrc/aes_fast_build.h"
 #include "../../audio-effects-simulator_b200/csrc/aes_biquad_build.h"
 #include "../../audio-effects-simulator_b200/csrc/aes_convreverb.cuh"
+#include "../../audio-effects-simulator_b200/csrc/aes_spectral.cuh"
 
 static char g_err[512];
 
@@ -118,5 +119,57 @@ int emu_convreverb(const float *ir, long long n_taps, const float *x, float *y, 
     // N / AESC_KT == 1 tile of 256 bins at this FFT size
     emu::launch(conv_k2, &l, (unsigned)((N / AESC_KT) * ((B + 1) / 2)), AESC_KT, 2 * P * AESC_KT * 8);
     emu::launch(conv_k3, &l, (unsigned)(B * nblk), AESC_NT, N * 8);
+    return 0;
+}
+
+// ---- SpectralFilter kernels (aes_spectral.cuh) on the emulator ---------------------------------
+struct SpecLaunch { SpecArgs a; int st, inv, mul; };
+static void sp_load(void *p) { aess_load_body(reinterpret_cast<SpecLaunch *>(p)->a); }
+static void sp_glob(void *p) { SpecLaunch *l = reinterpret_cast<SpecLaunch *>(p); aess_global_stage_body(l->a, l->st, l->inv); }
+static void sp_local(void *p) { SpecLaunch *l = reinterpret_cast<SpecLaunch *>(p); aess_local_body(l->a, l->inv, l->mul); }
+static void sp_gate(void *p) { aess_gate_body(reinterpret_cast<SpecLaunch *>(p)->a); }
+static void sp_zero(void *p) { aess_zero_pad_body(reinterpret_cast<SpecLaunch *>(p)->a); }
+static void sp_store(void *p) { aess_store_body(reinterpret_cast<SpecLaunch *>(p)->a); }
+
+static void emu_spec_fft(SpecLaunch &l, int inverse, int mul)
+{
+    const unsigned chunks = (unsigned)((long long)l.a.nb * l.a.P / 1024);
+    if (!inverse) {
+        for (int s = 0; s <= l.a.L - 11; ++s) { l.st = s; l.inv = 0; emu::launch(sp_glob, &l, 4, 256, 0); }
+        l.inv = 0; l.mul = mul; emu::launch(sp_local, &l, chunks, AESC_NT, 1024 * sizeof(cpx));
+    } else {
+        l.inv = 1; l.mul = 0; emu::launch(sp_local, &l, chunks, AESC_NT, 1024 * sizeof(cpx));
+        for (int s = 10; s < l.a.L; ++s) { l.st = s; l.inv = 1; emu::launch(sp_glob, &l, 4, 256, 0); }
+    }
+}
+
+// frames: [nb][M] windowed analysis frames; mask [nb][M/2+1] in/out; y [nb][M] out
+extern "C" __attribute__((visibility("default")))
+int emu_spectral_frames(const float *frames, float *mask, float *y, long long M, int nb, float thr, float red, float alpha)
+{
+    long long P = 1024; int L = 10;
+    while (P < 2 * M - 1) { P <<= 1; ++L; }
+    std::vector<cpx> chirp((size_t)M), v((size_t)P), twP((size_t)P / 2), tw1k(512), buf((size_t)nb * P);
+    for (long long n = 0; n < M; ++n) {
+        const long long r = (long long)(((unsigned long long)n * (unsigned long long)n) % (unsigned long long)(2 * M));
+        const double ang = -M_PI * (double)r / (double)M;
+        chirp[n].x = (float)cos(ang); chirp[n].y = (float)sin(ang);
+    }
+    for (auto &e : v) { e.x = 0.f; e.y = 0.f; }
+    for (long long m = 0; m < M; ++m) { cpx c; c.x = chirp[m].x / (float)P; c.y = -chirp[m].y / (float)P; v[m] = c; if (m > 0) v[P - m] = c; }
+    for (long long q = 0; q < P / 2; ++q) { const double ang = -2.0 * M_PI * (double)q / (double)P; twP[q].x = (float)cos(ang); twP[q].y = (float)sin(ang); }
+    for (int q = 0; q < 512; ++q) { const double ang = -2.0 * M_PI * q / 1024.0; tw1k[q].x = (float)cos(ang); tw1k[q].y = (float)sin(ang); }
+    SpecLaunch l; memset(&l, 0, sizeof l);
+    l.a.twP = twP.data(); l.a.tw1k = tw1k.data(); l.a.M = M; l.a.P = P; l.a.L = L;
+    l.a.buf = v.data(); l.a.nb = 1;
+    emu_spec_fft(l, 0, 0);                               // vhat = FFT(v)/P in place
+    l.a.buf = buf.data(); l.a.vhat = v.data(); l.a.chirp = chirp.data(); l.a.frames = frames; l.a.mask = mask; l.a.out = y;
+    l.a.nb = nb; l.a.thr = thr; l.a.red = red; l.a.alpha = alpha;
+    emu::launch(sp_load, &l, 4, 256, 0);
+    emu_spec_fft(l, 0, 1); emu_spec_fft(l, 1, 0);
+    emu::launch(sp_gate, &l, 4, 256, 0);
+    emu::launch(sp_zero, &l, 4, 256, 0);
+    emu_spec_fft(l, 0, 1); emu_spec_fft(l, 1, 0);
+    emu::launch(sp_store, &l, 4, 256, 0);
     return 0;
 }

@@ -144,8 +144,11 @@ def test_no_cpu_fallback_without_a_device():
     chain.add(ab.StereoDelayEffect())
     with pytest.raises(_native.AesimError):
         chain.process(np.zeros((1024, 1), np.float32), np.zeros((1024, 2), np.float32))
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(_native.AesimError):
         ab.SpectralFilter().process_into(np.zeros((8, 2), np.float32), np.zeros((8, 2), np.float32))
+    with pytest.raises(_native.AesimError):
+        ab.ConvolutionReverbEffect(np.ones((4, 2), np.float32)).process_into(np.zeros((8, 2), np.float32),
+                                                                               np.zeros((8, 2), np.float32))
 
 
 def test_product_never_imports_the_oracle():
