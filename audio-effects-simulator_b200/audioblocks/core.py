@@ -265,6 +265,67 @@ class EffectsChain:
         self._ensure_blocksize(frames)
         return _native.ChainPlan(self.stage_descs(frames), self.sr)
 
+    def device_pipeline(self, frames: int):
+        """Compile the chain for device-resident batches of (B, frames, 2) float32 clips.
+
+        Returns `run(x_ptr, y_ptr, tmp_ptr, n_clips, stream=0)` and the list of plan objects it keeps
+        alive.  x/y/tmp are CUDA device pointers of n_clips*frames*2 floats (tmp is only touched when
+        the chain has more than one segment); runs of fusable effects are one kernel launch each,
+        whole-clip FFT effects (SpectralFilter, ConvolutionReverbEffect) run between them."""
+        from .convreverb import ConvolutionReverbEffect
+        from .spectral import SpectralFilter
+        self._ensure_blocksize(frames)
+        steps, cur, plans = [], [], []
+
+        def flush():
+            if cur:
+                descs = []
+                for e in cur:
+                    e._require_fresh()
+                    descs.extend(e._stages(frames))
+                plan = _native.ChainPlan(descs, self.sr)
+                plans.append(plan)
+                steps.append(lambda xp, yp, B, st, plan=plan: plan.run_device(
+                    xp, _native.FMT_F32_STEREO, yp, _native.FMT_F32_STEREO, B, frames, st))
+                cur.clear()
+
+        for e in self.effects:
+            if isinstance(e, PlotDataTap):
+                continue
+            if isinstance(e, NativeEffect):
+                cur.append(e)
+            elif isinstance(e, SpectralFilter):
+                flush()
+                thr, red = e._params()
+                sp = e._plan(2 * frames)
+                plans.append(sp)
+                steps.append(lambda xp, yp, B, st, sp=sp, thr=thr, red=red, al=float(e.alpha_param):
+                             sp.run_device(xp, yp, B, frames, thr, red, al, st))
+            elif isinstance(e, ConvolutionReverbEffect):
+                flush()
+                cp = e.plan()
+                plans.append(cp)
+                steps.append(lambda xp, yp, B, st, cp=cp, e=e: cp.run_device(xp, yp, B, frames, e.mix_dry, e.mix_wet, st))
+            else:
+                raise TypeError(f"{type(e).__name__} has no CUDA implementation")
+        flush()
+        if not steps:
+            plan = _native.ChainPlan([], self.sr)
+            plans.append(plan)
+            steps.append(lambda xp, yp, B, st, plan=plan: plan.run_device(
+                xp, _native.FMT_F32_STEREO, yp, _native.FMT_F32_STEREO, B, frames, st))
+
+        def run(x_ptr, y_ptr, tmp_ptr, n_clips, stream=0):
+            src = x_ptr
+            for k, step in enumerate(steps):
+                # ping-pong so that the last segment lands in y
+                dst = y_ptr if (len(steps) - 1 - k) % 2 == 0 else tmp_ptr
+                step(src, dst, n_clips, stream)
+                src = dst
+
+        run.n_segments = len(steps)
+        return run, plans
+
     def process_batch(self, x: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
         """x: (B, frames, 1|2) float32 host array (or (B, frames, 2) int16 PCM, which is
         down-mixed like engine.py:78-84) -> (B, frames, 2) float32 or int16 (if `out`

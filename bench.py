@@ -142,6 +142,14 @@ def cpu_run(preset, n_clips, n_frames, threads, reps=1):
         x = np.concatenate([x] * ((n_clips + x.shape[0] - 1) // x.shape[0]))[:n_clips]
     x = np.ascontiguousarray(x)
     cfg = chain_config(preset)
+    if any(c["type"] in ("spectral", "convreverb") for c in cfg):
+        # no C driver for the numpy-FFT blocks: time the oracle's block wrappers, one clip at a time
+        n = min(2, x.shape[0])
+        t0 = time.perf_counter()
+        for b in range(n):
+            orc.run_file_path(cfg, x[b], FS)
+        dt = time.perf_counter() - t0
+        return n * x.shape[1] * 2 / dt / 1e6, dt
     orc.run_batch_c(cfg, x[:threads], FS, threads=threads, fast=True)      # page in / warm caches
     best = float("inf")
     for _ in range(reps):
@@ -293,16 +301,20 @@ def b200_arm(args):
     B = args.clips
     cfg = chain_config(args.preset)
     chain = file_chain(cfg, FS, channels_in=2)            # build@1024 + warm-up, as engine.py:86-99
-    plan = chain.prepare_batch(n_frames)                  # re-prepared at the file's frame count
-    info = plan.info()
+    pipe, plans = chain.device_pipeline(n_frames)         # re-prepared at the file's frame count
+    fused = pipe.n_segments == 1 and isinstance(plans[0], _native.ChainPlan)
+    plan = plans[0] if fused else None
+    info = plan.info() if fused else {"tile_frames": None, "smem_bytes": None, "ctas_per_sm": None,
+                                      "kernel": f"{pipe.n_segments} segments (whole-clip FFT block between fused runs)"}
 
     x = synth_device(torch, B, n_frames, rank * B, dev)
     y = torch.empty_like(x)
+    tmp = torch.empty_like(x) if pipe.n_segments > 1 else y
     stream = torch.cuda.current_stream()
     sptr = stream.cuda_stream
 
     def step():
-        plan.run_device(x.data_ptr(), _native.FMT_F32_STEREO, y.data_ptr(), _native.FMT_F32_STEREO, B, n_frames, sptr)
+        pipe(x.data_ptr(), y.data_ptr(), tmp.data_ptr(), B, sptr)
 
     def barrier():
         if world > 1:
@@ -335,11 +347,23 @@ def b200_arm(args):
         want = orc.run_file_path(cfg, np.ascontiguousarray(xs), FS)
         got = y[0, :n_chk].cpu().numpy()
         mx, snr = synth.err_stats(got, want)
-        parity = {"max_abs_err": mx, "snr_db": snr, "frames": n_chk}
+        parity = {"max_abs_err": mx, "snr_db": snr if np.isfinite(snr) else None, "frames": n_chk}
 
     # ---- end to end through the host-buffer call (pinned host memory, H2D + D2H timed)
     e2e = None
-    if not args.no_e2e:
+    if not args.no_e2e and not fused:
+        xh = _native.pinned_empty((B, n_frames, 2), np.float32)
+        yh = np.empty((B, n_frames, 2), np.float32)
+        torch.from_numpy(xh).copy_(x)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            file_chain(cfg, FS, channels_in=2).process_batch(xh, yh)
+        e2e_s = time.perf_counter() - t0
+        e2e = {"value": world * B * n_frames * 2 * args.e2e_steps / e2e_s / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": int(xh.nbytes), "d2h_bytes_per_step": int(yh.nbytes), "steps": args.e2e_steps,
+               "api": "EffectsChain.process_batch (host buffers, one H2D/D2H per chain segment)"}
+    elif not args.no_e2e:
         Be = B
         xh = _native.pinned_empty((Be, n_frames, 2), np.float32)
         yh = _native.pinned_empty((Be, n_frames, 2), np.float32)
@@ -394,10 +418,13 @@ def b200_arm(args):
             cores = os.cpu_count() or 1
             n_cpu = args.cpu_clips or max(cores, min(2 * cores, 128))
             v, dt = cpu_run(args.preset, n_cpu, n_frames, cores)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": f"{n_cpu} clips x {args.seconds:g} s, {cores} threads, {dt:.2f} s"}
+            numpy_fft = any(c["type"] in ("spectral", "convreverb") for c in cfg)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1 if numpy_fft else cores, "kind": "port",
+                                    "sample": (f"2 clips x {args.seconds:g} s, 1 thread (numpy FFT block), {dt:.2f} s" if numpy_fft
+                                               else f"{n_cpu} clips x {args.seconds:g} s, {cores} threads, {dt:.2f} s")}
         print(json.dumps(line))
-    plan.close()
+    for p in plans:
+        p.close()
     if world > 1:
         dist.destroy_process_group()
 
