@@ -36,6 +36,11 @@ def gather_clips(y_local, total: int, dst: int | None = 0, group=None):
     sizes = shard_sizes(total, world)
     if y_local.shape[0] != sizes[rank]:
         raise ValueError(f"rank {rank}: expected {sizes[rank]} clips, got {y_local.shape[0]}")
+    # NCCL has no 16-bit integer type: ship int16 PCM as bytes and view it back
+    as_bytes = y_local.dtype == torch.int16
+    orig_dtype = y_local.dtype
+    if as_bytes:
+        y_local = y_local.contiguous().view(torch.uint8)
     cap = max(sizes)
     pad = y_local
     if y_local.shape[0] < cap:
@@ -50,7 +55,8 @@ def gather_clips(y_local, total: int, dst: int | None = 0, group=None):
         dist.gather(pad, bufs, dst=dst, group=group)
         if rank != dst:
             return None
-    return torch.cat([b[:n] for b, n in zip(bufs, sizes)], dim=0)
+    full = torch.cat([b[:n] for b, n in zip(bufs, sizes)], dim=0)
+    return full.view(orig_dtype) if as_bytes else full
 
 
 def max_over_ranks(seconds: float, device=None, group=None) -> float:

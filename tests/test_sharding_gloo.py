@@ -49,6 +49,9 @@ def _worker(rank, world, port, total, n):
         y = emu.run(emu.resolved_descs(cfg, 48000, n, 2), 48000, x, grid=2)
         full = sharding.gather_clips(torch.from_numpy(y), total, dst=0)
         every = sharding.gather_clips(torch.from_numpy(y), total, dst=None)
+        q = (np.clip(y, -1, 1) * 32767).astype(np.int16)
+        qfull = sharding.gather_clips(torch.from_numpy(q), total, dst=None)      # int16 PCM travels as bytes
+        assert qfull.dtype == torch.int16 and torch.equal(qfull[lo:hi], torch.from_numpy(q))
         slow = sharding.max_over_ranks(1.0 + rank)
         assert slow == float(world)
         assert every.shape == (total, n, 2)
