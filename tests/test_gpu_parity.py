@@ -311,3 +311,62 @@ def test_clean_noise_removal_preset_and_spectral_golden(ab, orc):
     yb = file_chain(cfg, 48000, channels_in=2).process_batch(xb)
     for b in range(3):
         assert np.max(np.abs(yb[b] - orc.run_file_path(cfg, xb[b], 48000))) <= 1e-5
+
+
+def test_engine_process_wav_file_websocket_reply(ab, orc):
+    """engine.py:67-129 end to end: data-URL WAV in -> JSON reply with the processed WAV, the
+    reply shape the browser expects (assets/02_custom.js:377-390)."""
+    import asyncio
+    import base64
+    import io
+    import json
+    import queue
+    import scipy.io.wavfile
+
+    fs, n = 44100, 30000
+    rng = np.random.default_rng(11)
+    pcm = (rng.uniform(-0.6, 0.6, (n, 2)) * 32767).astype(np.int16)
+    buf = io.BytesIO()
+    scipy.io.wavfile.write(buf, fs, pcm)
+    url = "data:audio/wav;base64," + base64.b64encode(buf.getvalue()).decode("ascii")
+
+    class FakeSocket:
+        def __init__(self): self.sent = []
+        async def send(self, msg): self.sent.append(msg)
+
+    eng = ab.AudioEngine({"input": queue.Queue(10), "output": queue.Queue(10)})
+    cfg = [dict(c, effect_id=f"e{i}") for i, c in enumerate(synth.PRESETS["Robot Voice"])]
+    eng.build_chain(cfg)                                   # live chain: taps + effects + warm-up at 256
+    assert set(eng.effects_map) == {"e0", "e1", "e2"}
+    eng.update_param("e2", "feedback", 0.9)                # SmoothParam route (engine.py:139-143)
+    assert eng.effects_map["e2"].feedback.target == 0.9
+    eng.update_param("e2", "mix_wet", 0.25)                # setter route
+    assert eng.effects_map["e2"].mix_wet == 0.25
+    ws = FakeSocket()
+    asyncio.run(eng.process_wav_file(url, ws))
+    assert len(ws.sent) == 1 and not eng.is_processing_file
+    reply = json.loads(ws.sent[0])
+    assert reply["type"] == "file_processed" and reply["sample_rate"] == fs and reply["original_b64"] == url
+    assert len(reply["original_samples"]) == n and len(reply["processed_samples"]) == n
+    rfs, out_pcm = scipy.io.wavfile.read(io.BytesIO(base64.b64decode(reply["processed_b64"].split(",")[1])))
+    assert rfs == fs and out_pcm.shape == (n, 2) and out_pcm.dtype == np.int16
+    audio = pcm.astype(np.float32) / np.float32(32768.0)
+    mono = orc.mono_downmix(audio)
+    want = orc.quantize_i16(np.clip(orc.run_file_path(synth.PRESETS["Robot Voice"], mono, fs), -1.0, 1.0))
+    assert np.max(np.abs(out_pcm.astype(np.int32) - want.astype(np.int32))) <= 1
+    assert np.max(np.abs(np.array(reply["original_samples"], np.float32) - mono[:, 0])) == 0.0
+
+
+def test_second_block_through_used_delay_lines_fails_loudly(ab):
+    """Whole-clip kernels start from freshly prepared lines; continuing a clip in a second call
+    without prepare() must raise rather than silently drop the tail."""
+    from audioblocks import _native
+    fx = ab.StereoDelayEffect()
+    fx.prepare(48000, 2, 2, 4096)
+    x = synth.clip(1, 4096, 2)
+    out = np.zeros_like(x)
+    fx.process_into(x, out)
+    with pytest.raises(_native.AesimError, match="freshly prepared"):
+        fx.process_into(x, out)
+    fx.prepare(48000, 2, 2, 4096)
+    fx.process_into(x, out)
