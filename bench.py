@@ -385,7 +385,20 @@ def b200_arm(args):
                "h2d_bytes_per_step": int(xh.nbytes), "d2h_bytes_per_step": int(yh.nbytes),
                "steps": args.e2e_steps, "matches_device_path": e2e_ok,
                "api": "EffectsChain.prepare_batch(...).run_host -> aes_chain_process_host (pinned host buffers)"}
-        del xh, yh
+        # the same call fed like the WAV-file route feeds it (engine.py:78-84,104-105): int16 stereo
+        # PCM in (down-mixed on the device), int16 stereo PCM out -- half the PCIe bytes per frame
+        xq = _native.pinned_empty((Be, n_frames, 2), np.int16)
+        yq = _native.pinned_empty((Be, n_frames, 2), np.int16)
+        np.multiply(xh, 32767.0, out=yh)
+        xq[...] = yh.astype(np.int16)
+        plan.run_host(xq, _native.FMT_I16_DOWNMIX, yq, _native.FMT_I16_STEREO, Be, n_frames)
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            plan.run_host(xq, _native.FMT_I16_DOWNMIX, yq, _native.FMT_I16_STEREO, Be, n_frames)
+        pcm_s = time.perf_counter() - t0
+        e2e["pcm16_file_route"] = {"value": world * Be * n_frames * 2 * args.e2e_steps / pcm_s / 1e6, "unit": UNIT,
+                                   "h2d_bytes_per_step": int(xq.nbytes), "d2h_bytes_per_step": int(yq.nbytes)}
+        del xh, yh, xq, yq
 
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
