@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
         L.aes_spectral_frames_host.argtypes = [vp, vp, vp, vp, ci, C.c_double, C.c_double, C.c_double]
         L.aes_spectral_run.argtypes = [vp, vp, vp, i64, i64, C.c_double, C.c_double, C.c_double, vp]
         L.aes_spectral_process_host.argtypes = [vp, vp, vp, i64, i64, C.c_double, C.c_double, C.c_double]
+        L.aes_stream_process_host.argtypes = [C.POINTER(StageDesc), ci, vp, ci, vp, i64]
         if L.aes_abi_version() != 1:
             raise AesimError("libaesim.so ABI version mismatch")
         _lib = L
@@ -143,6 +144,42 @@ class ChainPlan:
             self.close()
         except Exception:
             pass
+
+
+class DeviceBlob:
+    """Zero-initialised device memory holding an effect's delay lines for the streaming path."""
+
+    def __init__(self, n_floats: int):
+        self.n_floats = int(n_floats)
+        self._p = C.c_void_p()
+        check(lib().aes_malloc(C.byref(self._p), max(4, 4 * self.n_floats)))
+        self.zero()
+
+    @property
+    def ptr(self) -> int:
+        return self._p.value
+
+    def zero(self):
+        check(lib().aes_memset(self._p, 0, max(4, 4 * self.n_floats), None))
+        check(lib().aes_stream_sync(None))
+
+    def close(self):
+        if self._p:
+            lib().aes_free(self._p)
+            self._p = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def stream_process(descs, x: np.ndarray, y: np.ndarray):
+    """aes_stream_process_host; `descs` (ctypes array) is updated in place."""
+    assert x.dtype == np.float32 and y.dtype == np.float32 and x.flags.c_contiguous and y.flags.c_contiguous
+    check(lib().aes_stream_process_host(descs, len(descs), C.c_void_p(x.ctypes.data), x.shape[1],
+                                        C.c_void_p(y.ctypes.data), x.shape[0]))
 
 
 class ConvReverbPlan:

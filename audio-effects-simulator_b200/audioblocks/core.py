@@ -98,64 +98,129 @@ class Effect:
         raise NotImplementedError
 
 
+# Blocks of at least this many frames through freshly prepared delay lines take the whole-clip
+# kernels; everything else (warm-up blocks, live 256-frame blocks, continuing a clip) takes the
+# block-streaming kernel with carried state.
+WHOLE_CLIP_MIN_FRAMES = 2048
+
+
 class NativeEffect(Effect):
-    """An effect executed by the CUDA library.  Subclasses resolve their parameters
-    into aes_stage_desc records (`_stages`) and advance their host-visible state
-    (`_advance`); the signal never touches a CPU implementation."""
+    """An effect executed by the CUDA library.  Subclasses resolve their parameters into
+    aes_stage_desc records (`_stages`), size their delay-line state (`_blob_floats`,
+    `_stream_fields`) and mirror the carried scalars on the host (`_advance`, `_absorb`); the
+    signal never touches a CPU implementation."""
 
     _sr = 48000
-    _dirty = False          # True once a non-silent block went through the delay lines
+    _dirty = False          # a non-silent block went through the streaming path: lines are not zero
+    _stale = False          # a whole-clip call consumed the lines without writing them back
+    _n_total = 0            # frames processed since prepare()
+    _blob = None            # device memory of the delay lines (streaming path), allocated lazily
 
     def _stages(self, frames: int) -> list:
         raise NotImplementedError
 
+    def _blob_floats(self) -> int:
+        return 0
+
+    def _stream_fields(self, desc):
+        """Fill the streaming-only descriptor fields (q[28] blob, q[29] frames so far, q[30] ring size)."""
+        desc.q[29] = self._n_total
+
+    def _reset_lines(self):
+        """prepare() rebuilt the delay lines: forget everything that went through them."""
+        self._dirty = False
+        self._stale = False
+        self._n_total = 0
+        self._blob_zero = True
+
+    def _stream_desc(self, frames: int):
+        descs = self._stages(frames)
+        n = self._blob_floats()
+        if n:
+            if self._blob is None or self._blob.n_floats != n:
+                if self._blob is not None:
+                    self._blob.close()
+                self._blob = _native.DeviceBlob(n)
+                self._blob_zero = False
+            elif getattr(self, "_blob_zero", False):
+                self._blob.zero()
+                self._blob_zero = False
+        for d in descs:
+            if n:
+                d.q[28] = self._blob.ptr
+            self._stream_fields(d)
+        return descs
+
     def _advance(self, frames: int, silent: bool, final=None):
-        """Host-visible state after a block of `frames`; `final` holds the stage's carried
+        """Host-visible state after a whole-clip call of `frames`; `final` holds the stage's carried
         scalars read back from the device (None when nothing was run)."""
+        self._n_total += frames
+        if not silent:
+            self._stale = True
+
+    def _absorb(self, desc, frames: int, silent: bool):
+        """Host-visible state after a streamed block: `desc` carries the final scalars."""
+        self._n_total += frames
         if not silent:
             self._dirty = True
 
     def _require_fresh(self):
-        if self._dirty:
+        if self._dirty or self._stale:
             raise _native.AesimError(
                 f"{type(self).__name__}: the whole-clip CUDA path starts every call from freshly "
                 "prepared delay lines; call prepare() (the chain does so whenever the frame count "
                 "changes) before processing another block")
+
+    def _require_usable(self):
+        if self._stale:
+            raise _native.AesimError(
+                f"{type(self).__name__}: a whole-clip call left the delay lines behind (they are not written "
+                "back); call prepare() before streaming further blocks through this effect")
 
     def process_into(self, x_in: np.ndarray, out: np.ndarray) -> None:
         run_native([self], self._sr, x_in, out)
 
 
 def run_native(effects, sample_rate, x_in: np.ndarray, out: np.ndarray):
-    """One fused launch over (frames, channels) host arrays for a run of native effects."""
+    """One block of (frames, channels) host arrays through a run of native effects: one fused
+    whole-clip launch when the block is long and the lines are fresh, else the streaming kernel."""
     frames = x_in.shape[0]
-    descs = []
-    for fx in effects:
-        fx._require_fresh()
-        descs.extend(fx._stages(frames))
     x = np.ascontiguousarray(x_in, np.float32)
-    if x.shape[1] == 1:
-        fmt_in = _native.FMT_F32_MONO
-    elif x.shape[1] == 2:
-        fmt_in = _native.FMT_F32_STEREO
-    else:
+    if x.shape[1] not in (1, 2):
         raise ValueError("audioblocks (B200) processes mono or stereo blocks")
     if out.shape != (frames, 2):
         raise ValueError("output block must be (frames, 2)")
     y = out if (out.dtype == np.float32 and out.flags.c_contiguous) else np.empty((frames, 2), np.float32)
-    finals = [None] * len(descs)
-    if frames > 0:
+    silent = not x.any()
+    whole = frames >= WHOLE_CLIP_MIN_FRAMES and not any(fx._dirty or fx._stale for fx in effects)
+    if frames == 0:
+        pass
+    elif whole:
+        descs = []
+        for fx in effects:
+            descs.extend(fx._stages(frames))
+        fmt_in = _native.FMT_F32_MONO if x.shape[1] == 1 else _native.FMT_F32_STEREO
         plan = _native.ChainPlan(descs, sample_rate)
         try:
             plan.run_host(x, fmt_in, y, _native.FMT_F32_STEREO, 1, frames)
             finals = [plan.final_state(s) for s in range(len(descs))]
         finally:
             plan.close()
+        for fx, final in zip(effects, finals):          # one stage per effect
+            fx._advance(frames, silent, final)
+    else:
+        per_fx = []
+        for fx in effects:
+            fx._require_usable()
+            per_fx.append(fx._stream_desc(frames))
+        arr = _native.desc_array([d for ds in per_fx for d in ds])
+        _native.stream_process(arr, x, y)
+        k = 0
+        for fx, ds in zip(effects, per_fx):
+            fx._absorb(arr[k], frames, silent)
+            k += len(ds)
     if y is not out:
         out[:, :] = y
-    silent = not x.any()
-    for fx, final in zip(effects, finals):          # one stage per effect
-        fx._advance(frames, silent, final)
 
 
 class PlotDataTap(Effect):

@@ -35,7 +35,14 @@ class StereoDelayEffect(NativeEffect):
         self._sr = sample_rate
         self._size = int(sample_rate * self.max_delay_ms / 1000.0) + 1
         self._delay_step_ms = 1000.0 * (self._step_samples / sample_rate)
-        self._dirty = False
+        self._reset_lines()
+
+    def _blob_floats(self):
+        return 2 * self._size
+
+    def _stream_fields(self, desc):
+        desc.q[29] = self._n_total
+        desc.q[30] = self._size
 
     def lags(self, d_left_ms: float):
         """Integer lags with the reference's own float expressions (delay.py:38-40,84);

@@ -27,3 +27,6 @@ class DistortionEffect(NativeEffect):
 
     def _advance(self, frames, silent, final=None):
         pass                      # memoryless
+
+    def _absorb(self, desc, frames, silent):
+        pass

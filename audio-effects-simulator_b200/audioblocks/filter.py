@@ -72,7 +72,13 @@ class FilterEffect(NativeEffect):
                 d.p[8 + 4 * c + k] = float(row[k])
         return [d]
 
+    def _absorb(self, desc, frames, silent):
+        self._n_total += frames
+        for c in range(self._state.shape[0]):
+            self._state[c, :] = [desc.p[8 + 4 * c + k] for k in range(4)]      # stored as f32, filter.py:35-40
+
     def _advance(self, frames, silent, final=None):
+        self._n_total += frames
         # The filter keeps no delay line: its DF-I scalars come back from the device and
         # are stored as float32 between calls, like the reference's state array (filter.py:35-40).
         if final is not None:

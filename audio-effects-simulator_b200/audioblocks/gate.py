@@ -41,6 +41,11 @@ class NoiseGateEffect(NativeEffect):
         self._rel_now = d.p[2]
         return [d]
 
+    def _absorb(self, desc, frames, silent):
+        self._n_total += frames
+        self._gain_state = float(desc.p[3])
+
     def _advance(self, frames, silent, final=None):
+        self._n_total += frames
         if final is not None:
             self._gain_state = float(final[0])      # gain after the block's last frame (gate.py:42)

@@ -28,7 +28,10 @@ class OctaverEffect(NativeEffect):
             # only a ring-size change resets the write pointer and the phasor
             # (octaver.py:108-114): the warm-up phase leaks into the file otherwise
             self.size, self.w, self.phasor = req, 0, 0.0
-            self._dirty = False
+            self._reset_lines()
+
+    def _blob_floats(self):
+        return self.size
 
     def _step(self, semi):
         return (1.0 - 2.0 ** (semi / 12.0)) / self.size          # octaver.py:121-122
@@ -43,7 +46,15 @@ class OctaverEffect(NativeEffect):
         d.p[0], d.p[1], d.p[2] = self.phasor, self._step_now, mix_now
         return [d]
 
+    def _absorb(self, desc, frames, silent):
+        # the streaming kernel iterates the reference's own phasor recurrence (octaver.py:77-80)
+        self.w, self.phasor = int(desc.q[1]), float(desc.p[0])
+        self._n_total += frames
+        if not silent:
+            self._dirty = True
+
     def _advance(self, frames, silent, final=None):
+        self._n_total += frames
         self.w = (self.w + frames) % self.size
         step, ph = self._step_now, self.phasor
         if frames <= 8192:            # the reference's running sum, bit for bit (octaver.py:77-80)
@@ -57,4 +68,4 @@ class OctaverEffect(NativeEffect):
             ph = (ph + frames * step) % 1.0
         self.phasor = ph
         if not silent:
-            self._dirty = True
+            self._stale = True

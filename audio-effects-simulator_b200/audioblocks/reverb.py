@@ -57,7 +57,17 @@ class ReverbEffect(NativeEffect):
         self._delay_step_ms = 1000.0 * (self._step_samples / float(self._fs))
         self._lines = (self._side_lengths(+self._jitter_ms), self._side_lengths(-self._jitter_ms))
         self._pre_size = max(1, int(self._fs * self._max_pre_ms / 1000.0) + 1)
-        self._dirty = False
+        self._reset_lines()
+
+    def _blob_floats(self):
+        n = 32                                            # double lp[2][8]
+        for combs, aps in self._lines:
+            n += self._pre_size + sum(c + 1 for c in combs) + sum(a + 1 for a in aps)
+        return n
+
+    def _stream_fields(self, desc):
+        desc.q[29] = self._n_total
+        desc.q[30] = self._pre_size
 
     def _g_from_rt60(self, L_samples: int, fs: int, rt60_s: float) -> float:
         return 10.0 ** (-3.0 * (float(L_samples) / float(fs)) / max(1e-3, rt60_s))

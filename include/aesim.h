@@ -129,6 +129,16 @@ const char *aes_chain_plan_kernel_name(const aes_chain_plan *plan);
 /* Number of kernel launches issued by this library since load (bench "gpu_launches"). */
 int64_t aes_launch_count(void);
 
+/* ---- block streaming with carried state (the chain's warm-up blocks core.py:131-136 and the
+ *      live 256-frame callback engine.py:156-163): any block size, reference ring layout, the
+ *      reference's per-sample loops in f64.  Extra descriptor fields: q[28] = device pointer of the
+ *      stage's state blob (DELAY ringL[size] ringR[size]; REVERB double lp[2][8] then per side
+ *      pre[size], comb rings L+1, all-pass rings L+1; OCTAVER ring[size]), q[29] = frames since
+ *      prepare(), q[30] = ring size (delay / reverb pre-delay).  `stages` is updated in place
+ *      (q[29], carried scalars) so the caller can keep streaming.  Host buffers. */
+int aes_stream_process_host(aes_stage_desc *stages, int n_stages, const float *x_host, int channels_in,
+                            float *y_host, int64_t frames);
+
 /* ---- single blocks, device pointers (one-stage chains; same semantics) ---------- */
 int aes_delay_f32(const float *x, float *y, int64_t n_clips, int64_t n_frames,
                   int64_t dS_L, int64_t dS_R, double feedback, double mix_dry, double mix_wet,

@@ -366,7 +366,57 @@ def test_second_block_through_used_delay_lines_fails_loudly(ab):
     x = synth.clip(1, 4096, 2)
     out = np.zeros_like(x)
     fx.process_into(x, out)
-    with pytest.raises(_native.AesimError, match="freshly prepared"):
+    with pytest.raises(_native.AesimError, match=r"call prepare\(\)"):
         fx.process_into(x, out)
     fx.prepare(48000, 2, 2, 4096)
     fx.process_into(x, out)
+
+
+@pytest.mark.parametrize("name", NATIVE)
+def test_live_256_frame_blocks_carry_state_like_the_reference(ab, orc, name):
+    """engine.py:38-65,156-163: chain built at blocksize 256, warmed up, then driven block by block;
+    rings, filter state, gate gain and octaver phase are carried from call to call."""
+    cfg = synth.PRESETS[name]
+    ours = ab.EffectsChain(48000, 1, 2, 256)
+    for c in cfg:
+        ours.add(ab.engine.make_effect(c))
+    ours.warmup()
+    ref = orc.build_chain(cfg, 48000, ci=1, bs=256)
+    ref.warmup()
+    x = synth.clip(33, 256 * 40, 1)
+    x = np.ascontiguousarray(np.roll(x, 3000, axis=0))
+    for k in range(40):
+        blk = np.ascontiguousarray(x[256 * k:256 * (k + 1)])
+        got, want = np.zeros((256, 2), np.float32), np.zeros((256, 2), np.float32)
+        ours.process(blk, got)
+        ref.process(blk, want)
+        assert np.max(np.abs(got - want)) <= 1e-5, (name, k)
+
+
+def test_exact_1024_frames_keeps_the_warmup_state(ab, orc):
+    """N == 1024: no re-prepare, the warm-up state of every block carries over (SURVEY 3.1 edge);
+    pinned by a golden vector from the reference."""
+    z, _ = goldens.load("presets")
+    x = synth.clip(9, 1024, 1, 48000)
+    y = run_file(ab, synth.PRESETS["Robot Voice"], x, 48000)
+    check(y, z["n1024_Robot_Voice"], what="n1024")
+
+
+def test_streaming_then_reprepare_then_whole_clip(ab, orc):
+    cfg = synth.PRESETS["Rain Delay"]
+    ours = ab.EffectsChain(48000, 2, 2, 512)
+    for c in cfg:
+        ours.add(ab.engine.make_effect(c))
+    ref = orc.build_chain(cfg, 48000, ci=2, bs=512)
+    x = synth.clip(14, 512 * 6, 2)
+    for k in range(6):                                   # dirty the lines through the streaming path
+        blk = np.ascontiguousarray(x[512 * k:512 * (k + 1)])
+        got, want = np.zeros((512, 2), np.float32), np.zeros((512, 2), np.float32)
+        ours.process(blk, got)
+        ref.process(blk, want)
+        assert np.max(np.abs(got - want)) <= 1e-5, k
+    big = synth.clip(15, 50000, 2)                       # new frame count: re-prepare, whole-clip kernel
+    got, want = np.zeros((50000, 2), np.float32), np.zeros((50000, 2), np.float32)
+    ours.process(big, got)
+    ref.process(big, want)
+    check(got, want, what="whole clip after streaming")
