@@ -1,5 +1,5 @@
-"""Small workload for compute-sanitizer (run on a GPU box):
-    compute-sanitizer --tool racecheck python tests/sanitizer_case.py
+"""Small all-kernels workload (run on a GPU box; compute-sanitizer is closed on this pool, so this is a plain stress run):
+    python tests/all_kernels_case.py
 Pushes every preset (fast + generic kernels), the biquad scan, the convolution reverb and the
 streaming kernel through short clips."""
 import os
