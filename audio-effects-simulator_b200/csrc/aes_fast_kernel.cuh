@@ -293,7 +293,10 @@ __device__ __forceinline__ void aesf_select4(const float4 A, const float4 B, int
 }
 
 // ---- one stage, specialised on its shape code ------------------------------------------------
-template <int FR, int CODE, int S>
+// MPAT >= 0: the comb rings' read misalignments (len - lag, 2 bits per ring, index ch*4+cc) are
+// compile-time constants, so the misalignment switch folds away and aligned rings skip the second
+// vector load; MPAT < 0: read them from the descriptors at run time.
+template <int FR, int CODE, int S, int MPAT>
 __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRegs &sr, float (&v)[2][FR],
                                            const float4 (&lnA)[2], const float4 (&lnB)[2], const double *sin, double *sout)
 {
@@ -381,7 +384,8 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
 #pragma unroll
             for (int cc = 0; cc < NC; ++cc) {
                 const FRing rg = st.ring[ch][cc];
-                aesf_read<FR, 0>(c.rings + rg.off, sr.w[ch][cc], rg.len - rg.lag, rg.len, y[ch][cc]);
+                const int m = MPAT >= 0 ? ((MPAT >> (2 * (ch * 4 + cc))) & 3) : rg.len - rg.lag;
+                aesf_read<FR, 0>(c.rings + rg.off, sr.w[ch][cc], m, rg.len, y[ch][cc]);
                 float u = 0.0f;
 #pragma unroll
                 for (int j = 0; j < FR; ++j) u = fmaf(h, u, y[ch][cc][j]);
@@ -703,7 +707,7 @@ __device__ __forceinline__ void aesf_issue_tile(const FastArgs &a, const FCtx &c
 #endif
 }
 
-template <int FR, int C0, int C1, int C2, int C3>
+template <int FR, int C0, int C1, int C2, int C3, int MPAT = -1>
 __device__ void aes_fast_body(const FastArgs &a)
 {
     constexpr int T = AES_NT * FR;
@@ -802,10 +806,10 @@ __device__ void aes_fast_body(const FastArgs &a)
             }
             const double *sin = state + par * NST;
             double *sout = state + (par ^ 1) * NST;
-            if (C0) aesf_stage<FR, C0, 0>(a, c, sr0, v, lnA, lnB, sin, sout);
-            if (C1) aesf_stage<FR, C1, 1>(a, c, sr1, v, lnA, lnB, sin + 8, sout + 8);
-            if (C2) aesf_stage<FR, C2, 2>(a, c, sr2, v, lnA, lnB, sin + 16, sout + 16);
-            if (C3) aesf_stage<FR, C3, 3>(a, c, sr3, v, lnA, lnB, sin + 24, sout + 24);
+            if (C0) aesf_stage<FR, C0, 0, MPAT>(a, c, sr0, v, lnA, lnB, sin, sout);
+            if (C1) aesf_stage<FR, C1, 1, MPAT>(a, c, sr1, v, lnA, lnB, sin + 8, sout + 8);
+            if (C2) aesf_stage<FR, C2, 2, MPAT>(a, c, sr2, v, lnA, lnB, sin + 16, sout + 16);
+            if (C3) aesf_stage<FR, C3, 3, MPAT>(a, c, sr3, v, lnA, lnB, sin + 24, sout + 24);
             aes_store_frames<FR>(io, b, n0, c.len, c.tid, v);
             if (C0) aesf_slots_advance<FR, C0, 0>(a, sr0);
             if (C1) aesf_slots_advance<FR, C1, 1>(a, sr1);
@@ -829,9 +833,9 @@ __device__ void aes_fast_body(const FastArgs &a)
 #define AESF_MIN_CTAS 2
 #endif
 #ifndef AES_CPU_EMU
-template <int FR, int C0, int C1, int C2, int C3>
+template <int FR, int C0, int C1, int C2, int C3, int MPAT>
 __global__ void __launch_bounds__(AES_NT, AESF_MIN_CTAS) aes_fast_kernel(const __grid_constant__ FastArgs a)
 {
-    aes_fast_body<FR, C0, C1, C2, C3>(a);
+    aes_fast_body<FR, C0, C1, C2, C3, MPAT>(a);
 }
 #endif
