@@ -28,7 +28,7 @@ struct HostSlot {
 
 // ---- shape-specialised kernels (aes_fast_kernel.cuh): launch table -----------------------
 typedef void (*fast_kernel_t)(const FastArgs);
-struct FastShape { int c[AESF_MAX_STAGES]; int mpat; fast_kernel_t fn; };
+struct FastShape { int c[AESF_MAX_STAGES]; int topo; fast_kernel_t fn; };
 #define X(c0, c1, c2, c3, mp) { { c0, c1, c2, c3 }, mp, aes_fast_kernel<4, c0, c1, c2, c3, mp> },
 static const FastShape g_fast_shapes[] = { AESF_SHAPES(X) };
 #undef X
@@ -153,10 +153,10 @@ AES_EXPORT int aes_chain_plan_create(const aes_stage_desc *stages, int n_stages,
         int codes[AESF_MAX_STAGES];
         if (!getenv("AES_NO_FAST") && aes_fast_build(pl->host, &pl->fast, codes, lane_tab)) {
             const size_t fast_smem = aes_fast_smem_bytes(pl->host);
-            const int mpat = aes_fast_mpat(pl->host);
-            for (const FastShape &sh : g_fast_shapes) {      // exact-misalignment instantiations come first
+            const int topo = aes_fast_topo(pl->host);
+            for (const FastShape &sh : g_fast_shapes) {      // compile-time topologies come first
                 if (memcmp(sh.c, codes, sizeof codes) != 0 || fast_smem > AES_SMEM_LIMIT) continue;
-                if (sh.mpat != AESF_MPAT_ANY && sh.mpat != mpat) continue;
+                if (sh.topo != AESF_TOPO_NONE && sh.topo != topo) continue;
                 AES_CUDA(cudaFuncSetAttribute(sh.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
                 int occ = 0;
                 AES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sh.fn, AES_NT, fast_smem));

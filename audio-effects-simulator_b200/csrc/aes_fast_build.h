@@ -16,50 +16,51 @@
 #define AESF_OCTAVER    AESF_CODE(AESK_OCTAVER, 0, 0, 0, 0, 0)
 #define AESF_DIST       AESF_CODE(AESK_DISTORTION, 0, 0, 0, 0, 0)
 
-// comb read misalignments (roundup4(L) - L, 2 bits per ring, index side*4 + comb) of the reference's
-// default reverb topology at 48 kHz: L = 1440 1795 1987 2112 | R = 1411 1766 1958 2083
-// (reverb.py:74-81,158-177) -> 0 1 1 0 | 1 2 2 1.  Every reverb preset uses it.
-#define AESF_MPAT_48K 0x6914
-#define AESF_MPAT_ANY (-1)
-
-// X(C0, C1, C2, C3, MPAT): the shapes instantiated for FR = 4 (T = 1024 frames).
+// X(C0, C1, C2, C3, TOPO): the shapes instantiated for FR = 4 (T = 1024 frames).  Reverb shapes come
+// with the compile-time topologies of aes_fast_kernel.cuh first and the run-time variant last.
 #define AESF_SHAPES(X)                                                                                  \
-    X(AESF_DELAY_PF, 0, 0, 0, AESF_MPAT_ANY)                       /* Slapback Echo                  */ \
-    X(AESF_DELAY_REG, 0, 0, 0, AESF_MPAT_ANY)                                                           \
-    X(AESF_DELAY_WALK, 0, 0, 0, AESF_MPAT_ANY)                                                          \
-    X(AESF_DELAY_PF, AESF_REVERB(0), 0, 0, AESF_MPAT_48K)          /* Rain Delay                     */ \
-    X(AESF_DELAY_PF, AESF_REVERB(0), 0, 0, AESF_MPAT_ANY)                                               \
-    X(AESF_REVERB(0), 0, 0, 0, AESF_MPAT_48K)                      /* default reverb                 */ \
-    X(AESF_REVERB(0), 0, 0, 0, AESF_MPAT_ANY)                                                           \
-    X(AESF_REVERB(1), 0, 0, 0, AESF_MPAT_ANY)                                                           \
-    X(AESF_REVERB(2), 0, 0, 0, AESF_MPAT_48K)                      /* Cathedral (20 ms pre-delay)    */ \
-    X(AESF_REVERB(2), 0, 0, 0, AESF_MPAT_ANY)                                                           \
-    X(AESF_BIQUAD, AESF_REVERB(0), 0, 0, AESF_MPAT_48K)            /* Guitar Filter                  */ \
-    X(AESF_BIQUAD, AESF_REVERB(0), 0, 0, AESF_MPAT_ANY)                                                 \
-    X(AESF_GATE, AESF_OCTAVER, AESF_DELAY_PF, 0, AESF_MPAT_ANY)    /* Robot Voice                    */ \
-    X(AESF_DIST, AESF_OCTAVER, AESF_DELAY_PF, 0, AESF_MPAT_ANY)    /* BASELINE configs[2]            */ \
-    X(AESF_BIQUAD, 0, 0, 0, AESF_MPAT_ANY)                                                              \
-    X(AESF_BIQUAD, AESF_BIQUAD, AESF_BIQUAD, AESF_BIQUAD, AESF_MPAT_ANY)   /* BASELINE configs[1]    */ \
-    X(AESF_GATE, 0, 0, 0, AESF_MPAT_ANY)                                                                \
-    X(AESF_OCTAVER, 0, 0, 0, AESF_MPAT_ANY)                                                             \
-    X(AESF_DIST, 0, 0, 0, AESF_MPAT_ANY)
+    X(AESF_DELAY_PF, 0, 0, 0, AESF_TOPO_NONE)                       /* Slapback Echo                  */ \
+    X(AESF_DELAY_REG, 0, 0, 0, AESF_TOPO_NONE)                                                           \
+    X(AESF_DELAY_WALK, 0, 0, 0, AESF_TOPO_NONE)                                                          \
+    X(AESF_DELAY_PF, AESF_REVERB(0), 0, 0, AESF_TOPO_48K)          /* Rain Delay                     */ \
+    X(AESF_DELAY_PF, AESF_REVERB(0), 0, 0, AESF_TOPO_44K)                                               \
+    X(AESF_DELAY_PF, AESF_REVERB(0), 0, 0, AESF_TOPO_NONE)                                               \
+    X(AESF_REVERB(0), 0, 0, 0, AESF_TOPO_48K)                      /* default reverb                 */ \
+    X(AESF_REVERB(0), 0, 0, 0, AESF_TOPO_44K)                                                           \
+    X(AESF_REVERB(0), 0, 0, 0, AESF_TOPO_NONE)                                                           \
+    X(AESF_REVERB(1), 0, 0, 0, AESF_TOPO_NONE)                                                           \
+    X(AESF_REVERB(2), 0, 0, 0, AESF_TOPO_48K)                      /* Cathedral (20 ms pre-delay)    */ \
+    X(AESF_REVERB(2), 0, 0, 0, AESF_TOPO_44K)                                                           \
+    X(AESF_REVERB(2), 0, 0, 0, AESF_TOPO_NONE)                                                           \
+    X(AESF_BIQUAD, AESF_REVERB(0), 0, 0, AESF_TOPO_48K)            /* Guitar Filter                  */ \
+    X(AESF_BIQUAD, AESF_REVERB(0), 0, 0, AESF_TOPO_44K)                                                 \
+    X(AESF_BIQUAD, AESF_REVERB(0), 0, 0, AESF_TOPO_NONE)                                                 \
+    X(AESF_GATE, AESF_OCTAVER, AESF_DELAY_PF, 0, AESF_TOPO_NONE)    /* Robot Voice                    */ \
+    X(AESF_DIST, AESF_OCTAVER, AESF_DELAY_PF, 0, AESF_TOPO_NONE)    /* BASELINE configs[2]            */ \
+    X(AESF_BIQUAD, 0, 0, 0, AESF_TOPO_NONE)                                                              \
+    X(AESF_BIQUAD, AESF_BIQUAD, AESF_BIQUAD, AESF_BIQUAD, AESF_TOPO_NONE)   /* BASELINE configs[1]    */ \
+    X(AESF_GATE, 0, 0, 0, AESF_TOPO_NONE)                                                                \
+    X(AESF_OCTAVER, 0, 0, 0, AESF_TOPO_NONE)                                                             \
+    X(AESF_DIST, 0, 0, 0, AESF_TOPO_NONE)
 
-// misalignment pattern of the plan's (single) reverb stage, or -1 when there is none / several
-static inline int aes_fast_mpat(const DevPlan &p)
+// compile-time topology (aes_fast_kernel.cuh) matching the plan's single reverb stage, or 0
+static inline int aes_fast_topo(const DevPlan &p)
 {
-    int pat = -1, n = 0;
+    int n = 0, topo = AESF_TOPO_NONE;
     for (int s = 0; s < p.n_stages; ++s) {
         const DevStage &d = p.stage[s];
         if (d.kind != AESK_REVERB) continue;
-        if (++n > 1 || d.nc != 4) return -1;
-        pat = 0;
-        for (int ch = 0; ch < 2; ++ch)
-            for (int c = 0; c < 4; ++c) {
-                const DevRing &r = p.ring[d.ring[ch][c]];
-                pat |= ((r.len - r.lag) & 3) << (2 * (ch * 4 + c));
+        if (++n > 1 || d.nc != 4 || d.na != 2) return AESF_TOPO_NONE;
+        for (int t = AESF_TOPO_48K; t <= AESF_TOPO_44K && topo == AESF_TOPO_NONE; ++t) {
+            bool same = true;
+            for (int ch = 0; ch < 2; ++ch) {
+                for (int c = 0; c < 4; ++c) same = same && p.ring[d.ring[ch][c]].lag == aesf_topo_comb(t, ch, c);
+                for (int k = 0; k < 2; ++k) same = same && p.ring[d.apring[ch][k]].lag == aesf_topo_ap(t, ch, k);
             }
+            if (same) topo = t;
+        }
     }
-    return pat;
+    return topo;
 }
 
 // dynamic shared memory of a specialised kernel: the generic layout (superset of what the

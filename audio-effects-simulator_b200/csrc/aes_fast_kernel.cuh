@@ -188,6 +188,42 @@ __device__ __forceinline__ void aesf_read(const float *rb, int a0, int m, int le
     }
 }
 
+// ---- compile-time reverb topologies ---------------------------------------------------------
+// The reference's reverb has one default set of comb / all-pass times (reverb.py:74-81,158-177;
+// SURVEY 3.1), so every reverb preset resolves to the same delay lengths at a given sample rate.
+// TOPO > 0 bakes them into the kernel: ring periods, wrap compares, tile increments and the
+// comb read misalignments become immediates, the misalignment switch folds away, and the
+// all-pass walks unroll completely.  TOPO == 0 reads everything from the descriptors.
+//   TOPO 1: 48 000 Hz    TOPO 2: 44 100 Hz
+#define AESF_TOPO_NONE 0
+#define AESF_TOPO_48K 1
+#define AESF_TOPO_44K 2
+__host__ __device__ constexpr int aesf_topo_comb(int topo, int ch, int cc)
+{
+    return topo == 1 ? (ch == 0 ? (cc == 0 ? 1440 : cc == 1 ? 1795 : cc == 2 ? 1987 : 2112)
+                                : (cc == 0 ? 1411 : cc == 1 ? 1766 : cc == 2 ? 1958 : 2083))
+         : topo == 2 ? (ch == 0 ? (cc == 0 ? 1323 : cc == 1 ? 1649 : cc == 2 ? 1825 : 1940)
+                                : (cc == 0 ? 1296 : cc == 1 ? 1622 : cc == 2 ? 1799 : 1913))
+                     : 0;
+}
+__host__ __device__ constexpr int aesf_topo_ap(int topo, int ch, int k)
+{
+    return topo == 1 ? (ch == 0 ? (k == 0 ? 242 : 84) : (k == 0 ? 237 : 78))
+         : topo == 2 ? (ch == 0 ? (k == 0 ? 223 : 77) : (k == 0 ? 217 : 72))
+                     : 0;
+}
+// comb ring descriptor: the offset always comes from the launch, the rest is constant under TOPO
+template <int TOPO, int FR>
+__device__ __forceinline__ FRing aesf_comb_ring(const FastStage &st, int ch, int cc)
+{
+    FRing rg = st.ring[ch][cc];
+    if (TOPO) {
+        const int L = aesf_topo_comb(TOPO, ch, cc), len = (L + 3) & ~3;
+        rg.len = len; rg.lag = L; rg.tinc = (AES_NT * FR) % len;
+    }
+    return rg;
+}
+
 // ---- phase walk on the smem tile for a WALK ring described in the parameter bank --------
 template <int FR, int OP>
 __device__ __forceinline__ void aesf_walk(const FCtx &c, const FRing rg, int ring_id, bool glob, float p0, float p1, float p2)
@@ -242,6 +278,66 @@ __device__ __forceinline__ void aesf_walk(const FCtx &c, const FRing rg, int rin
     }
 }
 
+// all-pass walk with a compile-time length L (< T): column j of the tile, seen as rows of L
+// samples, is one serial chain  y = line - g*x,  line' = x + g*y  down the rows; the chain's
+// state enters from / leaves to the ring (length L, phase `pos`).  Full tiles only.
+template <int FR, int L>
+__device__ __forceinline__ void aesf_ap_static(const FCtx &c, int off, int ring_id, float g)
+{
+    constexpr int T = AES_NT * FR;
+    static_assert(L > 0 && L < T, "");
+    const int ch = c.tid >> 7, j0 = c.tid & 127;
+    float *rb = c.rings + off;
+    const int pos = c.rpos[ring_id];
+    float *s = c.tile + ch * T;
+#pragma unroll
+    for (int r = 0; r < (L + 127) / 128; ++r) {
+        const int j = j0 + 128 * r;
+        if (128 * r + 127 < L || j < L) {
+            constexpr int KMAX = (T + L - 1) / L;           // rows that can hold column j
+            int slot = pos + j;
+            if (slot >= L) slot -= L;
+            float line = rb[slot];
+            if (c.n0 == 0) line = 0.0f;                     // L < T: only the first tile has no history
+            float xs[KMAX];
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                if (128 * r + 127 + k * L < T) xs[k] = s[j + k * L];            // row k is complete for this trip
+                else if (128 * r + k * L < T) xs[k] = (j + k * L < T) ? s[j + k * L] : 0.0f;
+            }
+#pragma unroll
+            for (int k = 0; k < KMAX; ++k) {
+                if (128 * r + 127 + k * L < T) {
+                    const float yo = fmaf(-g, xs[k], line);
+                    s[j + k * L] = yo;
+                    line = fmaf(g, yo, xs[k]);
+                } else if (128 * r + k * L < T) {
+                    if (j + k * L < T) {
+                        const float yo = fmaf(-g, xs[k], line);
+                        s[j + k * L] = yo;
+                        line = fmaf(g, yo, xs[k]);
+                    }
+                }
+            }
+            rb[slot] = line;
+        }
+    }
+}
+
+// all-pass K of a reverb stage over the tile in shared memory (threads 0..127 left, 128..255 right)
+template <int FR, int TOPO, int K>
+__device__ __forceinline__ void aesf_allpass(const FastArgs &a, const FastStage &st, const FCtx &c)
+{
+    const int ch = c.tid >> 7;
+    if (TOPO != 0 && c.len == AES_NT * FR) {            // full tile: unrolled walk, constant length
+        constexpr int TP = TOPO ? TOPO : 1;
+        if (ch == 0) aesf_ap_static<FR, aesf_topo_ap(TP, 0, K)>(c, a.walk[st.walk_ap[0][K]].off, st.walk_ap[0][K], st.a);
+        else         aesf_ap_static<FR, aesf_topo_ap(TP, 1, K)>(c, a.walk[st.walk_ap[1][K]].off, st.walk_ap[1][K], st.a);
+    } else {
+        aesf_walk<FR, 2>(c, a.walk[st.walk_ap[ch][K]], st.walk_ap[ch][K], false, st.a, 0.f, 0.f);
+    }
+}
+
 template <int FR> __device__ __forceinline__ void aesf_spill(const FCtx &c, const float (&v)[2][FR])
 {
     constexpr int T = AES_NT * FR;
@@ -293,10 +389,7 @@ __device__ __forceinline__ void aesf_select4(const float4 A, const float4 B, int
 }
 
 // ---- one stage, specialised on its shape code ------------------------------------------------
-// MPAT >= 0: the comb rings' read misalignments (len - lag, 2 bits per ring, index ch*4+cc) are
-// compile-time constants, so the misalignment switch folds away and aligned rings skip the second
-// vector load; MPAT < 0: read them from the descriptors at run time.
-template <int FR, int CODE, int S, int MPAT>
+template <int FR, int CODE, int S, int TOPO>
 __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRegs &sr, float (&v)[2][FR],
                                            const float4 (&lnA)[2], const float4 (&lnB)[2], const double *sin, double *sout)
 {
@@ -383,9 +476,8 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
         for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
             for (int cc = 0; cc < NC; ++cc) {
-                const FRing rg = st.ring[ch][cc];
-                const int m = MPAT >= 0 ? ((MPAT >> (2 * (ch * 4 + cc))) & 3) : rg.len - rg.lag;
-                aesf_read<FR, 0>(c.rings + rg.off, sr.w[ch][cc], m, rg.len, y[ch][cc]);
+                const FRing rg = aesf_comb_ring<TOPO, FR>(st, ch, cc);
+                aesf_read<FR, 0>(c.rings + rg.off, sr.w[ch][cc], rg.len - rg.lag, rg.len, y[ch][cc]);
                 float u = 0.0f;
 #pragma unroll
                 for (int j = 0; j < FR; ++j) u = fmaf(h, u, y[ch][cc][j]);
@@ -430,7 +522,7 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
                     for (int t = u0; t < warp; ++t) C = fmaf(hw, C, wt[(t * 2 + ch) * 4 + cc]);
                 }
                 float u = fmaf(hl, C, lane == 0 ? 0.0f : ex);
-                const FRing rg = st.ring[ch][cc];
+                const FRing rg = aesf_comb_ring<TOPO, FR>(st, ch, cc);
                 const float gs = st.gs[ch][cc];
                 float nb[FR];
 #pragma unroll
@@ -445,12 +537,9 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
         }
         aesf_spill<FR>(c, sum);
         __syncthreads();
-#pragma unroll
-        for (int k = 0; k < NA; ++k) {
-            const int ch = c.tid >> 7;
-            aesf_walk<FR, 2>(c, a.walk[st.walk_ap[ch][k]], st.walk_ap[ch][k], false, st.a, 0.f, 0.f);
-            __syncthreads();
-        }
+        static_assert(NA <= 2, "");
+        if (NA > 0) { aesf_allpass<FR, TOPO, 0>(a, st, c); __syncthreads(); }
+        if (NA > 1) { aesf_allpass<FR, TOPO, 1>(a, st, c); __syncthreads(); }
         aesf_reload<FR>(c, sum);
         const float dry = st.dry, wet = st.wet;
 #pragma unroll
@@ -622,7 +711,7 @@ __device__ __forceinline__ void aesf_slots_init(const FastArgs &a, int i0, SRegs
     }
 }
 
-template <int FR, int CODE, int S>
+template <int FR, int CODE, int S, int TOPO>
 __device__ __forceinline__ void aesf_slots_advance(const FastArgs &a, SRegs &sr)
 {
     constexpr int KIND = AESF_KIND(CODE);
@@ -648,7 +737,7 @@ __device__ __forceinline__ void aesf_slots_advance(const FastArgs &a, SRegs &sr)
         for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
             for (int cc = 0; cc < AESF_NC(CODE); ++cc) {
-                const FRing rg = st.ring[ch][cc];
+                const FRing rg = aesf_comb_ring<TOPO, FR>(st, ch, cc);
                 sr.w[ch][cc] = aesf_adv(sr.w[ch][cc], rg.tinc, rg.len);
             }
     }
@@ -707,7 +796,7 @@ __device__ __forceinline__ void aesf_issue_tile(const FastArgs &a, const FCtx &c
 #endif
 }
 
-template <int FR, int C0, int C1, int C2, int C3, int MPAT = -1>
+template <int FR, int C0, int C1, int C2, int C3, int TOPO = 0>
 __device__ void aes_fast_body(const FastArgs &a)
 {
     constexpr int T = AES_NT * FR;
@@ -806,15 +895,15 @@ __device__ void aes_fast_body(const FastArgs &a)
             }
             const double *sin = state + par * NST;
             double *sout = state + (par ^ 1) * NST;
-            if (C0) aesf_stage<FR, C0, 0, MPAT>(a, c, sr0, v, lnA, lnB, sin, sout);
-            if (C1) aesf_stage<FR, C1, 1, MPAT>(a, c, sr1, v, lnA, lnB, sin + 8, sout + 8);
-            if (C2) aesf_stage<FR, C2, 2, MPAT>(a, c, sr2, v, lnA, lnB, sin + 16, sout + 16);
-            if (C3) aesf_stage<FR, C3, 3, MPAT>(a, c, sr3, v, lnA, lnB, sin + 24, sout + 24);
+            if (C0) aesf_stage<FR, C0, 0, TOPO>(a, c, sr0, v, lnA, lnB, sin, sout);
+            if (C1) aesf_stage<FR, C1, 1, TOPO>(a, c, sr1, v, lnA, lnB, sin + 8, sout + 8);
+            if (C2) aesf_stage<FR, C2, 2, TOPO>(a, c, sr2, v, lnA, lnB, sin + 16, sout + 16);
+            if (C3) aesf_stage<FR, C3, 3, TOPO>(a, c, sr3, v, lnA, lnB, sin + 24, sout + 24);
             aes_store_frames<FR>(io, b, n0, c.len, c.tid, v);
-            if (C0) aesf_slots_advance<FR, C0, 0>(a, sr0);
-            if (C1) aesf_slots_advance<FR, C1, 1>(a, sr1);
-            if (C2) aesf_slots_advance<FR, C2, 2>(a, sr2);
-            if (C3) aesf_slots_advance<FR, C3, 3>(a, sr3);
+            if (C0) aesf_slots_advance<FR, C0, 0, TOPO>(a, sr0);
+            if (C1) aesf_slots_advance<FR, C1, 1, TOPO>(a, sr1);
+            if (C2) aesf_slots_advance<FR, C2, 2, TOPO>(a, sr2);
+            if (C3) aesf_slots_advance<FR, C3, 3, TOPO>(a, sr3);
             if (c.tid < nw) {
                 const FRing rg = a.walk[c.tid];
                 int p = c.rpos[c.tid] + rg.tinc;
@@ -833,9 +922,9 @@ __device__ void aes_fast_body(const FastArgs &a)
 #define AESF_MIN_CTAS 2
 #endif
 #ifndef AES_CPU_EMU
-template <int FR, int C0, int C1, int C2, int C3, int MPAT>
+template <int FR, int C0, int C1, int C2, int C3, int TOPO>
 __global__ void __launch_bounds__(AES_NT, AESF_MIN_CTAS) aes_fast_kernel(const __grid_constant__ FastArgs a)
 {
-    aes_fast_body<FR, C0, C1, C2, C3, MPAT>(a);
+    aes_fast_body<FR, C0, C1, C2, C3, TOPO>(a);
 }
 #endif

@@ -17,12 +17,12 @@ template <int C0, int C1, int C2, int C3, int MP> static void fentry(void *p)
 {
     aes_fast_body<4, C0, C1, C2, C3, MP>(*reinterpret_cast<FastArgs *>(p));
 }
-struct FastShape { int c[4]; int mpat; void (*fn)(void *); };
+struct FastShape { int c[4]; int topo; void (*fn)(void *); };
 #define X(c0, c1, c2, c3, mp) { { c0, c1, c2, c3 }, mp, fentry<c0, c1, c2, c3, mp> },
 static const FastShape g_shapes[] = { AESF_SHAPES(X) };
 #undef X
-static int g_last_fast = 0, g_last_mpat = -1;
-extern "C" __attribute__((visibility("default"))) int emu_last_mpat() { return g_last_mpat; }
+static int g_last_fast = 0, g_last_topo = 0;
+extern "C" __attribute__((visibility("default"))) int emu_last_topo() { return g_last_topo; }
 extern "C" __attribute__((visibility("default"))) int emu_last_was_fast() { return g_last_fast; }
 
 extern "C" __attribute__((visibility("default")))
@@ -44,11 +44,11 @@ int emu_chain_run(const aes_stage_desc *stages, int n, int fs, const void *x, in
     static float lane_tab[AESF_MAX_STAGES * 32 * FAST_LANE_STRIDE];
     int codes[4];
     if (!getenv("AES_NO_FAST") && aes_fast_build(plan, &fa, codes, lane_tab)) {
-        const int mpat = aes_fast_mpat(plan);
+        const int topo = aes_fast_topo(plan);
         for (const FastShape &sh : g_shapes) {
             if (memcmp(sh.c, codes, sizeof codes) != 0) continue;
-            if (sh.mpat != AESF_MPAT_ANY && sh.mpat != mpat) continue;
-            g_last_mpat = sh.mpat;
+            if (sh.topo != AESF_TOPO_NONE && sh.topo != topo) continue;
+            g_last_topo = sh.topo;
             fa.x = x; fa.y = y; fa.B = B; fa.N = N; fa.scratch = scratch.data(); fa.lane_tab = lane_tab;
             fa.state_out = state_out; fa.in_fmt = in_fmt; fa.out_fmt = out_fmt;
             emu::launch(sh.fn, &fa, grid, AES_NT, aes_fast_smem_bytes(plan));

@@ -137,3 +137,16 @@ def test_specialised_and_generic_kernels_agree_with_oracle(name, monkeypatch):
     for b in range(2):
         check(y_fast[b], want[b], exact=(name == "Slapback Echo"), what=(name, "fast", b))
         check(y_gen[b], want[b], exact=(name == "Slapback Echo"), what=(name, "generic", b))
+
+
+@pytest.mark.parametrize("fs,topo", [(48000, 1), (44100, 2), (40000, 0)])
+def test_reverb_topology_variants(fs, topo):
+    """Reverb shapes exist with the 48 kHz / 44.1 kHz default delay lengths baked in
+    (aes_fast_kernel.cuh, TOPO) and with run-time lengths; all three must match the oracle."""
+    cfg = synth.PRESETS["Rain Delay"]
+    n = 5000
+    x = synth.clip(41, n, 2, fs)
+    y = emu.run(emu.resolved_descs(cfg, fs, n, 2), fs, x[None])[0]
+    assert emu.lib().emu_last_was_fast() == 1
+    assert emu.lib().emu_last_topo() == topo
+    check(y, orc.run_file_path(cfg, x, fs), what=(fs, topo))
