@@ -415,6 +415,7 @@ def b200_arm(args):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         k_ms = sum(per_launch_ms) / len(per_launch_ms)
         achieved = B * n_frames * 2 * 8 / (k_ms * 1e-3) / 1e9
+        traffic, traffic_src = NCU_DRAM_TRAFFIC.get((args.preset, B, n_frames), (None, None))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -422,7 +423,8 @@ def b200_arm(args):
             "config": {**workload(args), "tile_frames": info["tile_frames"], "smem_bytes_per_cta": info["smem_bytes"],
                        "ctas_per_sm": info["ctas_per_sm"]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
                          "kernel": info["kernel"], "algorithmic_bytes_per_launch": B * n_frames * 16,
                          "launch_ms": k_ms},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "parity": parity,
@@ -440,6 +442,13 @@ def b200_arm(args):
         p.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of the chain kernel, per launch, from the committed
+# `ncu --set full` capture of exactly this workload: (preset, clips per GPU, frames per clip) -> bytes
+NCU_DRAM_TRAFFIC = {
+    ("Rain Delay", 1184, 480000): (4.714804e9 + 6.220897e9, "profiles/r1l_ncu_chain_kernel.csv"),
+}
 
 
 def main():
