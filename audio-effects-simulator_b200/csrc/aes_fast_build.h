@@ -54,8 +54,14 @@ static inline int aes_fast_topo(const DevPlan &p)
         for (int t = AESF_TOPO_48K; t <= AESF_TOPO_44K && topo == AESF_TOPO_NONE; ++t) {
             bool same = true;
             for (int ch = 0; ch < 2; ++ch) {
-                for (int c = 0; c < 4; ++c) same = same && p.ring[d.ring[ch][c]].lag == aesf_topo_comb(t, ch, c);
-                for (int k = 0; k < 2; ++k) same = same && p.ring[d.apring[ch][k]].lag == aesf_topo_ap(t, ch, k);
+                for (int c = 0; c < 4; ++c) {
+                    const DevRing &r = p.ring[d.ring[ch][c]];
+                    same = same && r.lag == aesf_topo_comb(t, ch, c) && r.off == aesf_topo_comb_off(t, ch, c);
+                }
+                for (int k = 0; k < 2; ++k) {
+                    const DevRing &r = p.ring[d.apring[ch][k]];
+                    same = same && r.lag == aesf_topo_ap(t, ch, k) && r.off == aesf_topo_ap_off(t, ch, k);
+                }
             }
             if (same) topo = t;
         }

@@ -145,7 +145,7 @@ struct FCtx {
 };
 
 struct SRegs {              // per-thread, per-stage persistent ring slots (floats)
-    int w[2][4];            // comb rings: write slot == aligned read base
+    int w[2][4];            // comb rings: write slot == aligned read base, as a BYTE offset in the ring
     int dw[2], da[2];       // delay / pre-delay REG line: write slot, aligned read base
 };
 
@@ -212,16 +212,49 @@ __host__ __device__ constexpr int aesf_topo_ap(int topo, int ch, int k)
          : topo == 2 ? (ch == 0 ? (k == 0 ? 223 : 77) : (k == 0 ? 217 : 72))
                      : 0;
 }
-// comb ring descriptor: the offset always comes from the launch, the rest is constant under TOPO
+// float offsets in the shared-memory ring area: the plan builder lays the reverb's comb rings out
+// first (side-major), then its all-pass rings, each padded to a multiple of 4 floats
+__host__ __device__ constexpr int aesf_topo_comb_off(int topo, int ch, int cc)
+{
+    int off = 0;
+    for (int i = 0; i < ch * 4 + cc; ++i) off += (aesf_topo_comb(topo, i >> 2, i & 3) + 3) & ~3;
+    return off;
+}
+__host__ __device__ constexpr int aesf_topo_ap_off(int topo, int ch, int k)
+{
+    int off = aesf_topo_comb_off(topo, 2, 0);
+    for (int i = 0; i < ch * 2 + k; ++i) off += (aesf_topo_ap(topo, i >> 1, i & 1) + 3) & ~3;
+    return off;
+}
+// comb ring descriptor: read from the launch parameters, or constant under TOPO (ch, cc are
+// unrolled loop counters, so everything below folds to immediates)
 template <int TOPO, int FR>
 __device__ __forceinline__ FRing aesf_comb_ring(const FastStage &st, int ch, int cc)
 {
-    FRing rg = st.ring[ch][cc];
     if (TOPO) {
         const int L = aesf_topo_comb(TOPO, ch, cc), len = (L + 3) & ~3;
-        rg.len = len; rg.lag = L; rg.tinc = (AES_NT * FR) % len;
+        FRing rg;
+        rg.off = aesf_topo_comb_off(TOPO, ch, cc); rg.len = len; rg.lag = L; rg.tinc = (AES_NT * FR) % len;
+        return rg;
     }
-    return rg;
+    return st.ring[ch][cc];
+}
+
+template <int FR> __device__ __forceinline__ void aesf_select4(const float4 A, const float4 B, int m, float (&o)[FR]);
+
+// Comb slots are kept as BYTE offsets inside their ring, so a ring access is base + slot with the
+// ring's constant offset folded into the instruction.
+template <int FR>
+__device__ __forceinline__ void aesf_comb_read(const float *ring, int wb, int m, int len, float (&o)[FR])
+{
+    static_assert(FR == 4, "");
+    const char *rb = reinterpret_cast<const char *>(ring);
+    const float4 A = aes_lds_v4(reinterpret_cast<const float *>(rb + wb));
+    if (m == 0) { o[0] = A.x; o[1] = A.y; o[2] = A.z; o[3] = A.w; return; }
+    int bb = wb + 16;
+    bb = bb >= 4 * len ? bb - 4 * len : bb;
+    const float4 B = aes_lds_v4(reinterpret_cast<const float *>(rb + bb));
+    aesf_select4<FR>(A, B, m, o);
 }
 
 // ---- phase walk on the smem tile for a WALK ring described in the parameter bank --------
@@ -331,8 +364,8 @@ __device__ __forceinline__ void aesf_allpass(const FastArgs &a, const FastStage 
     const int ch = c.tid >> 7;
     if (TOPO != 0 && c.len == AES_NT * FR) {            // full tile: unrolled walk, constant length
         constexpr int TP = TOPO ? TOPO : 1;
-        if (ch == 0) aesf_ap_static<FR, aesf_topo_ap(TP, 0, K)>(c, a.walk[st.walk_ap[0][K]].off, st.walk_ap[0][K], st.a);
-        else         aesf_ap_static<FR, aesf_topo_ap(TP, 1, K)>(c, a.walk[st.walk_ap[1][K]].off, st.walk_ap[1][K], st.a);
+        if (ch == 0) aesf_ap_static<FR, aesf_topo_ap(TP, 0, K)>(c, aesf_topo_ap_off(TP, 0, K), st.walk_ap[0][K], st.a);
+        else         aesf_ap_static<FR, aesf_topo_ap(TP, 1, K)>(c, aesf_topo_ap_off(TP, 1, K), st.walk_ap[1][K], st.a);
     } else {
         aesf_walk<FR, 2>(c, a.walk[st.walk_ap[ch][K]], st.walk_ap[ch][K], false, st.a, 0.f, 0.f);
     }
@@ -477,7 +510,7 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
 #pragma unroll
             for (int cc = 0; cc < NC; ++cc) {
                 const FRing rg = aesf_comb_ring<TOPO, FR>(st, ch, cc);
-                aesf_read<FR, 0>(c.rings + rg.off, sr.w[ch][cc], rg.len - rg.lag, rg.len, y[ch][cc]);
+                aesf_comb_read<FR>(c.rings + rg.off, sr.w[ch][cc], rg.len - rg.lag, rg.len, y[ch][cc]);
                 float u = 0.0f;
 #pragma unroll
                 for (int j = 0; j < FR; ++j) u = fmaf(h, u, y[ch][cc][j]);
@@ -531,7 +564,7 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
                     nb[j] = fmaf(gs, u, pre[ch][j]);            // buf[n] = x + g*(1-h)*u
                     sum[ch][j] = __fadd_rn(sum[ch][j], y[ch][cc][j]);
                 }
-                aes_stv<FR>(c.rings + rg.off + sr.w[ch][cc], nb);
+                aes_stv<FR>(reinterpret_cast<float *>(reinterpret_cast<char *>(c.rings + rg.off) + sr.w[ch][cc]), nb);
                 if (c.tid == AES_NT - 1) fsout[ch * 4 + cc] = u;
             }
         }
@@ -707,7 +740,7 @@ __device__ __forceinline__ void aesf_slots_init(const FastArgs &a, int i0, SRegs
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
-            for (int cc = 0; cc < AESF_NC(CODE); ++cc) sr.w[ch][cc] = i0;
+            for (int cc = 0; cc < AESF_NC(CODE); ++cc) sr.w[ch][cc] = 4 * i0;         // byte offset in the ring
     }
 }
 
@@ -738,7 +771,7 @@ __device__ __forceinline__ void aesf_slots_advance(const FastArgs &a, SRegs &sr)
 #pragma unroll
             for (int cc = 0; cc < AESF_NC(CODE); ++cc) {
                 const FRing rg = aesf_comb_ring<TOPO, FR>(st, ch, cc);
-                sr.w[ch][cc] = aesf_adv(sr.w[ch][cc], rg.tinc, rg.len);
+                sr.w[ch][cc] = aesf_adv(sr.w[ch][cc], 4 * rg.tinc, 4 * rg.len);
             }
     }
 }

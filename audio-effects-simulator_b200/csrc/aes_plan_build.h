@@ -37,6 +37,8 @@ struct AesPlanBuilder {
     long long smem_off = 0, glob_off = 0;
     char *err;
     size_t errlen;
+    int prio[AES_MAX_RINGS] = {};      // shared-memory layout order: 0 reverb combs, 1 all-passes, 2 everything else
+    int next_prio = 2;
 
     int fail(const char *msg) { snprintf(err, errlen, "%s", msg); return AES_ERR_INVALID; }
 
@@ -59,8 +61,24 @@ struct AesPlanBuilder {
             r.off = smem_off;
             smem_off += (period + 3) & ~3LL;
         }
+        prio[p->n_rings] = next_prio;
         *id = p->n_rings++;
         return 0;
+    }
+    // Final shared-memory offsets: the reverb's comb rings first, then its all-pass rings, then the
+    // rest, each group in creation order -- so that a chain with the default reverb topology has
+    // those rings at the fixed offsets the compile-time topologies assume (aes_fast_kernel.cuh).
+    void layout_smem()
+    {
+        long long off = 0;
+        for (int pass = 0; pass < 3; ++pass)
+            for (int i = 0; i < p->n_rings; ++i) {
+                DevRing &r = p->ring[i];
+                if (r.space != AES_SPACE_SMEM || prio[i] != pass) continue;
+                r.off = off;
+                off += (r.len + 3) & ~3LL;
+            }
+        smem_off = off;
     }
     int add_walk(long long lag, bool allow_global, int *id) { return add_ring(lag, lag, allow_global, id); }
     // register-path line without a barrier between its reads and writes: the period
@@ -76,7 +94,8 @@ static inline int aes_build_devplan(const aes_stage_desc *stages, int n, int fs,
 {
     (void)fs;
     memset(p, 0, sizeof *p);
-    AesPlanBuilder B{ p, 0, 0, err, errlen };
+    AesPlanBuilder B;
+    B.p = p; B.err = err; B.errlen = errlen;
     if (n < 0 || n > AES_MAX_STAGES) return B.fail("a chain holds 0..16 stages");
 
     // Tile size: every damped comb needs its lag >= T.
@@ -157,11 +176,18 @@ static inline int aes_build_devplan(const aes_stage_desc *stages, int n, int fs,
                 for (int c = 0; c < st.nc; ++c) {
                     const long long L = d.q[4 + 8 * side + c];
                     // reads and writes of a comb are separated by the scan barrier: period roundup4(L) suffices
-                    if ((rc = B.add_ring(L, aes_roundup4(L), false, &st.ring[side][c]))) return rc;
+                    B.next_prio = 0;
+                    rc = B.add_ring(L, aes_roundup4(L), false, &st.ring[side][c]);
+                    B.next_prio = 2;
+                    if (rc) return rc;
                     st.g[side][c] = (float)d.p[4 + 8 * side + c];
                 }
-                for (int k = 0; k < st.na; ++k)
-                    if ((rc = B.add_walk(d.q[20 + 4 * side + k], true, &st.apring[side][k]))) return rc;
+                for (int k = 0; k < st.na; ++k) {
+                    B.next_prio = 1;
+                    rc = B.add_walk(d.q[20 + 4 * side + k], true, &st.apring[side][k]);
+                    B.next_prio = 2;
+                    if (rc) return rc;
+                }
             }
             break;
         }
@@ -196,6 +222,7 @@ static inline int aes_build_devplan(const aes_stage_desc *stages, int n, int fs,
             return B.fail("unknown stage kind");
         }
     }
+    B.layout_smem();
     p->smem_floats = (int)B.smem_off;
     p->scratch_floats = B.glob_off > 0 ? B.glob_off : 32;
     if (aes_plan_smem_bytes(*p) > AES_SMEM_LIMIT) {
