@@ -440,9 +440,16 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
                 if (AESF_PF(CODE) && c.ln_stage != nullptr) {
                     // line samples staged by TMA a tile ago: [i0 + m, i0 + m + FR) of the staged span
                     constexpr int T = AES_NT * FR;
-                    const float *sp = c.ln_stage + ch * (T + 8) + i0;
-                    const float4 A = aes_lds_v4(sp), B = aes_lds_v4(sp + 4);
-                    aesf_select4<FR>(A, B, ((rg.lag + 3) & ~3) - rg.lag, line);
+                    // (no misalignment switch: an unaligned line costs four scalar loads instead)
+                    const int m = ((rg.lag + 3) & ~3) - rg.lag;
+                    const float *sp = c.ln_stage + ch * (T + 8) + i0 + m;
+                    if (m == 0) {
+                        const float4 A = aes_lds_v4(sp);
+                        line[0] = A.x; line[1 % FR] = A.y; line[2 % FR] = A.z; line[3 % FR] = A.w;
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < FR; ++j) line[j] = sp[j];
+                    }
                 } else if (AESF_PF(CODE)) {
                     aesf_select4<FR>(lnA[ch], lnB[ch], ((rg.lag + 3) & ~3) - rg.lag, line);
                 } else {
