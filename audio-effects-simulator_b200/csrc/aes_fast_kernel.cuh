@@ -807,8 +807,10 @@ __device__ __forceinline__ void aesf_prefetch(const FastArgs &a, const FCtx &c, 
 
 // issue the TMA copies for one tile (called by thread 0 only): input frames and, for a PF
 // delay stage PS, the T+4 line samples per channel starting at thread 0's aligned read base
+// `lnbase`: thread 0's aligned read base of each channel's line for the tile being staged, tracked
+// by every thread in CTA-uniform arithmetic (so the copy operands need no per-lane broadcast)
 template <int FR, int PCODE, int PS>
-__device__ __forceinline__ void aesf_issue_tile(const FastArgs &a, const FCtx &c, const SRegs &srp, int ahead,
+__device__ __forceinline__ void aesf_issue_tile(const FastArgs &a, const FCtx &c, const int (&lnbase)[2],
                                                 long long frame0, float *stage_x, float *stage_ln,
                                                 unsigned long long *bar)
 {
@@ -823,7 +825,7 @@ __device__ __forceinline__ void aesf_issue_tile(const FastArgs &a, const FCtx &c
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
             const FRing rg = st.ring[ch][0];
-            const int a0 = ahead ? aesf_adv(srp.da[ch], rg.tinc, rg.len) : srp.da[ch];   // thread 0: i0 == 0
+            const int a0 = lnbase[ch];
             const float *rb = c.gscr + rg.off;
             float *dst = stage_ln + ch * (T + 8);
             const int n1 = (rg.len - a0) < (T + 4) ? (rg.len - a0) : (T + 4);
@@ -885,14 +887,22 @@ __device__ void aes_fast_body(const FastArgs &a)
         if (C1) aesf_slots_init<FR, C1, 1>(a, i0, sr1);
         if (C2) aesf_slots_init<FR, C2, 2>(a, i0, sr2);
         if (C3) aesf_slots_init<FR, C3, 3>(a, i0, sr3);
-        SRegs &srp = PS == 0 ? sr0 : PS == 1 ? sr1 : PS == 2 ? sr2 : sr3;
+        int lnbase[2] = { 0, 0 };                       // staged line: thread 0's read base, next tile to stage
+        if (PS >= 0) {
+            const FastStage &pst = a.st[PS < 0 ? 0 : PS];
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                int w0;
+                aesf_line_init<FR>(pst.ring[ch][0], 0, w0, lnbase[ch]);
+            }
+        }
         __syncthreads();
 
         // a tile goes through TMA staging when it is full, 16-byte aligned and plain f32 stereo
         const bool clip_staged = STAGED && a.in_fmt == AESK_F32_STEREO && ((b * a.N) & 1) == 0;
         const long long clip_frame0 = b * a.N;
         if (clip_staged && a.N >= (long long)T && c.tid == 0)
-            aesf_issue_tile<FR, PCODE, PS < 0 ? 0 : PS>(a, c, srp, 0, clip_frame0, stage_x + (it_issue & 1) * 2 * T,
+            aesf_issue_tile<FR, PCODE, PS < 0 ? 0 : PS>(a, c, lnbase, clip_frame0, stage_x + (it_issue & 1) * 2 * T,
                                                        stage_ln + (it_issue & 1) * 2 * (T + 8), bars + (it_issue & 1));
         if (clip_staged && a.N >= (long long)T) ++it_issue;
         float4 lnA[2], lnB[2];
@@ -926,9 +936,14 @@ __device__ void aes_fast_body(const FastArgs &a)
                 }
             }
             // next tile: hand it to the TMA now, a whole tile of work ahead of its use
+            if (PS >= 0) {                              // the line base moves on with every tile, staged or not
+                const FastStage &pst = a.st[PS < 0 ? 0 : PS];
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) lnbase[ch] = aesf_adv(lnbase[ch], pst.ring[ch][0].tinc, pst.ring[ch][0].len);
+            }
             if (clip_staged && a.N - n0 - T >= (long long)T) {
                 if (c.tid == 0)
-                    aesf_issue_tile<FR, PCODE, PS < 0 ? 0 : PS>(a, c, srp, 1, clip_frame0 + n0 + T,
+                    aesf_issue_tile<FR, PCODE, PS < 0 ? 0 : PS>(a, c, lnbase, clip_frame0 + n0 + T,
                                                                stage_x + (it_issue & 1) * 2 * T,
                                                                stage_ln + (it_issue & 1) * 2 * (T + 8), bars + (it_issue & 1));
                 ++it_issue;
