@@ -84,6 +84,11 @@ def lib() -> C.CDLL:
         L.aes_spectral_run.argtypes = [vp, vp, vp, i64, i64, C.c_double, C.c_double, C.c_double, vp]
         L.aes_spectral_process_host.argtypes = [vp, vp, vp, i64, i64, C.c_double, C.c_double, C.c_double]
         L.aes_stream_process_host.argtypes = [C.POINTER(StageDesc), ci, vp, ci, vp, i64]
+        for fn in (L.aes_json_float_list, L.aes_json_stereo_mean_list):
+            fn.restype = i64
+            fn.argtypes = [vp, i64, vp, i64, ci]
+        L.aes_json_float_list_bound.restype = i64
+        L.aes_json_float_list_bound.argtypes = [i64]
         if L.aes_abi_version() != 1:
             raise AesimError("libaesim.so ABI version mismatch")
         _lib = L
@@ -276,3 +281,22 @@ def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
 
 
 _OWNERS: dict = {}
+
+
+def json_float_list(x: np.ndarray, stereo_mean: bool = False, threads: int = 0) -> str:
+    """The text `json.dumps(x.flatten().tolist())` would produce for a float32 array, or, with
+    `stereo_mean`, `json.dumps(x.mean(axis=1).flatten().tolist())` for a (frames, 2) float32 array
+    (reference engine.py:119-120), written by libaesim's parallel formatter."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    if stereo_mean:
+        if x.ndim != 2 or x.shape[1] != 2:
+            raise AesimError("json_float_list(stereo_mean=True) needs a (frames, 2) array")
+        n, fn = x.shape[0], lib().aes_json_stereo_mean_list
+    else:
+        n, fn = x.size, lib().aes_json_float_list
+    cap = lib().aes_json_float_list_bound(n)
+    buf = np.empty(cap, dtype=np.uint8)
+    got = fn(C.c_void_p(x.ctypes.data), n, C.c_void_p(buf.ctypes.data), cap, int(threads))
+    if got < 0:
+        check(int(got))
+    return buf[:got].tobytes().decode("ascii")

@@ -13,6 +13,7 @@ import numpy as np
 import scipy.io.wavfile
 
 import audioblocks as ab
+from audioblocks import _native
 
 try:
     import soundfile as sf
@@ -77,6 +78,19 @@ def file_chain(chain_config, fs, channels_in=1, blocksize=1024):
     return chain
 
 
+def file_processed_message(contents, processed_url, fs, mono, processed) -> str:
+    """The reply of the file route (reference engine.py:115-122), byte for byte what
+    `json.dumps({"type": "file_processed", ..., "original_samples": mono.flatten().tolist(),
+    "processed_samples": processed.mean(axis=1).flatten().tolist()})` returns.  The two sample lists
+    are 2 x N Python floats in the reference (2.05 s of a 2.3 s request on the shipped clip); here
+    libaesim writes their text straight from the float32 buffers (aes_json_float_list)."""
+    return ('{"type": "file_processed", "original_b64": ' + json.dumps(contents)
+            + ', "processed_b64": ' + json.dumps(processed_url)
+            + ', "sample_rate": ' + json.dumps(int(fs))
+            + ', "original_samples": ' + _native.json_float_list(mono)
+            + ', "processed_samples": ' + _native.json_float_list(processed, stereo_mean=True) + '}')
+
+
 class AudioEngine:
     def __init__(self, data_queues: dict[str, queue.Queue]):
         self.stream = None
@@ -129,14 +143,7 @@ class AudioEngine:
             with io.BytesIO() as out_io:
                 scipy.io.wavfile.write(out_io, fs, pcm)
                 processed_url = "data:audio/wav;base64," + base64.b64encode(out_io.getvalue()).decode("ascii")
-            await websocket.send(json.dumps({
-                "type": "file_processed",
-                "original_b64": contents,
-                "processed_b64": processed_url,
-                "sample_rate": fs,
-                "original_samples": mono.flatten().tolist(),
-                "processed_samples": processed.mean(axis=1).flatten().tolist(),
-            }))
+            await websocket.send(file_processed_message(contents, processed_url, fs, mono, processed))
         except Exception as e:
             print(f"Error processing WAV file: {e}")
         finally:

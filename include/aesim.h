@@ -147,6 +147,19 @@ int aes_biquad_cascade_f32(const float *x, float *y, int64_t n_clips, int64_t n_
                            int n_stages, const double *coeffs5, void *stream);
 int aes_quantize_i16(const float *x, int16_t *q, int64_t n_values, void *stream);
 
+/* ---- file-route reply serialisation (host buffers, host threads; engine.py:107-123) ----------
+ *      The reference's `file_processed` message carries both signals as JSON float lists,
+ *      `json.dumps(mono.flatten().tolist())` and `json.dumps(processed.mean(axis=1).flatten().tolist())`
+ *      -- 2.05 s of the 2.3 s request on the shipped clip.  These write the identical
+ *      text ("[a, b, ...]", every element printed as Python prints float(np.float32)) from the
+ *      float32 buffers.  `out` must hold aes_json_float_list_bound(n) bytes; the return value is
+ *      the number of bytes written (no terminator) or a negative aes_status.  threads <= 0: all
+ *      host threads.  The stereo variant averages each (L, R) frame the way numpy's float32
+ *      mean(axis=1) does before printing. */
+int64_t aes_json_float_list_bound(int64_t n_values);
+int64_t aes_json_float_list(const float *x_host, int64_t n_values, char *out, int64_t cap, int threads);
+int64_t aes_json_stereo_mean_list(const float *xy_host, int64_t n_frames, char *out, int64_t cap, int threads);
+
 /* ---- IR-convolution reverb (BASELINE configs[3]; no counterpart in the reference, whose
  *      reverb.py:72-277 is a Schroeder network): out = clip(dry*x + wet*(x (*) ir)) per channel.
  *      ir_host: (n_taps, 2) float32 host array; block_log2: FFT size 2^14 (0 = default), 2^11, 2^8. */
