@@ -299,4 +299,4 @@ def json_float_list(x: np.ndarray, stereo_mean: bool = False, threads: int = 0) 
     got = fn(C.c_void_p(x.ctypes.data), n, C.c_void_p(buf.ctypes.data), cap, int(threads))
     if got < 0:
         check(int(got))
-    return buf[:got].tobytes().decode("ascii")
+    return str(memoryview(buf)[:got], "ascii")
