@@ -12,7 +12,7 @@
 #include "aes_fast_build.h"
 #include "aes_biquad_build.h"
 
-#define AES_HOST_SLOTS 3
+#define AES_HOST_SLOTS 4
 
 struct HostSlot {
     cudaStream_t stream = nullptr;
@@ -314,9 +314,17 @@ AES_EXPORT int aes_chain_process_host(aes_chain_plan *pl, const void *x_host, in
     const size_t cap_bytes = (size_t)1 << 30;
     if ((size_t)per * in_clip > cap_bytes) per = std::max<int64_t>(1, (int64_t)(cap_bytes / in_clip));
     per = std::min<int64_t>(per, n_clips);
-    // keep at least AES_HOST_SLOTS sub-batches in flight when the batch allows it
-    if (n_clips >= 2 * AES_HOST_SLOTS && per * AES_HOST_SLOTS > n_clips)
-        per = (n_clips + AES_HOST_SLOTS - 1) / AES_HOST_SLOTS;
+    // The PCIe copies dominate (a sub-batch's kernel is ~10x shorter than either of its copies), so
+    // the pipeline's fill/drain bubble -- one H2D at the start, one D2H at the end that overlap
+    // nothing -- decides the end-to-end rate: cut the batch into ~AES_HOST_CHUNKS sub-batches, but
+    // keep every copy at 32 MiB or more.
+    {
+        int64_t chunks = 24;
+        if (const char *e = getenv("AES_HOST_CHUNKS")) chunks = std::max<int64_t>(1, atoll(e));
+        const int64_t min_clips = std::max<int64_t>(1, (int64_t)((((size_t)32 << 20) + in_clip - 1) / in_clip));
+        const int64_t fine = std::max<int64_t>((n_clips + chunks - 1) / chunks, min_clips);
+        per = std::min<int64_t>(per, fine);
+    }
     const bool pin_in = is_pinned(x_host), pin_out = is_pinned(y_host);
 
     int k = 0;

@@ -62,6 +62,13 @@ EXTRA_CHAINS = {
         {"type": "distortion", "params": {"drive": 4.0}},
         {"type": "octaver", "params": {"semitones": -12, "mix": 0.5}},
         {"type": "delay", "params": {"delay_ms": 120, "feedback": 0.3, "offset_ms": 10}}],
+    # single blocks with their constructor defaults: per-block cost
+    "block-delay": [{"type": "delay", "params": {}}],
+    "block-reverb": [{"type": "reverb", "params": {}}],
+    "block-filter": [{"type": "filter", "params": {}}],
+    "block-gate": [{"type": "gate", "params": {}}],
+    "block-octaver": [{"type": "octaver", "params": {}}],
+    "block-distortion": [{"type": "distortion", "params": {"drive": 4.0}}],
 }
 
 
