@@ -66,3 +66,37 @@ def max_over_ranks(seconds: float, device=None, group=None) -> float:
     t = torch.tensor([seconds], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
     return float(t.item())
+
+
+def _parse_cpulist(text: str) -> set[int]:
+    cpus: set[int] = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def bind_host_to_gpu(pci_bus_id: str) -> list[int] | None:
+    """Pin this process to the CPUs that sit on the GPU's own PCIe root / NUMA node
+    (`/sys/bus/pci/devices/<id>/local_cpulist`), BEFORE any pinned host buffer is allocated, so
+    staging memory is node-local and the H2D/D2H copies of different ranks do not cross the
+    inter-socket link.  With one process per GPU and unbound ranks the end-to-end rate of 8 ranks
+    was 1.4x that of one.  Returns the CPU list, or None when the topology cannot be read (then
+    nothing is changed)."""
+    import os
+    bus = pci_bus_id.lower()
+    if len(bus.split(":")[0]) == 8:               # nvml style 00000000:1B:00.0 -> sysfs 0000:1b:00.0
+        bus = bus[4:]
+    try:
+        with open(f"/sys/bus/pci/devices/{bus}/local_cpulist") as fh:
+            cpus = _parse_cpulist(fh.read())
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus or cpus == allowed:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return sorted(cpus)
+    except (OSError, ValueError, AttributeError):
+        return None

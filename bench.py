@@ -298,6 +298,13 @@ def b200_arm(args):
         dist.init_process_group("nccl", device_id=dev)
     L = _native.lib()
     _native.check(L.aes_set_device(local))
+    numa_cpus = None
+    if world > 1:                   # node-local staging memory: bind before any pinned allocation
+        from audioblocks.sharding import bind_host_to_gpu
+        pr = torch.cuda.get_device_properties(local)
+        if hasattr(pr, "pci_bus_id"):
+            numa_cpus = bind_host_to_gpu("%04x:%02x:%02x.0" % (getattr(pr, "pci_domain_id", 0), pr.pci_bus_id,
+                                                               getattr(pr, "pci_device_id", 0)))
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()              # nvidia-smi takes a while to start: launch it before the data is built
@@ -391,6 +398,7 @@ def b200_arm(args):
         e2e = {"value": world * Be * n_frames * 2 * args.e2e_steps / float(t.item()) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": int(xh.nbytes), "d2h_bytes_per_step": int(yh.nbytes),
                "steps": args.e2e_steps, "matches_device_path": e2e_ok,
+               "host_cpus_bound_to_gpu_node": len(numa_cpus) if numa_cpus else None,
                "api": "EffectsChain.prepare_batch(...).run_host -> aes_chain_process_host (pinned host buffers)"}
         # the same call fed like the WAV-file route feeds it (engine.py:78-84,104-105): int16 stereo
         # PCM in (down-mixed on the device), int16 stereo PCM out -- half the PCIe bytes per frame
@@ -399,10 +407,14 @@ def b200_arm(args):
         np.multiply(xh, 32767.0, out=yh)
         xq[...] = yh.astype(np.int16)
         plan.run_host(xq, _native.FMT_I16_DOWNMIX, yq, _native.FMT_I16_STEREO, Be, n_frames)
+        barrier()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             plan.run_host(xq, _native.FMT_I16_DOWNMIX, yq, _native.FMT_I16_STEREO, Be, n_frames)
-        pcm_s = time.perf_counter() - t0
+        t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pcm_s = float(t.item())
         e2e["pcm16_file_route"] = {"value": world * Be * n_frames * 2 * args.e2e_steps / pcm_s / 1e6, "unit": UNIT,
                                    "h2d_bytes_per_step": int(xq.nbytes), "d2h_bytes_per_step": int(yq.nbytes)}
         del xh, yh, xq, yq

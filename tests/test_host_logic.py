@@ -159,3 +159,13 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("no CPU fallback", ""), (f, "mentions the oracle")
                 assert "cuda_emu" not in src or f.endswith("aes_chain_kernel.cuh"), f
+
+
+def test_cpulist_parsing_and_harmless_bind():
+    from audioblocks.sharding import _parse_cpulist, bind_host_to_gpu
+    assert _parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11}
+    assert _parse_cpulist("") == set()
+    import os
+    before = os.sched_getaffinity(0)
+    assert bind_host_to_gpu("0000:ff:1f.0") is None          # no such device: nothing changes
+    assert os.sched_getaffinity(0) == before
