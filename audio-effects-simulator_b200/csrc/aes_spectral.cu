@@ -11,7 +11,9 @@
 
 __global__ void aess_load_kernel(const __grid_constant__ SpecArgs a) { aess_load_body(a); }
 __global__ void aess_global_stage_kernel(const __grid_constant__ SpecArgs a, int st, int inv) { aess_global_stage_body(a, st, inv); }
-__global__ void __launch_bounds__(AESC_NT) aess_local_kernel(const __grid_constant__ SpecArgs a, int inv, int mul) { aess_local_body(a, inv, mul); }
+template <int R>
+__global__ void __launch_bounds__(256) aess_global_pass_kernel(const __grid_constant__ SpecArgs a, int st, int inv) { aess_global_pass_body<R>(a, st, inv); }
+__global__ void __launch_bounds__(AESS_LOCAL_NT) aess_local_kernel(const __grid_constant__ SpecArgs a, int inv, int mul) { aess_local_body(a, inv, mul); }
 __global__ void aess_gate_kernel(const __grid_constant__ SpecArgs a) { aess_gate_body(a); }
 __global__ void aess_zero_pad_kernel(const __grid_constant__ SpecArgs a) { aess_zero_pad_body(a); }
 __global__ void aess_store_kernel(const __grid_constant__ SpecArgs a) { aess_store_body(a); }
@@ -60,13 +62,20 @@ static int spec_grid(const aes_spectral_plan *pl) { return pl->sms * 8; }
 static int spec_fft(const aes_spectral_plan *pl, const SpecArgs &a, int inverse, int mul, cudaStream_t st)
 {
     const int g = spec_grid(pl);
-    const unsigned chunks = (unsigned)((long long)a.nb * a.P / 1024);
-    if (!inverse) {
-        for (int s = 0; s <= a.L - 11; ++s) { aess_global_stage_kernel<<<g, 256, 0, st>>>(a, s, 0); aes_count_launch(); }
-        aess_local_kernel<<<chunks, AESC_NT, 1024 * sizeof(cpx), st>>>(a, 0, mul); aes_count_launch();
+    const long long pairs = ((long long)a.nb * a.P / 1024 + 1) / 2;    // two 1024-point chunks per CTA trip
+    const unsigned lgrid = (unsigned)std::min<long long>(pairs, (long long)pl->sms * 8);
+    auto pass = [&](int s, int r, int inv) {
+        if (r == 3) aess_global_pass_kernel<3><<<g, 256, 0, st>>>(a, s, inv);
+        else if (r == 2) aess_global_pass_kernel<2><<<g, 256, 0, st>>>(a, s, inv);
+        else aess_global_pass_kernel<1><<<g, 256, 0, st>>>(a, s, inv);
+        aes_count_launch();
+    };
+    if (!inverse) {                                             // stages 0 .. L-11 span >= 1024 points
+        for (int s = 0, r; s <= a.L - 11; s += r) pass(s, r = aess_pass_radix(a.L - 10 - s), 0);
+        aess_local_kernel<<<lgrid, AESS_LOCAL_NT, AESS_LOCAL_SMEM_CPX * sizeof(cpx), st>>>(a, 0, mul); aes_count_launch();
     } else {
-        aess_local_kernel<<<chunks, AESC_NT, 1024 * sizeof(cpx), st>>>(a, 1, 0); aes_count_launch();
-        for (int s = 10; s < a.L; ++s) { aess_global_stage_kernel<<<g, 256, 0, st>>>(a, s, 1); aes_count_launch(); }
+        aess_local_kernel<<<lgrid, AESS_LOCAL_NT, AESS_LOCAL_SMEM_CPX * sizeof(cpx), st>>>(a, 1, 0); aes_count_launch();
+        for (int s = 10, r; s < a.L; s += r) pass(s, r = aess_pass_radix(a.L - s), 1);
     }
     AES_CUDA(cudaGetLastError());
     return 0;
@@ -139,7 +148,7 @@ AES_EXPORT int aes_spectral_plan_create(int64_t frame_len, aes_spectral_plan **o
         AES_CUDA(cudaMemcpy(pl->d_twP, twP.data(), twP.size() * sizeof(cpx), cudaMemcpyHostToDevice));
         AES_CUDA(cudaMemcpy(pl->d_tw1k, tw1k.data(), tw1k.size() * sizeof(cpx), cudaMemcpyHostToDevice));
         AES_CUDA(cudaMemcpy(pl->d_window, win.data(), win.size() * sizeof(float), cudaMemcpyHostToDevice));
-        AES_CUDA(cudaFuncSetAttribute(aess_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 1024 * (int)sizeof(cpx)));
+        AES_CUDA(cudaFuncSetAttribute(aess_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AESS_LOCAL_SMEM_CPX * (int)sizeof(cpx)));
         // vhat = FFT_P(v) / P, kept in bit-reversed order
         for (auto &e : v) { e.x /= (float)P; e.y /= (float)P; }
         AES_CUDA(cudaMemcpy(pl->d_vhat, v.data(), v.size() * sizeof(cpx), cudaMemcpyHostToDevice));

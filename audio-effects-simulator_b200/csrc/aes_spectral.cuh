@@ -74,21 +74,163 @@ __device__ void aess_global_stage_body(const SpecArgs &a, int st, int inverse)
     }
 }
 
-// the 10 stages that stay inside aligned 1024-point chunks, in shared memory; when `mul` is set
-// the forward pass also multiplies by FFT(v) on the way out (bit-reversed order on both sides)
+// R consecutive radix-2 stages on the 2^R points a thread holds (p[k] = element base + k*d of a
+// 2^L-point transform, i = base mod d).  Forward (DIF): stages st, st+1, .. with the largest
+// distance first; inverse (DIT): stages st, st+1, .. with the smallest first, conjugate twiddles.
+// tw[q] = exp(-2*pi*i*q / 2^L), q < 2^(L-1).
+template <int R>
+__device__ __forceinline__ void aess_bfly(cpx (&p)[1 << R], long long i, long long d, int st, int inverse, int L,
+                                          const cpx *__restrict__ tw)
+{
+    constexpr int K = 1 << R;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const int dk = inverse ? (1 << r) : (1 << (R - 1 - r));     // butterfly distance in units of d
+        const int sh = inverse ? (L - 1 - (st + r)) : (st + r);     // twiddle exponent shift of this stage
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+            if (k & dk) continue;
+            const long long pos = (long long)(k & (dk - 1)) * d + i;
+            cpx w = tw[pos << sh];
+            const cpx u = p[k], v = p[k + dk];
+            if (!inverse) {
+                p[k] = c_add(u, v);
+                p[k + dk] = c_mul(c_sub(u, v), w);
+            } else {
+                w.y = -w.y;
+                const cpx t = c_mul(v, w);
+                p[k] = c_add(u, t);
+                p[k + dk] = c_sub(u, t);
+            }
+        }
+    }
+}
+
+// R (1..3) consecutive grid-wide stages in one pass over global memory: a thread owns the 2^R
+// points its butterflies connect, so the data makes one round trip per pass instead of one per
+// stage (11 global stages of a 2^21-point transform: 4 passes).  Forward (DIF) passes start at
+// stage `st` (largest distance first); inverse (DIT) passes start at stage `st` and climb.
+template <int R>
+__device__ void aess_global_pass_body(const SpecArgs &a, int st, int inverse)
+{
+    constexpr int K = 1 << R;
+    const long long per = a.P >> R;                             // threads' worth of work per transform
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long total = (long long)a.nb * per;
+    const long long d = inverse ? (1LL << st) : (a.P >> (st + R));      // distance between a thread's points
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
+        const long long b = e / per, rem = e % per;
+        const long long i = rem & (d - 1), blk = rem >> (inverse ? st : (a.L - st - R));
+        cpx *p0 = a.buf + b * a.P + blk * (d << R) + i;
+        cpx p[K];
+#pragma unroll
+        for (int k = 0; k < K; ++k) p[k] = p0[k * d];
+        aess_bfly<R>(p, i, d, st, inverse, a.L, a.twP);
+#pragma unroll
+        for (int k = 0; k < K; ++k) p0[k * d] = p[k];
+    }
+}
+// how many stages the next global pass takes when `remaining` are left
+__host__ __device__ inline int aess_pass_radix(int remaining) { return remaining >= 3 ? 3 : remaining; }
+
+// The 10 stages that stay inside aligned 1024-point chunks.  128 threads per chunk, 8 points per
+// thread, two chunks per 256-thread CTA, persistent over the chunks: three radix-8 passes and one
+// radix-2 pass, the outer passes straight from / to global memory (coalesced), the inner ones
+// through shared memory (index padded by 2 per 16 so the stride-16 and stride-2 passes stay at
+// the 2-wavefront minimum).  With `mul` the forward transform is multiplied by FFT(v) on the way
+// out (bit-reversed order on both sides).
+#define AESS_LOCAL_NT 256
+#define AESS_LOCAL_SMEM_CPX (2 * 1152)
+__device__ __forceinline__ int aess_pad(int idx) { return idx + 2 * (idx >> 4); }
+
 __device__ void aess_local_body(const SpecArgs &a, int inverse, int mul)
 {
-    AES_DYN_SMEM(cpx, s);
-    const int tid = threadIdx.x;
-    const long long chunk = blockIdx.x;                         // nb * P / 1024 chunks
-    cpx *d = a.buf + chunk * 1024;
-    const long long off = (chunk * 1024) % a.P;
-    s[tid] = d[tid];
-    __syncthreads();
-    if (!inverse) aesc_fft_dif<10>(s, a.tw1k, tid); else aesc_ifft_dit<10>(s, a.tw1k, tid);
-    cpx v = s[tid];
-    if (mul) v = c_mul(v, a.vhat[off + tid]);
-    d[tid] = v;
+    AES_DYN_SMEM(cpx, smem);
+    const int g = threadIdx.x >> 7, t = threadIdx.x & 127;
+    cpx *s = smem + g * 1152;
+    const long long nchunks = (long long)a.nb * a.P / 1024;
+    const cpx *tw = a.tw1k;
+    for (long long cp = blockIdx.x; 2 * cp < nchunks; cp += gridDim.x) {
+        const long long chunk = 2 * cp + g;
+        const bool valid = chunk < nchunks;
+        cpx *d = a.buf + chunk * 1024;
+        const long long off = (chunk * 1024) % a.P;
+        cpx p[8];
+        if (!inverse) {
+            if (valid) {                                        // stages 0-2: points t + 128k, from global
+#pragma unroll
+                for (int k = 0; k < 8; ++k) p[k] = d[t + 128 * k];
+                aess_bfly<3>(p, t, 128, 0, 0, 10, tw);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s[aess_pad(t + 128 * k)] = p[k];
+            }
+            __syncthreads();
+            if (valid) {                                        // stages 3-5: points 128*hi + lo + 16k
+                const int i = t & 15, base = (t >> 4) * 128 + i;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) p[k] = s[aess_pad(base + 16 * k)];
+                aess_bfly<3>(p, i, 16, 3, 0, 10, tw);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s[aess_pad(base + 16 * k)] = p[k];
+            }
+            __syncthreads();
+            if (valid) {                                        // stages 6-8: points 16*hi + lo + 2k
+                const int i = t & 1, base = (t >> 1) * 16 + i;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) p[k] = s[aess_pad(base + 2 * k)];
+                aess_bfly<3>(p, i, 2, 6, 0, 10, tw);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s[aess_pad(base + 2 * k)] = p[k];
+            }
+            __syncthreads();
+            if (valid) {                                        // stage 9 (twiddle 1): pairs (2q, 2q+1), to global
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int e = 2 * (t + 128 * q);
+                    const cpx u = s[aess_pad(e)], v = s[aess_pad(e) + 1];
+                    cpx o0 = c_add(u, v), o1 = c_sub(u, v);
+                    if (mul) { o0 = c_mul(o0, a.vhat[off + e]); o1 = c_mul(o1, a.vhat[off + e + 1]); }
+                    d[e] = o0; d[e + 1] = o1;
+                }
+            }
+        } else {
+            if (valid) {                                        // stage 0: pairs, from global
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int e = 2 * (t + 128 * q);
+                    const cpx u = d[e], v = d[e + 1];
+                    s[aess_pad(e)] = c_add(u, v); s[aess_pad(e) + 1] = c_sub(u, v);
+                }
+            }
+            __syncthreads();
+            if (valid) {                                        // stages 1-3: distances 2, 4, 8
+                const int i = t & 1, base = (t >> 1) * 16 + i;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) p[k] = s[aess_pad(base + 2 * k)];
+                aess_bfly<3>(p, i, 2, 1, 1, 10, tw);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s[aess_pad(base + 2 * k)] = p[k];
+            }
+            __syncthreads();
+            if (valid) {                                        // stages 4-6: distances 16, 32, 64
+                const int i = t & 15, base = (t >> 4) * 128 + i;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) p[k] = s[aess_pad(base + 16 * k)];
+                aess_bfly<3>(p, i, 16, 4, 1, 10, tw);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s[aess_pad(base + 16 * k)] = p[k];
+            }
+            __syncthreads();
+            if (valid) {                                        // stages 7-9: distances 128, 256, 512, to global
+#pragma unroll
+                for (int k = 0; k < 8; ++k) p[k] = s[aess_pad(t + 128 * k)];
+                aess_bfly<3>(p, t, 128, 7, 1, 10, tw);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) d[t + 128 * k] = p[k];
+            }
+        }
+        __syncthreads();                                        // the next chunk reuses the buffer
+    }
 }
 
 // forward result -> spectral gate -> conjugated Hermitian spectrum times chirp, ready for the

@@ -130,6 +130,12 @@ int emu_convreverb(const float *ir, long long n_taps, const float *x, float *y, 
 struct SpecLaunch { SpecArgs a; int st, inv, mul; };
 static void sp_load(void *p) { aess_load_body(reinterpret_cast<SpecLaunch *>(p)->a); }
 static void sp_glob(void *p) { SpecLaunch *l = reinterpret_cast<SpecLaunch *>(p); aess_global_stage_body(l->a, l->st, l->inv); }
+template <int R> static void sp_pass(void *p) { SpecLaunch *l = reinterpret_cast<SpecLaunch *>(p); aess_global_pass_body<R>(l->a, l->st, l->inv); }
+static void emu_spec_pass(SpecLaunch &l, int s, int r, int inv)
+{
+    l.st = s; l.inv = inv;
+    emu::launch(r == 3 ? sp_pass<3> : r == 2 ? sp_pass<2> : sp_pass<1>, &l, 4, 256, 0);
+}
 static void sp_local(void *p) { SpecLaunch *l = reinterpret_cast<SpecLaunch *>(p); aess_local_body(l->a, l->inv, l->mul); }
 static void sp_gate(void *p) { aess_gate_body(reinterpret_cast<SpecLaunch *>(p)->a); }
 static void sp_zero(void *p) { aess_zero_pad_body(reinterpret_cast<SpecLaunch *>(p)->a); }
@@ -137,13 +143,13 @@ static void sp_store(void *p) { aess_store_body(reinterpret_cast<SpecLaunch *>(p
 
 static void emu_spec_fft(SpecLaunch &l, int inverse, int mul)
 {
-    const unsigned chunks = (unsigned)((long long)l.a.nb * l.a.P / 1024);
+    const unsigned chunks = (unsigned)std::min<long long>(((long long)l.a.nb * l.a.P / 1024 + 1) / 2, 3);   // persistent: 3 CTAs
     if (!inverse) {
-        for (int s = 0; s <= l.a.L - 11; ++s) { l.st = s; l.inv = 0; emu::launch(sp_glob, &l, 4, 256, 0); }
-        l.inv = 0; l.mul = mul; emu::launch(sp_local, &l, chunks, AESC_NT, 1024 * sizeof(cpx));
+        for (int s = 0, r; s <= l.a.L - 11; s += r) emu_spec_pass(l, s, r = aess_pass_radix(l.a.L - 10 - s), 0);
+        l.inv = 0; l.mul = mul; emu::launch(sp_local, &l, chunks, AESS_LOCAL_NT, AESS_LOCAL_SMEM_CPX * sizeof(cpx));
     } else {
-        l.inv = 1; l.mul = 0; emu::launch(sp_local, &l, chunks, AESC_NT, 1024 * sizeof(cpx));
-        for (int s = 10; s < l.a.L; ++s) { l.st = s; l.inv = 1; emu::launch(sp_glob, &l, 4, 256, 0); }
+        l.inv = 1; l.mul = 0; emu::launch(sp_local, &l, chunks, AESS_LOCAL_NT, AESS_LOCAL_SMEM_CPX * sizeof(cpx));
+        for (int s = 10, r; s < l.a.L; s += r) emu_spec_pass(l, s, r = aess_pass_radix(l.a.L - s), 1);
     }
 }
 

@@ -8,7 +8,7 @@ import pytest
 import emu
 
 
-@pytest.mark.parametrize("M", [512, 600, 2 * 1029])
+@pytest.mark.parametrize("M", [512, 600, 1500, 2 * 1029, 5000, 12000])   # P = 2^10 .. 2^15: 0-5 grid-wide stages in passes of up to 3
 def test_gated_rfft_irfft_roundtrip(M):
     L = emu.lib()
     L.emu_spectral_frames.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_int, C.c_float, C.c_float, C.c_float]
