@@ -10,7 +10,6 @@
 #include "aes_spectral.cuh"
 
 __global__ void aess_load_kernel(const __grid_constant__ SpecArgs a) { aess_load_body(a); }
-__global__ void aess_global_stage_kernel(const __grid_constant__ SpecArgs a, int st, int inv) { aess_global_stage_body(a, st, inv); }
 template <int R>
 __global__ void __launch_bounds__(256) aess_global_pass_kernel(const __grid_constant__ SpecArgs a, int st, int inv) { aess_global_pass_body<R>(a, st, inv); }
 __global__ void __launch_bounds__(AESS_LOCAL_NT) aess_local_kernel(const __grid_constant__ SpecArgs a, int inv, int mul) { aess_local_body(a, inv, mul); }
@@ -192,7 +191,7 @@ AES_EXPORT int aes_spectral_frames_host(aes_spectral_plan *pl, const float *in_b
     SpecArgs a; memset(&a, 0, sizeof a);
     a.buf = (cpx *)w; a.frames = (float *)(w + s_buf); a.out = (float *)(w + s_buf + s_fr); a.mask = (float *)(w + s_buf + 2 * s_fr);
     a.vhat = pl->d_vhat; a.chirp = pl->d_chirp; a.twP = pl->d_twP; a.tw1k = pl->d_tw1k;
-    a.M = M; a.P = pl->P; a.L = pl->L; a.nb = 1;
+    a.M = M; a.P = pl->P; a.L = pl->L; a.nb = 1; a.nf = 1;
     a.thr = (float)thresh_lin; a.red = (float)reduction; a.alpha = (float)alpha;
     std::vector<float> tmp((size_t)M);
     std::vector<float> win((size_t)M);
@@ -219,10 +218,11 @@ AES_EXPORT int aes_spectral_run(aes_spectral_plan *pl, const float *x, float *y,
     AES_REQUIRE(x != nullptr && y != nullptr, "NULL device buffer");
     AES_REQUIRE(pl->M == 2 * n_frames, "plan frame length %lld != 2 * n_frames", pl->M);
     const long long M = pl->M, nbins = M / 2 + 1;
-    const size_t per = al256((size_t)pl->P * sizeof(cpx)) + 2 * al256((size_t)M * 4) + al256((size_t)nbins * 4);
+    // per clip: half a transform buffer (two clips share one), frame, output, mask
+    const size_t per = al256((size_t)pl->P * sizeof(cpx)) / 2 + 2 * al256((size_t)M * 4) + al256((size_t)nbins * 4);
     const size_t budget = (size_t)8 << 30;
-    int64_t chunk = std::max<int64_t>(1, std::min<int64_t>(n_clips, (int64_t)(budget / per)));
-    int rc = spec_reserve(pl, per * (size_t)chunk);
+    int64_t chunk = std::max<int64_t>(2, std::min<int64_t>(n_clips + (n_clips & 1), (int64_t)(budget / per) & ~(int64_t)1));
+    int rc = spec_reserve(pl, per * (size_t)chunk + al256((size_t)pl->P * sizeof(cpx)));
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     const int g = spec_grid(pl);
@@ -232,12 +232,12 @@ AES_EXPORT int aes_spectral_run(aes_spectral_plan *pl, const float *x, float *y,
         SpecArgs a; memset(&a, 0, sizeof a);
         // packed (unaligned-free) layout for nb frames: buf [nb][P] | frames [nb][M] | out [nb][M] | mask [nb][nbins]
         a.buf = (cpx *)w;
-        float *frames = (float *)(w + (size_t)chunk * al256((size_t)pl->P * sizeof(cpx)));
+        float *frames = (float *)(w + (size_t)((chunk + 1) / 2) * al256((size_t)pl->P * sizeof(cpx)));
         float *outp = frames + (size_t)chunk * M;
         float *maskp = outp + (size_t)chunk * M;
         a.frames = frames; a.out = outp; a.mask = maskp;
         a.vhat = pl->d_vhat; a.chirp = pl->d_chirp; a.twP = pl->d_twP; a.tw1k = pl->d_tw1k;
-        a.M = M; a.P = pl->P; a.L = pl->L; a.nb = (int)nb;
+        a.M = M; a.P = pl->P; a.L = pl->L; a.nb = (int)((nb + 1) / 2); a.nf = (int)nb;      // two clips per complex transform
         a.thr = (float)thresh_lin; a.red = (float)reduction; a.alpha = (float)alpha;
         aess_frames_from_clips_kernel<<<g, 256, 0, st>>>(x + (size_t)b0 * n_frames * 2, pl->d_window, frames, nb, n_frames);
         aess_fill_kernel<<<g, 256, 0, st>>>(maskp, 1.0f, nb * nbins);          // mask_smooth starts at ones

@@ -11,6 +11,10 @@
 // are grid-wide radix-2 passes over global memory, the last/first 10 stages run as independent
 // 1024-point transforms in shared memory (aesc_fft_dif<10> / aesc_ifft_dit<10>); the pointwise
 // product with FFT(v) happens in bit-reversed order, so no permutation pass exists.
+// Two real frames share one complex transform: z = f0 + i*f1 goes through the forward DFT, the
+// two spectra are separated by conjugate symmetry (X0[k] = (Z[k] + conj(Z[M-k]))/2,
+// X1[k] = (Z[k] - conj(Z[M-k]))/(2i)), gated each with its own mask, recombined as
+// W = P0 + i*P1 (both Hermitian) and one inverse DFT returns y0 + i*y1.
 #pragma once
 #include "aes_convreverb.cuh"
 
@@ -24,11 +28,12 @@ struct SpecArgs {
     float *mask;            // [nb][M/2+1] smoothed mask, in/out
     float *out;             // [nb][M] irfft of the processed spectrum
     long long M, P;
-    int L, nb;
+    int L, nb;              // nb: complex transforms = ceil(nf / 2)
+    int nf;                 // real frames (frames / mask / out rows)
     float thr, red, alpha;
 };
 
-// u[n] = frame[n]*c[n] (n < M), zero padding to P
+// u[n] = (f0[n] + i*f1[n]) * c[n] (n < M), zero padding to P; f1 = 0 for an unpaired last frame
 __device__ void aess_load_body(const SpecArgs &a)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -37,47 +42,15 @@ __device__ void aess_load_body(const SpecArgs &a)
         const long long b = e / a.P, n = e % a.P;
         cpx v; v.x = 0.f; v.y = 0.f;
         if (n < a.M) {
-            const float x = a.frames[b * a.M + n];
-            const cpx c = a.chirp[n];
-            v.x = x * c.x; v.y = x * c.y;
+            cpx z;
+            z.x = a.frames[2 * b * a.M + n];
+            z.y = 2 * b + 1 < a.nf ? a.frames[(2 * b + 1) * a.M + n] : 0.0f;
+            v = c_mul(z, a.chirp[n]);
         }
         a.buf[e] = v;
     }
 }
 
-// one grid-wide radix-2 stage (butterfly distance `half` >= 1024); inverse uses conjugate twiddles
-__device__ void aess_global_stage_body(const SpecArgs &a, int st, int inverse)
-{
-    const long long halfP = a.P >> 1;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long total = (long long)a.nb * halfP;
-    // forward DIF stage st: half = P >> (st+1), twiddle exponent pos << st
-    // inverse DIT stage st: half = 1 << st,     twiddle exponent pos << (L-1-st), conjugated
-    const long long half = inverse ? (1LL << st) : (a.P >> (st + 1));
-    const int sh = inverse ? (a.L - 1 - st) : st;
-    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
-        const long long b = e / halfP, bf = e % halfP;
-        const long long pos = bf & (half - 1);
-        const long long i0 = ((bf - pos) << 1) + pos, i1 = i0 + half;
-        cpx *d = a.buf + b * a.P;
-        cpx w = a.twP[pos << sh];
-        const cpx u = d[i0], v = d[i1];
-        if (!inverse) {
-            d[i0] = c_add(u, v);
-            d[i1] = c_mul(c_sub(u, v), w);
-        } else {
-            w.y = -w.y;
-            const cpx t = c_mul(v, w);
-            d[i0] = c_add(u, t);
-            d[i1] = c_sub(u, t);
-        }
-    }
-}
-
-// R consecutive radix-2 stages on the 2^R points a thread holds (p[k] = element base + k*d of a
-// 2^L-point transform, i = base mod d).  Forward (DIF): stages st, st+1, .. with the largest
-// distance first; inverse (DIT): stages st, st+1, .. with the smallest first, conjugate twiddles.
-// tw[q] = exp(-2*pi*i*q / 2^L), q < 2^(L-1).
 // exp(-2*pi*i * e / 2^L) without a table: in the grid-wide passes neighbouring threads need
 // twiddles 2^st entries apart, so table reads cost up to 32 cache lines per warp load and out-weigh
 // the data traffic (measured: 2.3 ms per pass against 0.93 ms for the unit-stride first pass);
@@ -249,27 +222,43 @@ __device__ void aess_local_body(const SpecArgs &a, int inverse, int mul)
     }
 }
 
-// forward result -> spectral gate -> conjugated Hermitian spectrum times chirp, ready for the
-// second (inverse) Bluestein round.  One thread per bin k in [0, M/2].
+// forward result -> the two frames' spectra -> spectral gate on each -> conjugated combined
+// spectrum times chirp, ready for the second (inverse) Bluestein round.  One thread per pair and
+// bin k in [0, M/2]; it alone touches elements k and M-k of the pair's buffer.
+__device__ __forceinline__ cpx aess_gate_one(cpx X, float *maskp, long long k, const SpecArgs &a)
+{
+    const float mag = sqrtf(X.x * X.x + X.y * X.y);
+    const float cur = mag > a.thr ? 1.0f : a.red;               // spectral.py:68
+    const float m = a.alpha * *maskp + (1.0f - a.alpha) * cur;  // spectral.py:71
+    *maskp = m;
+    cpx Pk; Pk.x = X.x * m; Pk.y = X.y * m;                     // mag*mask*exp(i*phase)
+    if (k == 0 || 2 * k == a.M) Pk.y = 0.f;                     // irfft ignores the imaginary part of DC / Nyquist
+    return Pk;
+}
+
 __device__ void aess_gate_body(const SpecArgs &a)
 {
     const long long nbins = a.M / 2 + 1;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)a.nb * nbins; e += stride) {
         const long long b = e / nbins, k = e % nbins;
+        const long long km = k == 0 ? 0 : a.M - k;
+        const bool two = 2 * b + 1 < a.nf;
         cpx *d = a.buf + b * a.P;
-        const cpx X = c_mul(a.chirp[k], d[k]);                  // rfft bin k
-        const float mag = sqrtf(X.x * X.x + X.y * X.y);
-        const float cur = mag > a.thr ? 1.0f : a.red;           // spectral.py:68
-        const float m = a.alpha * a.mask[e] + (1.0f - a.alpha) * cur;      // spectral.py:71
-        a.mask[e] = m;
-        cpx Pk; Pk.x = X.x * m; Pk.y = X.y * m;                 // mag*mask*exp(i*phase)
-        if (k == 0 || 2 * k == a.M) Pk.y = 0.f;                 // irfft ignores the imaginary part of DC / Nyquist
-        // inverse DFT via forward DFT: y = conj(DFT(conj(Pfull))) / M; conj(Pfull)[k] = conj(Pk), [M-k] = Pk
-        cpx lo; lo.x = Pk.x; lo.y = -Pk.y;
-        // in place: d[k] is read only by this thread, d[M-k] (> M/2) by nobody in this kernel
-        d[k] = c_mul(lo, a.chirp[k]);
-        if (k != 0 && 2 * k != a.M) d[a.M - k] = c_mul(Pk, a.chirp[a.M - k]);
+        const cpx Zk = c_mul(a.chirp[k], d[k]), Zm = c_mul(a.chirp[km], d[km]);
+        cpx X0, X1;                                             // rfft bin k of frame 2b / 2b+1
+        X0.x = 0.5f * (Zk.x + Zm.x); X0.y = 0.5f * (Zk.y - Zm.y);
+        X1.x = 0.5f * (Zk.y + Zm.y); X1.y = 0.5f * (Zm.x - Zk.x);
+        const cpx P0 = aess_gate_one(X0, a.mask + (2 * b) * nbins + k, k, a);
+        cpx P1; P1.x = 0.f; P1.y = 0.f;
+        if (two) P1 = aess_gate_one(X1, a.mask + (2 * b + 1) * nbins + k, k, a);
+        // inverse DFT via a forward one: y0 + i*y1 = conj(DFT(conj(W))) / M with W = P0full + i*P1full,
+        // W[k] = P0 + i*P1, W[M-k] = conj(P0) + i*conj(P1)
+        cpx ck, cm;                                             // conj(W[k]), conj(W[M-k])
+        ck.x = P0.x - P1.y; ck.y = -P0.y - P1.x;
+        cm.x = P0.x + P1.y; cm.y = P0.y - P1.x;
+        d[k] = c_mul(ck, a.chirp[k]);
+        if (k != 0 && 2 * k != a.M) d[km] = c_mul(cm, a.chirp[km]);
     }
 }
 
@@ -285,7 +274,7 @@ __device__ void aess_zero_pad_body(const SpecArgs &a)
     }
 }
 
-// y[n] = Re(conj(c[n]*Y[n])) / M
+// y0[n] + i*y1[n] = conj(c[n]*Y[n]) / M
 __device__ void aess_store_body(const SpecArgs &a)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -293,6 +282,7 @@ __device__ void aess_store_body(const SpecArgs &a)
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < (long long)a.nb * a.M; e += stride) {
         const long long b = e / a.M, n = e % a.M;
         const cpx y = c_mul(a.chirp[n], a.buf[b * a.P + n]);
-        a.out[e] = y.x * inv;
+        a.out[2 * b * a.M + n] = y.x * inv;
+        if (2 * b + 1 < a.nf) a.out[(2 * b + 1) * a.M + n] = -y.y * inv;
     }
 }

@@ -129,7 +129,6 @@ int emu_convreverb(const float *ir, long long n_taps, const float *x, float *y, 
 // ---- SpectralFilter kernels (aes_spectral.cuh) on the emulator ---------------------------------
 struct SpecLaunch { SpecArgs a; int st, inv, mul; };
 static void sp_load(void *p) { aess_load_body(reinterpret_cast<SpecLaunch *>(p)->a); }
-static void sp_glob(void *p) { SpecLaunch *l = reinterpret_cast<SpecLaunch *>(p); aess_global_stage_body(l->a, l->st, l->inv); }
 template <int R> static void sp_pass(void *p) { SpecLaunch *l = reinterpret_cast<SpecLaunch *>(p); aess_global_pass_body<R>(l->a, l->st, l->inv); }
 static void emu_spec_pass(SpecLaunch &l, int s, int r, int inv)
 {
@@ -159,7 +158,7 @@ int emu_spectral_frames(const float *frames, float *mask, float *y, long long M,
 {
     long long P = 1024; int L = 10;
     while (P < 2 * M - 1) { P <<= 1; ++L; }
-    std::vector<cpx> chirp((size_t)M), v((size_t)P), twP((size_t)P / 2), tw1k(512), buf((size_t)nb * P);
+    std::vector<cpx> chirp((size_t)M), v((size_t)P), twP((size_t)P / 2), tw1k(512), buf((size_t)((nb + 1) / 2) * P);
     for (long long n = 0; n < M; ++n) {
         const long long r = (long long)(((unsigned long long)n * (unsigned long long)n) % (unsigned long long)(2 * M));
         const double ang = -M_PI * (double)r / (double)M;
@@ -171,10 +170,10 @@ int emu_spectral_frames(const float *frames, float *mask, float *y, long long M,
     for (int q = 0; q < 512; ++q) { const double ang = -2.0 * M_PI * q / 1024.0; tw1k[q].x = (float)cos(ang); tw1k[q].y = (float)sin(ang); }
     SpecLaunch l; memset(&l, 0, sizeof l);
     l.a.twP = twP.data(); l.a.tw1k = tw1k.data(); l.a.M = M; l.a.P = P; l.a.L = L;
-    l.a.buf = v.data(); l.a.nb = 1;
+    l.a.buf = v.data(); l.a.nb = 1; l.a.nf = 1;
     emu_spec_fft(l, 0, 0);                               // vhat = FFT(v)/P in place
     l.a.buf = buf.data(); l.a.vhat = v.data(); l.a.chirp = chirp.data(); l.a.frames = frames; l.a.mask = mask; l.a.out = y;
-    l.a.nb = nb; l.a.thr = thr; l.a.red = red; l.a.alpha = alpha;
+    l.a.nb = (nb + 1) / 2; l.a.nf = nb; l.a.thr = thr; l.a.red = red; l.a.alpha = alpha;
     emu::launch(sp_load, &l, 4, 256, 0);
     emu_spec_fft(l, 0, 1); emu_spec_fft(l, 1, 0);
     emu::launch(sp_gate, &l, 4, 256, 0);
