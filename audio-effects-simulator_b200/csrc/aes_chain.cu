@@ -101,6 +101,8 @@ static int launch_chain(aes_chain_plan *pl, const void *x, int in_fmt, void *y, 
     ChainArgs a{ pl->dev, x, y, B, N, scratch, in_fmt, out_fmt, state_out };
     const unsigned grid = (unsigned)std::min<long long>(B, pl->grid_max);
     if (pl->fast_fn) {
+        // the specialised kernels index frames inside a clip with 32 bits (12 h of audio at 48 kHz)
+        AES_REQUIRE(N < (1LL << 31) - 8192, "clips of 2^31 frames or more are not supported by this chain's kernel");
         FastArgs fa = pl->fast;
         fa.x = x; fa.y = y; fa.B = B; fa.N = N; fa.scratch = scratch; fa.lane_tab = pl->d_lane_tab;
         fa.state_out = state_out; fa.in_fmt = in_fmt; fa.out_fmt = out_fmt;

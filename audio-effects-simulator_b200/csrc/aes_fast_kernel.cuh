@@ -139,7 +139,7 @@ struct FCtx {
     float *tile, *rings, *gscr;
     double *wtot;
     int *rpos;              // current parity
-    long long n0;
+    int n0;                 // first frame of the tile inside its clip (clips hold < 2^31 frames)
     int len, tid, lane, warp;
     const float *ln_stage;  // this tile's staged delay line: [2 ch][T + 8] floats (PF shapes), or null
 };
@@ -455,7 +455,7 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
                 } else {
                     aesf_line_read<FR>(c, rg, st.glob != 0, sr.da[ch], line);
                 }
-                if (c.n0 < (long long)rg.lag) {                     // only the first tiles of a clip: zero history
+                if (c.n0 < rg.lag) {                                // only the first tiles of a clip: zero history
 #pragma unroll
                     for (int j = 0; j < FR; ++j)
                         if (c.n0 + i0 + j < rg.lag) line[j] = 0.0f;
@@ -491,7 +491,7 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
             for (int ch = 0; ch < 2; ++ch) {
                 const FRing rg = st.pre[ch];
                 aesf_line_read<FR>(c, rg, st.glob != 0, sr.da[ch], pre[ch]);
-                if (c.n0 < (long long)rg.lag) {
+                if (c.n0 < rg.lag) {
 #pragma unroll
                     for (int j = 0; j < FR; ++j)
                         if (c.n0 + i0 + j < rg.lag) pre[ch][j] = 0.0f;
@@ -899,18 +899,20 @@ __device__ void aes_fast_body(const FastArgs &a)
         __syncthreads();
 
         // a tile goes through TMA staging when it is full, 16-byte aligned and plain f32 stereo
+        const int N = (int)a.N;                         // the host routes clips of 2^31 frames or more to the generic kernel
         const bool clip_staged = STAGED && a.in_fmt == AESK_F32_STEREO && ((b * a.N) & 1) == 0;
         const long long clip_frame0 = b * a.N;
-        if (clip_staged && a.N >= (long long)T && c.tid == 0)
+        if (clip_staged && N >= T && c.tid == 0)
             aesf_issue_tile<FR, PCODE, PS < 0 ? 0 : PS>(a, c, lnbase, clip_frame0, stage_x + (it_issue & 1) * 2 * T,
                                                        stage_ln + (it_issue & 1) * 2 * (T + 8), bars + (it_issue & 1));
-        if (clip_staged && a.N >= (long long)T) ++it_issue;
+        if (clip_staged && N >= T) ++it_issue;
         float4 lnA[2], lnB[2];
         lnA[0] = lnA[1] = lnB[0] = lnB[1] = make_float4(0.f, 0.f, 0.f, 0.f);
         int par = 0;
-        for (long long n0 = 0; n0 < a.N; n0 += T, par ^= 1) {
+        for (int n0 = 0; n0 < N; n0 += T, par ^= 1) {
             c.n0 = n0;
-            c.len = (a.N - n0 < (long long)T) ? (int)(a.N - n0) : T;
+            const int rem = N - n0;
+            c.len = rem < T ? rem : T;
             c.rpos = rpos2 + par * nw;
             float v[2][FR];
             const bool staged = clip_staged && c.len == T;
@@ -941,7 +943,7 @@ __device__ void aes_fast_body(const FastArgs &a)
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch) lnbase[ch] = aesf_adv(lnbase[ch], pst.ring[ch][0].tinc, pst.ring[ch][0].len);
             }
-            if (clip_staged && a.N - n0 - T >= (long long)T) {
+            if (clip_staged && rem >= 2 * T) {
                 if (c.tid == 0)
                     aesf_issue_tile<FR, PCODE, PS < 0 ? 0 : PS>(a, c, lnbase, clip_frame0 + n0 + T,
                                                                stage_x + (it_issue & 1) * 2 * T,
