@@ -450,8 +450,8 @@ def b200_arm(args):
         }
         if not args.no_cpu:
             cores = os.cpu_count() or 1
-            n_cpu = args.cpu_clips or max(cores, min(2 * cores, 128))
-            v, dt = cpu_run(args.preset, n_cpu, n_frames, cores)
+            n_cpu = args.cpu_clips or max(cores, min(20 * cores, 512))     # ~20 s of CPU work on all threads
+            v, dt = cpu_run(args.preset, n_cpu, n_frames, cores, reps=2)
             numpy_fft = any(c["type"] in ("spectral", "convreverb") for c in cfg)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1 if numpy_fft else cores, "kind": "port",
                                     "sample": (f"2 clips x {args.seconds:g} s, 1 thread (numpy FFT block), {dt:.2f} s" if numpy_fft
