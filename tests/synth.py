@@ -64,3 +64,21 @@ def err_stats(got: np.ndarray, want: np.ndarray):
     p_err = float(np.sum(d ** 2))
     snr = float("inf") if p_err == 0.0 else 10.0 * np.log10(max(p_sig, 1e-300) / p_err)
     return mx, snr
+
+
+# parameter corners shared by the emulator (CPU) and the GPU parity tests
+REVERB_VARIANTS = {
+    "heavy-damping": {"damp": 0.9, "rt60_s": 4.0},                          # slow one-pole: full scan depth, cross-warp carries
+    "max-damping": {"damp": 0.99, "rt60_s": 10.0},
+    "long-predelay": {"pre_delay_ms": 60.0},                                # 2880 samples >= tile: register line
+    "short-predelay": {"pre_delay_ms": 3.0},                                # 144 samples: phase walk
+    "other-combs": {"comb_times_ms": (31.3, 36.0, 40.7, 45.1), "allpass_times_ms": (6.1, 2.3), "jitter_ms": 0.7},
+    "long-tail": {"rt60_s": 9.5, "mix_wet": 0.9, "mix_dry": 0.2},           # drives the output into the clipper
+}
+
+DELAY_VARIANTS = {
+    "max-feedback": {"delay_ms": 333.3, "feedback": 0.95, "offset_ms": 17.7},       # odd lags, long tail
+    "short": {"delay_ms": 1.0, "feedback": 0.5, "offset_ms": 0.0},                  # 48 samples: phase walk
+    "mid": {"delay_ms": 30.0, "feedback": 0.6, "offset_ms": 5.5},                   # 1440 / 1704: register line in smem
+    "longest": {"delay_ms": 1499.0, "feedback": 0.3, "offset_ms": 30.0},            # clamps at max_delay - 1
+}

@@ -150,3 +150,21 @@ def test_reverb_topology_variants(fs, topo):
     assert emu.lib().emu_last_was_fast() == 1
     assert emu.lib().emu_last_topo() == topo
     check(y, orc.run_file_path(cfg, x, fs), what=(fs, topo))
+
+
+@pytest.mark.parametrize("variant", sorted(synth.REVERB_VARIANTS))
+def test_reverb_parameter_corners(variant):
+    cfg = [{"type": "reverb", "params": dict(synth.REVERB_VARIANTS[variant])}]
+    n = 7000
+    x = synth.clip(61, n, 2, 48000)
+    y = emu.run(emu.resolved_descs(cfg, 48000, n, 2), 48000, x[None])[0]
+    check(y, orc.run_file_path(cfg, x, 48000), what=variant)
+
+
+@pytest.mark.parametrize("variant", sorted(synth.DELAY_VARIANTS))
+def test_delay_parameter_corners(variant):
+    cfg = [{"type": "delay", "params": dict(synth.DELAY_VARIANTS[variant])}]
+    n = 40000 if variant != "longest" else 80000
+    x = synth.clip(62, n, 2, 48000)
+    y = emu.run(emu.resolved_descs(cfg, 48000, n, 2), 48000, x[None])[0]
+    check(y, orc.run_file_path(cfg, x, 48000), what=variant)

@@ -420,3 +420,47 @@ def test_streaming_then_reprepare_then_whole_clip(ab, orc):
     ours.process(big, got)
     ref.process(big, want)
     check(got, want, what="whole clip after streaming")
+
+
+@pytest.mark.parametrize("fs", [44100, 40000])
+@pytest.mark.parametrize("name", NATIVE)
+def test_presets_at_other_sample_rates(ab, orc, name, fs):
+    """44.1 kHz takes the second compile-time reverb topology and misaligned delay lags; 40 kHz has
+    no baked topology, so the reverb shapes run with descriptor-driven lengths (same kernels)."""
+    cfg = synth.PRESETS[name]
+    x = synth.clip(51, 40000, 2, fs)
+    check(run_file(ab, cfg, x, fs), orc.run_file_path(cfg, x, fs), exact=(name == "Slapback Echo"), what=(name, fs))
+
+
+REVERB_VARIANTS = synth.REVERB_VARIANTS
+
+
+@pytest.mark.parametrize("variant", sorted(REVERB_VARIANTS))
+def test_reverb_parameter_corners(ab, orc, variant):
+    cfg = [{"type": "reverb", "params": dict(REVERB_VARIANTS[variant])}]
+    x = synth.clip(61, 60000, 2, 48000)
+    check(run_file(ab, cfg, x, 48000), orc.run_file_path(cfg, x, 48000), what=variant)
+
+
+DELAY_VARIANTS = synth.DELAY_VARIANTS
+
+
+@pytest.mark.parametrize("variant", sorted(DELAY_VARIANTS))
+def test_delay_parameter_corners(ab, orc, variant):
+    cfg = [{"type": "delay", "params": dict(DELAY_VARIANTS[variant])}]
+    x = synth.clip(62, 150000, 2, 48000)
+    check(run_file(ab, cfg, x, 48000), orc.run_file_path(cfg, x, 48000), what=variant)
+
+
+@pytest.mark.parametrize("B", [1, 2, 297, 593])
+def test_batch_sizes_around_the_grid(ab, orc, B):
+    """One clip, fewer clips than CTAs, one more than a full grid (296 resident CTAs), two grids + 1."""
+    from audioblocks.engine import file_chain
+    cfg = synth.PRESETS["Rain Delay"]
+    n = 6000
+    base = synth.batch(70, 3, n)
+    x = np.ascontiguousarray(base[np.arange(B) % 3])
+    y = file_chain(cfg, 48000, channels_in=2).process_batch(x)
+    want = [orc.run_file_path(cfg, base[k], 48000) for k in range(3)]
+    for b in range(B):
+        check(y[b], want[b % 3], what=(B, b))
