@@ -422,6 +422,28 @@ __device__ __forceinline__ void aesf_select4(const float4 A, const float4 B, int
 }
 
 // ---- one stage, specialised on its shape code ------------------------------------------------
+// Hermite read of the octaver ring: the four taps sit d0, d0-1, d0-2, d0-3 samples behind frame n,
+// each wrapped into [0, size) as the reference's modulo does (octaver.py:41-58).  Away from the
+// two ends of that range the taps are four consecutive slots and need no per-tap wrap.
+__device__ __forceinline__ float aes_octaver_taps(const float *rb, int mask, int n, int size, int d0, float frac)
+{
+    float t[4];
+    if (d0 >= 3 && d0 < size) {
+        const int b = n - d0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t[k] = rb[(b + k) & mask];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int d = d0 - k;
+            if (d < 0) d += size;
+            if (d >= size) d -= size;
+            t[k] = rb[(n - d) & mask];
+        }
+    }
+    return aes_hermite(frac, t[0], t[1], t[2], t[3]);
+}
+
 template <int FR, int CODE, int S, int TOPO>
 __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRegs &sr, float (&v)[2][FR],
                                            const float4 (&lnA)[2], const float4 (&lnB)[2], const double *sin, double *sout)
@@ -692,29 +714,46 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
         __syncthreads();
     } else if constexpr (KIND == AESK_OCTAVER) {
         float *rb = c.rings + st.ring[0][0].off;
-        const int mask = st.oct_mask, size = st.oct_size;
+        const int mask = st.oct_mask, size = st.oct_size, half = size >> 1;
+        const bool even = (size & 1) == 0;
         float mono[FR];
 #pragma unroll
         for (int j = 0; j < FR; ++j) mono[j] = __fmul_rn(__fadd_rn(v[0][j], v[1][j]), 0.5f);
-        aes_stv<FR>(rb + (int)((c.n0 + i0) & mask), mono);
+        aes_stv<FR>(rb + ((c.n0 + i0) & mask), mono);
         __syncthreads();
         const float wet_g = st.mix, dry_g = (float)(1.0 - (double)st.mix);
-        const double ph0 = st.ph0, step = st.step, fsize = st.fsize;
+        const double step = st.step, fsize = st.fsize;
+        // phasor of the thread's first frame in closed form, then one add (+ wrap) per frame
+        double ph = st.ph0 + (double)(c.n0 + i0) * step;
+        ph -= floor(ph);
 #pragma unroll
         for (int j = 0; j < FR; ++j) {
-            const long long n = c.n0 + i0 + j;
-            double ph = ph0 + (double)n * step;
-            ph -= floor(ph);
-            double p2 = ph + 0.5;
-            if (p2 >= 1.0) p2 -= 1.0;
-            const float s1 = aes_octaver_tap(rb, mask, n, size, fsize, ph);
-            const float s2 = aes_octaver_tap(rb, mask, n, size, fsize, p2);
+            const int n = c.n0 + i0 + j;
+            // grain 1 reads size*(1-ph) samples behind the write pointer (octaver.py:39); grain 2 runs
+            // half a period apart, so for an even ring its read position is exactly size/2 away:
+            // same fraction, integer part shifted -- one f64 -> (int, frac) split serves both
+            const double raw = fsize - ph * fsize;
+            const int m = (int)raw;
+            const float frac = (float)(raw - (double)m);
+            float s1, s2;
+            s1 = aes_octaver_taps(rb, mask, n, size, size - m + 1, frac);
+            if (even) {
+                const int m2 = ph < 0.5 ? m - half : m + half;
+                s2 = aes_octaver_taps(rb, mask, n, size, size - m2 + 1, frac);
+            } else {
+                double p2 = ph + 0.5;
+                if (p2 >= 1.0) p2 -= 1.0;
+                s2 = aes_octaver_tap(rb, mask, n, size, fsize, p2);
+            }
             const float sn = sinpif((float)ph);
             const float g1 = sn * sn;
             const float g2 = 1.0f - g1;
             const float wet = __fmul_rn(s1 * g1 + s2 * g2, wet_g);
             v[0][j] = __fadd_rn(__fmul_rn(v[0][j], dry_g), wet);
             v[1][j] = __fadd_rn(__fmul_rn(v[1][j], dry_g), wet);
+            ph += step;
+            if (ph >= 1.0) ph -= 1.0;
+            else if (ph < 0.0) ph += 1.0;
         }
     } else if constexpr (KIND == AESK_DISTORTION) {
         const float drive = st.drive, mix = st.mix, dry = 1.0f - st.mix;

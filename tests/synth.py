@@ -82,3 +82,10 @@ DELAY_VARIANTS = {
     "mid": {"delay_ms": 30.0, "feedback": 0.6, "offset_ms": 5.5},                   # 1440 / 1704: register line in smem
     "longest": {"delay_ms": 1499.0, "feedback": 0.3, "offset_ms": 30.0},            # clamps at max_delay - 1
 }
+
+OCTAVER_VARIANTS = {
+    "octave-down": {"semitones": -12.0, "mix": 0.5},
+    "fifth-up": {"semitones": 7.0, "mix": 1.0},                  # negative phasor step
+    "odd-window": {"semitones": -5.0, "mix": 0.7, "window_ms": 30.03},   # ring of 1441 samples: grains not an integer apart
+    "two-octaves-up": {"semitones": 24.0, "mix": 0.3, "window_ms": 10.0},
+}

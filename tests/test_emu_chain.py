@@ -168,3 +168,13 @@ def test_delay_parameter_corners(variant):
     x = synth.clip(62, n, 2, 48000)
     y = emu.run(emu.resolved_descs(cfg, 48000, n, 2), 48000, x[None])[0]
     check(y, orc.run_file_path(cfg, x, 48000), what=variant)
+
+
+@pytest.mark.parametrize("variant", sorted(synth.OCTAVER_VARIANTS))
+def test_octaver_parameter_corners(variant):
+    cfg = [{"type": "octaver", "params": dict(synth.OCTAVER_VARIANTS[variant])}]
+    n = 12000
+    x = synth.clip(63, n, 2, 48000)
+    y = emu.run(emu.resolved_descs(cfg, 48000, n, 2), 48000, x[None])[0]
+    assert emu.lib().emu_last_was_fast() == 1
+    check(y, orc.run_file_path(cfg, x, 48000), what=variant)

@@ -464,3 +464,10 @@ def test_batch_sizes_around_the_grid(ab, orc, B):
     want = [orc.run_file_path(cfg, base[k], 48000) for k in range(3)]
     for b in range(B):
         check(y[b], want[b % 3], what=(B, b))
+
+
+@pytest.mark.parametrize("variant", sorted(synth.OCTAVER_VARIANTS))
+def test_octaver_parameter_corners(ab, orc, variant):
+    cfg = [{"type": "octaver", "params": dict(synth.OCTAVER_VARIANTS[variant])}]
+    x = synth.clip(63, 100000, 2, 48000)
+    check(run_file(ab, cfg, x, 48000), orc.run_file_path(cfg, x, 48000), what=variant)
