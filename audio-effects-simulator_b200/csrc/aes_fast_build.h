@@ -147,6 +147,14 @@ static inline bool aes_fast_build(const DevPlan &p, FastArgs *fa, int codes[AESF
         case AESK_BIQUAD:
             for (int i = 0; i < 5; ++i) f.bq[i] = d.bq[i];
             memcpy(f.bq_pow, d.bq_pow, sizeof f.bq_pow);
+            {   // row 0 of (A^T)^j, A^T = [[-a1, 1], [-a2, 0]]
+                double r0 = 1.0, r1 = 0.0;
+                for (int j = 0; j < 4; ++j) {
+                    f.bq_row[j][0] = r0; f.bq_row[j][1] = r1;
+                    const double n0 = -r0 * d.bq[3] - r1 * d.bq[4], n1 = r0;
+                    r0 = n0; r1 = n1;
+                }
+            }
             for (int l = 0; l < 32; ++l) memcpy(lt + l * FAST_LANE_STRIDE + 4, d.bq_lane[l], 4 * sizeof(double));
             for (int i = 0; i < 8; ++i) fa->init[s][i] = d.init[i];
             codes[s] = AESF_BIQUAD;

@@ -50,6 +50,7 @@ struct FastStage {
     int oct_size, oct_mask;
     double bq[5];
     double bq_pow[6][4];
+    double bq_row[4][2];    // first row of (A^T)^j, j = 0..3: what an incoming TDF-II state adds to output j
     double thr, att, rel;
     double ph0, step, fsize;
 };
@@ -609,24 +610,25 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
 #pragma unroll
             for (int j = 0; j < FR; ++j) v[ch][j] = aes_mix_clip(dry, v[ch][j], wet, sum[ch][j]);
     } else if constexpr (KIND == AESK_BIQUAD) {
-        constexpr int T = AES_NT * FR;
+        // Transposed direct form II: y = b0*x + s1, s1' = b1*x - a1*y + s2, s2' = b2*x - a2*y.  The
+        // 2-vector (s1, s2) is the whole state -- no input history -- so a thread needs nothing from
+        // its neighbours before the scan.  Transition matrix A^T (A: the DF-I companion matrix whose
+        // powers the plan tabulates).  Pass 1 runs the chunk from zero state and keeps the outputs;
+        // the carried-in state S then adds row0((A^T)^j) . S to output j (independent FMAs).
         const double b0 = st.bq[0], b1 = st.bq[1], b2 = st.bq[2], a1 = st.bq[3], a2 = st.bq[4];
-        aesf_spill<FR>(c, v);
-        __syncthreads();
-        double xm1[2], xm2[2], e1[2], e2[2];
+        double yz[2][FR], e1[2], e2[2];
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
-            const float *xc = c.tile + ch * T;
-            xm1[ch] = i0 >= 1 ? (double)xc[i0 - 1] : sin[4 * ch + 0];
-            xm2[ch] = i0 >= 2 ? (double)xc[i0 - 2] : (i0 == 1 ? sin[4 * ch + 0] : sin[4 * ch + 1]);
-            double y1 = 0.0, y2 = 0.0, p1 = xm1[ch], p2 = xm2[ch];
+            double s1 = 0.0, s2 = 0.0;
 #pragma unroll
             for (int j = 0; j < FR; ++j) {
                 const double xj = (double)v[ch][j];
-                const double y = b0 * xj + b1 * p1 + b2 * p2 - a1 * y1 - a2 * y2;
-                y2 = y1; y1 = y; p2 = p1; p1 = xj;
+                const double y = fma(b0, xj, s1);
+                s1 = fma(b1, xj, fma(-a1, y, s2));
+                s2 = fma(b2, xj, -a2 * y);
+                yz[ch][j] = y;
             }
-            e1[ch] = y1; e2[ch] = y2;
+            e1[ch] = s1; e2[ch] = s2;
         }
 #pragma unroll
         for (int s = 0; s < 5; ++s) {
@@ -636,8 +638,8 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
                 const double u1 = __shfl_up_sync(0xffffffffu, e1[ch], 1 << s);
                 const double u2 = __shfl_up_sync(0xffffffffu, e2[ch], 1 << s);
                 if (lane >= (1 << s)) {
-                    e1[ch] += m0 * u1 + m1 * u2;
-                    e2[ch] += m2 * u1 + m3 * u2;
+                    e1[ch] += m0 * u1 + m2 * u2;                 // (A^k)^T u
+                    e2[ch] += m1 * u1 + m3 * u2;
                 }
             }
         }
@@ -654,28 +656,27 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
         const double l0 = lt[0], l1 = lt[1], l2 = lt[2], l3 = lt[3];
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
-            double C1 = sin[4 * ch + 2], C2 = sin[4 * ch + 3];
+            // state carried between tiles is the reference's (x1, x2, y1, y2) (filter.py:35-40)
+            const double cx1 = sin[4 * ch + 0], cx2 = sin[4 * ch + 1], cy1 = sin[4 * ch + 2], cy2 = sin[4 * ch + 3];
+            double C1 = b1 * cx1 + b2 * cx2 - a1 * cy1 - a2 * cy2;
+            double C2 = b2 * cx1 - a2 * cy1;
             for (int t = 0; t < warp; ++t) {
-                const double t1 = w0 * C1 + w1 * C2 + c.wtot[(t * 2 + ch) * 2];
-                const double t2 = w2 * C1 + w3 * C2 + c.wtot[(t * 2 + ch) * 2 + 1];
+                const double t1 = w0 * C1 + w2 * C2 + c.wtot[(t * 2 + ch) * 2];
+                const double t2 = w1 * C1 + w3 * C2 + c.wtot[(t * 2 + ch) * 2 + 1];
                 C1 = t1; C2 = t2;
             }
             double x1 = __shfl_up_sync(0xffffffffu, e1[ch], 1), x2 = __shfl_up_sync(0xffffffffu, e2[ch], 1);
             if (lane == 0) { x1 = 0.0; x2 = 0.0; }
-            double y1 = x1 + l0 * C1 + l1 * C2;
-            double y2 = x2 + l2 * C1 + l3 * C2;
-            double p1 = xm1[ch], p2 = xm2[ch];
+            const double S1 = x1 + l0 * C1 + l2 * C2;            // state entering this thread's chunk
+            const double S2 = x2 + l1 * C1 + l3 * C2;
 #pragma unroll
             for (int j = 0; j < FR; ++j) {
-                const double xj = (double)v[ch][j];
-                const double y = b0 * xj + b1 * p1 + b2 * p2 - a1 * y1 - a2 * y2;
+                const double y = j == 0 ? yz[ch][0] + S1 : fma(st.bq_row[j][0], S1, fma(st.bq_row[j][1], S2, yz[ch][j]));
+                if (i0 + j == c.len - 1) { sout[4 * ch + 0] = (double)v[ch][j]; sout[4 * ch + 2] = y; }
+                if (i0 + j == c.len - 2) { sout[4 * ch + 1] = (double)v[ch][j]; sout[4 * ch + 3] = y; }
                 v[ch][j] = (float)y;
-                y2 = y1; y1 = y; p2 = p1; p1 = xj;
-                if (i0 + j == c.len - 1) {
-                    sout[4 * ch + 0] = p1; sout[4 * ch + 1] = p2;
-                    sout[4 * ch + 2] = y1; sout[4 * ch + 3] = y2;
-                }
             }
+            if (c.len == 1 && c.tid == 0) { sout[4 * ch + 1] = cx1; sout[4 * ch + 3] = cy1; }
         }
         __syncthreads();
     } else if constexpr (KIND == AESK_GATE) {
