@@ -163,7 +163,8 @@ __device__ __forceinline__ int aes_rslot(int wpos, int i0, const DevRing &rg)
 {
     int r = wpos + i0 - rg.lag;            // > -len because i0 >= 0, wpos >= 0, lag <= len
     if (r < 0) r += rg.len;
-    return r;                              // < len because wpos + i0 < len + lag (i0 < T <= lag)
+    if (r >= rg.len) r -= rg.len;          // only a REGB line (lag < T) can land here: wpos + i0 < len + T
+    return r;
 }
 __device__ __forceinline__ int aes_wslot(int wpos, int i0, const DevRing &rg)
 {
@@ -360,12 +361,23 @@ __device__ void aes_stage_reverb(const DevStage &st, const KCtx &c, float (&v)[2
                 if (c.n0 + i0 + j < rg.lag) pre[ch][j] = 0.0f;
             aes_stv<FR>(rb + aes_wslot(c.rpos[rid], i0, rg), v[ch]);
         }
-    } else {
-        aes_spill<FR>(c, v);
+    } else {                                    // AES_MODE_REGB: lag < T, so part of what is read is written in this tile
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const int rid = st.pre_ring[ch];
+            const DevRing rg = c.P->ring[rid];
+            aes_stv<FR>(aes_ring_base(c, rg) + aes_wslot(c.rpos[rid], i0, rg), v[ch]);
+        }
         __syncthreads();
-        aes_walk<FR, 1>(c, st.pre_ring[c.tid >> 7], 0.f, 0.f, 0.f);
-        __syncthreads();
-        aes_reload<FR>(c, pre);
+#pragma unroll
+        for (int ch = 0; ch < 2; ++ch) {
+            const int rid = st.pre_ring[ch];
+            const DevRing rg = c.P->ring[rid];
+            aes_ring_read<FR>(aes_ring_base(c, rg), aes_rslot(c.rpos[rid], i0, rg), rg.len, pre[ch]);
+#pragma unroll
+            for (int j = 0; j < FR; ++j)
+                if (c.n0 + i0 + j < rg.lag) pre[ch][j] = 0.0f;
+        }
     }
 
     // damped combs (reverb.py:33-46), 4 per side at a time; sum in comb order in f32

@@ -29,9 +29,9 @@
     X(AESF_REVERB(0), 0, 0, 0, AESF_TOPO_44K)                                                           \
     X(AESF_REVERB(0), 0, 0, 0, AESF_TOPO_NONE)                                                           \
     X(AESF_REVERB(1), 0, 0, 0, AESF_TOPO_NONE)                                                           \
-    X(AESF_REVERB(2), 0, 0, 0, AESF_TOPO_48K)                      /* Cathedral (20 ms pre-delay)    */ \
-    X(AESF_REVERB(2), 0, 0, 0, AESF_TOPO_44K)                                                           \
-    X(AESF_REVERB(2), 0, 0, 0, AESF_TOPO_NONE)                                                           \
+    X(AESF_REVERB(3), 0, 0, 0, AESF_TOPO_48K)                      /* Cathedral (20 ms pre-delay)    */ \
+    X(AESF_REVERB(3), 0, 0, 0, AESF_TOPO_44K)                                                           \
+    X(AESF_REVERB(3), 0, 0, 0, AESF_TOPO_NONE)                                                           \
     X(AESF_BIQUAD, AESF_REVERB(0), 0, 0, AESF_TOPO_48K)            /* Guitar Filter                  */ \
     X(AESF_BIQUAD, AESF_REVERB(0), 0, 0, AESF_TOPO_44K)                                                 \
     X(AESF_BIQUAD, AESF_REVERB(0), 0, 0, AESF_TOPO_NONE)                                                 \
@@ -74,7 +74,8 @@ static inline int aes_fast_topo(const DevPlan &p)
 static inline size_t aes_fast_smem_bytes(const DevPlan &p)
 {
     const size_t T = (size_t)p.T;
-    return aes_plan_smem_bytes(p) + 16 + (4 * T + 4 * (T + 8)) * sizeof(float) + 2 * sizeof(unsigned long long) + 16;
+    // + TMA staging: 2 input tiles, 2 x [2 ch][T+8] line samples when a feedback delay is prefetched, 2 mbarriers
+    return aes_plan_smem_bytes(p) + 16 + (4 * T + (p.pf_stage >= 0 ? 4 * (T + 8) : 0)) * sizeof(float) + 2 * sizeof(unsigned long long) + 16;
 }
 
 static inline FRing aesf_ring(const DevRing &r)
@@ -127,8 +128,8 @@ static inline bool aes_fast_build(const DevPlan &p, FastArgs *fa, int codes[AESF
                 const DevRing &r0 = p.ring[d.pre_ring[0]], &r1 = p.ring[d.pre_ring[1]];
                 if (r0.space != r1.space) return false;
                 f.glob = r0.space == AES_SPACE_GLOBAL;
-                if (d.mode == AES_MODE_REG) { pm = 1; f.pre[0] = aesf_ring(r0); f.pre[1] = aesf_ring(r1); }
-                else { pm = 2; if (!add_walk(d.pre_ring[0], &f.walk_pre[0]) || !add_walk(d.pre_ring[1], &f.walk_pre[1])) return false; }
+                pm = d.mode == AES_MODE_REG ? 1 : 3;
+                f.pre[0] = aesf_ring(r0); f.pre[1] = aesf_ring(r1);
             }
             for (int ch = 0; ch < 2; ++ch) {
                 for (int c = 0; c < 4; ++c) {

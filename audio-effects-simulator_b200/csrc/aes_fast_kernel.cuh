@@ -27,7 +27,7 @@
 #define AESF_NC(c) (((c) >> 4) & 15)
 #define AESF_NA(c) (((c) >> 8) & 15)
 #define AESF_MODE(c) (((c) >> 12) & 3)
-#define AESF_PREMODE(c) (((c) >> 14) & 3)      // 0 none, 1 REG, 2 WALK
+#define AESF_PREMODE(c) (((c) >> 14) & 3)      // 0 none, 1 REG (lag >= T), 3 REGB (lag < T: write, barrier, read)
 #define AESF_PF(c) (((c) >> 16) & 1)
 
 struct FRing {
@@ -504,12 +504,12 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
     } else if constexpr (KIND == AESK_REVERB) {
         constexpr int NC = AESF_NC(CODE), NA = AESF_NA(CODE), PM = AESF_PREMODE(CODE);
         float pre[2][FR];
-        if (PM == 0) {
+        if constexpr (PM == 0) {
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
                 for (int j = 0; j < FR; ++j) pre[ch][j] = v[ch][j];
-        } else if (PM == 1) {
+        } else if constexpr (PM == 1) {
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 const FRing rg = st.pre[ch];
@@ -523,12 +523,24 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
                 else         aes_stv<FR>(c.rings + rg.off + sr.dw[ch], v[ch]);
             }
         } else {
-            aesf_spill<FR>(c, v);
+            static_assert(PM == 3, "");
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const FRing rg = st.pre[ch];
+                if (st.glob) aes_stv<FR>(c.gscr + rg.off + sr.dw[ch], v[ch]);
+                else         aes_stv<FR>(c.rings + rg.off + sr.dw[ch], v[ch]);
+            }
             __syncthreads();
-            const int ch = c.tid >> 7;
-            aesf_walk<FR, 1>(c, a.walk[st.walk_pre[ch]], st.walk_pre[ch], st.glob != 0, 0.f, 0.f, 0.f);
-            __syncthreads();
-            aesf_reload<FR>(c, pre);
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const FRing rg = st.pre[ch];
+                aesf_line_read<FR>(c, rg, st.glob != 0, sr.da[ch], pre[ch]);
+                if (c.n0 < rg.lag) {
+#pragma unroll
+                    for (int j = 0; j < FR; ++j)
+                        if (c.n0 + i0 + j < rg.lag) pre[ch][j] = 0.0f;
+                }
+            }
         }
 
         // damped combs on u = lp/(1-h)
@@ -780,7 +792,7 @@ __device__ __forceinline__ void aesf_slots_init(const FastArgs &a, int i0, SRegs
         for (int ch = 0; ch < 2; ++ch) aesf_line_init<FR>(st.ring[ch][0], i0, sr.dw[ch], sr.da[ch]);
     }
     if constexpr (KIND == AESK_REVERB) {
-        if (AESF_PREMODE(CODE) == 1) {
+        if (AESF_PREMODE(CODE) != 0) {
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) aesf_line_init<FR>(st.pre[ch], i0, sr.dw[ch], sr.da[ch]);
         }
@@ -805,7 +817,7 @@ __device__ __forceinline__ void aesf_slots_advance(const FastArgs &a, SRegs &sr)
         }
     }
     if constexpr (KIND == AESK_REVERB) {
-        if (AESF_PREMODE(CODE) == 1) {
+        if (AESF_PREMODE(CODE) != 0) {
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 const FRing rg = st.pre[ch];
@@ -906,7 +918,7 @@ __device__ void aes_fast_body(const FastArgs &a)
     float *stg = reinterpret_cast<float *>((reinterpret_cast<size_t>(rpos2 + 2 * AESF_MAX_WALK) + 15) & ~(size_t)15);
     float *stage_x = stg;                           // [2][2T]
     float *stage_ln = stg + 4 * T;                  // [2][2][T+8]
-    unsigned long long *bars = reinterpret_cast<unsigned long long *>(stage_ln + 4 * (T + 8));
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(stage_ln + (PS >= 0 ? 4 * (T + 8) : 0));
     c.gscr = a.scratch + (long long)blockIdx.x * a.scratch_floats;
     c.ln_stage = nullptr;
     const int nw = a.n_walk, i0 = FR * c.tid;

@@ -21,7 +21,7 @@ enum { AES_SPACE_SMEM = 0, AES_SPACE_GLOBAL = 1 };
 //        multiple of 4, slot(n) = n mod len, so the 4 consecutive frames of a thread are
 //        one aligned float4 on the write side; the read side at (n - lag) mod len is
 //        misaligned by a per-ring constant and is served by two aligned float4 loads.
-enum { AES_MODE_WALK = 0, AES_MODE_REG = 1 };
+enum { AES_MODE_WALK = 0, AES_MODE_REG = 1, AES_MODE_REGB = 2 };   // REGB: REG ring for a PURE delay shorter than the tile: written first, read behind a barrier
 
 struct DevRing {
     int len;        // ring period in floats

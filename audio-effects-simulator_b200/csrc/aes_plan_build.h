@@ -166,12 +166,12 @@ static inline int aes_build_devplan(const aes_stage_desc *stages, int n, int fs,
             for (double v = hw; v >= eps && st.nxw < 8; v *= hw) ++st.nxw;
             for (int l = 0; l < 32; ++l) st.hlane[l] = (float)pow(h, (double)FR * l);
             if (d.q[2] < 0) return B.fail("reverb: negative pre-delay");
-            st.mode = d.q[2] >= T ? AES_MODE_REG : AES_MODE_WALK;
+            // the pre-delay has no feedback: a line shorter than the tile needs no phase walk, only
+            // its writes ahead of its reads (period lag + T either way, see add_reg_line)
+            st.mode = d.q[2] >= T ? AES_MODE_REG : AES_MODE_REGB;
             for (int side = 0; side < 2; ++side) {
                 if (d.q[2] > 0) {
-                    rc = st.mode == AES_MODE_REG ? B.add_reg_line(d.q[2], &st.pre_ring[side])
-                                                 : B.add_walk(d.q[2], true, &st.pre_ring[side]);
-                    if (rc) return rc;
+                    if ((rc = B.add_reg_line(d.q[2], &st.pre_ring[side]))) return rc;
                 }
                 for (int c = 0; c < st.nc; ++c) {
                     const long long L = d.q[4 + 8 * side + c];

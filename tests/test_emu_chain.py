@@ -178,3 +178,19 @@ def test_octaver_parameter_corners(variant):
     y = emu.run(emu.resolved_descs(cfg, 48000, n, 2), 48000, x[None])[0]
     assert emu.lib().emu_last_was_fast() == 1
     check(y, orc.run_file_path(cfg, x, 48000), what=variant)
+
+
+@pytest.mark.parametrize("fs", [48000, 44100, 22050, 11025])
+@pytest.mark.parametrize("pre_ms", [0.05, 3.0, 21.3, 60.0])
+def test_predelay_lengths_both_kernels(pre_ms, fs, monkeypatch):
+    """Pre-delays below the tile use a register line written ahead of its reads (barrier in
+    between), longer ones the plain register line; 1-sample to 60 ms, aligned and not, on the
+    specialised kernel where one exists and on the generic interpreter."""
+    cfg = [{"type": "reverb", "params": {"pre_delay_ms": pre_ms}}]
+    n = 6000
+    x = synth.clip(5, n, 2, fs)
+    want = orc.run_file_path(cfg, x, fs)
+    d = emu.resolved_descs(cfg, fs, n, 2)
+    check(emu.run(d, fs, x[None])[0], want, what=(pre_ms, fs, "default"))
+    monkeypatch.setenv("AES_NO_FAST", "1")
+    check(emu.run(d, fs, x[None])[0], want, what=(pre_ms, fs, "generic"))
