@@ -151,7 +151,9 @@ AES_EXPORT int aes_chain_plan_create(const aes_stage_desc *stages, int n_stages,
         AES_CUDA(cudaGetDevice(&pl->device));
         AES_CUDA(cudaDeviceGetAttribute(&pl->sm_count, cudaDevAttrMultiProcessorCount, pl->device));
         // a specialised kernel, when the chain's shape is one of the pre-instantiated ones
-        static float lane_tab[AESF_MAX_STAGES * 32 * FAST_LANE_STRIDE];
+        std::vector<float> lane_tab_v((size_t)AESF_MAX_STAGES * 32 * FAST_LANE_STRIDE);   // (not static: plans may be built concurrently)
+        float *lane_tab = lane_tab_v.data();
+        const size_t lane_tab_bytes = lane_tab_v.size() * sizeof(float);
         int codes[AESF_MAX_STAGES];
         if (!getenv("AES_NO_FAST") && aes_fast_build(pl->host, &pl->fast, codes, lane_tab)) {
             const size_t fast_smem = aes_fast_smem_bytes(pl->host);
@@ -164,8 +166,8 @@ AES_EXPORT int aes_chain_plan_create(const aes_stage_desc *stages, int n_stages,
                 AES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sh.fn, AES_NT, fast_smem));
                 if (occ < 1) break;
                 pl->smem_bytes = fast_smem;
-                AES_CUDA(cudaMalloc(&pl->d_lane_tab, sizeof lane_tab));
-                AES_CUDA(cudaMemcpy(pl->d_lane_tab, lane_tab, sizeof lane_tab, cudaMemcpyHostToDevice));
+                AES_CUDA(cudaMalloc(&pl->d_lane_tab, lane_tab_bytes));
+                AES_CUDA(cudaMemcpy(pl->d_lane_tab, lane_tab, lane_tab_bytes, cudaMemcpyHostToDevice));
                 pl->fast_fn = sh.fn;
                 pl->ctas_per_sm = occ;
                 break;
@@ -187,15 +189,17 @@ AES_EXPORT int aes_chain_plan_create(const aes_stage_desc *stages, int n_stages,
         bool all_bq = n_stages >= 1 && n_stages <= AESB_MAX_STAGES;
         for (int s2 = 0; s2 < n_stages && all_bq; ++s2) all_bq = stages[s2].kind == AES_STAGE_BIQUAD;
         if (all_bq) {
-            static double tab[AESB_MAX_STAGES * 128 + AESB_MAX_STAGES * AES_NT * 4];
+            std::vector<double> tab_v((size_t)AESB_MAX_STAGES * 128 + (size_t)AESB_MAX_STAGES * AES_NT * 4);
+            double *tab = tab_v.data();
+            const size_t tab_bytes = tab_v.size() * sizeof(double);
             double co[5 * AESB_MAX_STAGES], dfi[AESB_MAX_STAGES * 8];
             for (int s2 = 0; s2 < n_stages; ++s2) {
                 for (int i = 0; i < 5; ++i) co[5 * s2 + i] = stages[s2].p[i];
                 for (int i = 0; i < 8; ++i) dfi[8 * s2 + i] = stages[s2].p[8 + i];
             }
             aes_biquad_build(n_stages, co, dfi, &pl->bq, tab, tab + AESB_MAX_STAGES * 128);
-            AES_CUDA(cudaMalloc(&pl->d_bq_tab, sizeof tab));
-            AES_CUDA(cudaMemcpy(pl->d_bq_tab, tab, sizeof tab, cudaMemcpyHostToDevice));
+            AES_CUDA(cudaMalloc(&pl->d_bq_tab, tab_bytes));
+            AES_CUDA(cudaMemcpy(pl->d_bq_tab, tab, tab_bytes, cudaMemcpyHostToDevice));
             pl->bq_ok = true;
         }
         AES_CUDA(cudaMalloc(&pl->d_state, sizeof pl->h_state));
