@@ -722,8 +722,13 @@ __device__ void aes_chain_body(const ChainArgs &a)
                 switch (st.kind) {
                 case AESK_DELAY:
                     if (st.mode == AES_MODE_REG) {
-                        if (s != pf_stage) aes_delay_fetch<FR>(st, c, 0, ln);
-                        aes_stage_delay_reg<FR>(st, c, v, ln);
+                        if (s != pf_stage) {                     // fetched on the spot, into its own registers:
+                            float ln_now[2][FR];                 // `ln` holds the prefetched stage's line
+                            aes_delay_fetch<FR>(st, c, 0, ln_now);
+                            aes_stage_delay_reg<FR>(st, c, v, ln_now);
+                        } else {
+                            aes_stage_delay_reg<FR>(st, c, v, ln);
+                        }
                     } else {
                         aes_spill<FR>(c, v);
                         __syncthreads();

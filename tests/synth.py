@@ -89,3 +89,50 @@ OCTAVER_VARIANTS = {
     "odd-window": {"semitones": -5.0, "mix": 0.7, "window_ms": 30.03},   # ring of 1441 samples: grains not an integer apart
     "two-octaves-up": {"semitones": 24.0, "mix": 0.3, "window_ms": 10.0},
 }
+
+
+def random_chain(rng, max_blocks: int = 4):
+    """A random chain config (reference parameter names, values inside the SmoothParam clamps of
+    SURVEY 8b) for the fuzz tests; no spectral block (whole-file FFT, tested separately)."""
+    def delay():
+        return {"type": "delay", "params": {"delay_ms": float(rng.choice([1.0, 7.3, 21.4, 120.0, 375.0, 900.0])),
+                                            "feedback": float(rng.uniform(0.0, 0.95)),
+                                            "offset_ms": float(rng.choice([0.0, 3.3, 30.0])),
+                                            "mix_dry": float(rng.uniform(0.2, 1.0)), "mix_wet": float(rng.uniform(0.0, 1.0))}}
+
+    def reverb():
+        p = {"rt60_s": float(rng.uniform(0.2, 8.0)), "damp": float(rng.uniform(0.0, 0.95)),
+             "pre_delay_ms": float(rng.choice([0.0, 0.0, 2.0, 20.0, 45.0, 100.0])),
+             "mix_dry": float(rng.uniform(0.2, 1.0)), "mix_wet": float(rng.uniform(0.0, 0.8))}
+        if rng.random() < 0.3:
+            p["comb_times_ms"] = tuple(float(v) for v in np.sort(rng.uniform(30.0, 48.0, 4)))
+            p["allpass_times_ms"] = (float(rng.uniform(3.0, 8.0)), float(rng.uniform(1.0, 2.9)))
+        return {"type": "reverb", "params": p}
+
+    def filt():
+        return {"type": "filter", "params": {"filter_type": int(rng.integers(0, 3)),
+                                             "cutoff_hz": float(np.exp(rng.uniform(np.log(30.0), np.log(15000.0)))),
+                                             "q": float(rng.uniform(0.3, 6.0))}}
+
+    def octaver():
+        return {"type": "octaver", "params": {"semitones": float(rng.choice([-24, -12, -7, -5, 3, 7, 12])),
+                                              "mix": float(rng.uniform(0.1, 1.0))}}
+
+    def gate():
+        return {"type": "gate", "params": {"threshold_db": float(rng.uniform(-60.0, -10.0)),
+                                           "attack_ms": float(rng.uniform(1.0, 50.0)),
+                                           "release_ms": float(rng.uniform(10.0, 400.0))}}
+
+    def distortion():
+        return {"type": "distortion", "params": {"drive": float(rng.uniform(0.5, 8.0)), "mix": float(rng.uniform(0.1, 1.0))}}
+
+    makers = [delay, reverb, filt, octaver, gate, distortion]
+    n = int(rng.integers(1, max_blocks + 1))
+    chain, have_reverb = [], False
+    for _ in range(n):
+        mk = makers[int(rng.integers(0, len(makers)))]
+        if mk is reverb and have_reverb:
+            mk = filt                                   # one reverb per chain keeps shared memory within one CTA's budget
+        have_reverb |= mk is reverb
+        chain.append(mk())
+    return chain
