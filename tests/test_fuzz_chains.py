@@ -57,3 +57,48 @@ def test_random_chain_on_the_gpu(seed):
     y = file_chain(cfg, fs, channels_in=2).process_batch(x)
     for b in range(B):
         check(y[b], orc.run_file_path(cfg, x[b], fs), (seed, b, cfg, fs, n), cfg)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(40))
+def test_random_chain_streamed_in_blocks_on_the_gpu(seed):
+    """The live route (engine.py:38-65,156-163): chain built at a block size, warmed up, then fed
+    block after block with state carried between calls -- random chains, mono or stereo input,
+    block sizes 64..1024."""
+    import audioblocks as ab
+    from audioblocks import _native
+    _native.lib()
+    cfg, fs, rng = case(1000 + seed)
+    bs = int(rng.choice([64, 256, 333, 1024]))
+    ci = int(rng.choice([1, 2]))
+    ours = ab.EffectsChain(fs, ci, 2, bs)
+    for c in cfg:
+        ours.add(ab.engine.make_effect(c))
+    ours.warmup()
+    ref = orc.build_chain(cfg, fs, ci=ci, bs=bs)
+    ref.warmup()
+    nblk = 24
+    x = synth.clip(500 + seed, bs * nblk, ci, fs)
+    for k in range(nblk):
+        blk = np.ascontiguousarray(x[bs * k:bs * (k + 1)])
+        got, want = np.zeros((bs, 2), np.float32), np.zeros((bs, 2), np.float32)
+        ours.process(blk, got)
+        ref.process(blk, want)
+        check(got, want, (seed, k, cfg, fs, bs, ci), cfg)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(24))
+def test_random_chain_mono_file_route_on_the_gpu(seed):
+    """The WAV-file route feeds the chain one mono clip (engine.py:81-102): build@1024, warm-up,
+    one whole-clip call with (N, 1) input fanned out to both channels."""
+    from audioblocks import _native
+    from audioblocks.engine import file_chain
+    _native.lib()
+    cfg, fs, rng = case(2000 + seed)
+    n = int(rng.choice([1, 1023, 1024, 4097, 50000]))
+    x = synth.clip(600 + seed, n, 1, fs)
+    chain = file_chain(cfg, fs, channels_in=1)
+    got = np.zeros((n, 2), np.float32)
+    chain.process(x, got)
+    check(got, orc.run_file_path(cfg, x, fs), (seed, cfg, fs, n), cfg)
