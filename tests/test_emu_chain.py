@@ -194,3 +194,17 @@ def test_predelay_lengths_both_kernels(pre_ms, fs, monkeypatch):
     check(emu.run(d, fs, x[None])[0], want, what=(pre_ms, fs, "default"))
     monkeypatch.setenv("AES_NO_FAST", "1")
     check(emu.run(d, fs, x[None])[0], want, what=(pre_ms, fs, "generic"))
+
+
+def test_several_reverbs_in_one_chain_and_the_shared_memory_limit():
+    """Ring state of every reverb lives in the clip's CTA: three default reverbs still fit one CTA per
+    SM (generic kernel), a fourth is refused with the byte count instead of running wrong."""
+    R = {"type": "reverb", "params": {}}
+    n = 4000
+    x = synth.clip(3, n, 2, 48000)
+    for k in (2, 3):
+        cfg = [R] * k
+        y = emu.run(emu.resolved_descs(cfg, 48000, n, 2), 48000, x[None])[0]
+        check(y, orc.run_file_path(cfg, x, 48000), what=k)
+    with pytest.raises(RuntimeError, match="shared memory"):
+        emu.run(emu.resolved_descs([R] * 4, 48000, n, 2), 48000, x[None])
