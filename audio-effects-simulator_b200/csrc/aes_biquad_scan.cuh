@@ -62,7 +62,7 @@ __device__ __forceinline__ void bq_matvec(const double m[4], double v1, double v
 
 #ifdef AES_CPU_EMU
 static inline int bq_ld_flag(const int *p) { return *p; }
-static inline void bq_acquire_fence() {}
+static inline int bq_ld_flag_acquire(const int *p) { return *p; }
 static inline void bq_st_flag(int *p, int v) { *p = v; }
 static inline void __threadfence() {}
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p += v; return o; }
@@ -75,7 +75,13 @@ __device__ __forceinline__ int bq_ld_flag(const int *p)
     asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void bq_acquire_fence() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+// (re-reading the flag with ld.acquire orders the record reads after it without a full fence)
+__device__ __forceinline__ int bq_ld_flag_acquire(const int *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void bq_st_flag(int *p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -194,7 +200,7 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
                 if (pt >= 0) {
                     const long long prec = rec - 1 - base - tid;
                     do { f = bq_ld_flag(a.flag + prec); } while (f == 0);
-                    bq_acquire_fence();
+                    f = bq_ld_flag_acquire(a.flag + prec);      // >= the value just seen: flags only go 0 -> 1 -> 2
                     const bool incl_ok = !(a.dbg_skip > 0 && pt % a.dbg_skip != 0);   // tests: force the aggregate path
                     if (f == 2 && !incl_ok) f = 1;
                     const double *src = (f == 2 ? a.inc : a.agg) + prec * 4;
