@@ -471,3 +471,39 @@ def test_octaver_parameter_corners(ab, orc, variant):
     cfg = [{"type": "octaver", "params": dict(synth.OCTAVER_VARIANTS[variant])}]
     x = synth.clip(63, 100000, 2, 48000)
     check(run_file(ab, cfg, x, 48000), orc.run_file_path(cfg, x, 48000), what=variant)
+
+
+def test_spectral_whole_file_with_partial_gating_pairs_and_odd_batches(ab, orc):
+    """Whole-file SpectralFilter on clips scaled so that about half of the bins fall under the gate:
+    the output (leakage of the gated bins into the zero half of the frame) is then far above rounding
+    noise, and clips travel two per complex transform (odd batch: the last one alone).  A bin whose
+    magnitude sits on the threshold may flip between the f32 device FFT and numpy's, so the bar is
+    relative: 1 % of the output's peak; a pairing mix-up would be an error of order one."""
+    from audioblocks.engine import file_chain
+    cfg = [{"type": "spectral", "params": {"threshold_db": -40.0, "reduction": 0.1, "smoothing": 0.5}}]
+    for B, n in ((3, 20011), (2, 16384), (1, 9000)):
+        x = synth.batch(31, B, n) * np.float32(4e-4)
+        x[0] *= np.float32(3.0)                         # a louder partner inside the first pair
+        y = file_chain(cfg, 48000, channels_in=2).process_batch(x)
+        for b in range(B):
+            want = orc.run_file_path(cfg, x[b], 48000)
+            peak = float(np.max(np.abs(want)))
+            assert peak > 1e-6, (B, n, b, peak)         # the case really exercises the gate
+            assert np.max(np.abs(y[b] - want)) <= 1e-2 * peak, (B, n, b, peak)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_convolution_reverb_random_sizes(ab, orc, seed):
+    rng = np.random.default_rng(8100 + seed)
+    log2n = int(rng.choice([8, 11, 14]))
+    taps = int(rng.integers(1, {8: 700, 11: 6000, 14: 40000}[log2n]))
+    n = int(rng.integers(1, 60000))
+    B = int(rng.integers(1, 4))
+    ir = orc.synthetic_ir(taps, rt60=float(rng.uniform(0.01, 0.5)))
+    x = synth.batch(700 + seed, B, n)
+    dry, wet = float(rng.uniform(0.0, 1.0)), float(rng.uniform(0.1, 1.0))
+    y = ab.ConvolutionReverbEffect(ir, dry, wet, block_log2=log2n).process_batch(x)
+    for b in range(B):
+        want = np.zeros_like(x[b])
+        orc.OConvReverb(ir, dry, wet).process_into(x[b], want)
+        check(y[b], want, what=(seed, log2n, taps, n, b))
