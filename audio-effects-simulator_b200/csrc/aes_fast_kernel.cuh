@@ -445,13 +445,20 @@ __device__ __forceinline__ float aes_octaver_taps(const float *rb, int mask, int
     return aes_hermite(frac, t[0], t[1], t[2], t[3]);
 }
 
-template <int FR, int CODE, int S, int TOPO>
+// stages that hand per-warp totals through shared memory (reverb, biquad, gate) alternate between
+// two 32-double halves of the exchange area (WPAR = parity of the stage among them): a warp still
+// reading stage k's totals is at most one user behind, and user k+2 only writes after user k+1's
+// barrier -- so no stage needs a trailing barrier just to protect the area
+#define AESF_USES_WTOT(code) (AESF_KIND(code) == AESK_REVERB || AESF_KIND(code) == AESK_BIQUAD || AESF_KIND(code) == AESK_GATE)
+
+template <int FR, int CODE, int S, int TOPO, int WPAR>
 __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRegs &sr, float (&v)[2][FR],
                                            const float4 (&lnA)[2], const float4 (&lnB)[2], const double *sin, double *sout)
 {
     constexpr int KIND = AESF_KIND(CODE);
     const FastStage &st = a.st[S];
     const int i0 = FR * c.tid, lane = c.lane, warp = c.warp;
+    double *const wtot = c.wtot + WPAR * 32;
 
     if constexpr (KIND == AESK_DELAY) {
         if (AESF_MODE(CODE) == AES_MODE_REG) {
@@ -569,7 +576,7 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
                     if (lane >= (1 << s)) e[ch][cc] = fmaf(m, t, e[ch][cc]);
                 }
         }
-        float *wt = reinterpret_cast<float *>(c.wtot);          // [8 warps][2][4]
+        float *wt = reinterpret_cast<float *>(wtot);            // [8 warps][2][4]
         if (lane == 31) {
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch)
@@ -658,8 +665,8 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
         if (lane == 31) {
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
-                c.wtot[(warp * 2 + ch) * 2] = e1[ch];
-                c.wtot[(warp * 2 + ch) * 2 + 1] = e2[ch];
+                wtot[(warp * 2 + ch) * 2] = e1[ch];
+                wtot[(warp * 2 + ch) * 2 + 1] = e2[ch];
             }
         }
         __syncthreads();
@@ -673,8 +680,8 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
             double C1 = b1 * cx1 + b2 * cx2 - a1 * cy1 - a2 * cy2;
             double C2 = b2 * cx1 - a2 * cy1;
             for (int t = 0; t < warp; ++t) {
-                const double t1 = w0 * C1 + w2 * C2 + c.wtot[(t * 2 + ch) * 2];
-                const double t2 = w1 * C1 + w3 * C2 + c.wtot[(t * 2 + ch) * 2 + 1];
+                const double t1 = w0 * C1 + w2 * C2 + wtot[(t * 2 + ch) * 2];
+                const double t2 = w1 * C1 + w3 * C2 + wtot[(t * 2 + ch) * 2 + 1];
                 C1 = t1; C2 = t2;
             }
             double x1 = __shfl_up_sync(0xffffffffu, e1[ch], 1), x2 = __shfl_up_sync(0xffffffffu, e2[ch], 1);
@@ -690,7 +697,6 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
             }
             if (c.len == 1 && c.tid == 0) { sout[4 * ch + 1] = cx1; sout[4 * ch + 3] = cy1; }
         }
-        __syncthreads();
     } else if constexpr (KIND == AESK_GATE) {
         const double thr = st.thr, ka = 1.0 - st.att, kr = 1.0 - st.rel, att = st.att;
         bool open[FR];
@@ -709,10 +715,10 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
             const double Bu = __shfl_up_sync(0xffffffffu, Bv, 1 << s);
             if (lane >= (1 << s)) { Bv = A * Bu + Bv; A = A * Au; }
         }
-        if (lane == 31) { c.wtot[2 * warp] = A; c.wtot[2 * warp + 1] = Bv; }
+        if (lane == 31) { wtot[2 * warp] = A; wtot[2 * warp + 1] = Bv; }
         __syncthreads();
         double g = sin[0];
-        for (int t = 0; t < warp; ++t) g = c.wtot[2 * t] * g + c.wtot[2 * t + 1];
+        for (int t = 0; t < warp; ++t) g = wtot[2 * t] * g + wtot[2 * t + 1];
         double Ae = __shfl_up_sync(0xffffffffu, A, 1), Be = __shfl_up_sync(0xffffffffu, Bv, 1);
         if (lane == 0) { Ae = 1.0; Be = 0.0; }
         g = Ae * g + Be;
@@ -724,7 +730,6 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
             v[1][f] *= gf;
             if (i0 + f == c.len - 1) sout[0] = g;
         }
-        __syncthreads();
     } else if constexpr (KIND == AESK_OCTAVER) {
         float *rb = c.rings + st.ring[0][0].off;
         const int mask = st.oct_mask, size = st.oct_size, half = size >> 1;
@@ -1004,10 +1009,10 @@ __device__ void aes_fast_body(const FastArgs &a)
             }
             const double *sin = state + par * NST;
             double *sout = state + (par ^ 1) * NST;
-            if (C0) aesf_stage<FR, C0, 0, TOPO>(a, c, sr0, v, lnA, lnB, sin, sout);
-            if (C1) aesf_stage<FR, C1, 1, TOPO>(a, c, sr1, v, lnA, lnB, sin + 8, sout + 8);
-            if (C2) aesf_stage<FR, C2, 2, TOPO>(a, c, sr2, v, lnA, lnB, sin + 16, sout + 16);
-            if (C3) aesf_stage<FR, C3, 3, TOPO>(a, c, sr3, v, lnA, lnB, sin + 24, sout + 24);
+            if (C0) aesf_stage<FR, C0, 0, TOPO, (0) & 1>(a, c, sr0, v, lnA, lnB, sin, sout);
+            if (C1) aesf_stage<FR, C1, 1, TOPO, (AESF_USES_WTOT(C0)) & 1>(a, c, sr1, v, lnA, lnB, sin + 8, sout + 8);
+            if (C2) aesf_stage<FR, C2, 2, TOPO, (AESF_USES_WTOT(C0) + AESF_USES_WTOT(C1)) & 1>(a, c, sr2, v, lnA, lnB, sin + 16, sout + 16);
+            if (C3) aesf_stage<FR, C3, 3, TOPO, (AESF_USES_WTOT(C0) + AESF_USES_WTOT(C1) + AESF_USES_WTOT(C2)) & 1>(a, c, sr3, v, lnA, lnB, sin + 24, sout + 24);
             aes_store_frames<FR>(io, b, n0, c.len, c.tid, v);
             if (C0) aesf_slots_advance<FR, C0, 0, TOPO>(a, sr0);
             if (C1) aesf_slots_advance<FR, C1, 1, TOPO>(a, sr1);
