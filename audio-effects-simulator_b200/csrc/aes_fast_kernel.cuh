@@ -907,6 +907,8 @@ __device__ void aes_fast_body(const FastArgs &a)
                      : (AESF_KIND(C3) == AESK_DELAY && AESF_PF(C3)) ? 3 : -1;
     constexpr int PCODE = PS == 0 ? C0 : PS == 1 ? C1 : PS == 2 ? C2 : PS == 3 ? C3 : 0;
     constexpr bool STAGED = FR == 4;               // TMA staging needs 16-byte granules per thread
+    constexpr int LASTC = C3 ? C3 : C2 ? C2 : C1 ? C1 : C0;
+    constexpr bool ENDS_IN_REVERB = AESF_KIND(LASTC) == AESK_REVERB;
     AES_DYN_SMEM(float, smem);
     FCtx c;
     c.tid = threadIdx.x;
@@ -1024,7 +1026,11 @@ __device__ void aes_fast_body(const FastArgs &a)
                 if (p >= rg.len) p -= rg.len;
                 rpos2[(par ^ 1) * nw + c.tid] = p;
             }
-            __syncthreads();
+            // A chain that ENDS in a reverb needs no tile-end barrier: after the reverb's last barrier
+            // (behind the second all-pass) a thread only touches its own tile entries, registers and
+            // parity-switched words, and everything the next tile overwrites (staging slot, exchange
+            // area, carried state of the other parity, ring slots) was last read before that barrier.
+            if (!ENDS_IN_REVERB) __syncthreads();
         }
         if (a.state_out != nullptr)
             for (int i = c.tid; i < NST; i += AES_NT)
