@@ -176,7 +176,7 @@ def reference_arm(args):
         return
     cores = os.cpu_count() or 1
     n_frames = int(args.seconds * FS)
-    n_clips = args.cpu_clips or max(cores, min(4 * cores, 256))
+    n_clips = args.cpu_clips or max(cores, min(20 * cores, 512))      # same sample as the B200 arm's cpu_baseline
     cpu_run(args.preset, cores, n_frames, cores)
     times = []
     for _ in range(args.warmup):
