@@ -10,9 +10,9 @@
 #include "aes_spectral.cuh"
 
 __global__ void aess_load_kernel(const __grid_constant__ SpecArgs a) { aess_load_body(a); }
-template <int R>
-__global__ void __launch_bounds__(256) aess_global_pass_kernel(const __grid_constant__ SpecArgs a, int st, int inv) { aess_global_pass_body<R>(a, st, inv); }
-__global__ void __launch_bounds__(AESS_LOCAL_NT) aess_local_kernel(const __grid_constant__ SpecArgs a, int inv, int mul) { aess_local_body(a, inv, mul); }
+template <int R, int IN, int OUT>
+__global__ void __launch_bounds__(256) aess_global_pass_kernel(const __grid_constant__ SpecArgs a, int st, int inv) { aess_global_pass_body<R, IN, OUT>(a, st, inv); }
+__global__ void __launch_bounds__(AESS_LOCAL_NT, 3) aess_local_kernel(const __grid_constant__ SpecArgs a, int inv, int mul) { aess_local_body(a, inv, mul); }
 __global__ void aess_gate_kernel(const __grid_constant__ SpecArgs a) { aess_gate_body(a); }
 __global__ void aess_zero_pad_kernel(const __grid_constant__ SpecArgs a) { aess_zero_pad_body(a); }
 __global__ void aess_store_kernel(const __grid_constant__ SpecArgs a) { aess_store_body(a); }
@@ -58,23 +58,38 @@ struct aes_spectral_plan {
 
 static int spec_grid(const aes_spectral_plan *pl) { return pl->sms * 8; }
 
-static int spec_fft(const aes_spectral_plan *pl, const SpecArgs &a, int inverse, int mul, cudaStream_t st)
+// `in_mode` applies to the first pass of a forward transform, `out_mode` to the last pass of an
+// inverse one (see aess_global_pass_body); both need at least one grid-wide stage (L > 10)
+template <int IN, int OUT>
+static void spec_pass(const aes_spectral_plan *pl, const SpecArgs &a, int s, int r, int inv, cudaStream_t st)
 {
     const int g = spec_grid(pl);
+    if (r == 3) aess_global_pass_kernel<3, IN, OUT><<<g, 256, 0, st>>>(a, s, inv);
+    else if (r == 2) aess_global_pass_kernel<2, IN, OUT><<<g, 256, 0, st>>>(a, s, inv);
+    else aess_global_pass_kernel<1, IN, OUT><<<g, 256, 0, st>>>(a, s, inv);
+    aes_count_launch();
+}
+
+static int spec_fft(const aes_spectral_plan *pl, const SpecArgs &a, int inverse, int mul, cudaStream_t st,
+                    int in_mode = 0, int out_mode = 0)
+{
     const long long pairs = ((long long)a.nb * a.P / 1024 + 1) / 2;    // two 1024-point chunks per CTA trip
     const unsigned lgrid = (unsigned)std::min<long long>(pairs, (long long)pl->sms * 8);
-    auto pass = [&](int s, int r, int inv) {
-        if (r == 3) aess_global_pass_kernel<3><<<g, 256, 0, st>>>(a, s, inv);
-        else if (r == 2) aess_global_pass_kernel<2><<<g, 256, 0, st>>>(a, s, inv);
-        else aess_global_pass_kernel<1><<<g, 256, 0, st>>>(a, s, inv);
-        aes_count_launch();
-    };
     if (!inverse) {                                             // stages 0 .. L-11 span >= 1024 points
-        for (int s = 0, r; s <= a.L - 11; s += r) pass(s, r = aess_pass_radix(a.L - 10 - s), 0);
+        for (int s = 0, r; s <= a.L - 11; s += r) {
+            r = aess_pass_radix(a.L - 10 - s);
+            if (s == 0 && in_mode == 1) spec_pass<1, 0>(pl, a, s, r, 0, st);
+            else if (s == 0 && in_mode == 2) spec_pass<2, 0>(pl, a, s, r, 0, st);
+            else spec_pass<0, 0>(pl, a, s, r, 0, st);
+        }
         aess_local_kernel<<<lgrid, AESS_LOCAL_NT, AESS_LOCAL_SMEM_CPX * sizeof(cpx), st>>>(a, 0, mul); aes_count_launch();
     } else {
         aess_local_kernel<<<lgrid, AESS_LOCAL_NT, AESS_LOCAL_SMEM_CPX * sizeof(cpx), st>>>(a, 1, 0); aes_count_launch();
-        for (int s = 10, r; s < a.L; s += r) pass(s, r = aess_pass_radix(a.L - s), 1);
+        for (int s = 10, r; s < a.L; s += r) {
+            r = aess_pass_radix(a.L - s);
+            if (s + r == a.L && out_mode == 1) spec_pass<0, 1>(pl, a, s, r, 1, st);
+            else spec_pass<0, 0>(pl, a, s, r, 1, st);
+        }
     }
     AES_CUDA(cudaGetLastError());
     return 0;
@@ -84,15 +99,16 @@ static int spec_fft(const aes_spectral_plan *pl, const SpecArgs &a, int inverse,
 static int spec_process(const aes_spectral_plan *pl, SpecArgs a, cudaStream_t st)
 {
     const int g = spec_grid(pl);
+    const bool fuse = a.L > 10;                                 // a grid-wide pass exists to fold load / pad / store into
     int rc;
-    aess_load_kernel<<<g, 256, 0, st>>>(a); aes_count_launch();
-    if ((rc = spec_fft(pl, a, 0, 1, st))) return rc;
+    if (!fuse) { aess_load_kernel<<<g, 256, 0, st>>>(a); aes_count_launch(); }
+    if ((rc = spec_fft(pl, a, 0, 1, st, fuse ? 1 : 0, 0))) return rc;
     if ((rc = spec_fft(pl, a, 1, 0, st))) return rc;
     aess_gate_kernel<<<g, 256, 0, st>>>(a); aes_count_launch();
-    aess_zero_pad_kernel<<<g, 256, 0, st>>>(a); aes_count_launch();
-    if ((rc = spec_fft(pl, a, 0, 1, st))) return rc;
-    if ((rc = spec_fft(pl, a, 1, 0, st))) return rc;
-    aess_store_kernel<<<g, 256, 0, st>>>(a); aes_count_launch();
+    if (!fuse) { aess_zero_pad_kernel<<<g, 256, 0, st>>>(a); aes_count_launch(); }
+    if ((rc = spec_fft(pl, a, 0, 1, st, fuse ? 2 : 0, 0))) return rc;
+    if ((rc = spec_fft(pl, a, 1, 0, st, 0, fuse ? 1 : 0))) return rc;
+    if (!fuse) { aess_store_kernel<<<g, 256, 0, st>>>(a); aes_count_launch(); }
     AES_CUDA(cudaGetLastError());
     return 0;
 }

@@ -99,7 +99,12 @@ __device__ __forceinline__ void aess_bfly(cpx (&p)[1 << R], long long i, long lo
 // points its butterflies connect, so the data makes one round trip per pass instead of one per
 // stage (11 global stages of a 2^21-point transform: 4 passes).  Forward (DIF) passes start at
 // stage `st` (largest distance first); inverse (DIT) passes start at stage `st` and climb.
-template <int R>
+// IN : 0 read the work buffer | 1 first pass of the analysis round: (f0 + i*f1)*chirp straight from
+//      the frames, zeros beyond M (replaces aess_load_body) | 2 first pass of the synthesis round:
+//      the work buffer below M, zeros beyond (replaces aess_zero_pad_body)
+// OUT: 0 write the work buffer | 1 last pass of the synthesis round: conj(chirp*Y)/M straight to
+//      the two output frames (replaces aess_store_body)
+template <int R, int IN, int OUT>
 __device__ void aess_global_pass_body(const SpecArgs &a, int st, int inverse)
 {
     constexpr int K = 1 << R;
@@ -107,16 +112,47 @@ __device__ void aess_global_pass_body(const SpecArgs &a, int st, int inverse)
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long total = (long long)a.nb * per;
     const long long d = inverse ? (1LL << st) : (a.P >> (st + R));      // distance between a thread's points
+    const float inv = 1.0f / (float)a.M;
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += stride) {
         const long long b = e / per, rem = e % per;
         const long long i = rem & (d - 1), blk = rem >> (inverse ? st : (a.L - st - R));
-        cpx *p0 = a.buf + b * a.P + blk * (d << R) + i;
+        const long long n0 = blk * (d << R) + i;                 // index of point 0 inside the transform
+        cpx *p0 = a.buf + b * a.P + n0;
         cpx p[K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) p[k] = p0[k * d];
+        for (int k = 0; k < K; ++k) {
+            const long long n = n0 + k * d;
+            if (IN == 0) {
+                p[k] = p0[k * d];
+            } else {
+                cpx v; v.x = 0.f; v.y = 0.f;
+                if (n < a.M) {
+                    if (IN == 1) {
+                        cpx z;
+                        z.x = a.frames[2 * b * a.M + n];
+                        z.y = 2 * b + 1 < a.nf ? a.frames[(2 * b + 1) * a.M + n] : 0.0f;
+                        v = c_mul(z, a.chirp[n]);
+                    } else {
+                        v = p0[k * d];
+                    }
+                }
+                p[k] = v;
+            }
+        }
         aess_bfly<R, false>(p, i, d, st, inverse, a.L, a.twP);
 #pragma unroll
-        for (int k = 0; k < K; ++k) p0[k * d] = p[k];
+        for (int k = 0; k < K; ++k) {
+            if (OUT == 0) {
+                p0[k * d] = p[k];
+            } else {
+                const long long n = n0 + k * d;
+                if (n < a.M) {
+                    const cpx y = c_mul(a.chirp[n], p[k]);
+                    a.out[2 * b * a.M + n] = y.x * inv;
+                    if (2 * b + 1 < a.nf) a.out[(2 * b + 1) * a.M + n] = -y.y * inv;
+                }
+            }
+        }
     }
 }
 // how many stages the next global pass takes when `remaining` are left
@@ -139,16 +175,33 @@ __device__ void aess_local_body(const SpecArgs &a, int inverse, int mul)
     cpx *s = smem + g * 1152;
     const long long nchunks = (long long)a.nb * a.P / 1024;
     const cpx *tw = a.tw1k;
+    // the chunk's 8 points per thread are fetched one trip ahead (registers q), so the global
+    // latency hides behind the three shared-memory passes of the current chunk
+    cpx q[8];
+    auto fetch = [&](long long cpn) {
+        const long long chn = 2 * cpn + g;
+        if (chn >= nchunks) return;
+        const cpx *dn = a.buf + chn * 1024;
+        if (!inverse) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) q[k] = dn[t + 128 * k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const int e = 2 * (t + 128 * k); q[2 * k] = dn[e]; q[2 * k + 1] = dn[e + 1]; }
+        }
+    };
+    if (2 * (long long)blockIdx.x < nchunks) fetch(blockIdx.x);
     for (long long cp = blockIdx.x; 2 * cp < nchunks; cp += gridDim.x) {
         const long long chunk = 2 * cp + g;
         const bool valid = chunk < nchunks;
         cpx *d = a.buf + chunk * 1024;
         const long long off = (chunk * 1024) % a.P;
         cpx p[8];
-        if (!inverse) {
-            if (valid) {                                        // stages 0-2: points t + 128k, from global
 #pragma unroll
-                for (int k = 0; k < 8; ++k) p[k] = d[t + 128 * k];
+        for (int k = 0; k < 8; ++k) p[k] = q[k];
+        if (2 * (cp + gridDim.x) < nchunks) fetch(cp + gridDim.x);
+        if (!inverse) {
+            if (valid) {                                        // stages 0-2: points t + 128k (fetched from global)
                 aess_bfly<3, true>(p, t, 128, 0, 0, 10, tw);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) s[aess_pad(t + 128 * k)] = p[k];
@@ -174,8 +227,8 @@ __device__ void aess_local_body(const SpecArgs &a, int inverse, int mul)
             __syncthreads();
             if (valid) {                                        // stage 9 (twiddle 1): pairs (2q, 2q+1), to global
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int e = 2 * (t + 128 * q);
+                for (int k = 0; k < 4; ++k) {
+                    const int e = 2 * (t + 128 * k);
                     const cpx u = s[aess_pad(e)], v = s[aess_pad(e) + 1];
                     cpx o0 = c_add(u, v), o1 = c_sub(u, v);
                     if (mul) { o0 = c_mul(o0, a.vhat[off + e]); o1 = c_mul(o1, a.vhat[off + e + 1]); }
@@ -183,11 +236,11 @@ __device__ void aess_local_body(const SpecArgs &a, int inverse, int mul)
                 }
             }
         } else {
-            if (valid) {                                        // stage 0: pairs, from global
+            if (valid) {                                        // stage 0: pairs (fetched from global)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int e = 2 * (t + 128 * q);
-                    const cpx u = d[e], v = d[e + 1];
+                for (int k = 0; k < 4; ++k) {
+                    const int e = 2 * (t + 128 * k);
+                    const cpx u = p[2 * k], v = p[2 * k + 1];
                     s[aess_pad(e)] = c_add(u, v); s[aess_pad(e) + 1] = c_sub(u, v);
                 }
             }

@@ -129,26 +129,35 @@ int emu_convreverb(const float *ir, long long n_taps, const float *x, float *y, 
 // ---- SpectralFilter kernels (aes_spectral.cuh) on the emulator ---------------------------------
 struct SpecLaunch { SpecArgs a; int st, inv, mul; };
 static void sp_load(void *p) { aess_load_body(reinterpret_cast<SpecLaunch *>(p)->a); }
-template <int R> static void sp_pass(void *p) { SpecLaunch *l = reinterpret_cast<SpecLaunch *>(p); aess_global_pass_body<R>(l->a, l->st, l->inv); }
-static void emu_spec_pass(SpecLaunch &l, int s, int r, int inv)
+template <int R, int IN, int OUT> static void sp_pass(void *p) { SpecLaunch *l = reinterpret_cast<SpecLaunch *>(p); aess_global_pass_body<R, IN, OUT>(l->a, l->st, l->inv); }
+template <int IN, int OUT> static void emu_spec_pass(SpecLaunch &l, int s, int r, int inv)
 {
     l.st = s; l.inv = inv;
-    emu::launch(r == 3 ? sp_pass<3> : r == 2 ? sp_pass<2> : sp_pass<1>, &l, 4, 256, 0);
+    emu::launch(r == 3 ? sp_pass<3, IN, OUT> : r == 2 ? sp_pass<2, IN, OUT> : sp_pass<1, IN, OUT>, &l, 4, 256, 0);
 }
 static void sp_local(void *p) { SpecLaunch *l = reinterpret_cast<SpecLaunch *>(p); aess_local_body(l->a, l->inv, l->mul); }
 static void sp_gate(void *p) { aess_gate_body(reinterpret_cast<SpecLaunch *>(p)->a); }
 static void sp_zero(void *p) { aess_zero_pad_body(reinterpret_cast<SpecLaunch *>(p)->a); }
 static void sp_store(void *p) { aess_store_body(reinterpret_cast<SpecLaunch *>(p)->a); }
 
-static void emu_spec_fft(SpecLaunch &l, int inverse, int mul)
+static void emu_spec_fft(SpecLaunch &l, int inverse, int mul, int in_mode = 0, int out_mode = 0)
 {
     const unsigned chunks = (unsigned)std::min<long long>(((long long)l.a.nb * l.a.P / 1024 + 1) / 2, 3);   // persistent: 3 CTAs
     if (!inverse) {
-        for (int s = 0, r; s <= l.a.L - 11; s += r) emu_spec_pass(l, s, r = aess_pass_radix(l.a.L - 10 - s), 0);
+        for (int s = 0, r; s <= l.a.L - 11; s += r) {
+            r = aess_pass_radix(l.a.L - 10 - s);
+            if (s == 0 && in_mode == 1) emu_spec_pass<1, 0>(l, s, r, 0);
+            else if (s == 0 && in_mode == 2) emu_spec_pass<2, 0>(l, s, r, 0);
+            else emu_spec_pass<0, 0>(l, s, r, 0);
+        }
         l.inv = 0; l.mul = mul; emu::launch(sp_local, &l, chunks, AESS_LOCAL_NT, AESS_LOCAL_SMEM_CPX * sizeof(cpx));
     } else {
         l.inv = 1; l.mul = 0; emu::launch(sp_local, &l, chunks, AESS_LOCAL_NT, AESS_LOCAL_SMEM_CPX * sizeof(cpx));
-        for (int s = 10, r; s < l.a.L; s += r) emu_spec_pass(l, s, r = aess_pass_radix(l.a.L - s), 1);
+        for (int s = 10, r; s < l.a.L; s += r) {
+            r = aess_pass_radix(l.a.L - s);
+            if (s + r == l.a.L && out_mode == 1) emu_spec_pass<0, 1>(l, s, r, 1);
+            else emu_spec_pass<0, 0>(l, s, r, 1);
+        }
     }
 }
 
@@ -174,11 +183,12 @@ int emu_spectral_frames(const float *frames, float *mask, float *y, long long M,
     emu_spec_fft(l, 0, 0);                               // vhat = FFT(v)/P in place
     l.a.buf = buf.data(); l.a.vhat = v.data(); l.a.chirp = chirp.data(); l.a.frames = frames; l.a.mask = mask; l.a.out = y;
     l.a.nb = (nb + 1) / 2; l.a.nf = nb; l.a.thr = thr; l.a.red = red; l.a.alpha = alpha;
-    emu::launch(sp_load, &l, 4, 256, 0);
-    emu_spec_fft(l, 0, 1); emu_spec_fft(l, 1, 0);
+    const bool fuse = L > 10;                            // same orchestration as spec_process (aes_spectral.cu)
+    if (!fuse) emu::launch(sp_load, &l, 4, 256, 0);
+    emu_spec_fft(l, 0, 1, fuse ? 1 : 0, 0); emu_spec_fft(l, 1, 0);
     emu::launch(sp_gate, &l, 4, 256, 0);
-    emu::launch(sp_zero, &l, 4, 256, 0);
-    emu_spec_fft(l, 0, 1); emu_spec_fft(l, 1, 0);
-    emu::launch(sp_store, &l, 4, 256, 0);
+    if (!fuse) emu::launch(sp_zero, &l, 4, 256, 0);
+    emu_spec_fft(l, 0, 1, fuse ? 2 : 0, 0); emu_spec_fft(l, 1, 0, 0, fuse ? 1 : 0);
+    if (!fuse) emu::launch(sp_store, &l, 4, 256, 0);
     return 0;
 }
