@@ -67,8 +67,8 @@ __device__ __forceinline__ cpx aess_twiddle(long long e, int L)
     return w;
 }
 
-template <int R, bool TABLE>
-__device__ __forceinline__ void aess_bfly(cpx (&p)[1 << R], long long i, long long d, int st, int inverse, int L,
+template <int R, bool TABLE, typename I>
+__device__ __forceinline__ void aess_bfly(cpx (&p)[1 << R], I i, I d, int st, int inverse, int L,
                                           const cpx *__restrict__ tw)
 {
     constexpr int K = 1 << R;
@@ -79,8 +79,8 @@ __device__ __forceinline__ void aess_bfly(cpx (&p)[1 << R], long long i, long lo
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             if (k & dk) continue;
-            const long long pos = (long long)(k & (dk - 1)) * d + i;
-            cpx w = TABLE ? tw[pos << sh] : aess_twiddle(pos << sh, L);
+            const I pos = (I)(k & (dk - 1)) * d + i;
+            cpx w = TABLE ? tw[pos << sh] : aess_twiddle((long long)pos << sh, L);
             const cpx u = p[k], v = p[k + dk];
             if (!inverse) {
                 p[k] = c_add(u, v);
@@ -139,7 +139,7 @@ __device__ void aess_global_pass_body(const SpecArgs &a, int st, int inverse)
                 p[k] = v;
             }
         }
-        aess_bfly<R, false>(p, i, d, st, inverse, a.L, a.twP);
+        aess_bfly<R, false, long long>(p, i, d, st, inverse, a.L, a.twP);
 #pragma unroll
         for (int k = 0; k < K; ++k) {
             if (OUT == 0) {
@@ -202,7 +202,7 @@ __device__ void aess_local_body(const SpecArgs &a, int inverse, int mul)
         if (2 * (cp + gridDim.x) < nchunks) fetch(cp + gridDim.x);
         if (!inverse) {
             if (valid) {                                        // stages 0-2: points t + 128k (fetched from global)
-                aess_bfly<3, true>(p, t, 128, 0, 0, 10, tw);
+                aess_bfly<3, true, int>(p, t, 128, 0, 0, 10, tw);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) s[aess_pad(t + 128 * k)] = p[k];
             }
@@ -211,7 +211,7 @@ __device__ void aess_local_body(const SpecArgs &a, int inverse, int mul)
                 const int i = t & 15, base = (t >> 4) * 128 + i;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) p[k] = s[aess_pad(base + 16 * k)];
-                aess_bfly<3, true>(p, i, 16, 3, 0, 10, tw);
+                aess_bfly<3, true, int>(p, i, 16, 3, 0, 10, tw);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) s[aess_pad(base + 16 * k)] = p[k];
             }
@@ -220,7 +220,7 @@ __device__ void aess_local_body(const SpecArgs &a, int inverse, int mul)
                 const int i = t & 1, base = (t >> 1) * 16 + i;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) p[k] = s[aess_pad(base + 2 * k)];
-                aess_bfly<3, true>(p, i, 2, 6, 0, 10, tw);
+                aess_bfly<3, true, int>(p, i, 2, 6, 0, 10, tw);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) s[aess_pad(base + 2 * k)] = p[k];
             }
@@ -249,7 +249,7 @@ __device__ void aess_local_body(const SpecArgs &a, int inverse, int mul)
                 const int i = t & 1, base = (t >> 1) * 16 + i;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) p[k] = s[aess_pad(base + 2 * k)];
-                aess_bfly<3, true>(p, i, 2, 1, 1, 10, tw);
+                aess_bfly<3, true, int>(p, i, 2, 1, 1, 10, tw);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) s[aess_pad(base + 2 * k)] = p[k];
             }
@@ -258,7 +258,7 @@ __device__ void aess_local_body(const SpecArgs &a, int inverse, int mul)
                 const int i = t & 15, base = (t >> 4) * 128 + i;
 #pragma unroll
                 for (int k = 0; k < 8; ++k) p[k] = s[aess_pad(base + 16 * k)];
-                aess_bfly<3, true>(p, i, 16, 4, 1, 10, tw);
+                aess_bfly<3, true, int>(p, i, 16, 4, 1, 10, tw);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) s[aess_pad(base + 16 * k)] = p[k];
             }
@@ -266,7 +266,7 @@ __device__ void aess_local_body(const SpecArgs &a, int inverse, int mul)
             if (valid) {                                        // stages 7-9: distances 128, 256, 512, to global
 #pragma unroll
                 for (int k = 0; k < 8; ++k) p[k] = s[aess_pad(t + 128 * k)];
-                aess_bfly<3, true>(p, t, 128, 7, 1, 10, tw);
+                aess_bfly<3, true, int>(p, t, 128, 7, 1, 10, tw);
 #pragma unroll
                 for (int k = 0; k < 8; ++k) d[t + 128 * k] = p[k];
             }
