@@ -67,11 +67,15 @@ static int configure_kernel(aes_chain_plan *pl)
     return 0;
 }
 
+// `allow_scan`: the host pipeline decides on the WHOLE batch whether the time-parallel biquad scan
+// runs, not per sub-batch -- the two kernels agree to an ulp, not bit for bit, and a clip's result
+// must not depend on where in a batch it sits
 static int launch_chain(aes_chain_plan *pl, const void *x, int in_fmt, void *y, int out_fmt,
-                        long long B, long long N, float *scratch, cudaStream_t st, double *state_out = nullptr)
+                        long long B, long long N, float *scratch, cudaStream_t st, double *state_out = nullptr,
+                        bool allow_scan = true)
 {
     if (B <= 0 || N <= 0) return 0;
-    if (pl->bq_ok && B < pl->grid_max && in_fmt == AES_FMT_F32_STEREO && out_fmt == AES_FMT_F32_STEREO &&
+    if (pl->bq_ok && allow_scan && B < pl->grid_max && in_fmt == AES_FMT_F32_STEREO && out_fmt == AES_FMT_F32_STEREO &&
         !getenv("AES_NO_SCAN")) {
         // fewer clips than resident CTAs: go parallel in time (one CTA per 1024-frame tile)
         const long long nt = (N + AESB_T - 1) / AESB_T;
@@ -349,7 +353,8 @@ AES_EXPORT int aes_chain_process_host(aes_chain_plan *pl, const void *x_host, in
         }
         AES_CUDA(cudaMemcpyAsync(s.d_in, src, (size_t)nb * in_clip, cudaMemcpyHostToDevice, s.stream));
         double *st_out = n_clips == 1 ? pl->d_state : nullptr;
-        if ((rc = launch_chain(pl, s.d_in, in_fmt, s.d_out, out_fmt, nb, n_frames, s.scratch, s.stream, st_out))) return rc;
+        if ((rc = launch_chain(pl, s.d_in, in_fmt, s.d_out, out_fmt, nb, n_frames, s.scratch, s.stream, st_out,
+                               n_clips < pl->grid_max))) return rc;
         if (st_out)
             AES_CUDA(cudaMemcpyAsync(pl->h_state, pl->d_state, (size_t)pl->host.n_state * sizeof(double),
                                      cudaMemcpyDeviceToHost, s.stream));

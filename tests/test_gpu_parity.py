@@ -507,3 +507,35 @@ def test_convolution_reverb_random_sizes(ab, orc, seed):
         want = np.zeros_like(x[b])
         orc.OConvReverb(ir, dry, wet).process_into(x[b], want)
         check(y[b], want, what=(seed, log2n, taps, n, b))
+
+
+RACE_CHAINS = dict(synth.PRESETS)
+RACE_CHAINS.pop("Clean Noise Removal")
+RACE_CHAINS["c2-biquads"] = [
+    {"type": "filter", "params": {"filter_type": 0, "cutoff_hz": 8000, "q": 0.707}},
+    {"type": "filter", "params": {"filter_type": 1, "cutoff_hz": 80, "q": 0.707}},
+    {"type": "filter", "params": {"filter_type": 2, "cutoff_hz": 1000, "q": 0.8}},
+    {"type": "filter", "params": {"filter_type": 3, "cutoff_hz": 1000, "q": 1.0, "gain_db": 6.0}}]
+RACE_CHAINS["gate-filter-gate"] = [
+    {"type": "gate", "params": {"threshold_db": -35}}, {"type": "filter", "params": {"cutoff_hz": 300.0}},
+    {"type": "gate", "params": {"threshold_db": -25}}]
+RACE_CHAINS["filter-dist-filter"] = [
+    {"type": "filter", "params": {"cutoff_hz": 2000.0}}, {"type": "distortion", "params": {"drive": 3.0}},
+    {"type": "filter", "params": {"filter_type": 1, "cutoff_hz": 200.0}}]
+
+
+@pytest.mark.parametrize("name", sorted(RACE_CHAINS))
+def test_copies_of_one_clip_come_out_identical_on_every_cta(ab, name):
+    """Race detector for the barrier-light kernels: 900 copies of two clips run on 296 CTAs at
+    different phases (three waves, two CTAs sharing each SM); every copy must match bit for bit."""
+    from audioblocks.engine import file_chain
+    cfg = RACE_CHAINS[name]
+    n, B = 12000, 900
+    base = synth.batch(95, 2, n)
+    x = np.ascontiguousarray(base[np.arange(B) % 2])
+    chain = file_chain(cfg, 48000, channels_in=2)
+    for rep in range(3):
+        y = chain.process_batch(x) if rep == 0 else file_chain(cfg, 48000, channels_in=2).process_batch(x)
+        for k in range(2):
+            same = (y[k::2] == y[k]).all(axis=(1, 2))
+            assert same.all(), (name, rep, k, int(np.argmin(same)))
