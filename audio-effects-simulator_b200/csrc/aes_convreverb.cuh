@@ -242,13 +242,26 @@ __device__ void aesc_mac_body(const ConvArgs &a, int clips_per_cta)
                 const cpx z = zc[(size_t)q * N + i];
                 cpx zm = zc[(size_t)q * N + im];
                 zm.y = -zm.y;
+                const int p0 = j0 - q;                          // partition that maps block q to output j0
+                if (p0 >= 0 && p0 + AESC_JB <= a.P) {
+                    // interior of the window: all JB outputs take this block, partitions p0 .. p0+JB-1
+                    // at constant offsets -- no per-output bounds test or index arithmetic
+                    const cpx *pa = sA + p0 * AESC_KT + tid, *pb = sB + p0 * AESC_KT + tid;
 #pragma unroll
-                for (int u = 0; u < AESC_JB; ++u) {
-                    const int p = j0 + u - q;
-                    if (p >= 0 && p < a.P) {
-                        const cpx ca = sA[p * AESC_KT + tid], cb = sB[p * AESC_KT + tid];
+                    for (int u = 0; u < AESC_JB; ++u) {
+                        const cpx ca = pa[u * AESC_KT], cb = pb[u * AESC_KT];
                         acc[u].x += ca.x * z.x - ca.y * z.y + cb.x * zm.x - cb.y * zm.y;
                         acc[u].y += ca.x * z.y + ca.y * z.x + cb.x * zm.y + cb.y * zm.x;
+                    }
+                } else {
+#pragma unroll
+                    for (int u = 0; u < AESC_JB; ++u) {
+                        const int p = p0 + u;
+                        if (p >= 0 && p < a.P) {
+                            const cpx ca = sA[p * AESC_KT + tid], cb = sB[p * AESC_KT + tid];
+                            acc[u].x += ca.x * z.x - ca.y * z.y + cb.x * zm.x - cb.y * zm.y;
+                            acc[u].y += ca.x * z.y + ca.y * z.x + cb.x * zm.y + cb.y * zm.x;
+                        }
                     }
                 }
             }
