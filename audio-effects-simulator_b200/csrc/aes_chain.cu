@@ -19,12 +19,24 @@ struct HostSlot {
     cudaEvent_t done = nullptr;
     void *d_in = nullptr, *d_out = nullptr;     // device staging for one sub-batch
     void *h_in = nullptr, *h_out = nullptr;     // pinned staging (only for pageable user buffers)
-    float *scratch = nullptr;
-    size_t in_cap = 0, out_cap = 0, hin_cap = 0, hout_cap = 0;
+    void *scratch = nullptr;                    // global-memory delay lines of the CTAs of one launch
+    size_t in_cap = 0, out_cap = 0, hin_cap = 0, hout_cap = 0, scratch_cap = 0;
     // pending copy-out of a finished sub-batch from pinned staging to the user's buffer
     void *pend_dst = nullptr;
     size_t pend_bytes = 0;
 };
+
+// The host pipeline's slots (streams, events, device and pinned staging, line scratch) belong to
+// the calling host thread, not to a plan: the file route builds a fresh plan per request
+// (engine.py:86-99 re-creates its chain every time), and allocating ~200 MB of staging per request
+// cost 40-200 ms of cudaMalloc / cudaHostAlloc / cudaFree against 3 ms of copies and kernel.
+// Buffers only grow; aes_release_host_cache() frees them.
+struct SlotCache {
+    HostSlot slot[AES_HOST_SLOTS];
+    bool ready = false;
+    int device = -1;
+};
+static thread_local SlotCache t_cache;
 
 // ---- shape-specialised kernels (aes_fast_kernel.cuh): launch table -----------------------
 typedef void (*fast_kernel_t)(const FastArgs);
@@ -47,12 +59,11 @@ struct aes_chain_plan {
     DevPlan *dev = nullptr;
     int fs = 0, device = 0, sm_count = 0, ctas_per_sm = 0, grid_max = 0;
     size_t smem_bytes = 0;
-    float *scratch = nullptr;                   // grid_max * scratch_floats, for aes_chain_run
+    void *scratch = nullptr;                    // lines of the CTAs of an aes_chain_run launch (grown on demand)
+    size_t scratch_cap = 0;
     double *d_state = nullptr;                  // final carried scalars of a single-clip host call
     double h_state[16 * AES_MAX_STAGES];
     bool state_valid = false;
-    HostSlot slot[AES_HOST_SLOTS];
-    bool slots_ready = false;
 };
 
 template <int K>
@@ -188,7 +199,6 @@ AES_EXPORT int aes_chain_plan_create(const aes_stage_desc *stages, int n_stages,
         pl->grid_max = pl->sm_count * pl->ctas_per_sm;
         AES_CUDA(cudaMalloc(&pl->dev, sizeof(DevPlan)));
         AES_CUDA(cudaMemcpy(pl->dev, &pl->host, sizeof(DevPlan), cudaMemcpyHostToDevice));
-        AES_CUDA(cudaMalloc(&pl->scratch, (size_t)pl->grid_max * pl->host.scratch_floats * sizeof(float)));
         // all-biquad chains also get the time-parallel scan kernel
         bool all_bq = n_stages >= 1 && n_stages <= AESB_MAX_STAGES;
         for (int s2 = 0; s2 < n_stages && all_bq; ++s2) all_bq = stages[s2].kind == AES_STAGE_BIQUAD;
@@ -218,16 +228,6 @@ AES_EXPORT int aes_chain_plan_create(const aes_stage_desc *stages, int n_stages,
 AES_EXPORT int aes_chain_plan_destroy(aes_chain_plan *pl)
 {
     if (!pl) return 0;
-    for (HostSlot &s : pl->slot) {
-        if (s.stream) cudaStreamSynchronize(s.stream);
-        if (s.d_in) cudaFree(s.d_in);
-        if (s.d_out) cudaFree(s.d_out);
-        if (s.h_in) cudaFreeHost(s.h_in);
-        if (s.h_out) cudaFreeHost(s.h_out);
-        if (s.scratch) cudaFree(s.scratch);
-        if (s.done) cudaEventDestroy(s.done);
-        if (s.stream) cudaStreamDestroy(s.stream);
-    }
     if (pl->dev) cudaFree(pl->dev);
     if (pl->scratch) cudaFree(pl->scratch);
     if (pl->d_state) cudaFree(pl->d_state);
@@ -255,6 +255,66 @@ AES_EXPORT const char *aes_chain_plan_kernel_name(const aes_chain_plan *pl)
     return pl->fast_fn ? "aes_fast_kernel<FR=4, shape-specialised>" : "aes_chain_kernel<generic interpreter>";
 }
 
+static int grow(void **p, size_t *cap, size_t need, bool host)
+{
+    if (*cap >= need) return 0;
+    if (*p) { if (host) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *cap = 0; }
+    if (host) AES_CUDA(cudaMallocHost(p, need)); else AES_CUDA(cudaMalloc(p, need));
+    *cap = need;
+    return 0;
+}
+
+static void release_cache(SlotCache &c)
+{
+    for (HostSlot &s : c.slot) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        if (s.d_in) cudaFree(s.d_in);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.h_in) cudaFreeHost(s.h_in);
+        if (s.h_out) cudaFreeHost(s.h_out);
+        if (s.scratch) cudaFree(s.scratch);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        s = HostSlot();
+    }
+    c.ready = false;
+    c.device = -1;
+}
+
+// the calling thread's slots, created on first use and re-created when it switched device
+static int ensure_slots(SlotCache &c)
+{
+    int dev = 0;
+    AES_CUDA(cudaGetDevice(&dev));
+    if (c.ready && c.device == dev) return 0;
+    if (c.ready) {                                  // buffers of another device: release them there
+        cudaSetDevice(c.device);
+        release_cache(c);
+        cudaSetDevice(dev);
+    }
+    for (HostSlot &s : c.slot) {
+        AES_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        AES_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+    c.ready = true;
+    c.device = dev;
+    return 0;
+}
+
+// Frees the calling thread's cached pipeline buffers (device and pinned staging, line scratch,
+// streams).  They are otherwise kept for the life of the thread.
+AES_EXPORT int aes_release_host_cache(void)
+{
+    if (t_cache.ready) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaSetDevice(t_cache.device);
+        release_cache(t_cache);
+        cudaSetDevice(dev);
+    }
+    return 0;
+}
+
 AES_EXPORT int aes_chain_run(aes_chain_plan *pl, const void *x, int in_fmt, void *y, int out_fmt,
                              int64_t n_clips, int64_t n_frames, void *stream)
 {
@@ -265,28 +325,14 @@ AES_EXPORT int aes_chain_run(aes_chain_plan *pl, const void *x, int in_fmt, void
     AES_REQUIRE(((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0, "buffers must be 16-byte aligned");
     int rc = check_formats(in_fmt, out_fmt);
     if (rc) return rc;
-    return launch_chain(pl, x, in_fmt, y, out_fmt, n_clips, n_frames, pl->scratch, (cudaStream_t)stream);
-}
-
-static int ensure_slots(aes_chain_plan *pl)
-{
-    if (pl->slots_ready) return 0;
-    for (HostSlot &s : pl->slot) {
-        AES_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        AES_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-        AES_CUDA(cudaMalloc(&s.scratch, (size_t)pl->grid_max * pl->host.scratch_floats * sizeof(float)));
+    // line scratch for the CTAs of this launch (kept by the plan: launches of one plan on one stream
+    // are ordered; growing it waits for the device, which only happens on the first, largest call)
+    const size_t need = (size_t)std::min<int64_t>(n_clips, pl->grid_max) * pl->host.scratch_floats * sizeof(float);
+    if (pl->scratch_cap < need) {
+        AES_CUDA(cudaDeviceSynchronize());
+        if ((rc = grow(&pl->scratch, &pl->scratch_cap, need, false))) return rc;
     }
-    pl->slots_ready = true;
-    return 0;
-}
-
-static int grow(void **p, size_t *cap, size_t need, bool host)
-{
-    if (*cap >= need) return 0;
-    if (*p) { if (host) cudaFreeHost(*p); else cudaFree(*p); *p = nullptr; *cap = 0; }
-    if (host) AES_CUDA(cudaMallocHost(p, need)); else AES_CUDA(cudaMalloc(p, need));
-    *cap = need;
-    return 0;
+    return launch_chain(pl, x, in_fmt, y, out_fmt, n_clips, n_frames, (float *)pl->scratch, (cudaStream_t)stream);
 }
 
 static bool is_pinned(const void *p)
@@ -315,7 +361,8 @@ AES_EXPORT int aes_chain_process_host(aes_chain_plan *pl, const void *x_host, in
     AES_REQUIRE(x_host != nullptr && y_host != nullptr, "NULL host buffer");
     int rc = check_formats(in_fmt, out_fmt);
     if (rc) return rc;
-    if ((rc = ensure_slots(pl))) return rc;
+    SlotCache &cache = t_cache;
+    if ((rc = ensure_slots(cache))) return rc;
 
     const size_t in_clip = (size_t)n_frames * in_frame_bytes(in_fmt);
     const size_t out_clip = (size_t)n_frames * out_frame_bytes(out_fmt);
@@ -340,8 +387,10 @@ AES_EXPORT int aes_chain_process_host(aes_chain_plan *pl, const void *x_host, in
     int k = 0;
     for (int64_t b0 = 0; b0 < n_clips; b0 += per, ++k) {
         const int64_t nb = std::min<int64_t>(per, n_clips - b0);
-        HostSlot &s = pl->slot[k % AES_HOST_SLOTS];
+        HostSlot &s = cache.slot[k % AES_HOST_SLOTS];
         if (k >= AES_HOST_SLOTS && (rc = drain_slot(s))) return rc;
+        if ((rc = grow(&s.scratch, &s.scratch_cap,
+                       (size_t)std::min<int64_t>(per, pl->grid_max) * pl->host.scratch_floats * sizeof(float), false))) return rc;
         if ((rc = grow(&s.d_in, &s.in_cap, (size_t)per * in_clip, false))) return rc;
         if ((rc = grow(&s.d_out, &s.out_cap, (size_t)per * out_clip, false))) return rc;
         const char *src = (const char *)x_host + (size_t)b0 * in_clip;
@@ -353,7 +402,7 @@ AES_EXPORT int aes_chain_process_host(aes_chain_plan *pl, const void *x_host, in
         }
         AES_CUDA(cudaMemcpyAsync(s.d_in, src, (size_t)nb * in_clip, cudaMemcpyHostToDevice, s.stream));
         double *st_out = n_clips == 1 ? pl->d_state : nullptr;
-        if ((rc = launch_chain(pl, s.d_in, in_fmt, s.d_out, out_fmt, nb, n_frames, s.scratch, s.stream, st_out,
+        if ((rc = launch_chain(pl, s.d_in, in_fmt, s.d_out, out_fmt, nb, n_frames, (float *)s.scratch, s.stream, st_out,
                                n_clips < pl->grid_max))) return rc;
         if (st_out)
             AES_CUDA(cudaMemcpyAsync(pl->h_state, pl->d_state, (size_t)pl->host.n_state * sizeof(double),
@@ -370,7 +419,7 @@ AES_EXPORT int aes_chain_process_host(aes_chain_plan *pl, const void *x_host, in
     }
     const int used = std::min(k, AES_HOST_SLOTS);
     for (int i = 0; i < used; ++i)
-        if ((rc = drain_slot(pl->slot[i]))) return rc;
+        if ((rc = drain_slot(cache.slot[i]))) return rc;
     pl->state_valid = (n_clips == 1);
     return 0;
 }

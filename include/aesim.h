@@ -139,6 +139,12 @@ int64_t aes_launch_count(void);
 int aes_stream_process_host(aes_stage_desc *stages, int n_stages, const float *x_host, int channels_in,
                             float *y_host, int64_t frames);
 
+/* The host-buffer entries keep their pipeline resources (streams, device and pinned staging,
+ * line scratch) per calling host thread and reuse them across plans -- the file route builds a
+ * new chain, hence a new plan, for every request (engine.py:86-99).  This releases the calling
+ * thread's cache. */
+int aes_release_host_cache(void);
+
 /* ---- single blocks, device pointers (one-stage chains; same semantics) ---------- */
 int aes_delay_f32(const float *x, float *y, int64_t n_clips, int64_t n_frames,
                   int64_t dS_L, int64_t dS_R, double feedback, double mix_dry, double mix_wet,
