@@ -41,6 +41,32 @@ __global__ void aess_clips_from_frames_kernel(const float *out, float *y, long l
         reinterpret_cast<float2 *>(y)[e] = make_float2(v, v);
     }
 }
+// plan tables, built on the device (on the host the 2M+P sincos calls of a whole-file plan cost
+// ~150 ms per request of the file route): chirp c[n] = exp(-i*pi*n^2/M) with n^2 reduced mod 2M
+// in exact integer arithmetic, the Hann window np.hanning(M) as float32, and the Bluestein kernel
+// v[m] = conj(c[|m|]) / P laid out on [0, P)
+__global__ void aess_tables_kernel(cpx *chirp, float *window, cpx *v, long long M, long long P)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const double invP = 1.0 / (double)P;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < P; e += stride) {
+        cpx out; out.x = 0.f; out.y = 0.f;
+        const long long m = e < M ? e : (e > P - M ? P - e : -1);
+        if (m >= 0) {
+            const unsigned long long r = ((unsigned long long)m * (unsigned long long)m) % (unsigned long long)(2 * M);
+            double sn, cs;
+            sincospi(-(double)r / (double)M, &sn, &cs);
+            if (e < M) {
+                cpx c; c.x = (float)cs; c.y = (float)sn;
+                chirp[e] = c;
+                window[e] = (float)(0.5 - 0.5 * cospi(2.0 * (double)e / (double)(M - 1)));
+            }
+            out.x = (float)((double)(float)cs * invP);
+            out.y = (float)(-(double)(float)sn * invP);
+        }
+        v[e] = out;
+    }
+}
 __global__ void aess_fill_kernel(float *p, float v, long long n)
 {
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -50,13 +76,34 @@ __global__ void aess_fill_kernel(float *p, float v, long long n)
 struct aes_spectral_plan {
     long long M = 0, P = 0;
     int L = 0, sms = 148;
-    cpx *d_vhat = nullptr, *d_chirp = nullptr, *d_twP = nullptr, *d_tw1k = nullptr;
+    cpx *d_vhat = nullptr, *d_chirp = nullptr, *d_tw1k = nullptr;
     float *d_window = nullptr;
     void *d_work = nullptr;          // buf | frames | mask | out | (x | y for the clip entry)
     size_t work_cap = 0;
 };
 
 static int spec_grid(const aes_spectral_plan *pl) { return pl->sms * 8; }
+
+// Device buffers of the spectral plans come from the device's stream-ordered memory pool with the
+// release threshold raised to 1 GB, so the ~150 MB a whole-file plan needs is carved out of memory kept
+// from the previous request instead of going to the driver each time (the file route creates and
+// drops a plan per request; cudaMalloc + cudaFree of these sizes cost 40-150 ms).
+static int spec_alloc(void **p, size_t bytes)
+{
+    static thread_local int pool_dev = -1;
+    int dev = 0;
+    AES_CUDA(cudaGetDevice(&dev));
+    if (pool_dev != dev) {
+        cudaMemPool_t pool;
+        AES_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        unsigned long long keep = 1ULL << 30;        // a whole-file plan is ~150 MB; batch work buffers (GBs) still go back
+        AES_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        pool_dev = dev;
+    }
+    AES_CUDA(cudaMallocAsync(p, bytes, (cudaStream_t)0));
+    return 0;
+}
+static void spec_free(void *p) { if (p) cudaFreeAsync(p, (cudaStream_t)0); }
 
 // `in_mode` applies to the first pass of a forward transform, `out_mode` to the last pass of an
 // inverse one (see aess_global_pass_body); both need at least one grid-wide stage (L > 10)
@@ -116,12 +163,12 @@ static int spec_process(const aes_spectral_plan *pl, SpecArgs a, cudaStream_t st
 AES_EXPORT int aes_spectral_plan_destroy(aes_spectral_plan *pl)
 {
     if (!pl) return 0;
-    if (pl->d_vhat) cudaFree(pl->d_vhat);
-    if (pl->d_chirp) cudaFree(pl->d_chirp);
-    if (pl->d_twP) cudaFree(pl->d_twP);
-    if (pl->d_tw1k) cudaFree(pl->d_tw1k);
-    if (pl->d_window) cudaFree(pl->d_window);
-    if (pl->d_work) cudaFree(pl->d_work);
+    cudaDeviceSynchronize();                        // launches on the caller's streams may still use the buffers
+    spec_free(pl->d_vhat);
+    spec_free(pl->d_chirp);
+    spec_free(pl->d_tw1k);
+    spec_free(pl->d_window);
+    spec_free(pl->d_work);
     delete pl;
     return 0;
 }
@@ -138,37 +185,20 @@ AES_EXPORT int aes_spectral_plan_create(int64_t frame_len, aes_spectral_plan **o
     pl->M = M; pl->P = P; pl->L = L;
     int rc = [&]() -> int {
         aes_device_sm_count(&pl->sms);
-        std::vector<cpx> chirp((size_t)M), v((size_t)P), twP((size_t)P / 2), tw1k(512);
-        for (long long n = 0; n < M; ++n) {
-            const long long r = (long long)(((unsigned long long)n * (unsigned long long)n) % (unsigned long long)(2 * M));   // n^2 mod 2M, exact
-            const double ang = -M_PI * (double)r / (double)M;
-            chirp[n].x = (float)cos(ang); chirp[n].y = (float)sin(ang);
-        }
-        memset(v.data(), 0, v.size() * sizeof(cpx));
-        for (long long m = 0; m < M; ++m) {                   // v[m] = conj(c[|m|]) at index m mod P
-            cpx c; c.x = chirp[m].x; c.y = -chirp[m].y;
-            v[m] = c;
-            if (m > 0) v[P - m] = c;
-        }
-        for (long long q = 0; q < P / 2; ++q) { const double ang = -2.0 * M_PI * (double)q / (double)P; twP[q].x = (float)cos(ang); twP[q].y = (float)sin(ang); }
+        std::vector<cpx> tw1k(512);
         for (int q = 0; q < 512; ++q) { const double ang = -2.0 * M_PI * q / 1024.0; tw1k[q].x = (float)cos(ang); tw1k[q].y = (float)sin(ang); }
-        std::vector<float> win((size_t)M);
-        for (long long n = 0; n < M; ++n) win[n] = (float)(0.5 - 0.5 * cos(2.0 * M_PI * (double)n / (double)(M - 1)));   // np.hanning(M).astype(f32)
-        AES_CUDA(cudaMalloc(&pl->d_chirp, chirp.size() * sizeof(cpx)));
-        AES_CUDA(cudaMalloc(&pl->d_vhat, v.size() * sizeof(cpx)));
-        AES_CUDA(cudaMalloc(&pl->d_twP, twP.size() * sizeof(cpx)));
-        AES_CUDA(cudaMalloc(&pl->d_tw1k, tw1k.size() * sizeof(cpx)));
-        AES_CUDA(cudaMalloc(&pl->d_window, win.size() * sizeof(float)));
-        AES_CUDA(cudaMemcpy(pl->d_chirp, chirp.data(), chirp.size() * sizeof(cpx), cudaMemcpyHostToDevice));
-        AES_CUDA(cudaMemcpy(pl->d_twP, twP.data(), twP.size() * sizeof(cpx), cudaMemcpyHostToDevice));
+        int ra;
+        if ((ra = spec_alloc((void **)&pl->d_chirp, (size_t)M * sizeof(cpx)))) return ra;
+        if ((ra = spec_alloc((void **)&pl->d_vhat, (size_t)P * sizeof(cpx)))) return ra;
+        if ((ra = spec_alloc((void **)&pl->d_tw1k, tw1k.size() * sizeof(cpx)))) return ra;
+        if ((ra = spec_alloc((void **)&pl->d_window, (size_t)M * sizeof(float)))) return ra;
         AES_CUDA(cudaMemcpy(pl->d_tw1k, tw1k.data(), tw1k.size() * sizeof(cpx), cudaMemcpyHostToDevice));
-        AES_CUDA(cudaMemcpy(pl->d_window, win.data(), win.size() * sizeof(float), cudaMemcpyHostToDevice));
         AES_CUDA(cudaFuncSetAttribute(aess_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AESS_LOCAL_SMEM_CPX * (int)sizeof(cpx)));
+        aess_tables_kernel<<<spec_grid(pl), 256>>>(pl->d_chirp, pl->d_window, pl->d_vhat, M, P);
+        aes_count_launch();
         // vhat = FFT_P(v) / P, kept in bit-reversed order
-        for (auto &e : v) { e.x /= (float)P; e.y /= (float)P; }
-        AES_CUDA(cudaMemcpy(pl->d_vhat, v.data(), v.size() * sizeof(cpx), cudaMemcpyHostToDevice));
         SpecArgs a; memset(&a, 0, sizeof a);
-        a.buf = pl->d_vhat; a.twP = pl->d_twP; a.tw1k = pl->d_tw1k; a.M = M; a.P = P; a.L = L; a.nb = 1;
+        a.buf = pl->d_vhat; a.twP = nullptr; a.tw1k = pl->d_tw1k; a.M = M; a.P = P; a.L = L; a.nb = 1;
         int r2 = spec_fft(pl, a, 0, 0, nullptr);
         if (r2) return r2;
         AES_CUDA(cudaDeviceSynchronize());
@@ -182,9 +212,10 @@ AES_EXPORT int aes_spectral_plan_create(int64_t frame_len, aes_spectral_plan **o
 static int spec_reserve(aes_spectral_plan *pl, size_t bytes)
 {
     if (pl->work_cap >= bytes) return 0;
-    if (pl->d_work) cudaFree(pl->d_work);
+    if (pl->d_work) { cudaDeviceSynchronize(); spec_free(pl->d_work); }
     pl->d_work = nullptr; pl->work_cap = 0;
-    AES_CUDA(cudaMalloc(&pl->d_work, bytes));
+    { int ra = spec_alloc(&pl->d_work, bytes); if (ra) return ra; }
+    AES_CUDA(cudaStreamSynchronize((cudaStream_t)0));       // allocated in legacy-stream order, used on the caller's stream
     pl->work_cap = bytes;
     return 0;
 }
@@ -206,7 +237,7 @@ AES_EXPORT int aes_spectral_frames_host(aes_spectral_plan *pl, const float *in_b
     char *w = (char *)pl->d_work;
     SpecArgs a; memset(&a, 0, sizeof a);
     a.buf = (cpx *)w; a.frames = (float *)(w + s_buf); a.out = (float *)(w + s_buf + s_fr); a.mask = (float *)(w + s_buf + 2 * s_fr);
-    a.vhat = pl->d_vhat; a.chirp = pl->d_chirp; a.twP = pl->d_twP; a.tw1k = pl->d_tw1k;
+    a.vhat = pl->d_vhat; a.chirp = pl->d_chirp; a.twP = nullptr; a.tw1k = pl->d_tw1k;
     a.M = M; a.P = pl->P; a.L = pl->L; a.nb = 1; a.nf = 1;
     a.thr = (float)thresh_lin; a.red = (float)reduction; a.alpha = (float)alpha;
     std::vector<float> tmp((size_t)M);
@@ -252,7 +283,7 @@ AES_EXPORT int aes_spectral_run(aes_spectral_plan *pl, const float *x, float *y,
         float *outp = frames + (size_t)chunk * M;
         float *maskp = outp + (size_t)chunk * M;
         a.frames = frames; a.out = outp; a.mask = maskp;
-        a.vhat = pl->d_vhat; a.chirp = pl->d_chirp; a.twP = pl->d_twP; a.tw1k = pl->d_tw1k;
+        a.vhat = pl->d_vhat; a.chirp = pl->d_chirp; a.twP = nullptr; a.tw1k = pl->d_tw1k;
         a.M = M; a.P = pl->P; a.L = pl->L; a.nb = (int)((nb + 1) / 2); a.nf = (int)nb;      // two clips per complex transform
         a.thr = (float)thresh_lin; a.red = (float)reduction; a.alpha = (float)alpha;
         aess_frames_from_clips_kernel<<<g, 256, 0, st>>>(x + (size_t)b0 * n_frames * 2, pl->d_window, frames, nb, n_frames);
@@ -274,16 +305,18 @@ AES_EXPORT int aes_spectral_process_host(aes_spectral_plan *pl, const float *x_h
     const size_t clip_bytes = (size_t)n_frames * 2 * sizeof(float);
     const int64_t step = std::max<int64_t>(1, std::min<int64_t>(n_clips, (int64_t)(((size_t)1 << 30) / clip_bytes)));
     float *dx = nullptr, *dy = nullptr;
-    AES_CUDA(cudaMalloc(&dx, clip_bytes * step));
-    if (cudaMalloc(&dy, clip_bytes * step) != cudaSuccess) { cudaFree(dx); aes_set_error("out of device memory"); return AES_ERR_NOMEM; }
-    int rc = 0;
+    int rc = spec_alloc((void **)&dx, clip_bytes * step);
+    if (rc) return rc;
+    if ((rc = spec_alloc((void **)&dy, clip_bytes * step))) { spec_free(dx); return rc; }
+    AES_CUDA(cudaStreamSynchronize((cudaStream_t)0));
     for (int64_t b0 = 0; b0 < n_clips && !rc; b0 += step) {
         const int64_t nb = std::min<int64_t>(step, n_clips - b0);
         if (cudaMemcpy(dx, x_host + (size_t)b0 * n_frames * 2, clip_bytes * nb, cudaMemcpyHostToDevice) != cudaSuccess) { rc = AES_ERR_CUDA; break; }
         rc = aes_spectral_run(pl, dx, dy, nb, n_frames, thresh_lin, reduction, alpha, nullptr);
         if (!rc && cudaMemcpy(y_host + (size_t)b0 * n_frames * 2, dy, clip_bytes * nb, cudaMemcpyDeviceToHost) != cudaSuccess) rc = AES_ERR_CUDA;
     }
-    cudaFree(dx); cudaFree(dy);
+    cudaDeviceSynchronize();
+    spec_free(dx); spec_free(dy);
     if (rc == AES_ERR_CUDA) aes_set_error("CUDA copy failed: %s", cudaGetErrorString(cudaGetLastError()));
     return rc;
 }

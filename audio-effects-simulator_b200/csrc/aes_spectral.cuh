@@ -22,7 +22,7 @@ struct SpecArgs {
     cpx *buf;               // [nb][P] work buffer (in place)
     const cpx *vhat;        // [P] FFT(v), bit-reversed order, 1/P folded in
     const cpx *chirp;       // [M] c[n]
-    const cpx *twP;         // [P/2] exp(-2*pi*i*q/P)
+    const cpx *twP;         // unused on the device (grid-wide twiddles come from sincospif); the emulator build keeps a table
     const cpx *tw1k;        // [512] exp(-2*pi*i*q/1024)
     const float *frames;    // [nb][M] windowed analysis frames
     float *mask;            // [nb][M/2+1] smoothed mask, in/out
