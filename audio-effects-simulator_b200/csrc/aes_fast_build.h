@@ -148,6 +148,21 @@ static inline bool aes_fast_build(const DevPlan &p, FastArgs *fa, int codes[AESF
         case AESK_BIQUAD:
             for (int i = 0; i < 5; ++i) f.bq[i] = d.bq[i];
             memcpy(f.bq_pow, d.bq_pow, sizeof f.bq_pow);
+            {   // How far back the state still matters: a filter whose A^(4*2^s) has decayed below
+                // 2^-40 needs no scan step over 2^s lanes or beyond, one whose A^128 has decayed needs
+                // only the previous warp's total (the damped combs truncate their scan the same way).
+                // A step is dropped only if every longer span has decayed too (A^k of a stable
+                // biquad may grow before it decays).
+                const double eps = ldexp(1.0, -40);
+                auto small = [&](const double *m) { return fabs(m[0]) < eps && fabs(m[1]) < eps && fabs(m[2]) < eps && fabs(m[3]) < eps; };
+                double wp[4], acc[4];
+                memcpy(wp, d.bq_pow[5], sizeof wp);                     // A^128
+                memcpy(acc, wp, sizeof acc);
+                f.nxw = 1;
+                while (f.nxw < 8 && !small(acc)) { aes_mat2_mul(acc, wp, acc); ++f.nxw; }
+                f.nscan = 5;
+                if (small(wp)) while (f.nscan > 0 && small(d.bq_pow[f.nscan - 1])) --f.nscan;
+            }
             {   // row 0 of (A^T)^j, A^T = [[-a1, 1], [-a2, 0]]
                 double r0 = 1.0, r1 = 0.0;
                 for (int j = 0; j < 4; ++j) {

@@ -649,8 +649,8 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
             }
             e1[ch] = s1; e2[ch] = s2;
         }
-#pragma unroll
-        for (int s = 0; s < 5; ++s) {
+        const int bq_nscan = st.nscan;                  // scan steps / previous warps that still matter (aes_fast_build.h)
+        for (int s = 0; s < bq_nscan; ++s) {
             const double m0 = st.bq_pow[s][0], m1 = st.bq_pow[s][1], m2 = st.bq_pow[s][2], m3 = st.bq_pow[s][3];
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
@@ -679,7 +679,9 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
             const double cx1 = sin[4 * ch + 0], cx2 = sin[4 * ch + 1], cy1 = sin[4 * ch + 2], cy2 = sin[4 * ch + 3];
             double C1 = b1 * cx1 + b2 * cx2 - a1 * cy1 - a2 * cy2;
             double C2 = b2 * cx1 - a2 * cy1;
-            for (int t = 0; t < warp; ++t) {
+            const int u0 = warp > st.nxw ? warp - st.nxw : 0;
+            if (u0 > 0) { C1 = 0.0; C2 = 0.0; }                 // the tile-start state has decayed by then
+            for (int t = u0; t < warp; ++t) {
                 const double t1 = w0 * C1 + w2 * C2 + wtot[(t * 2 + ch) * 2];
                 const double t2 = w1 * C1 + w3 * C2 + wtot[(t * 2 + ch) * 2 + 1];
                 C1 = t1; C2 = t2;
