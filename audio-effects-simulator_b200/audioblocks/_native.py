@@ -300,3 +300,9 @@ def json_float_list(x: np.ndarray, stereo_mean: bool = False, threads: int = 0) 
     if got < 0:
         check(int(got))
     return str(memoryview(buf)[:got], "ascii")
+
+
+def release_host_cache():
+    """Free the calling thread's cached pipeline buffers (aes_release_host_cache): streams, device
+    and pinned staging, delay-line scratch kept between host-buffer calls."""
+    check(lib().aes_release_host_cache())

@@ -302,7 +302,8 @@ static int ensure_slots(SlotCache &c)
 }
 
 // Frees the calling thread's cached pipeline buffers (device and pinned staging, line scratch,
-// streams).  They are otherwise kept for the life of the thread.
+// streams).  Nothing else frees them: a host thread that made host-buffer calls should call this
+// before it ends (no destructor runs CUDA calls at thread or process exit on purpose).
 AES_EXPORT int aes_release_host_cache(void)
 {
     if (t_cache.ready) {

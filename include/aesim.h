@@ -142,7 +142,7 @@ int aes_stream_process_host(aes_stage_desc *stages, int n_stages, const float *x
 /* The host-buffer entries keep their pipeline resources (streams, device and pinned staging,
  * line scratch) per calling host thread and reuse them across plans -- the file route builds a
  * new chain, hence a new plan, for every request (engine.py:86-99).  This releases the calling
- * thread's cache. */
+ * thread's cache; a thread that made host-buffer calls should call it before it ends. */
 int aes_release_host_cache(void);
 
 /* ---- single blocks, device pointers (one-stage chains; same semantics) ---------- */

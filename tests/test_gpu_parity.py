@@ -539,3 +539,18 @@ def test_copies_of_one_clip_come_out_identical_on_every_cta(ab, name):
         for k in range(2):
             same = (y[k::2] == y[k]).all(axis=(1, 2))
             assert same.all(), (name, rep, k, int(np.argmin(same)))
+
+
+def test_host_cache_release_and_reuse(ab, orc):
+    """The host pipeline keeps its staging per thread across plans; releasing it must leave the next
+    call working (and re-allocating)."""
+    from audioblocks import _native
+    from audioblocks.engine import file_chain
+    cfg = synth.PRESETS["Rain Delay"]
+    x = synth.batch(12, 3, 9000)
+    y1 = file_chain(cfg, 48000, channels_in=2).process_batch(x)
+    _native.release_host_cache()
+    _native.release_host_cache()                      # idempotent
+    y2 = file_chain(cfg, 48000, channels_in=2).process_batch(x)
+    assert np.array_equal(y1, y2)
+    check(y2[1], orc.run_file_path(cfg, x[1], 48000), what="after release")
