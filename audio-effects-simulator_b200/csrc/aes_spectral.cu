@@ -240,13 +240,10 @@ AES_EXPORT int aes_spectral_frames_host(aes_spectral_plan *pl, const float *in_b
     a.vhat = pl->d_vhat; a.chirp = pl->d_chirp; a.twP = nullptr; a.tw1k = pl->d_tw1k;
     a.M = M; a.P = pl->P; a.L = pl->L; a.nb = 1; a.nf = 1;
     a.thr = (float)thresh_lin; a.red = (float)reduction; a.alpha = (float)alpha;
-    std::vector<float> tmp((size_t)M);
-    std::vector<float> win((size_t)M);
-    AES_CUDA(cudaMemcpy(win.data(), pl->d_window, (size_t)M * 4, cudaMemcpyDeviceToHost));
+    a.window = pl->d_window;                        // the raw buffer is windowed on load (f32 product like numpy's)
     for (int f = 0; f < n_frames; ++f) {
         const float *src = in_buffers + (size_t)f * M;
-        for (long long n = 0; n < M; ++n) tmp[n] = src[n] * win[n];            // f32 product like numpy
-        AES_CUDA(cudaMemcpy((void *)a.frames, tmp.data(), (size_t)M * 4, cudaMemcpyHostToDevice));
+        AES_CUDA(cudaMemcpy((void *)a.frames, src, (size_t)M * 4, cudaMemcpyHostToDevice));
         AES_CUDA(cudaMemcpy(a.mask, mask + (size_t)f * nbins, (size_t)nbins * 4, cudaMemcpyHostToDevice));
         if ((rc = spec_process(pl, a, nullptr))) return rc;
         AES_CUDA(cudaMemcpy(y + (size_t)f * M, a.out, (size_t)M * 4, cudaMemcpyDeviceToHost));

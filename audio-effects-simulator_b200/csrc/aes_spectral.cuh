@@ -24,7 +24,8 @@ struct SpecArgs {
     const cpx *chirp;       // [M] c[n]
     const cpx *twP;         // unused on the device (grid-wide twiddles come from sincospif); the emulator build keeps a table
     const cpx *tw1k;        // [512] exp(-2*pi*i*q/1024)
-    const float *frames;    // [nb][M] windowed analysis frames
+    const float *frames;    // [nf][M] analysis frames: already windowed, or raw when `window` is set
+    const float *window;    // [M] Hann window applied on load (f32 product, as numpy's), or null
     float *mask;            // [nb][M/2+1] smoothed mask, in/out
     float *out;             // [nb][M] irfft of the processed spectrum
     long long M, P;
@@ -45,6 +46,7 @@ __device__ void aess_load_body(const SpecArgs &a)
             cpx z;
             z.x = a.frames[2 * b * a.M + n];
             z.y = 2 * b + 1 < a.nf ? a.frames[(2 * b + 1) * a.M + n] : 0.0f;
+            if (a.window != nullptr) { const float w = a.window[n]; z.x = __fmul_rn(z.x, w); z.y = __fmul_rn(z.y, w); }
             v = c_mul(z, a.chirp[n]);
         }
         a.buf[e] = v;
@@ -131,6 +133,7 @@ __device__ void aess_global_pass_body(const SpecArgs &a, int st, int inverse)
                         cpx z;
                         z.x = a.frames[2 * b * a.M + n];
                         z.y = 2 * b + 1 < a.nf ? a.frames[(2 * b + 1) * a.M + n] : 0.0f;
+                        if (a.window != nullptr) { const float w = a.window[n]; z.x = __fmul_rn(z.x, w); z.y = __fmul_rn(z.y, w); }
                         v = c_mul(z, a.chirp[n]);
                     } else {
                         v = p0[k * d];
