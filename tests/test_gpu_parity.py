@@ -492,7 +492,7 @@ def test_spectral_whole_file_with_partial_gating_pairs_and_odd_batches(ab, orc):
             assert np.max(np.abs(y[b] - want)) <= 1e-2 * peak, (B, n, b, peak)
 
 
-@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("seed", range(10 * int(__import__("os").environ.get("AES_FUZZ_SCALE", "1"))))
 def test_convolution_reverb_random_sizes(ab, orc, seed):
     rng = np.random.default_rng(8100 + seed)
     log2n = int(rng.choice([8, 11, 14]))
