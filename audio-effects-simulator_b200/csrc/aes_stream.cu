@@ -49,7 +49,7 @@ AES_EXPORT int aes_stream_process_host(aes_stage_desc *stages, int n_stages, con
         AES_CUDA(cudaMalloc(&g_ctx.d_stages, AES_MAX_STAGES * sizeof(aes_stage_desc)));
         AES_CUDA(cudaMalloc(&g_ctx.d_state, AES_MAX_STAGES * 16 * sizeof(double)));
         AES_CUDA(cudaFuncSetAttribute(aes_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      AESS_MAX_FRAMES * 8 * (int)sizeof(float)));
+                                      (int)(AESS_SMEM_FLOATS(AESS_MAX_FRAMES) * sizeof(float))));
         g_ctx.device = dev;
     }
     double fin[AES_MAX_STAGES * 16];
@@ -61,7 +61,7 @@ AES_EXPORT int aes_stream_process_host(aes_stage_desc *stages, int n_stages, con
         StreamArgs a;
         a.stages = g_ctx.d_stages; a.n_stages = n_stages; a.ci = channels_in;
         a.x = g_ctx.d_x; a.y = g_ctx.d_y; a.frames = nf; a.state_out = g_ctx.d_state;
-        aes_stream_kernel<<<1, AESS_NT, (size_t)nf * 8 * sizeof(float)>>>(a);
+        aes_stream_kernel<<<1, AESS_NT, AESS_SMEM_FLOATS(nf) * sizeof(float)>>>(a);
         aes_count_launch();
         AES_CUDA(cudaGetLastError());
         AES_CUDA(cudaMemcpy(y_host + f0 * 2, g_ctx.d_y, (size_t)nf * 2 * sizeof(float), cudaMemcpyDeviceToHost));

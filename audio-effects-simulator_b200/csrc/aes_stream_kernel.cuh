@@ -7,8 +7,9 @@
 // the reference's own layout (size, write pointer), the reference's per-sample loops in their
 // original order and promoted f64 arithmetic (delay.py:7-22, reverb.py:11-67, filter.py:8-40,
 // gate.py:6-42, octaver.py:17-82).  It is latency-oriented, not throughput-oriented: one CTA per
-// call, one thread per channel/side (threads 0 and 32), stages separated by CTA barriers; a
-// 256-frame block through a preset takes tens of microseconds against a 5.3 ms audio period.
+// call, one thread per channel/side (threads 0 and 32; a reverb's combs each get their own), stages
+// separated by CTA barriers; a 256-frame block through a preset takes 0.1-0.5 ms against a 5.3 ms
+// audio period.
 //
 // Stage descriptors are the aes_stage_desc records of include/aesim.h with three extra fields:
 //   q[28] device pointer of the stage's state blob (float*), q[29] frames processed since
@@ -23,7 +24,8 @@
 #include "aes_plan.h"
 #include "../../include/aesim.h"
 
-#define AESS_MAX_FRAMES 4096
+#define AESS_MAX_FRAMES 2048
+#define AESS_SMEM_FLOATS(nf) ((size_t)(nf) * (8 + 2 * AES_MAX_COMB))     // cur 2F | scratch 6F | comb outputs 2*8*F
 #define AESS_NT 64
 
 __device__ __forceinline__ long long aess_pymod(long long a, long long m)
@@ -93,53 +95,67 @@ __device__ void aes_stream_body(const StreamArgs &a)
                 }
             }
         } else if (d.kind == AES_STAGE_REVERB) {
-            if (side >= 0) {
-                const int nc = (int)d.q[0], na = (int)d.q[1];
-                const long long pre_dS = d.q[2], pre_size = d.q[30];
-                double *lps = reinterpret_cast<double *>(blob) + side * 8;
-                // ring area of this side
-                long long off = 32;                              // 16 doubles of lp state
-                for (int sd = 0; sd < side; ++sd) {
-                    off += pre_size;
-                    for (int c = 0; c < nc; ++c) off += d.q[4 + 8 * sd + c] + 1;
-                    for (int k = 0; k < na; ++k) off += d.q[20 + 4 * sd + k] + 1;
+            // The combs of a side are independent given the pre-delayed input, so they run on their
+            // own threads (thread c of warp `side`): pre-delay by the side's first thread, barrier,
+            // nc comb loops side by side, barrier, then the first thread sums them IN COMB ORDER
+            // (f32, as reverb.py does) and runs the all-passes and the mix.
+            const int wside = tid >> 5, wl = tid & 31;              // warp 0: left, warp 1: right
+            const int nc = (int)d.q[0], na = (int)d.q[1];
+            const long long pre_dS = d.q[2], pre_size = d.q[30];
+            double *lps = reinterpret_cast<double *>(blob) + wside * 8;
+            long long off0 = 32;                                    // 16 doubles of lp state, then side 0's rings
+            for (int sd = 0; sd < wside; ++sd) {
+                off0 += pre_size;
+                for (int c = 0; c < nc; ++c) off0 += d.q[4 + 8 * sd + c] + 1;
+                for (int k = 0; k < na; ++k) off0 += d.q[20 + 4 * sd + k] + 1;
+            }
+            float *xc = cur + wside * F;
+            float *pre = tmp + wside * 3 * F, *t1 = pre + F, *sum = pre + 2 * F;
+            float *yc = sm + 8 * F + (size_t)wside * AES_MAX_COMB * F;   // [nc][F] comb outputs of this side
+            if (wl == 0) {
+                float *ring = blob + off0;
+                long long w = n_tot % pre_size;
+                for (int n = 0; n < F; ++n) {
+                    const float v = xc[n];
+                    pre[n] = pre_dS == 0 ? v : ring[aess_pymod(w - pre_dS, pre_size)];
+                    ring[w] = v;
+                    if (++w == pre_size) w = 0;
                 }
-                float *xc = cur + side * F;
-                float *pre = tmp + side * 3 * F, *t1 = pre + F, *sum = pre + 2 * F;
-                {
-                    float *ring = blob + off;
-                    long long w = n_tot % pre_size;
-                    for (int n = 0; n < F; ++n) {
-                        const float v = xc[n];
-                        pre[n] = pre_dS == 0 ? v : ring[aess_pymod(w - pre_dS, pre_size)];
-                        ring[w] = v;
-                        if (++w == pre_size) w = 0;
-                    }
-                    off += pre_size;
+            }
+            __syncthreads();
+            if (wl < nc) {
+                const int c = wl;
+                long long off = off0 + pre_size;
+                for (int c2 = 0; c2 < c; ++c2) off += d.q[4 + 8 * wside + c2] + 1;
+                const long long L = d.q[4 + 8 * wside + c], size = L + 1;
+                float *ring = blob + off;
+                long long w = n_tot % size;
+                const double h = d.p[2], g = d.p[4 + 8 * wside + c];
+                double lp = lps[c];
+                float *yo = yc + (size_t)c * F;
+                for (int n = 0; n < F; ++n) {
+                    const float yv = ring[aess_pymod(w - L, size)];
+                    const double damped = (1.0 - h) * (double)yv + h * lp;
+                    lp = damped;
+                    ring[w] = (float)((double)pre[n] + g * damped);
+                    if (++w == size) w = 0;
+                    yo[n] = yv;
                 }
-                for (int n = 0; n < F; ++n) sum[n] = 0.0f;
-                const double h = d.p[2];
-                for (int c = 0; c < nc; ++c) {
-                    const long long L = d.q[4 + 8 * side + c], size = L + 1;
-                    float *ring = blob + off;
-                    long long w = n_tot % size;
-                    const double g = d.p[4 + 8 * side + c];
-                    double lp = lps[c];
-                    for (int n = 0; n < F; ++n) {
-                        const float yv = ring[aess_pymod(w - L, size)];
-                        const double damped = (1.0 - h) * (double)yv + h * lp;
-                        lp = damped;
-                        ring[w] = (float)((double)pre[n] + g * damped);
-                        if (++w == size) w = 0;
-                        sum[n] = __fadd_rn(sum[n], yv);
-                    }
-                    lps[c] = lp;
-                    off += size;
+                lps[c] = lp;
+            }
+            __syncthreads();
+            if (wl == 0) {
+                for (int n = 0; n < F; ++n) {
+                    float acc = 0.0f;
+                    for (int c = 0; c < nc; ++c) acc = __fadd_rn(acc, yc[(size_t)c * F + n]);
+                    sum[n] = acc;
                 }
+                long long off = off0 + pre_size;
+                for (int c = 0; c < nc; ++c) off += d.q[4 + 8 * wside + c] + 1;
                 const double ag = d.p[3];
                 float *src = sum, *dst = t1;
                 for (int k = 0; k < na; ++k) {
-                    const long long L = d.q[20 + 4 * side + k], size = L + 1;
+                    const long long L = d.q[20 + 4 * wside + k], size = L + 1;
                     float *ring = blob + off;
                     long long w = n_tot % size;
                     for (int n = 0; n < F; ++n) {
