@@ -466,7 +466,7 @@ def b200_arm(args):
 # dram__bytes_read.sum + dram__bytes_write.sum of the chain kernel, per launch, from the committed
 # `ncu --set full` capture of exactly this workload: (preset, clips per GPU, frames per clip) -> bytes
 NCU_DRAM_TRAFFIC = {
-    ("Rain Delay", 1184, 480000): (4.714804e9 + 6.220897e9, "profiles/r1l_ncu_chain_kernel.csv"),
+    ("Rain Delay", 1184, 480000): (4.613200e9 + 5.971754e9, "profiles/r1o_ncu_chain_kernel.csv"),
 }
 
 
