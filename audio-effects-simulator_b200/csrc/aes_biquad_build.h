@@ -1,6 +1,7 @@
 // aes_biquad_build.h -- host tables of the time-parallel biquad cascade (pure host C++,
 // shared with tests/cpu_emu).
 #pragma once
+#include <math.h>
 #include <string.h>
 #include "aes_plan_build.h"
 #include "aes_biquad_scan.cuh"
@@ -23,6 +24,19 @@ static inline void aes_biquad_build(int n_stages, const double *coeffs5, const d
         aes_mat2_pow(A, (long long)AES_NT * AESB_T, st.tile256);
         for (int l = 0; l < 32; ++l) aes_mat2_pow(A, (long long)AESB_FR * l, lane_pw + (s * 32 + l) * 4);
         for (int l = 0; l < AES_NT; ++l) aes_mat2_pow(A, (long long)AESB_T * l, tile_pw + ((size_t)s * AES_NT + l) * 4);
+        // look-back depth: one past the last tile distance whose transition M^i still matters.  The
+        // carry-in of a tile is sum_i M^i E(t-1-i); with |M^i|_F < 2^-44 for every i >= lb_k the dropped
+        // tail is ~1e-13 of the state, far below the f32 rounding of each stage's output.  0 (chained
+        // look-back) when the filter remembers further than one 256-tile window.
+        {
+            int last = -1;
+            for (int l = 0; l <= AES_NT; ++l) {
+                const double *m = l < AES_NT ? tile_pw + ((size_t)s * AES_NT + l) * 4 : st.tile256;
+                const double fro = sqrt(m[0] * m[0] + m[1] * m[1] + m[2] * m[2] + m[3] * m[3]);
+                if (!(fro < ldexp(1.0, -44))) last = l;
+            }
+            st.lb_k = last + 1 < AES_NT - 8 ? (last + 1 < 1 ? 1 : last + 1) : 0;
+        }
         for (int ch = 0; ch < 2; ++ch) {
             st.init[ch][0] = st.init[ch][1] = 0.0;
             if (dfi_state) {

@@ -33,6 +33,8 @@ struct BqStage {
     double tile[4];         // M = A^1024
     double tile256[4];      // M^256 (one look-back window)
     double init[2][2];      // TDF-II state at the start of the clip, per channel
+    int lb_k;               // > 0: tiles further back than lb_k contribute < 2^-44 (aes_biquad_build.h): the
+    int pad_;               //      look-back sums lb_k aggregates and never chains; 0: chained look-back
 };
 
 struct BqArgs {
@@ -184,7 +186,8 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
                 }
                 E1[ch] = c1; E2[ch] = c2;
             }
-            if (tile > 0 && tid == 0) {                     // publish the aggregate first: successors may run ahead
+            const int K = a.dbg_skip > 0 ? 0 : st.lb_k;
+            if ((tile > 0 || K > 0) && tid == 0) {          // publish the aggregate first: successors may run ahead
                 a.agg[rec * 4 + 0] = E1[0]; a.agg[rec * 4 + 1] = E2[0];
                 a.agg[rec * 4 + 2] = E1[1]; a.agg[rec * 4 + 3] = E2[1];
                 bq_st_flag(a.flag + rec, 1);                // st.release orders the record before the flag
@@ -192,7 +195,41 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
             double acc[4] = { 0.0, 0.0, 0.0, 0.0 };         // carry-in, accumulated identically by every thread
             double W[4] = { 1.0, 0.0, 0.0, 1.0 };           // M^base
             long long base = 0;
-            for (;;) {
+            if (K > 0) {
+                // Truncated look-back: the filter forgets, M^K is below 2^-44, so the state at the tile
+                // start is the sum of the K nearest AGGREGATES (zero-state tile responses, published
+                // before any look-back) -- no tile waits for another tile's look-back, and the sum has
+                // a fixed order, so the output is reproducible bit for bit.
+                const int nw = (K + 31) >> 5;               // warps that hold a predecessor
+                if (warp < nw) {
+                    const long long pt = tile - 1 - tid;
+                    double t[4] = { 0.0, 0.0, 0.0, 0.0 };
+                    if (tid < K && pt >= -1) {
+                        double val[4];
+                        if (pt >= 0) {
+                            const long long prec = rec - 1 - tid;
+                            while (bq_ld_flag(a.flag + prec) == 0) { }
+                            (void)bq_ld_flag_acquire(a.flag + prec);
+                            const double *src = a.agg + prec * 4;
+                            val[0] = src[0]; val[1] = src[1]; val[2] = src[2]; val[3] = src[3];
+                        } else {
+                            val[0] = st.init[0][0]; val[1] = st.init[0][1]; val[2] = st.init[1][0]; val[3] = st.init[1][1];
+                        }
+                        const double *tp = a.tile_pw + ((long long)s * AES_NT + tid) * 4;          // M^tid
+                        bq_matvec(tp, val[0], val[1], t[0], t[1]);
+                        bq_matvec(tp, val[2], val[3], t[2], t[3]);
+                    }
+#pragma unroll
+                    for (int k = 16; k >= 1; k >>= 1)
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) t[q] += __shfl_xor_sync(0xffffffffu, t[q], k);
+                    if (lane == 0) { lb[warp * 5 + 0] = t[0]; lb[warp * 5 + 1] = t[1]; lb[warp * 5 + 2] = t[2]; lb[warp * 5 + 3] = t[3]; }
+                }
+                __syncthreads();
+                for (int w = 0; w < nw; ++w) {
+                    acc[0] += lb[w * 5 + 0]; acc[1] += lb[w * 5 + 1]; acc[2] += lb[w * 5 + 2]; acc[3] += lb[w * 5 + 3];
+                }
+            } else for (;;) {
                 // thread i looks at predecessor tile-1-base-i; index -1 is the clip's initial state (inclusive)
                 const long long pt = tile - 1 - base - tid;
                 int f = 2;
@@ -243,7 +280,7 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
                 W[0] = n0w; W[1] = n1w; W[2] = n2w; W[3] = n3w;
                 base += AES_NT;
             }
-            if (tid == 0) {
+            if (K == 0 && tid == 0) {
                 double i0v, i1v, i2v, i3v;
                 bq_matvec(st.tile, acc[0], acc[1], i0v, i1v);
                 bq_matvec(st.tile, acc[2], acc[3], i2v, i3v);

@@ -100,6 +100,8 @@ static int launch_chain(aes_chain_plan *pl, const void *x, int in_fmt, void *y, 
         }
         BqArgs a = pl->bq;
         a.x = (const float *)x; a.y = (float *)y; a.N = N; a.n_tiles = nt; a.B = B; a.dbg_skip = 0;
+        if (getenv("AES_SCAN_CHAINED"))             // tests: the chained look-back, which otherwise only slowly forgetting filters take
+            for (int s = 0; s < a.n_stages; ++s) a.st[s].lb_k = 0;
         a.agg = (double *)pl->d_bq_scan;
         a.inc = a.agg + recs * 4;
         a.flag = (int *)(a.inc + recs * 4);

@@ -98,6 +98,18 @@ int emu_biquad_scan(const float *x, float *y, long long B, long long N, int n_st
     return 0;
 }
 
+// look-back depth the host tables choose per stage (aes_biquad_build.h)
+extern "C" __attribute__((visibility("default")))
+int emu_biquad_lookback_depth(int n_stages, const double *coeffs5, int *out)
+{
+    if (n_stages < 1 || n_stages > AESB_MAX_STAGES) return -1;
+    static BqArgs a;
+    std::vector<double> lane_pw((size_t)n_stages * 128), tile_pw((size_t)n_stages * AES_NT * 4);
+    aes_biquad_build(n_stages, coeffs5, nullptr, &a, lane_pw.data(), tile_pw.data());
+    for (int s = 0; s < n_stages; ++s) out[s] = a.st[s].lb_k;
+    return 0;
+}
+
 // ---- IR-convolution reverb (aes_convreverb.cuh) on the emulator, FFT size 2^8 -----------------
 struct ConvLaunch { ConvArgs a; int cpc; const float *ir; int n_taps; cpx *A, *B; const cpx *tw; };
 static void conv_k1(void *p) { aesc_fft_blocks_body<8>(reinterpret_cast<ConvLaunch *>(p)->a); }

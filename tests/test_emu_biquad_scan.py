@@ -49,6 +49,34 @@ def test_scan_matches_sequential_reference_loop(cfg, n, skip):
         assert mx <= 1e-5 * max(1.0, float(np.abs(want).max())) and snr >= 100.0, (n, skip, b, mx, snr)
 
 
+def lookback_depth(co, n_stages):
+    L = emu.lib()
+    L.emu_biquad_lookback_depth.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
+    out = np.zeros(n_stages, np.int32)
+    assert L.emu_biquad_lookback_depth(n_stages, co.ctypes.data, out.ctypes.data) == 0
+    return out.tolist()
+
+
+def test_truncated_lookback_depth_and_agreement_with_the_chained_lookback():
+    """A stable biquad forgets: once |A^(1024 i)| < 2^-44 the look-back stops at i tiles and sums
+    aggregates only (no chain across tiles).  The depths follow the pole radius; the chained path
+    (skip > 0 forces it) and the truncated one agree to an f32 ulp; a filter that remembers more
+    than a 256-tile window keeps the chained look-back."""
+    n = 40 * 1024 + 5
+    x = synth.batch(3, 1, n)
+    co = coeffs_of(CASCADE, 48000, n)
+    depth = lookback_depth(co, 4)
+    assert depth[0] == 1 and 3 <= depth[1] <= 6 and all(1 <= d <= 6 for d in depth), depth
+    y_trunc = scan(x, co, 4, 0)
+    y_chain = scan(x, co, 4, 1000)
+    assert np.max(np.abs(y_trunc - y_chain)) <= 2.4e-7 * max(1.0, float(np.abs(y_chain).max()))
+    co_s = coeffs_of(STRESS, 48000, n)
+    d_s = lookback_depth(co_s, 2)
+    assert 30 <= d_s[0] <= 120 and 2 <= d_s[1] <= 40, d_s
+    slow = coeffs_of([{"type": "filter", "params": {"filter_type": 0, "cutoff_hz": 20, "q": 10.0}}], 96000, n)
+    assert lookback_depth(slow, 1) == [0]
+
+
 def test_scan_honours_a_carried_dfi_state():
     """filter.py:17-20: the kernel starts from state[c] = [x1, x2, y1, y2]."""
     n = 9000

@@ -236,6 +236,30 @@ def test_time_parallel_scan_equals_batch_kernel_on_a_single_clip(ab, orc, monkey
         assert np.max(np.abs(st - ofx.state)) <= 1e-5 * max(1.0, float(np.abs(ofx.state).max()))
 
 
+def test_truncated_lookback_matches_chained_lookback_and_is_reproducible(ab, orc, monkeypatch):
+    """aes_biquad_scan.cuh: filters that forget within a 256-tile window sum a fixed number of tile
+    aggregates instead of chaining look-backs.  Same audio as the chained look-back (forced by
+    AES_SCAN_CHAINED) to an f32 ulp, bit-identical from run to run, and within the bar of the oracle
+    for BASELINE configs[1]'s cascade and the low-cutoff stress pair."""
+    n = 48000 * 20 + 77
+    x = synth.clip(9, n, 2)
+    cascade = [{"type": "filter", "params": {"filter_type": 0, "cutoff_hz": 8000, "q": 0.707}},
+               {"type": "filter", "params": {"filter_type": 1, "cutoff_hz": 80, "q": 0.707}},
+               {"type": "filter", "params": {"filter_type": 2, "cutoff_hz": 1000, "q": 0.8}},
+               {"type": "filter", "params": {"filter_type": 3, "cutoff_hz": 1000, "q": 1.0, "gain_db": 6.0}}]
+    stress = [{"type": "filter", "params": {"filter_type": 0, "cutoff_hz": 40, "q": 5.0}},
+              {"type": "filter", "params": {"filter_type": 1, "cutoff_hz": 20, "q": 0.707}}]
+    for cfg in (cascade, stress):
+        y1 = run_file(ab, cfg, x, 48000)
+        y2 = run_file(ab, cfg, x, 48000)
+        assert np.array_equal(y1, y2)
+        check(y1, orc.run_file_path(cfg, x, 48000), what="truncated look-back")
+        monkeypatch.setenv("AES_SCAN_CHAINED", "1")
+        y3 = run_file(ab, cfg, x, 48000)
+        monkeypatch.delenv("AES_SCAN_CHAINED")
+        assert np.max(np.abs(y1 - y3)) <= 2.4e-7 * max(1.0, float(np.abs(y3).max()))
+
+
 def test_convolution_reverb_3s_ir(ab, orc):
     """BASELINE configs[3] shape at test size: 3 s synthetic IR (144 000 taps, 18 partitions of
     the 16384-point FFT), 5 s clips; float64 fftconvolve oracle (parity unpinned by the reference)."""
