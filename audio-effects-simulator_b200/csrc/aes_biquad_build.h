@@ -19,7 +19,8 @@ static inline void aes_biquad_build(int n_stages, const double *coeffs5, const d
         st.b0 = c[0]; st.b1 = c[1]; st.b2 = c[2]; st.a1 = c[3]; st.a2 = c[4];
         const double A[4] = { -c[3], 1.0, -c[4], 0.0 };          // zero-input TDF-II transition
         for (int k = 0; k < 5; ++k) aes_mat2_pow(A, (long long)AESB_FR << k, st.pw[k]);
-        aes_mat2_pow(A, 32LL * AESB_FR, st.pw[5]);
+        for (int w = 0; w < 8; ++w) aes_mat2_pow(A, 32LL * AESB_FR * w, st.wp[w]);
+        for (int j = 1; j < 4; ++j) { double m[4]; aes_mat2_pow(A, j, m); st.row[j - 1][0] = m[0]; st.row[j - 1][1] = m[1]; }
         aes_mat2_pow(A, (long long)AESB_T, st.tile);
         aes_mat2_pow(A, (long long)AES_NT * AESB_T, st.tile256);
         for (int l = 0; l < 32; ++l) aes_mat2_pow(A, (long long)AESB_FR * l, lane_pw + (s * 32 + l) * 4);

@@ -29,7 +29,9 @@
 
 struct BqStage {
     double b0, b1, b2, a1, a2;
-    double pw[6][4];        // A^(4*2^k), k=0..4 ; pw[5] = A^128 (one warp)
+    double pw[5][4];        // A^(4*2^k), k=0..4
+    double wp[8][4];        // P^w, P = A^128 (one warp of 4-frame chunks)
+    double row[3][2];       // first row of A^j, j = 1..3: what a start state adds to output j
     double tile[4];         // M = A^1024
     double tile256[4];      // M^256 (one look-back window)
     double init[2][2];      // TDF-II state at the start of the clip, per channel
@@ -95,7 +97,6 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
     AES_DYN_SMEM(double, sm);                     // [8 warps][2 ch][2] totals | [2 ch][2] carry | ticket
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     double *wtot = sm;                            // 32 doubles
-    double *carry = sm + 32;                      // 4 doubles
     unsigned *tk = reinterpret_cast<unsigned *>(sm + 36);
     double *lb = sm + 40;                         // look-back: [8 warps][4 partial sums + found]
 
@@ -124,31 +125,32 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
         const BqStage &st = a.st[s];
         const double b0 = st.b0, b1 = st.b1, b2 = st.b2, a1 = st.a1, a2 = st.a2;
         const long long rec = (clip * a.n_stages + s) * a.n_tiles + tile;
-        // 1. zero-state chunk response
-        double e1[2], e2[2];
+        // 1. zero-state chunk response: outputs kept, the true start state only adds row0(A^j).S later
+        double yz[2][AESB_FR], e1[2], e2[2];
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
             double s1 = 0.0, s2 = 0.0;
 #pragma unroll
             for (int j = 0; j < AESB_FR; ++j) {
                 const double xj = v[ch][j];
-                const double y = b0 * xj + s1;
-                s1 = b1 * xj - a1 * y + s2;
-                s2 = b2 * xj - a2 * y;
+                const double y = fma(b0, xj, s1);
+                s1 = fma(b1, xj, fma(-a1, y, s2));
+                s2 = fma(b2, xj, -a2 * y);
+                yz[ch][j] = y;
             }
             e1[ch] = s1; e2[ch] = s2;
         }
-        // 2. warp scan + cross-warp chain -> state at this thread's first frame for a zero tile start
+        // 2. warp Kogge-Stone scan of the chunk end states
 #pragma unroll
         for (int k = 0; k < 5; ++k) {
+            const double m0 = st.pw[k][0], m1 = st.pw[k][1], m2 = st.pw[k][2], m3 = st.pw[k][3];
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
                 const double u1 = __shfl_up_sync(0xffffffffu, e1[ch], 1 << k);
                 const double u2 = __shfl_up_sync(0xffffffffu, e2[ch], 1 << k);
                 if (lane >= (1 << k)) {
-                    double o1, o2;
-                    bq_matvec(st.pw[k], u1, u2, o1, o2);
-                    e1[ch] += o1; e2[ch] += o2;
+                    e1[ch] = fma(m0, u1, fma(m1, u2, e1[ch]));
+                    e2[ch] = fma(m2, u1, fma(m3, u2, e2[ch]));
                 }
             }
         }
@@ -157,34 +159,41 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
             for (int ch = 0; ch < 2; ++ch) { wtot[(warp * 2 + ch) * 2] = e1[ch]; wtot[(warp * 2 + ch) * 2 + 1] = e2[ch]; }
         }
         __syncthreads();
-        double p1[2], p2[2];                      // zero-start state at this thread's first frame
-        double E1[2], E2[2];                      // tile aggregate
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-            double c1 = 0.0, c2 = 0.0;
-            for (int w = 0; w < warp; ++w) {
-                double o1, o2;
-                bq_matvec(st.pw[5], c1, c2, o1, o2);
-                c1 = o1 + wtot[(w * 2 + ch) * 2]; c2 = o2 + wtot[(w * 2 + ch) * 2 + 1];
-            }
-            double x1 = __shfl_up_sync(0xffffffffu, e1[ch], 1), x2 = __shfl_up_sync(0xffffffffu, e2[ch], 1);
-            if (lane == 0) { x1 = 0.0; x2 = 0.0; }
-            const double *lp = a.lane_pw + (s * 32 + lane) * 4;
-            double o1, o2;
-            bq_matvec(lp, c1, c2, o1, o2);
-            p1[ch] = x1 + o1; p2[ch] = x2 + o2;
-        }
-        // 3. tile aggregate, CTA-wide look-back (one predecessor per thread, 256 per step), inclusive state
+        // zero-start state at the warp's first frame (Horner over the previous warps' totals, P = A^128)
+        // and, per thread, the exclusive scan value inside the warp
+        double c1[2], c2[2], x1[2], x2[2];
         {
+            const double P0 = st.wp[1][0], P1 = st.wp[1][1], P2 = st.wp[1][2], P3 = st.wp[1][3];
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) {
-                double c1 = 0.0, c2 = 0.0;
-                for (int w = 0; w < 8; ++w) {
-                    double o1, o2;
-                    bq_matvec(st.pw[5], c1, c2, o1, o2);
-                    c1 = o1 + wtot[(w * 2 + ch) * 2]; c2 = o2 + wtot[(w * 2 + ch) * 2 + 1];
+                double q1 = 0.0, q2 = 0.0;
+                for (int w = 0; w < warp; ++w) {
+                    const double n1 = fma(P0, q1, fma(P1, q2, wtot[(w * 2 + ch) * 2]));
+                    const double n2 = fma(P2, q1, fma(P3, q2, wtot[(w * 2 + ch) * 2 + 1]));
+                    q1 = n1; q2 = n2;
                 }
-                E1[ch] = c1; E2[ch] = c2;
+                c1[ch] = q1; c2[ch] = q2;
+                x1[ch] = __shfl_up_sync(0xffffffffu, e1[ch], 1); x2[ch] = __shfl_up_sync(0xffffffffu, e2[ch], 1);
+                if (lane == 0) { x1[ch] = 0.0; x2[ch] = 0.0; }
+            }
+        }
+        // 3. tile aggregate (only thread 0 publishes it: warp 0 computes it), look-back, inclusive state
+        double acc[4] = { 0.0, 0.0, 0.0, 0.0 };         // carry-in, accumulated identically by every thread
+        {
+            double E1[2] = { 0.0, 0.0 }, E2[2] = { 0.0, 0.0 };
+            if (warp == 0) {
+                const double P0 = st.wp[1][0], P1 = st.wp[1][1], P2 = st.wp[1][2], P3 = st.wp[1][3];
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    double q1 = 0.0, q2 = 0.0;
+#pragma unroll
+                    for (int w = 0; w < 8; ++w) {
+                        const double n1 = fma(P0, q1, fma(P1, q2, wtot[(w * 2 + ch) * 2]));
+                        const double n2 = fma(P2, q1, fma(P3, q2, wtot[(w * 2 + ch) * 2 + 1]));
+                        q1 = n1; q2 = n2;
+                    }
+                    E1[ch] = q1; E2[ch] = q2;
+                }
             }
             const int K = a.dbg_skip > 0 ? 0 : st.lb_k;
             if ((tile > 0 || K > 0) && tid == 0) {          // publish the aggregate first: successors may run ahead
@@ -192,7 +201,6 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
                 a.agg[rec * 4 + 2] = E1[1]; a.agg[rec * 4 + 3] = E2[1];
                 bq_st_flag(a.flag + rec, 1);                // st.release orders the record before the flag
             }
-            double acc[4] = { 0.0, 0.0, 0.0, 0.0 };         // carry-in, accumulated identically by every thread
             double W[4] = { 1.0, 0.0, 0.0, 1.0 };           // M^base
             long long base = 0;
             if (K > 0) {
@@ -288,32 +296,32 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
                 a.inc[rec * 4 + 2] = E1[1] + i2v; a.inc[rec * 4 + 3] = E2[1] + i3v;
                 bq_st_flag(a.flag + rec, 2);
             }
-            carry[0] = acc[0]; carry[1] = acc[1]; carry[2] = acc[2]; carry[3] = acc[3];   // same value from every thread
         }
-        // 4. true state at this thread's first frame = zero-start state + A^(4*tid) * C, then the real pass
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch) {
-            double c1 = carry[2 * ch], c2 = carry[2 * ch + 1];
-            for (int w = 0; w < warp; ++w) { double o1, o2; bq_matvec(st.pw[5], c1, c2, o1, o2); c1 = o1; c2 = o2; }
+        // 4. true state at this thread's first frame: exclusive scan value + A^(4*lane) (warp carry + P^warp C);
+        //    the outputs are the zero-state outputs plus row0(A^j) . state
+        {
             const double *lp = a.lane_pw + (s * 32 + lane) * 4;
-            double o1, o2;
-            bq_matvec(lp, c1, c2, o1, o2);
-            double s1 = p1[ch] + o1, s2 = p2[ch] + o2;
+            const double l0 = lp[0], l1 = lp[1], l2 = lp[2], l3 = lp[3];
+            const double W0 = st.wp[warp][0], W1 = st.wp[warp][1], W2 = st.wp[warp][2], W3 = st.wp[warp][3];
 #pragma unroll
-            for (int j = 0; j < AESB_FR; ++j) {
-                const double xj = v[ch][j];
-                const double y = b0 * xj + s1;
-                s1 = b1 * xj - a1 * y + s2;
-                s2 = b2 * xj - a2 * y;
-                v[ch][j] = (double)(float)y;          // the reference stores every stage's output as f32
-                if (a.final_state != nullptr && tile == a.n_tiles - 1) {
-                    double *fs = a.final_state + (clip * a.n_stages + s) * 16 + 4 * ch;
-                    if (i0 + j == len - 1) { fs[0] = xj; fs[2] = y; }
-                    if (i0 + j == len - 2) { fs[1] = xj; fs[3] = y; }
+            for (int ch = 0; ch < 2; ++ch) {
+                const double C1 = acc[2 * ch], C2 = acc[2 * ch + 1];
+                const double cw1 = fma(W0, C1, fma(W1, C2, c1[ch])), cw2 = fma(W2, C1, fma(W3, C2, c2[ch]));
+                const double s1 = fma(l0, cw1, fma(l1, cw2, x1[ch])), s2 = fma(l2, cw1, fma(l3, cw2, x2[ch]));
+#pragma unroll
+                for (int j = 0; j < AESB_FR; ++j) {
+                    const double xj = v[ch][j];
+                    const double y = j == 0 ? yz[ch][0] + s1 : fma(st.row[j - (j > 0)][0], s1, fma(st.row[j - (j > 0)][1], s2, yz[ch][j]));
+                    v[ch][j] = (double)(float)y;          // the reference stores every stage's output as f32
+                    if (a.final_state != nullptr && tile == a.n_tiles - 1) {
+                        double *fs = a.final_state + (clip * a.n_stages + s) * 16 + 4 * ch;
+                        if (i0 + j == len - 1) { fs[0] = xj; fs[2] = y; }
+                        if (i0 + j == len - 2) { fs[1] = xj; fs[3] = y; }
+                    }
                 }
             }
         }
-        __syncthreads();                              // wtot / carry are reused by the next stage
+        // (no barrier here: every read of wtot / lb above sits before a barrier the next stage's writes come after)
     }
     {
         float2 *yp = reinterpret_cast<float2 *>(a.y) + clip * a.N + n0 + i0;
