@@ -39,6 +39,12 @@ struct BqStage {
     int pad_;               //      look-back sums lb_k aggregates and never chains; 0: chained look-back
 };
 
+// One published double of a tile aggregate with the launch's epoch beside it: written and read as ONE
+// 16-byte access, so a reader that sees the epoch has the value -- no flag, no fence, no clearing
+// between launches (the packing CUB's decoupled look-back uses for its tile descriptors).
+struct alignas(16) BqRec { double v; unsigned long long tag; };
+#define AESB_SMEM_DOUBLES 112
+
 struct BqArgs {
     BqStage st[AESB_MAX_STAGES];
     const float *x;
@@ -52,7 +58,10 @@ struct BqArgs {
     double *agg;            // 4 doubles (2 ch x 2) per record
     double *inc;
     int *flag;              // 0 none, 1 aggregate, 2 inclusive
-    unsigned int *ticket;   // one counter
+    unsigned int *ticket;   // one counter, never reset: a launch's tickets start at ticket_base
+    unsigned int ticket_base;
+    BqRec *rec16;           // truncated look-back: 4 self-validating (value, epoch) pairs per record
+    unsigned long long epoch;   // this launch's tag (never 0; the array starts zeroed and is never cleared again)
     const double *lane_pw;  // [stage][32][4]  A^(4*lane)
     const double *tile_pw;  // [stage][256][4] M^i, i = look-back distance - 1
     double *final_state;    // optional [clip][stage][16]: [4*ch + {0,1,2,3}] = x1,x2,y1,y2 (DF-I view) at the clip end
@@ -69,6 +78,8 @@ static inline int bq_ld_flag(const int *p) { return *p; }
 static inline int bq_ld_flag_acquire(const int *p) { return *p; }
 static inline void bq_st_flag(int *p, int v) { *p = v; }
 static inline void __threadfence() {}
+static inline void bq_st_rec(BqRec *p, double v, unsigned long long tag) { p->v = v; p->tag = tag; }
+static inline bool bq_ld_rec(const BqRec *p, unsigned long long tag, double &v) { v = p->v; return p->tag == tag; }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { unsigned o = *p; *p += v; return o; }
 #else
 // spin with relaxed loads (no L1 invalidation per iteration); one acquire fence once the
@@ -86,6 +97,17 @@ __device__ __forceinline__ int bq_ld_flag_acquire(const int *p)
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void bq_st_rec(BqRec *p, double v, unsigned long long tag)
+{
+    asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(tag) : "memory");
+}
+__device__ __forceinline__ bool bq_ld_rec(const BqRec *p, unsigned long long tag, double &v)
+{
+    long long b; unsigned long long t;
+    asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(b), "=l"(t) : "l"(p) : "memory");
+    v = __longlong_as_double(b);
+    return t == tag;
+}
 __device__ __forceinline__ void bq_st_flag(int *p, int v)
 {
     asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -94,13 +116,12 @@ __device__ __forceinline__ void bq_st_flag(int *p, int v)
 
 __device__ void aes_biquad_scan_body(const BqArgs &a)
 {
-    AES_DYN_SMEM(double, sm);                     // [8 warps][2 ch][2] totals | [2 ch][2] carry | ticket
+    AES_DYN_SMEM(double, sm);                     // 2 x [8 warps][2 ch][2] totals (by stage parity) | ticket | look-back
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    double *wtot = sm;                            // 32 doubles
-    unsigned *tk = reinterpret_cast<unsigned *>(sm + 36);
-    double *lb = sm + 40;                         // look-back: [8 warps][4 partial sums + found]
+    unsigned *tk = reinterpret_cast<unsigned *>(sm + 64);
+    double *lb = sm + 66;                         // chained look-back: [8 warps][4 partial sums + found]
 
-    if (tid == 0) *tk = atomicAdd(a.ticket, 1u);
+    if (tid == 0) *tk = atomicAdd(a.ticket, 1u) - a.ticket_base;
     __syncthreads();
     const long long work = (long long)*tk;        // ordered: clip-major, tile-minor
     if (work >= a.B * a.n_tiles) return;
@@ -125,6 +146,7 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
         const BqStage &st = a.st[s];
         const double b0 = st.b0, b1 = st.b1, b2 = st.b2, a1 = st.a1, a2 = st.a2;
         const long long rec = (clip * a.n_stages + s) * a.n_tiles + tile;
+        double *const wtot = sm + 32 * (s & 1);     // a warp may be one stage ahead of another, never two
         // 1. zero-state chunk response: outputs kept, the true start state only adds row0(A^j).S later
         double yz[2][AESB_FR], e1[2], e2[2];
 #pragma unroll
@@ -177,11 +199,55 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
                 if (lane == 0) { x1[ch] = 0.0; x2[ch] = 0.0; }
             }
         }
-        // 3. tile aggregate (only thread 0 publishes it: warp 0 computes it), look-back, inclusive state
-        double acc[4] = { 0.0, 0.0, 0.0, 0.0 };         // carry-in, accumulated identically by every thread
-        {
+        // 3. tile aggregate, look-back -> state C at the tile start
+        double acc[4] = { 0.0, 0.0, 0.0, 0.0 };         // carry-in, the same in every thread
+        const int K = a.dbg_skip > 0 ? 0 : st.lb_k;
+        if (K > 0) {
+            // Truncated look-back: the filter forgets, M^K is below 2^-44, so C is the sum of the K nearest
+            // AGGREGATES (zero-state tile responses, published before any look-back): no tile waits for
+            // another tile's look-back, and the sum has a fixed order (bit-reproducible output).
+            // The last warp publishes (its Horner carry covers warps 0..6); EVERY warp then looks back on
+            // its own, so the CTA needs no barrier here and its warps drift apart by up to one stage.
+            if (warp == 7) {
+                const double P0 = st.wp[1][0], P1 = st.wp[1][1], P2 = st.wp[1][2], P3 = st.wp[1][3];
+                double ev = 0.0;
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    const double E1 = fma(P0, c1[ch], fma(P1, c2[ch], wtot[(7 * 2 + ch) * 2]));
+                    const double E2 = fma(P2, c1[ch], fma(P3, c2[ch], wtot[(7 * 2 + ch) * 2 + 1]));
+                    if (lane == 2 * ch) ev = E1;
+                    if (lane == 2 * ch + 1) ev = E2;
+                }
+                if (lane < 4) bq_st_rec(a.rec16 + rec * 4 + lane, ev, a.epoch);
+            }
+            int KP = 1;
+            while (KP < K && KP < 32) KP <<= 1;
+            // lane i (mod KP) takes predecessors i, i + KP, ...; groups of KP lanes work redundantly so the
+            // butterfly below leaves the sum in every lane
+            for (int i = lane & (KP - 1); i < K; i += KP) {
+                const long long pt = tile - 1 - i;
+                if (pt < -1) break;
+                double val[4];
+                if (pt >= 0) {
+                    const BqRec *r = a.rec16 + (rec - 1 - i) * 4;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                        while (!bq_ld_rec(r + q, a.epoch, val[q])) { }
+                } else {                                    // the clip's initial state sits where tile -1 would
+                    val[0] = st.init[0][0]; val[1] = st.init[0][1]; val[2] = st.init[1][0]; val[3] = st.init[1][1];
+                }
+                const double *tp = a.tile_pw + ((long long)s * AES_NT + i) * 4;            // M^i
+                acc[0] = fma(tp[0], val[0], fma(tp[1], val[1], acc[0]));
+                acc[1] = fma(tp[2], val[0], fma(tp[3], val[1], acc[1]));
+                acc[2] = fma(tp[0], val[2], fma(tp[1], val[3], acc[2]));
+                acc[3] = fma(tp[2], val[2], fma(tp[3], val[3], acc[3]));
+            }
+            for (int k = KP >> 1; k >= 1; k >>= 1)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], k);
+        } else {
             double E1[2] = { 0.0, 0.0 }, E2[2] = { 0.0, 0.0 };
-            if (warp == 0) {
+            if (warp == 0) {                                // only thread 0 publishes
                 const double P0 = st.wp[1][0], P1 = st.wp[1][1], P2 = st.wp[1][2], P3 = st.wp[1][3];
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch) {
@@ -195,49 +261,14 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
                     E1[ch] = q1; E2[ch] = q2;
                 }
             }
-            const int K = a.dbg_skip > 0 ? 0 : st.lb_k;
-            if ((tile > 0 || K > 0) && tid == 0) {          // publish the aggregate first: successors may run ahead
+            if (tile > 0 && tid == 0) {                     // publish the aggregate first: successors may run ahead
                 a.agg[rec * 4 + 0] = E1[0]; a.agg[rec * 4 + 1] = E2[0];
                 a.agg[rec * 4 + 2] = E1[1]; a.agg[rec * 4 + 3] = E2[1];
                 bq_st_flag(a.flag + rec, 1);                // st.release orders the record before the flag
             }
             double W[4] = { 1.0, 0.0, 0.0, 1.0 };           // M^base
             long long base = 0;
-            if (K > 0) {
-                // Truncated look-back: the filter forgets, M^K is below 2^-44, so the state at the tile
-                // start is the sum of the K nearest AGGREGATES (zero-state tile responses, published
-                // before any look-back) -- no tile waits for another tile's look-back, and the sum has
-                // a fixed order, so the output is reproducible bit for bit.
-                const int nw = (K + 31) >> 5;               // warps that hold a predecessor
-                if (warp < nw) {
-                    const long long pt = tile - 1 - tid;
-                    double t[4] = { 0.0, 0.0, 0.0, 0.0 };
-                    if (tid < K && pt >= -1) {
-                        double val[4];
-                        if (pt >= 0) {
-                            const long long prec = rec - 1 - tid;
-                            while (bq_ld_flag(a.flag + prec) == 0) { }
-                            (void)bq_ld_flag_acquire(a.flag + prec);
-                            const double *src = a.agg + prec * 4;
-                            val[0] = src[0]; val[1] = src[1]; val[2] = src[2]; val[3] = src[3];
-                        } else {
-                            val[0] = st.init[0][0]; val[1] = st.init[0][1]; val[2] = st.init[1][0]; val[3] = st.init[1][1];
-                        }
-                        const double *tp = a.tile_pw + ((long long)s * AES_NT + tid) * 4;          // M^tid
-                        bq_matvec(tp, val[0], val[1], t[0], t[1]);
-                        bq_matvec(tp, val[2], val[3], t[2], t[3]);
-                    }
-#pragma unroll
-                    for (int k = 16; k >= 1; k >>= 1)
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) t[q] += __shfl_xor_sync(0xffffffffu, t[q], k);
-                    if (lane == 0) { lb[warp * 5 + 0] = t[0]; lb[warp * 5 + 1] = t[1]; lb[warp * 5 + 2] = t[2]; lb[warp * 5 + 3] = t[3]; }
-                }
-                __syncthreads();
-                for (int w = 0; w < nw; ++w) {
-                    acc[0] += lb[w * 5 + 0]; acc[1] += lb[w * 5 + 1]; acc[2] += lb[w * 5 + 2]; acc[3] += lb[w * 5 + 3];
-                }
-            } else for (;;) {
+            for (;;) {
                 // thread i looks at predecessor tile-1-base-i; index -1 is the clip's initial state (inclusive)
                 const long long pt = tile - 1 - base - tid;
                 int f = 2;
@@ -288,7 +319,7 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
                 W[0] = n0w; W[1] = n1w; W[2] = n2w; W[3] = n3w;
                 base += AES_NT;
             }
-            if (K == 0 && tid == 0) {
+            if (tid == 0) {
                 double i0v, i1v, i2v, i3v;
                 bq_matvec(st.tile, acc[0], acc[1], i0v, i1v);
                 bq_matvec(st.tile, acc[2], acc[3], i2v, i3v);
@@ -332,7 +363,10 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
 }
 
 #ifndef AES_CPU_EMU
-__global__ void __launch_bounds__(AES_NT, 4) aes_biquad_scan_kernel(const __grid_constant__ BqArgs a)
+#ifndef AESB_MIN_CTAS
+#define AESB_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(AES_NT, AESB_MIN_CTAS) aes_biquad_scan_kernel(const __grid_constant__ BqArgs a)
 {
     aes_biquad_scan_body(a);
 }

@@ -50,6 +50,9 @@ struct aes_chain_plan {
     // time-parallel biquad cascade (aes_biquad_scan.cuh) for few long clips
     bool bq_ok = false;
     BqArgs bq;
+    size_t bq_scan_recs = 0;                    // record count the scan scratch is laid out (and zeroed) for
+    unsigned bq_ticket_base = 0;                // tickets handed out by earlier launches (the counter is never reset)
+    unsigned long long bq_epoch = 0;            // tag of the last launch's look-back records
     double *d_bq_tab = nullptr;                 // lane_pw [8][32][4] | tile_pw [8][256][4]
     void *d_bq_scan = nullptr;                  // agg | inc | flag | ticket, grown on demand
     size_t bq_scan_cap = 0;
@@ -91,26 +94,39 @@ static int launch_chain(aes_chain_plan *pl, const void *x, int in_fmt, void *y, 
         // fewer clips than resident CTAs: go parallel in time (one CTA per 1024-frame tile)
         const long long nt = (N + AESB_T - 1) / AESB_T;
         const size_t recs = (size_t)B * pl->bq.n_stages * nt;
-        const size_t need = recs * (8 * sizeof(double) + sizeof(int)) + 64;
+        const size_t need = recs * (sizeof(BqRec) * 4 + 8 * sizeof(double) + sizeof(int)) + 64;
         if (pl->bq_scan_cap < need) {
             if (pl->d_bq_scan) cudaFree(pl->d_bq_scan);
             pl->d_bq_scan = nullptr; pl->bq_scan_cap = 0;
             AES_CUDA(cudaMalloc(&pl->d_bq_scan, need));
             pl->bq_scan_cap = need;
+            pl->bq_scan_recs = 0;
+        }
+        if (pl->bq_scan_recs != recs) {             // new layout: epoch records and the ticket start at 0, once
+            AES_CUDA(cudaMemsetAsync(pl->d_bq_scan, 0, need, st));
+            pl->bq_scan_recs = recs;
+            pl->bq_ticket_base = 0;
         }
         BqArgs a = pl->bq;
         a.x = (const float *)x; a.y = (float *)y; a.N = N; a.n_tiles = nt; a.B = B; a.dbg_skip = 0;
         if (getenv("AES_SCAN_CHAINED"))             // tests: the chained look-back, which otherwise only slowly forgetting filters take
             for (int s = 0; s < a.n_stages; ++s) a.st[s].lb_k = 0;
-        a.agg = (double *)pl->d_bq_scan;
+        // the ticket lives at the FRONT so that it keeps its place when recs changes under the same capacity
+        a.ticket = (unsigned *)pl->d_bq_scan;
+        a.ticket_base = pl->bq_ticket_base;
+        pl->bq_ticket_base += (unsigned)(B * nt);
+        a.epoch = ++pl->bq_epoch;
+        a.rec16 = (BqRec *)((char *)pl->d_bq_scan + 64);
+        a.agg = (double *)(a.rec16 + recs * 4);
         a.inc = a.agg + recs * 4;
         a.flag = (int *)(a.inc + recs * 4);
-        a.ticket = (unsigned *)(a.flag + recs);
         a.lane_pw = pl->d_bq_tab;
         a.tile_pw = pl->d_bq_tab + (size_t)AESB_MAX_STAGES * 128;
         a.final_state = state_out;
-        AES_CUDA(cudaMemsetAsync(a.flag, 0, (recs + 1) * sizeof(int), st));
-        aes_biquad_scan_kernel<<<(unsigned)(B * nt), AES_NT, 80 * sizeof(double), st>>>(a);
+        bool chained = false;
+        for (int s = 0; s < a.n_stages; ++s) chained |= a.st[s].lb_k == 0;
+        if (chained) AES_CUDA(cudaMemsetAsync(a.flag, 0, recs * sizeof(int), st));
+        aes_biquad_scan_kernel<<<(unsigned)(B * nt), AES_NT, AESB_SMEM_DOUBLES * sizeof(double), st>>>(a);
         aes_count_launch();
         AES_CUDA(cudaGetLastError());
         return 0;

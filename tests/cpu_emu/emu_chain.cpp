@@ -90,11 +90,14 @@ int emu_biquad_scan(const float *x, float *y, long long B, long long N, int n_st
     const size_t recs = (size_t)(B * n_stages * nt);
     std::vector<double> agg(recs * 4, 1e300), inc(recs * 4, 1e300);
     std::vector<int> flag(recs, 0);
-    unsigned ticket = 0;
+    unsigned ticket = 40;                                        // the counter is never reset: a launch starts at its base
+    std::vector<BqRec> rec16(recs * 4);
+    for (auto &r : rec16) { r.v = 1e300; r.tag = 6; }            // records of an earlier launch
+    a.rec16 = rec16.data(); a.epoch = 7; a.ticket_base = 40;
     a.x = x; a.y = y; a.N = N; a.n_tiles = nt; a.B = B; a.dbg_skip = dbg_skip;
     a.agg = agg.data(); a.inc = inc.data(); a.flag = flag.data(); a.ticket = &ticket;
     a.lane_pw = lane_pw.data(); a.tile_pw = tile_pw.data(); a.final_state = nullptr;
-    emu::launch(bq_entry, &a, (unsigned)(B * nt), AES_NT, 80 * sizeof(double));
+    emu::launch(bq_entry, &a, (unsigned)(B * nt), AES_NT, AESB_SMEM_DOUBLES * sizeof(double));
     return 0;
 }
 
