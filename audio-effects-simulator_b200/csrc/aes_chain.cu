@@ -50,6 +50,9 @@ struct aes_chain_plan {
     // time-parallel biquad cascade (aes_biquad_scan.cuh) for few long clips
     bool bq_ok = false;
     BqArgs bq;
+    cudaEvent_t bq_done = nullptr;              // last scan launch: the scratch below is shared, so scan launches of one
+                                                // plan are chained by this event even when they sit on different streams
+    cudaStream_t bq_stream = nullptr;           // stream of the last scan launch
     size_t bq_scan_recs = 0;                    // record count the scan scratch is laid out (and zeroed) for
     unsigned bq_ticket_base = 0;                // tickets handed out by earlier launches (the counter is never reset)
     unsigned long long bq_epoch = 0;            // tag of the last launch's look-back records
@@ -93,6 +96,9 @@ static int launch_chain(aes_chain_plan *pl, const void *x, int in_fmt, void *y, 
         !getenv("AES_NO_SCAN")) {
         // fewer clips than resident CTAs: go parallel in time (one CTA per 1024-frame tile)
         const long long nt = (N + AESB_T - 1) / AESB_T;
+        if (!pl->bq_done) AES_CUDA(cudaEventCreateWithFlags(&pl->bq_done, cudaEventDisableTiming));
+        else if (st != pl->bq_stream) AES_CUDA(cudaStreamWaitEvent(st, pl->bq_done, 0));
+        pl->bq_stream = st;
         const size_t recs = (size_t)B * pl->bq.n_stages * nt;
         const size_t need = recs * (sizeof(BqRec) * 4 + 8 * sizeof(double) + sizeof(int)) + 64;
         if (pl->bq_scan_cap < need) {
@@ -127,6 +133,7 @@ static int launch_chain(aes_chain_plan *pl, const void *x, int in_fmt, void *y, 
         for (int s = 0; s < a.n_stages; ++s) chained |= a.st[s].lb_k == 0;
         if (chained) AES_CUDA(cudaMemsetAsync(a.flag, 0, recs * sizeof(int), st));
         aes_biquad_scan_kernel<<<(unsigned)(B * nt), AES_NT, AESB_SMEM_DOUBLES * sizeof(double), st>>>(a);
+        AES_CUDA(cudaEventRecord(pl->bq_done, st));
         aes_count_launch();
         AES_CUDA(cudaGetLastError());
         return 0;
@@ -251,6 +258,7 @@ AES_EXPORT int aes_chain_plan_destroy(aes_chain_plan *pl)
     if (pl->d_state) cudaFree(pl->d_state);
     if (pl->d_lane_tab) cudaFree(pl->d_lane_tab);
     if (pl->d_bq_tab) cudaFree(pl->d_bq_tab);
+    if (pl->bq_done) cudaEventDestroy(pl->bq_done);
     if (pl->d_bq_scan) cudaFree(pl->d_bq_scan);
     delete pl;
     return 0;

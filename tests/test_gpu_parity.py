@@ -260,6 +260,24 @@ def test_truncated_lookback_matches_chained_lookback_and_is_reproducible(ab, orc
         assert np.max(np.abs(y1 - y3)) <= 2.4e-7 * max(1.0, float(np.abs(y3).max()))
 
 
+def test_scan_sub_batches_on_different_streams_share_one_scratch(ab, orc):
+    """A host call with a few long clips is cut into sub-batches that run on the pipeline's four
+    streams; every one of them takes the time-parallel scan, whose look-back records, ticket and
+    epoch live in ONE per-plan scratch (launches are chained by an event; the last, smaller
+    sub-batch re-lays the scratch out).  Twice through the same plan, against the oracle."""
+    n, B = 2_600_000, 7
+    x = synth.batch(70, B, n)
+    cfg = [{"type": "filter", "params": {"filter_type": 1, "cutoff_hz": 120, "q": 0.9}},
+           {"type": "filter", "params": {"filter_type": 0, "cutoff_hz": 5000, "q": 0.707}}]
+    from audioblocks.engine import file_chain
+    chain = file_chain(cfg, 48000, channels_in=2)
+    y1 = chain.process_batch(x)
+    y2 = chain.process_batch(x)
+    assert np.array_equal(y1, y2)
+    for b in (0, 3, 6):
+        check(y1[b], orc.run_file_path(cfg, x[b], 48000), what=("scan sub-batch", b))
+
+
 def test_convolution_reverb_3s_ir(ab, orc):
     """BASELINE configs[3] shape at test size: 3 s synthetic IR (144 000 taps, 18 partitions of
     the 16384-point FFT), 5 s clips; float64 fftconvolve oracle (parity unpinned by the reference)."""
