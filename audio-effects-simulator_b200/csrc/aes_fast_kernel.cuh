@@ -657,8 +657,8 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
                 const double u1 = __shfl_up_sync(0xffffffffu, e1[ch], 1 << s);
                 const double u2 = __shfl_up_sync(0xffffffffu, e2[ch], 1 << s);
                 if (lane >= (1 << s)) {
-                    e1[ch] += m0 * u1 + m2 * u2;                 // (A^k)^T u
-                    e2[ch] += m1 * u1 + m3 * u2;
+                    e1[ch] = fma(m0, u1, fma(m2, u2, e1[ch]));   // += (A^k)^T u, two dependent DFMAs
+                    e2[ch] = fma(m1, u1, fma(m3, u2, e2[ch]));
                 }
             }
         }
@@ -682,14 +682,14 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
             const int u0 = warp > st.nxw ? warp - st.nxw : 0;
             if (u0 > 0) { C1 = 0.0; C2 = 0.0; }                 // the tile-start state has decayed by then
             for (int t = u0; t < warp; ++t) {
-                const double t1 = w0 * C1 + w2 * C2 + wtot[(t * 2 + ch) * 2];
-                const double t2 = w1 * C1 + w3 * C2 + wtot[(t * 2 + ch) * 2 + 1];
+                const double t1 = fma(w0, C1, fma(w2, C2, wtot[(t * 2 + ch) * 2]));
+                const double t2 = fma(w1, C1, fma(w3, C2, wtot[(t * 2 + ch) * 2 + 1]));
                 C1 = t1; C2 = t2;
             }
             double x1 = __shfl_up_sync(0xffffffffu, e1[ch], 1), x2 = __shfl_up_sync(0xffffffffu, e2[ch], 1);
             if (lane == 0) { x1 = 0.0; x2 = 0.0; }
-            const double S1 = x1 + l0 * C1 + l2 * C2;            // state entering this thread's chunk
-            const double S2 = x2 + l1 * C1 + l3 * C2;
+            const double S1 = fma(l0, C1, fma(l2, C2, x1));      // state entering this thread's chunk
+            const double S2 = fma(l1, C1, fma(l3, C2, x2));
 #pragma unroll
             for (int j = 0; j < FR; ++j) {
                 const double y = j == 0 ? yz[ch][0] + S1 : fma(st.bq_row[j][0], S1, fma(st.bq_row[j][1], S2, yz[ch][j]));
