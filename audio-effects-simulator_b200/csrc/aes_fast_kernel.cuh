@@ -656,7 +656,7 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
             for (int ch = 0; ch < 2; ++ch) {
                 const double u1 = __shfl_up_sync(0xffffffffu, e1[ch], 1 << s);
                 const double u2 = __shfl_up_sync(0xffffffffu, e2[ch], 1 << s);
-                if (lane >= (1 << s)) {
+                if (lane >= (1 << s)) {                          // (ptxas turns a predicated DFMA into DFMA + 2 FSEL too)
                     e1[ch] = fma(m0, u1, fma(m2, u2, e1[ch]));   // += (A^k)^T u, two dependent DFMAs
                     e2[ch] = fma(m1, u1, fma(m3, u2, e2[ch]));
                 }
@@ -693,8 +693,17 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
 #pragma unroll
             for (int j = 0; j < FR; ++j) {
                 const double y = j == 0 ? yz[ch][0] + S1 : fma(st.bq_row[j][0], S1, fma(st.bq_row[j][1], S2, yz[ch][j]));
-                if (i0 + j == c.len - 1) { sout[4 * ch + 0] = (double)v[ch][j]; sout[4 * ch + 2] = y; }
-                if (i0 + j == c.len - 2) { sout[4 * ch + 1] = (double)v[ch][j]; sout[4 * ch + 3] = y; }
+                // the last two frames of the tile are the next tile's (x1, x2, y1, y2): in a full tile
+                // (FR >= 2) they sit in the last thread -- one uniform branch instead of 4 predicated stores
+                // per frame
+                if (FR >= 2 && c.len == AES_NT * FR) {
+                    if (j >= FR - 2 && c.tid == AES_NT - 1) {
+                        sout[4 * ch + (FR - 1 - j)] = (double)v[ch][j]; sout[4 * ch + 2 + (FR - 1 - j)] = y;
+                    }
+                } else {
+                    if (i0 + j == c.len - 1) { sout[4 * ch + 0] = (double)v[ch][j]; sout[4 * ch + 2] = y; }
+                    if (i0 + j == c.len - 2) { sout[4 * ch + 1] = (double)v[ch][j]; sout[4 * ch + 3] = y; }
+                }
                 v[ch][j] = (float)y;
             }
             if (c.len == 1 && c.tid == 0) { sout[4 * ch + 1] = cx1; sout[4 * ch + 3] = cy1; }
@@ -730,7 +739,8 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
             const float gf = (float)g;
             v[0][f] *= gf;
             v[1][f] *= gf;
-            if (i0 + f == c.len - 1) sout[0] = g;
+            if (c.len == AES_NT * FR) { if (f == FR - 1 && c.tid == AES_NT - 1) sout[0] = g; }
+            else if (i0 + f == c.len - 1) sout[0] = g;
         }
     } else if constexpr (KIND == AESK_OCTAVER) {
         float *rb = c.rings + st.ring[0][0].off;
