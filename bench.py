@@ -435,6 +435,12 @@ def b200_arm(args):
         k_ms = sum(per_launch_ms) / len(per_launch_ms)
         achieved = B * n_frames * 2 * 8 / (k_ms * 1e-3) / 1e9
         traffic, traffic_src = NCU_DRAM_TRAFFIC.get((args.preset, B, n_frames), (None, None))
+        kernel = info["kernel"]
+        if args.preset == "c2-biquad-cascade" and info["ctas_per_sm"] and not os.environ.get("AES_NO_SCAN") and \
+                B < info["ctas_per_sm"] * torch.cuda.get_device_properties(0).multi_processor_count:
+            # fewer clips than resident CTAs: launch_chain (aes_chain.cu) takes the time-parallel scan
+            kernel = "aes_biquad_scan_kernel (one CTA per 1024-frame tile, %s look-back)" % (
+                "chained" if os.environ.get("AES_SCAN_CHAINED") else "truncated")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -444,7 +450,7 @@ def b200_arm(args):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peak_src,
-                         "kernel": info["kernel"], "algorithmic_bytes_per_launch": B * n_frames * 16,
+                         "kernel": kernel, "algorithmic_bytes_per_launch": B * n_frames * 16,
                          "launch_ms": k_ms},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "parity": parity,
         }
