@@ -476,7 +476,7 @@ def b200_arm(args):
                          "launch_ms": k_ms},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "parity": parity,
         }
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:          # the CPU baseline is reported at N = 1 only
             cores = os.cpu_count() or 1
             n_cpu = args.cpu_clips or max(cores, min(20 * cores, 512))     # ~20 s of CPU work on all threads
             v, dt = cpu_run(args.preset, n_cpu, n_frames, cores, reps=2)
