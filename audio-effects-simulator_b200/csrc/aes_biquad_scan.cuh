@@ -24,14 +24,18 @@
 #include "aes_plan.h"
 
 #define AESB_MAX_STAGES 8
-#define AESB_FR 4
-#define AESB_T (AES_NT * AESB_FR)
+#ifndef AESB_FR
+#define AESB_FR 8                       // frames per thread: the scan / Horner / look-back cost is per warp, not per frame
+#endif
+#define AESB_T 1024                     // frames per tile (CTA)
+#define AESB_NT (AESB_T / AESB_FR)      // threads per CTA
+#define AESB_NW (AESB_NT / 32)          // warps per CTA
 
 struct BqStage {
     double b0, b1, b2, a1, a2;
     double pw[5][4];        // A^(4*2^k), k=0..4
-    double wp[8][4];        // P^w, P = A^128 (one warp of 4-frame chunks)
-    double row[3][2];       // first row of A^j, j = 1..3: what a start state adds to output j
+    double wp[8][4];        // P^w, P = A^(32*AESB_FR) (one warp of chunks); w < AESB_NW used
+    double row[AESB_FR - 1][2];   // first row of A^j, j = 1..AESB_FR-1: what a start state adds to output j
     double tile[4];         // M = A^1024
     double tile256[4];      // M^256 (one look-back window)
     double init[2][2];      // TDF-II state at the start of the clip, per channel
@@ -130,15 +134,15 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
     const int len = (a.N - n0 < (long long)AESB_T) ? (int)(a.N - n0) : AESB_T;
     const int i0 = AESB_FR * tid;
 
-    // load 4 frames x 2 channels
-    double v[2][AESB_FR];
+    // load AESB_FR frames x 2 channels; between stages the samples stay f32 (what the reference stores)
+    float v[2][AESB_FR];
     {
         const float2 *xp = reinterpret_cast<const float2 *>(a.x) + clip * a.N + n0 + i0;
 #pragma unroll
         for (int j = 0; j < AESB_FR; ++j) {
             float2 t = make_float2(0.f, 0.f);
             if (i0 + j < len) t = xp[j];
-            v[0][j] = (double)t.x; v[1][j] = (double)t.y;
+            v[0][j] = t.x; v[1][j] = t.y;
         }
     }
 
@@ -154,7 +158,7 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
             double s1 = 0.0, s2 = 0.0;
 #pragma unroll
             for (int j = 0; j < AESB_FR; ++j) {
-                const double xj = v[ch][j];
+                const double xj = (double)v[ch][j];
                 const double y = fma(b0, xj, s1);
                 s1 = fma(b1, xj, fma(-a1, y, s2));
                 s2 = fma(b2, xj, -a2 * y);
@@ -209,13 +213,13 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
             // The last warp publishes (its Horner carry covers warps 0..6); the first warp, which has no
             // Horner steps and gets here first, looks back for the CTA (a look-back in every warp cost
             // 8x the polling instructions for the same wait: 138 vs 106 us per 60 s clip).
-            if (warp == 7) {
+            if (warp == AESB_NW - 1) {
                 const double P0 = st.wp[1][0], P1 = st.wp[1][1], P2 = st.wp[1][2], P3 = st.wp[1][3];
                 double ev = 0.0;
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch) {
-                    const double E1 = fma(P0, c1[ch], fma(P1, c2[ch], wtot[(7 * 2 + ch) * 2]));
-                    const double E2 = fma(P2, c1[ch], fma(P3, c2[ch], wtot[(7 * 2 + ch) * 2 + 1]));
+                    const double E1 = fma(P0, c1[ch], fma(P1, c2[ch], wtot[((AESB_NW - 1) * 2 + ch) * 2]));
+                    const double E2 = fma(P2, c1[ch], fma(P3, c2[ch], wtot[((AESB_NW - 1) * 2 + ch) * 2 + 1]));
                     if (lane == 2 * ch) ev = E1;
                     if (lane == 2 * ch + 1) ev = E2;
                 }
@@ -238,7 +242,7 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
                 } else {                                    // the clip's initial state sits where tile -1 would
                     val[0] = st.init[0][0]; val[1] = st.init[0][1]; val[2] = st.init[1][0]; val[3] = st.init[1][1];
                 }
-                const double *tp = a.tile_pw + ((long long)s * AES_NT + i) * 4;            // M^i
+                const double *tp = a.tile_pw + ((long long)s * AESB_NT + i) * 4;            // M^i
                 acc[0] = fma(tp[0], val[0], fma(tp[1], val[1], acc[0]));
                 acc[1] = fma(tp[2], val[0], fma(tp[3], val[1], acc[1]));
                 acc[2] = fma(tp[0], val[2], fma(tp[1], val[3], acc[2]));
@@ -259,7 +263,7 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
                 for (int ch = 0; ch < 2; ++ch) {
                     double q1 = 0.0, q2 = 0.0;
 #pragma unroll
-                    for (int w = 0; w < 8; ++w) {
+                    for (int w = 0; w < AESB_NW; ++w) {
                         const double n1 = fma(P0, q1, fma(P1, q2, wtot[(w * 2 + ch) * 2]));
                         const double n2 = fma(P2, q1, fma(P3, q2, wtot[(w * 2 + ch) * 2 + 1]));
                         q1 = n1; q2 = n2;
@@ -295,7 +299,7 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
                 const int first = incl ? __ffs((int)incl) - 1 : 32;
                 double t[4] = { 0.0, 0.0, 0.0, 0.0 };
                 if (lane <= first && pt >= -1) {
-                    const double *tp = a.tile_pw + ((long long)s * AES_NT + tid) * 4;      // M^tid
+                    const double *tp = a.tile_pw + ((long long)s * AESB_NT + tid) * 4;      // M^tid
                     bq_matvec(tp, val[0], val[1], t[0], t[1]);
                     bq_matvec(tp, val[2], val[3], t[2], t[3]);
                 }
@@ -310,7 +314,7 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
                 __syncthreads();
                 double sm4[4] = { 0.0, 0.0, 0.0, 0.0 };
                 bool found = false;
-                for (int w = 0; w < 8 && !found; ++w) {
+                for (int w = 0; w < AESB_NW && !found; ++w) {
                     sm4[0] += lb[w * 5 + 0]; sm4[1] += lb[w * 5 + 1]; sm4[2] += lb[w * 5 + 2]; sm4[3] += lb[w * 5 + 3];
                     found = lb[w * 5 + 4] != 0.0;
                 }
@@ -323,7 +327,7 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
                 const double n0w = W[0] * st.tile256[0] + W[1] * st.tile256[2], n1w = W[0] * st.tile256[1] + W[1] * st.tile256[3];
                 const double n2w = W[2] * st.tile256[0] + W[3] * st.tile256[2], n3w = W[2] * st.tile256[1] + W[3] * st.tile256[3];
                 W[0] = n0w; W[1] = n1w; W[2] = n2w; W[3] = n3w;
-                base += AES_NT;
+                base += AESB_NT;
             }
             if (tid == 0) {
                 double i0v, i1v, i2v, i3v;
@@ -347,9 +351,9 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
                 const double s1 = fma(l0, cw1, fma(l1, cw2, x1[ch])), s2 = fma(l2, cw1, fma(l3, cw2, x2[ch]));
 #pragma unroll
                 for (int j = 0; j < AESB_FR; ++j) {
-                    const double xj = v[ch][j];
+                    const double xj = (double)v[ch][j];
                     const double y = j == 0 ? yz[ch][0] + s1 : fma(st.row[j - (j > 0)][0], s1, fma(st.row[j - (j > 0)][1], s2, yz[ch][j]));
-                    v[ch][j] = (double)(float)y;          // the reference stores every stage's output as f32
+                    v[ch][j] = (float)y;                  // the reference stores every stage's output as f32
                     if (a.final_state != nullptr && tile == a.n_tiles - 1) {
                         double *fs = a.final_state + (clip * a.n_stages + s) * 16 + 4 * ch;
                         if (i0 + j == len - 1) { fs[0] = xj; fs[2] = y; }
@@ -364,15 +368,15 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
         float2 *yp = reinterpret_cast<float2 *>(a.y) + clip * a.N + n0 + i0;
 #pragma unroll
         for (int j = 0; j < AESB_FR; ++j)
-            if (i0 + j < len) yp[j] = make_float2((float)v[0][j], (float)v[1][j]);
+            if (i0 + j < len) yp[j] = make_float2(v[0][j], v[1][j]);
     }
 }
 
 #ifndef AES_CPU_EMU
 #ifndef AESB_MIN_CTAS
-#define AESB_MIN_CTAS 4
+#define AESB_MIN_CTAS (AESB_FR == 8 ? 5 : 4)
 #endif
-__global__ void __launch_bounds__(AES_NT, AESB_MIN_CTAS) aes_biquad_scan_kernel(const __grid_constant__ BqArgs a)
+__global__ void __launch_bounds__(AESB_NT, AESB_MIN_CTAS) aes_biquad_scan_kernel(const __grid_constant__ BqArgs a)
 {
     aes_biquad_scan_body(a);
 }

@@ -132,7 +132,7 @@ static int launch_chain(aes_chain_plan *pl, const void *x, int in_fmt, void *y, 
         bool chained = false;
         for (int s = 0; s < a.n_stages; ++s) chained |= a.st[s].lb_k == 0;
         if (chained) AES_CUDA(cudaMemsetAsync(a.flag, 0, recs * sizeof(int), st));
-        aes_biquad_scan_kernel<<<(unsigned)(B * nt), AES_NT, AESB_SMEM_DOUBLES * sizeof(double), st>>>(a);
+        aes_biquad_scan_kernel<<<(unsigned)(B * nt), AESB_NT, AESB_SMEM_DOUBLES * sizeof(double), st>>>(a);
         AES_CUDA(cudaEventRecord(pl->bq_done, st));
         aes_count_launch();
         AES_CUDA(cudaGetLastError());

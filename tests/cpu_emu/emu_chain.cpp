@@ -97,7 +97,7 @@ int emu_biquad_scan(const float *x, float *y, long long B, long long N, int n_st
     a.x = x; a.y = y; a.N = N; a.n_tiles = nt; a.B = B; a.dbg_skip = dbg_skip;
     a.agg = agg.data(); a.inc = inc.data(); a.flag = flag.data(); a.ticket = &ticket;
     a.lane_pw = lane_pw.data(); a.tile_pw = tile_pw.data(); a.final_state = nullptr;
-    emu::launch(bq_entry, &a, (unsigned)(B * nt), AES_NT, AESB_SMEM_DOUBLES * sizeof(double));
+    emu::launch(bq_entry, &a, (unsigned)(B * nt), AESB_NT, AESB_SMEM_DOUBLES * sizeof(double));
     return 0;
 }
 
