@@ -7,7 +7,7 @@
 #include "aes_biquad_scan.cuh"
 
 // coeffs5: n_stages x (b0,b1,b2,a1,a2); dfi_state: optional n_stages x 2 ch x (x1,x2,y1,y2).
-// lane_pw: n_stages x 32 x 4 doubles; tile_pw: n_stages x AESB_NT x 4 doubles.
+// lane_pw: n_stages x 32 x 4 doubles; tile_pw: n_stages x AESB_LBW x 4 doubles.
 static inline void aes_biquad_build(int n_stages, const double *coeffs5, const double *dfi_state,
                                     BqArgs *a, double *lane_pw, double *tile_pw)
 {
@@ -24,19 +24,19 @@ static inline void aes_biquad_build(int n_stages, const double *coeffs5, const d
         aes_mat2_pow(A, (long long)AESB_T, st.tile);
         aes_mat2_pow(A, (long long)AESB_NT * AESB_T, st.tile256);     // one look-back window of AESB_NT tiles
         for (int l = 0; l < 32; ++l) aes_mat2_pow(A, (long long)AESB_FR * l, lane_pw + (s * 32 + l) * 4);
-        for (int l = 0; l < AESB_NT; ++l) aes_mat2_pow(A, (long long)AESB_T * l, tile_pw + ((size_t)s * AESB_NT + l) * 4);
+        for (int l = 0; l < AESB_LBW; ++l) aes_mat2_pow(A, (long long)AESB_T * l, tile_pw + ((size_t)s * AESB_LBW + l) * 4);
         // look-back depth: one past the last tile distance whose transition M^i still matters.  The
         // carry-in of a tile is sum_i M^i E(t-1-i); with |M^i|_F < 2^-44 for every i >= lb_k the dropped
         // tail is ~1e-13 of the state, far below the f32 rounding of each stage's output.  0 (chained
         // look-back) when the filter remembers further than one 256-tile window.
         {
             int last = -1;
-            for (int l = 0; l <= AESB_NT; ++l) {
-                const double *m = l < AESB_NT ? tile_pw + ((size_t)s * AESB_NT + l) * 4 : st.tile256;
+            for (int l = 0; l < AESB_LBW; ++l) {
+                const double *m = tile_pw + ((size_t)s * AESB_LBW + l) * 4;
                 const double fro = sqrt(m[0] * m[0] + m[1] * m[1] + m[2] * m[2] + m[3] * m[3]);
                 if (!(fro < ldexp(1.0, -44))) last = l;
             }
-            st.lb_k = last + 1 < AESB_NT - 8 ? (last + 1 < 1 ? 1 : last + 1) : 0;
+            st.lb_k = last + 1 < AESB_LBW - 8 ? (last + 1 < 1 ? 1 : last + 1) : 0;
         }
         for (int ch = 0; ch < 2; ++ch) {
             st.init[ch][0] = st.init[ch][1] = 0.0;

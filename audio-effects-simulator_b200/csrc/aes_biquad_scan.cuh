@@ -12,24 +12,27 @@
 // promotes to f64; f32 state misses the 1e-5 bar below ~100 Hz); the
 // difference to DF-I is rounding at the 1e-16 level.
 //
-// Tile t, stage s:
-//   1. zero-state pass over the thread's 4 frames -> chunk end state e
-//   2. warp Kogge-Stone scan with A^(4*2^k), 8-warp carry chain in smem -> tile aggregate E
-//   3. publish E (flag 1); look back over predecessors' aggregates / inclusive states with
-//      the constant tile transition M = A^1024 (256 predecessors per step, one per thread)
-//      -> true state C at the tile start; publish inclusive state E + M*C (flag 2)
-//   4. second pass from the true state -> outputs, which are stage s+1's inputs (registers)
+// Tile t (one CTA of AESB_NT = 1024 / AESB_FR threads), stage s:
+//   1. zero-state pass over the thread's AESB_FR frames -> outputs yz (kept) and chunk end state e
+//   2. warp Kogge-Stone scan with A^(FR*2^k), Horner over the warp totals in smem -> tile aggregate E
+//   3. look-back -> true state C at the tile start.  Filters that forget within AESB_LBW tiles (all
+//      but extreme low-cutoff / high-Q ones): C = sum of the lb_k nearest AGGREGATES, which are
+//      published as self-validating 16-byte (value, epoch) records before any look-back -- no chain
+//      across tiles.  Otherwise the original chained decoupled look-back: flags, aggregates and
+//      inclusive states E + M*C, AESB_NT predecessors per window.
+//   4. outputs = yz + row0(A^j) . (state at the thread's first frame); they are stage s+1's inputs
 // Tiles take their index from an atomic ticket so every predecessor is resident or done.
 #pragma once
 #include "aes_plan.h"
 
 #define AESB_MAX_STAGES 8
 #ifndef AESB_FR
-#define AESB_FR 8                       // frames per thread: the scan / Horner / look-back cost is per warp, not per frame
+#define AESB_FR 16                      // frames per thread: the scan / Horner / look-back cost is per warp, not per frame
 #endif
 #define AESB_T 1024                     // frames per tile (CTA)
 #define AESB_NT (AESB_T / AESB_FR)      // threads per CTA
 #define AESB_NW (AESB_NT / 32)          // warps per CTA
+#define AESB_LBW 256                    // tile-power table entries per stage = deepest truncated look-back
 
 struct BqStage {
     double b0, b1, b2, a1, a2;
@@ -67,7 +70,7 @@ struct BqArgs {
     BqRec *rec16;           // truncated look-back: 4 self-validating (value, epoch) pairs per record
     unsigned long long epoch;   // this launch's tag (never 0; the array starts zeroed and is never cleared again)
     const double *lane_pw;  // [stage][32][4]  A^(4*lane)
-    const double *tile_pw;  // [stage][256][4] M^i, i = look-back distance - 1
+    const double *tile_pw;  // [stage][AESB_LBW][4] M^i, i = look-back distance - 1
     double *final_state;    // optional [clip][stage][16]: [4*ch + {0,1,2,3}] = x1,x2,y1,y2 (DF-I view) at the clip end
 };
 
@@ -242,7 +245,7 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
                 } else {                                    // the clip's initial state sits where tile -1 would
                     val[0] = st.init[0][0]; val[1] = st.init[0][1]; val[2] = st.init[1][0]; val[3] = st.init[1][1];
                 }
-                const double *tp = a.tile_pw + ((long long)s * AESB_NT + i) * 4;            // M^i
+                const double *tp = a.tile_pw + ((long long)s * AESB_LBW + i) * 4;            // M^i
                 acc[0] = fma(tp[0], val[0], fma(tp[1], val[1], acc[0]));
                 acc[1] = fma(tp[2], val[0], fma(tp[3], val[1], acc[1]));
                 acc[2] = fma(tp[0], val[2], fma(tp[1], val[3], acc[2]));
@@ -299,7 +302,7 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
                 const int first = incl ? __ffs((int)incl) - 1 : 32;
                 double t[4] = { 0.0, 0.0, 0.0, 0.0 };
                 if (lane <= first && pt >= -1) {
-                    const double *tp = a.tile_pw + ((long long)s * AESB_NT + tid) * 4;      // M^tid
+                    const double *tp = a.tile_pw + ((long long)s * AESB_LBW + tid) * 4;      // M^tid
                     bq_matvec(tp, val[0], val[1], t[0], t[1]);
                     bq_matvec(tp, val[2], val[3], t[2], t[3]);
                 }
@@ -374,7 +377,7 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
 
 #ifndef AES_CPU_EMU
 #ifndef AESB_MIN_CTAS
-#define AESB_MIN_CTAS (AESB_FR == 8 ? 5 : 4)
+#define AESB_MIN_CTAS (AESB_FR == 16 ? 10 : AESB_FR == 8 ? 5 : 4)
 #endif
 __global__ void __launch_bounds__(AESB_NT, AESB_MIN_CTAS) aes_biquad_scan_kernel(const __grid_constant__ BqArgs a)
 {

@@ -228,7 +228,7 @@ AES_EXPORT int aes_chain_plan_create(const aes_stage_desc *stages, int n_stages,
         bool all_bq = n_stages >= 1 && n_stages <= AESB_MAX_STAGES;
         for (int s2 = 0; s2 < n_stages && all_bq; ++s2) all_bq = stages[s2].kind == AES_STAGE_BIQUAD;
         if (all_bq) {
-            std::vector<double> tab_v((size_t)AESB_MAX_STAGES * 128 + (size_t)AESB_MAX_STAGES * AES_NT * 4);
+            std::vector<double> tab_v((size_t)AESB_MAX_STAGES * 128 + (size_t)AESB_MAX_STAGES * AESB_LBW * 4);
             double *tab = tab_v.data();
             const size_t tab_bytes = tab_v.size() * sizeof(double);
             double co[5 * AESB_MAX_STAGES], dfi[AESB_MAX_STAGES * 8];

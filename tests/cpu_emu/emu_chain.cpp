@@ -84,7 +84,7 @@ int emu_biquad_scan(const float *x, float *y, long long B, long long N, int n_st
 {
     if (n_stages < 1 || n_stages > AESB_MAX_STAGES) return -1;
     static BqArgs a;
-    std::vector<double> lane_pw((size_t)n_stages * 128), tile_pw((size_t)n_stages * AES_NT * 4);
+    std::vector<double> lane_pw((size_t)n_stages * 128), tile_pw((size_t)n_stages * AESB_LBW * 4);
     aes_biquad_build(n_stages, coeffs5, dfi_state, &a, lane_pw.data(), tile_pw.data());
     const long long nt = (N + AESB_T - 1) / AESB_T;
     const size_t recs = (size_t)(B * n_stages * nt);
@@ -107,7 +107,7 @@ int emu_biquad_lookback_depth(int n_stages, const double *coeffs5, int *out)
 {
     if (n_stages < 1 || n_stages > AESB_MAX_STAGES) return -1;
     static BqArgs a;
-    std::vector<double> lane_pw((size_t)n_stages * 128), tile_pw((size_t)n_stages * AES_NT * 4);
+    std::vector<double> lane_pw((size_t)n_stages * 128), tile_pw((size_t)n_stages * AESB_LBW * 4);
     aes_biquad_build(n_stages, coeffs5, nullptr, &a, lane_pw.data(), tile_pw.data());
     for (int s = 0; s < n_stages; ++s) out[s] = a.st[s].lb_k;
     return 0;
