@@ -32,6 +32,9 @@
 #define AESB_T 1024                     // frames per tile (CTA)
 #define AESB_NT (AESB_T / AESB_FR)      // threads per CTA
 #define AESB_NW (AESB_NT / 32)          // warps per CTA
+#ifndef AESB_KEEP_YZ
+#define AESB_KEEP_YZ (AESB_FR <= 8)     // keep the zero-state outputs (2 DFMA per frame in step 4) or rerun the recurrence (5)
+#endif
 #define AESB_LBW 256                    // tile-power table entries per stage = deepest truncated look-back
 
 struct BqStage {
@@ -155,7 +158,7 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
         const long long rec = (clip * a.n_stages + s) * a.n_tiles + tile;
         double *const wtot = sm + 32 * (s & 1);     // a warp may be one stage ahead of another, never two
         // 1. zero-state chunk response: outputs kept, the true start state only adds row0(A^j).S later
-        double yz[2][AESB_FR], e1[2], e2[2];
+        double yz[2][AESB_KEEP_YZ ? AESB_FR : 1], e1[2], e2[2];
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch) {
             double s1 = 0.0, s2 = 0.0;
@@ -165,7 +168,7 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
                 const double y = fma(b0, xj, s1);
                 s1 = fma(b1, xj, fma(-a1, y, s2));
                 s2 = fma(b2, xj, -a2 * y);
-                yz[ch][j] = y;
+                if (AESB_KEEP_YZ) yz[ch][AESB_KEEP_YZ ? j : 0] = y;
             }
             e1[ch] = s1; e2[ch] = s2;
         }
@@ -351,11 +354,19 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
             for (int ch = 0; ch < 2; ++ch) {
                 const double C1 = acc[2 * ch], C2 = acc[2 * ch + 1];
                 const double cw1 = fma(W0, C1, fma(W1, C2, c1[ch])), cw2 = fma(W2, C1, fma(W3, C2, c2[ch]));
-                const double s1 = fma(l0, cw1, fma(l1, cw2, x1[ch])), s2 = fma(l2, cw1, fma(l3, cw2, x2[ch]));
+                double s1 = fma(l0, cw1, fma(l1, cw2, x1[ch])), s2 = fma(l2, cw1, fma(l3, cw2, x2[ch]));
 #pragma unroll
                 for (int j = 0; j < AESB_FR; ++j) {
                     const double xj = (double)v[ch][j];
-                    const double y = j == 0 ? yz[ch][0] + s1 : fma(st.row[j - (j > 0)][0], s1, fma(st.row[j - (j > 0)][1], s2, yz[ch][j]));
+                    double y;
+                    if (AESB_KEEP_YZ) {
+                        y = j == 0 ? yz[ch][0] + s1
+                                   : fma(st.row[j - (j > 0)][0], s1, fma(st.row[j - (j > 0)][1], s2, yz[ch][AESB_KEEP_YZ ? j : 0]));
+                    } else {                              // many frames per thread: rerun the recurrence, keep no outputs
+                        y = fma(b0, xj, s1);
+                        s1 = fma(b1, xj, fma(-a1, y, s2));
+                        s2 = fma(b2, xj, -a2 * y);
+                    }
                     v[ch][j] = (float)y;                  // the reference stores every stage's output as f32
                     if (a.final_state != nullptr && tile == a.n_tiles - 1) {
                         double *fs = a.final_state + (clip * a.n_stages + s) * 16 + 4 * ch;
@@ -377,7 +388,7 @@ __device__ void aes_biquad_scan_body(const BqArgs &a)
 
 #ifndef AES_CPU_EMU
 #ifndef AESB_MIN_CTAS
-#define AESB_MIN_CTAS (AESB_FR == 16 ? 10 : AESB_FR == 8 ? 5 : 4)
+#define AESB_MIN_CTAS (AESB_FR == 32 ? 16 : AESB_FR == 16 ? 10 : AESB_FR == 8 ? 5 : 4)
 #endif
 __global__ void __launch_bounds__(AESB_NT, AESB_MIN_CTAS) aes_biquad_scan_kernel(const __grid_constant__ BqArgs a)
 {
