@@ -92,7 +92,7 @@ static int launch_chain(aes_chain_plan *pl, const void *x, int in_fmt, void *y, 
                         bool allow_scan = true)
 {
     if (B <= 0 || N <= 0) return 0;
-    if (pl->bq_ok && allow_scan && B < pl->grid_max && in_fmt == AES_FMT_F32_STEREO && out_fmt == AES_FMT_F32_STEREO &&
+    if (pl->bq_ok && allow_scan && (B < pl->grid_max || getenv("AES_FORCE_SCAN")) && in_fmt == AES_FMT_F32_STEREO && out_fmt == AES_FMT_F32_STEREO &&
         !getenv("AES_NO_SCAN")) {
         // fewer clips than resident CTAs: go parallel in time (one CTA per 1024-frame tile)
         const long long nt = (N + AESB_T - 1) / AESB_T;
