@@ -10,6 +10,7 @@
 #include "aes_plan_build.h"
 #include "aes_chain_kernel.cuh"
 #include "aes_fast_build.h"
+#include "aes_rv_build.h"
 #include "aes_biquad_build.h"
 
 #define AES_HOST_SLOTS 4
@@ -45,6 +46,12 @@ struct FastShape { int c[AESF_MAX_STAGES]; int topo; fast_kernel_t fn; };
 static const FastShape g_fast_shapes[] = { AESF_SHAPES(X) };
 #undef X
 
+// ---- pipelined reverb-chain kernels (aes_rv_kernel.cuh): launch table ------------------------
+struct RvShape { int topo, pre, pm; fast_kernel_t fn; };
+#define X(topo, pre, pm) { topo, pre, pm, aes_rv_kernel<topo, pre, pm> },
+static const RvShape g_rv_shapes[] = { AESRV_SHAPES(X) };
+#undef X
+
 struct aes_chain_plan {
     DevPlan host;
     // time-parallel biquad cascade (aes_biquad_scan.cuh) for few long clips
@@ -61,6 +68,7 @@ struct aes_chain_plan {
     size_t bq_scan_cap = 0;
     FastArgs fast;                              // flattened descriptors when a specialised kernel fits
     fast_kernel_t fast_fn = nullptr;
+    bool rv = false;                            // fast_fn is an aes_rv_kernel instantiation
     float *d_lane_tab = nullptr;
     DevPlan *dev = nullptr;
     int fs = 0, device = 0, sm_count = 0, ctas_per_sm = 0, grid_max = 0;
@@ -198,6 +206,26 @@ AES_EXPORT int aes_chain_plan_create(const aes_stage_desc *stages, int n_stages,
         if (!getenv("AES_NO_FAST") && aes_fast_build(pl->host, &pl->fast, codes, lane_tab)) {
             const size_t fast_smem = aes_fast_smem_bytes(pl->host);
             const int topo = aes_fast_topo(pl->host);
+            // chains ending in the default reverb: the software-pipelined kernel
+            int rv_pre = 0, rv_pm = 0;
+            if (!getenv("AES_NO_RV") && aes_rv_shape(pl->fast, codes, topo, &rv_pre, &rv_pm)) {
+                const size_t rv_smem = aes_rv_smem_bytes(pl->host.smem_floats);
+                for (const RvShape &sh : g_rv_shapes) {
+                    if (sh.topo != topo || sh.pre != rv_pre || sh.pm != rv_pm || rv_smem > AES_SMEM_LIMIT) continue;
+                    AES_CUDA(cudaFuncSetAttribute(sh.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rv_smem));
+                    int occ = 0;
+                    AES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sh.fn, AES_NT, rv_smem));
+                    if (occ < 1) break;
+                    pl->smem_bytes = rv_smem;
+                    AES_CUDA(cudaMalloc(&pl->d_lane_tab, lane_tab_bytes));
+                    AES_CUDA(cudaMemcpy(pl->d_lane_tab, lane_tab, lane_tab_bytes, cudaMemcpyHostToDevice));
+                    pl->fast_fn = sh.fn;
+                    pl->rv = true;
+                    pl->ctas_per_sm = occ;
+                    break;
+                }
+            }
+            if (!pl->fast_fn)
             for (const FastShape &sh : g_fast_shapes) {      // compile-time topologies come first
                 if (memcmp(sh.c, codes, sizeof codes) != 0 || fast_smem > AES_SMEM_LIMIT) continue;
                 if (sh.topo != AESF_TOPO_NONE && sh.topo != topo) continue;
@@ -278,6 +306,7 @@ AES_EXPORT int aes_chain_plan_info(const aes_chain_plan *pl, int *tile_frames, i
 AES_EXPORT const char *aes_chain_plan_kernel_name(const aes_chain_plan *pl)
 {
     if (!pl) return "";
+    if (pl->rv) return "aes_rv_kernel<pipelined reverb chain>";
     return pl->fast_fn ? "aes_fast_kernel<FR=4, shape-specialised>" : "aes_chain_kernel<generic interpreter>";
 }
 

@@ -6,6 +6,7 @@
 #include "../../audio-effects-simulator_b200/csrc/aes_plan_build.h"
 #include "../../audio-effects-simulator_b200/csrc/aes_chain_kernel.cuh"
 #include "../../audio-effects-simulator_b200/csrc/aes_fast_build.h"
+#include "../../audio-effects-simulator_b200/csrc/aes_rv_build.h"
 #include "../../audio-effects-simulator_b200/csrc/aes_biquad_build.h"
 #include "../../audio-effects-simulator_b200/csrc/aes_convreverb.cuh"
 #include "../../audio-effects-simulator_b200/csrc/aes_spectral.cuh"
@@ -20,6 +21,11 @@ template <int C0, int C1, int C2, int C3, int MP> static void fentry(void *p)
 struct FastShape { int c[4]; int topo; void (*fn)(void *); };
 #define X(c0, c1, c2, c3, mp) { { c0, c1, c2, c3 }, mp, fentry<c0, c1, c2, c3, mp> },
 static const FastShape g_shapes[] = { AESF_SHAPES(X) };
+#undef X
+template <int TOPO, int PRE, int PM> static void rventry(void *p) { aes_rv_body<TOPO, PRE, PM>(*reinterpret_cast<FastArgs *>(p)); }
+struct RvShape { int topo, pre, pm; void (*fn)(void *); };
+#define X(topo, pre, pm) { topo, pre, pm, rventry<topo, pre, pm> },
+static const RvShape g_rv_shapes[] = { AESRV_SHAPES(X) };
 #undef X
 static int g_last_fast = 0, g_last_topo = 0;
 extern "C" __attribute__((visibility("default"))) int emu_last_topo() { return g_last_topo; }
@@ -45,6 +51,18 @@ int emu_chain_run(const aes_stage_desc *stages, int n, int fs, const void *x, in
     int codes[4];
     if (!getenv("AES_NO_FAST") && aes_fast_build(plan, &fa, codes, lane_tab)) {
         const int topo = aes_fast_topo(plan);
+        int rv_pre = 0, rv_pm = 0;
+        if (!getenv("AES_NO_RV") && aes_rv_shape(fa, codes, topo, &rv_pre, &rv_pm)) {
+            for (const RvShape &sh : g_rv_shapes) {
+                if (sh.topo != topo || sh.pre != rv_pre || sh.pm != rv_pm) continue;
+                g_last_topo = sh.topo;
+                fa.x = x; fa.y = y; fa.B = B; fa.N = N; fa.scratch = scratch.data(); fa.lane_tab = lane_tab;
+                fa.state_out = state_out; fa.in_fmt = in_fmt; fa.out_fmt = out_fmt;
+                emu::launch(sh.fn, &fa, grid, AES_NT, aes_rv_smem_bytes(plan.smem_floats));
+                g_last_fast = 2;
+                return 0;
+            }
+        }
         for (const FastShape &sh : g_shapes) {
             if (memcmp(sh.c, codes, sizeof codes) != 0) continue;
             if (sh.topo != AESF_TOPO_NONE && sh.topo != topo) continue;

@@ -120,23 +120,68 @@ def test_final_state_of_filter_and_gate_matches_oracle():
         assert np.max(np.abs(got - filt.state.astype(np.float64))) < 1e-6 * max(1.0, np.abs(filt.state).max())
 
 
+RV_PRESETS = ("Rain Delay", "Cathedral", "Guitar Filter")     # chains ending in the default reverb
+
+
 @pytest.mark.parametrize("name", NATIVE)
 def test_specialised_and_generic_kernels_agree_with_oracle(name, monkeypatch):
-    """Every preset has a shape-specialised kernel (aes_fast_kernel.cuh); the generic
-    interpreter (aes_chain_kernel.cuh) must give the same answer when forced."""
+    """Every preset has a shape-specialised kernel (aes_fast_kernel.cuh); chains that end in the default
+    reverb run on the software-pipelined kernel (aes_rv_kernel.cuh) first.  All of them and the generic
+    interpreter (aes_chain_kernel.cuh) must give the oracle's answer."""
     cfg = synth.PRESETS[name]
     n = 26000
     x = synth.batch(30, 2, n)
     want = [orc.run_file_path(cfg, x[b], 48000) for b in range(2)]
     d = emu.resolved_descs(cfg, 48000, n, 2)
-    y_fast = emu.run(d, 48000, x)
+    runs = {}
+    runs["default"] = emu.run(d, 48000, x)
+    assert emu.lib().emu_last_was_fast() == (2 if name in RV_PRESETS else 1), name
+    monkeypatch.setenv("AES_NO_RV", "1")
+    runs["fast"] = emu.run(d, 48000, x)
     assert emu.lib().emu_last_was_fast() == 1, name
     monkeypatch.setenv("AES_NO_FAST", "1")
-    y_gen = emu.run(d, 48000, x)
+    runs["generic"] = emu.run(d, 48000, x)
     assert emu.lib().emu_last_was_fast() == 0
-    for b in range(2):
-        check(y_fast[b], want[b], exact=(name == "Slapback Echo"), what=(name, "fast", b))
-        check(y_gen[b], want[b], exact=(name == "Slapback Echo"), what=(name, "generic", b))
+    for which, y in runs.items():
+        for b in range(2):
+            check(y[b], want[b], exact=(name == "Slapback Echo"), what=(name, which, b))
+
+
+@pytest.mark.parametrize("name", RV_PRESETS)
+@pytest.mark.parametrize("fs", [48000, 44100])
+@pytest.mark.parametrize("n", [1, 777, 1024, 2048, 3100, 19000])
+def test_pipelined_reverb_kernel_tile_edges(name, fs, n):
+    """aes_rv_kernel.cuh works one tile behind itself (all-pass walks, mix and store of tile i-1 in the
+    phases of tile i): clips of less than one tile, exact multiples and ragged tails, two clips per CTA."""
+    cfg = synth.PRESETS[name]
+    x = synth.batch(77, 3, n, fs=fs)
+    y = emu.run(emu.resolved_descs(cfg, fs, n, 2), fs, x, grid=2)
+    assert emu.lib().emu_last_was_fast() == 2
+    for b in range(3):
+        check(y[b], orc.run_file_path(cfg, x[b], fs), what=(name, fs, n, b))
+
+
+def test_pipelined_reverb_kernel_formats_and_final_biquad_state():
+    """Mono / int16 input and int16 output through the pipelined kernel, and the biquad's DF-I state at
+    the end of the clip (what a later streamed block continues from)."""
+    cfg = synth.PRESETS["Guitar Filter"]
+    n = 5000
+    x = synth.clip(9, n, 1)
+    d = emu.resolved_descs(cfg, 48000, n, 1)
+    st = np.zeros((1, 32))
+    y = emu.run(d, 48000, x[None], state_out=st)[0]
+    assert emu.lib().emu_last_was_fast() == 2
+    want = orc.run_file_path(cfg, x, 48000)
+    check(y, want, what="mono in")
+    ch = orc.build_chain(cfg, 48000, ci=1)
+    ch.warmup()
+    ch.process(x, np.zeros((n, 2), np.float32))
+    filt = ch.fx[0]
+    got = st[0, 0:8].reshape(2, 4)
+    assert np.max(np.abs(got - filt.state.astype(np.float64))) < 1e-6 * max(1.0, np.abs(filt.state).max())
+    q = emu.run(d, 48000, x[None], out_dtype=np.int16)[0]
+    wq = (np.clip(want, -1.0, 1.0) * np.float32(32767.0)).astype(np.int16)
+    assert np.max(np.abs(q.astype(np.int32) - wq.astype(np.int32))) <= 1
 
 
 @pytest.mark.parametrize("fs,topo", [(48000, 1), (44100, 2), (40000, 0)])
@@ -147,7 +192,7 @@ def test_reverb_topology_variants(fs, topo):
     n = 5000
     x = synth.clip(41, n, 2, fs)
     y = emu.run(emu.resolved_descs(cfg, fs, n, 2), fs, x[None])[0]
-    assert emu.lib().emu_last_was_fast() == 1
+    assert emu.lib().emu_last_was_fast() == (2 if topo else 1)       # compile-time topology: the pipelined kernel
     assert emu.lib().emu_last_topo() == topo
     check(y, orc.run_file_path(cfg, x, fs), what=(fs, topo))
 
