@@ -154,7 +154,7 @@ static int launch_chain(aes_chain_plan *pl, const void *x, int in_fmt, void *y, 
         FastArgs fa = pl->fast;
         fa.x = x; fa.y = y; fa.B = B; fa.N = N; fa.scratch = scratch; fa.lane_tab = pl->d_lane_tab;
         fa.state_out = state_out; fa.in_fmt = in_fmt; fa.out_fmt = out_fmt;
-        pl->fast_fn<<<grid, AES_NT, pl->smem_bytes, st>>>(fa);
+        pl->fast_fn<<<grid, pl->rv ? AESRV_NT : AES_NT, pl->smem_bytes, st>>>(fa);
         aes_count_launch();
         AES_CUDA(cudaGetLastError());
         return 0;
@@ -209,12 +209,12 @@ AES_EXPORT int aes_chain_plan_create(const aes_stage_desc *stages, int n_stages,
             // chains ending in the default reverb: the software-pipelined kernel
             int rv_pre = 0, rv_pm = 0;
             if (!getenv("AES_NO_RV") && aes_rv_shape(pl->fast, codes, topo, &rv_pre, &rv_pm)) {
-                const size_t rv_smem = aes_rv_smem_bytes(pl->host.smem_floats);
+                const size_t rv_smem = aes_rv_smem_bytes(pl->host.smem_floats, rv_pre);
                 for (const RvShape &sh : g_rv_shapes) {
                     if (sh.topo != topo || sh.pre != rv_pre || sh.pm != rv_pm || rv_smem > AES_SMEM_LIMIT) continue;
                     AES_CUDA(cudaFuncSetAttribute(sh.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rv_smem));
                     int occ = 0;
-                    AES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sh.fn, AES_NT, rv_smem));
+                    AES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sh.fn, AESRV_NT, rv_smem));
                     if (occ < 1) break;
                     pl->smem_bytes = rv_smem;
                     AES_CUDA(cudaMalloc(&pl->d_lane_tab, lane_tab_bytes));

@@ -119,10 +119,19 @@ __device__ __forceinline__ void aes_mbar_wait(unsigned long long *bar, unsigned 
                      : "=r"(done) : "r"(a), "r"(parity) : "memory");
     } while (!done);
 }
+__device__ __forceinline__ void aes_mbar_wait_parity(unsigned long long *bar, unsigned parity)
+{
+    aes_mbar_wait(bar, parity);                     // (only the low bit of the use index is looked at)
+}
 // generic-proxy global stores -> visible to later async-proxy (TMA) reads.  Executed by the
 // issuing thread only, after the CTA barrier that orders every thread's ring stores before it
 // (fences are cumulative); a per-thread fence after the stores cost 15 % of all stall samples.
 __device__ __forceinline__ void aes_fence_proxy_async() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+// ... and the same for every state space (shared-memory buffers that the TMA overwrites after ordinary accesses)
+__device__ __forceinline__ void aes_fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// ... for this CTA's shared memory only (buffers that the TMA overwrites after ordinary loads / stores); the
+// all-spaces form costs a MEMBAR.ALL.GPU
+__device__ __forceinline__ void aes_fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 #else
 // emulator: the copy completes at issue; the barrier word counts completed uses
 static inline void aes_mbar_init(unsigned long long *bar, unsigned) { *bar = 0; }
@@ -133,7 +142,24 @@ static inline unsigned long long aes_policy_evict_first() { return 0; }
 static inline unsigned long long aes_policy_evict_last() { return 0; }
 static inline void aes_mbar_complete_emu(unsigned long long *bar) { *bar += 1; }
 static inline void aes_mbar_wait(unsigned long long *bar, unsigned use_index) { while (*bar <= use_index) emu::yield(); }
+// the phase with parity `parity` has completed once the count of completed phases has the other parity
+static inline void aes_mbar_wait_parity(unsigned long long *bar, unsigned parity) { while ((*bar & 1u) == (parity & 1u)) emu::yield(); }
 static inline void aes_fence_proxy_async() {}
+static inline void aes_fence_proxy_async_all() {}
+static inline void aes_fence_proxy_async_smem() {}
+#endif
+
+// ---- named barriers and per-role register budgets (warp-specialised kernels) ---------------------
+#ifndef AES_CPU_EMU
+__device__ __forceinline__ void aes_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void aes_bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+template <int R> __device__ __forceinline__ void aes_setmaxnreg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R)); }
+template <int R> __device__ __forceinline__ void aes_setmaxnreg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R)); }
+#else
+static inline void aes_bar_sync(int id, int nthreads) { emu::named_sync(id, nthreads); }
+static inline void aes_bar_arrive(int id, int nthreads) { emu::named_arrive(id, nthreads); }
+template <int R> static inline void aes_setmaxnreg_inc() {}
+template <int R> static inline void aes_setmaxnreg_dec() {}
 #endif
 
 struct FCtx {
@@ -152,8 +178,10 @@ struct SRegs {              // per-thread, per-stage persistent ring slots (floa
 
 __device__ __forceinline__ int aesf_adv(int s, int inc, int len)
 {
-    s += inc;
-    return s >= len ? s - len : s;
+    // (s + inc) mod len for 0 <= s, inc < len: as unsigned, the wrapped candidate is the smaller one
+    // exactly when it did not underflow (add + add-min instead of add + compare + select)
+    const unsigned a = (unsigned)s + (unsigned)inc, b = a - (unsigned)len;
+    return (int)(a < b ? a : b);
 }
 
 // FR consecutive elements starting m (< FR) past the aligned base a0; the next aligned
@@ -218,7 +246,7 @@ __host__ __device__ constexpr int aesf_topo_ap(int topo, int ch, int k)
 __host__ __device__ constexpr int aesf_topo_comb_off(int topo, int ch, int cc)
 {
     int off = 0;
-    for (int i = 0; i < ch * 4 + cc; ++i) off += (aesf_topo_comb(topo, i >> 2, i & 3) + 3) & ~3;
+    for (int i = 0; i < ch * 4 + cc; ++i) off += ((aesf_topo_comb(topo, i >> 2, i & 3) + 3) & ~3) + AES_COMB_RING_PAD;
     return off;
 }
 __host__ __device__ constexpr int aesf_topo_ap_off(int topo, int ch, int k)

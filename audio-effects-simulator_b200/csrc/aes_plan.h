@@ -8,6 +8,9 @@
 #define AES_MAX_RINGS 64
 #define AES_MAX_COMB 8
 #define AES_MAX_AP 4
+// Every reverb comb ring is followed by 4 spare floats in shared memory: the pipelined kernel
+// (aes_rv_kernel.cuh) lays misaligned comb rings out in planes with one guard element per plane.
+#define AES_COMB_RING_PAD 4
 
 // Where a ring lives.  Small, hot rings (combs, all-passes, octaver) sit in shared
 // memory; long ones (feedback delay, pre-delay) in a per-CTA global scratch that is

@@ -76,7 +76,7 @@ struct AesPlanBuilder {
                 DevRing &r = p->ring[i];
                 if (r.space != AES_SPACE_SMEM || prio[i] != pass) continue;
                 r.off = off;
-                off += (r.len + 3) & ~3LL;
+                off += ((r.len + 3) & ~3LL) + (pass == 0 ? AES_COMB_RING_PAD : 0);
             }
         smem_off = off;
     }

@@ -1,6 +1,7 @@
 // aes_rv_build.h -- host side of the pipelined reverb-chain kernels (aes_rv_kernel.cuh): which
 // instantiation, if any, serves a plan.  Pure host C++ (shared with tests/cpu_emu).
 #pragma once
+#include <stdlib.h>
 #include "aes_fast_build.h"
 #include "aes_rv_kernel.cuh"
 
@@ -23,8 +24,18 @@ static inline bool aes_rv_shape(const FastArgs &fa, const int codes[AESF_MAX_STA
     int sr;
     if (codes[1] == 0 && codes[2] == 0 && codes[3] == 0) { *pre = AESRV_PRE_NONE; sr = 0; }
     else if (codes[2] == 0 && codes[3] == 0 && codes[0] == AESF_DELAY_PF) { *pre = AESRV_PRE_DELAY; sr = 1; }
-    else if (codes[2] == 0 && codes[3] == 0 && codes[0] == AESF_BIQUAD) { *pre = AESRV_PRE_BIQUAD; sr = 1; }
+    else if (codes[2] == 0 && codes[3] == 0 && codes[0] == AESF_BIQUAD) {
+        // The f64 biquad in front of the reverb does not fit the comb warps' 104 registers without spilling
+        // (141 against 163 Gsamples/s for aes_fast_kernel on Guitar Filter, B200): off unless asked for.
+        if (!getenv("AES_RV_BIQUAD")) return false;
+        *pre = AESRV_PRE_BIQUAD; sr = 1;
+    }
     else return false;
+    if (*pre == AESRV_PRE_DELAY) {
+        // the walkers stage a tile's line samples two tiles ahead: everything it reads must have been stored by then
+        for (int ch = 0; ch < 2; ++ch)
+            if (fa.st[0].ring[ch][0].lag < 2 * AES_NT * 4 + 4) return false;
+    }
     const int rc = codes[sr];
     if (AESF_KIND(rc) != AESK_REVERB || AESF_NC(rc) != 4 || AESF_NA(rc) != 2) return false;
     const int premode = AESF_PREMODE(rc);

@@ -24,67 +24,184 @@
 // Arithmetic per sample is exactly that of aes_fast_kernel (same parity tests).  Any other chain
 // shape / sample rate / comb set keeps using aes_fast_kernel or the interpreter.
 #pragma once
+#include <type_traits>
 #include "aes_fast_kernel.cuh"
 
-#define AESRV_PRE_NONE 0
-#define AESRV_PRE_DELAY 1           // prefetched feedback delay ahead of the reverb (lag >= 2T, global lines)
-#define AESRV_PRE_BIQUAD 2          // one biquad ahead of the reverb
-
-// shared memory (floats): S[2][2][T] | rings[smem_floats] | wt[8][8] | cst[2][8] | f64: wtot[32] | bst[2][8]
-__host__ __device__ inline size_t aes_rv_smem_bytes(int smem_floats)
+// compile-time loop: f(std::integral_constant<int, I>) for I = 0 .. N-1 (ring lengths are template arguments)
+template <int I, int N, class F>
+__device__ __forceinline__ void aes_static_for(F &&f)
 {
-    const size_t T = AES_NT * 4;
-    size_t f = (4 * T + (size_t)smem_floats + 3) & ~(size_t)3;
-    return (f + 64 + 16) * 4 + (32 + 16) * 8 + 16;
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        aes_static_for<I + 1, N>(f);
+    }
 }
 
-// all-pass walk over one channel's tile `s` (T samples): column j of the tile, seen as rows of L
-// samples, is one serial chain  y = line - g*x,  line' = x + g*y  (reverb.py:48-67) down the rows;
-// the chain's state enters from / leaves to the ring (length L, phase `pos` = tile start mod L).
-template <int L>
-__device__ __forceinline__ void aesrv_walk(float *s, float *rb, int pos, int j0, float g)
+#define AESRV_PRE_NONE 0
+#define AESRV_PRE_DELAY 1           // prefetched feedback delay ahead of the reverb (lag >= 2T + 4, global lines)
+#define AESRV_PRE_BIQUAD 2          // one biquad ahead of the reverb
+
+// CTA: 8 "comb" warps (threads 0..255: frames in registers, everything but the all-passes) and
+// 4 "walker" warps (threads 256..383: the two all-pass stages of tile i-1 -- two warps per channel --
+// and the TMA copies of tile i+2).  The register file is split with setmaxnreg: 104 + 32 registers.
+#define AESRV_NT 384
+#define AESRV_NW 128
+#define AESRV_REGS_COMB 104
+#define AESRV_REGS_WALK 32
+#define AESRV_NXS 4                 // tile buffers (8 KB each): TMA input -> comb sum -> all-pass output
+// named barriers (0 is __syncthreads over all 384 threads)
+#define AESRV_BAR_COMB 1            // the comb warps between their two phases (256 threads)
+#define AESRV_BAR_FULL 2            // +parity: comb sum of a tile is in its buffer (comb warps arrive, walkers wait)
+#define AESRV_BAR_DONE 4            // +parity: all-pass output of a tile is in its buffer (walkers arrive, comb warps wait)
+#define AESRV_BAR_CHAN 6            // +channel: the 64 walkers of one channel between the two all-passes
+
+// shared memory (floats): XS[4][2][T] | rings[smem_floats] | wt[8][8] | cst[2][8] | f64: wtot[32] | bst[2][8] |
+//                         LN[2][2][T+8] (feedback-delay shapes only) | 4 mbarriers
+__host__ __device__ inline size_t aes_rv_smem_bytes(int smem_floats, int pre)
 {
-    constexpr int T = AES_NT * 4;
-    static_assert(L > 0 && L < T, "");
+    const size_t T = AES_NT * 4;
+    size_t f = (2 * AESRV_NXS * T + (size_t)smem_floats + 3) & ~(size_t)3;
+    return (f + 64 + 16) * 4 + (32 + 16) * 8 + (pre == AESRV_PRE_DELAY ? 4 * (T + 8) * 4 : 0) + AESRV_NXS * 8 + 16;
+}
+
+// ---- comb rings: bank-conflict-free layouts ------------------------------------------------------
+// A thread reads the four samples L behind its frames and writes four new ones; both as one float4
+// only if L is a multiple of 4.  In a linear ring the misaligned reads cost twice the wavefronts
+// (ptxas narrows the second vector to scalar / 64-bit loads that conflict 4- / 2-way; ncu r2e: 273 of
+// 1765 shared-memory wavefronts per tile were conflicts, the data pipe 80 % busy).  So the layout of a
+// ring follows its misalignment m = roundup4(L) - L, all at compile time:
+//   m == 0  LIN : linear; float4 slot u at byte 16u;                        LDS.128 / STS.128
+//   m == 2  P2  : two planes of 8-byte units, unit k -> plane k&1, index k>>1; LDS.64 x2 / STS.64 x2
+//   m odd   P4  : four planes of floats, element q -> plane q&3, index q>>2;   LDS.32 x4 / STS.32 x4
+// Every plane ends in one guard entry that mirrors its entry 0 (written with it), so a read that runs
+// one slot past the thread's own never needs a wrap.  The slot register holds u in the layout's own
+// bytes (16u / 8u / 4u) and advances by one add-min per tile.
+template <int L> struct AesrvComb {
+    static constexpr int P = (L + 3) & ~3, M = P - L, NSLOT = P / 4;
+    static constexpr int KIND = M == 0 ? 0 : (M == 2 ? 2 : 4);
+    static constexpr int SB = KIND == 0 ? 16 : (KIND == 2 ? 8 : 4);        // slot bytes
+    static constexpr int WRAP = NSLOT * SB;
+    static constexpr int TINC = ((AES_NT * 4 / 4) % NSLOT) * SB;
+    static constexpr int PS = (NSLOT + 1) * SB;                            // plane stride (P2 / P4), guard included
+};
+
+// y[j] = ring sample L behind frame j of the thread (slot register s, ring base rb in bytes)
+template <int L>
+__device__ __forceinline__ void aesrv_comb_read(const char *rb, int s, float (&y)[4])
+{
+    using C = AesrvComb<L>;
+    if constexpr (C::KIND == 0) {
+        const float4 A = aes_lds_v4(reinterpret_cast<const float *>(rb + s));
+        y[0] = A.x; y[1] = A.y; y[2] = A.z; y[3] = A.w;
+    } else if constexpr (C::KIND == 2) {
+        const float2 a = *reinterpret_cast<const float2 *>(rb + C::PS + s);        // unit 2u+1: plane 1, index u
+        const float2 b = *reinterpret_cast<const float2 *>(rb + s + 8);            // unit 2u+2: plane 0, index u+1
+        y[0] = a.x; y[1] = a.y; y[2] = b.x; y[3] = b.y;
+    } else {
 #pragma unroll
-    for (int r = 0; r < (L + 127) / 128; ++r) {
-        const int j = j0 + 128 * r;
-        if (128 * r + 127 < L || j < L) {
-            constexpr int KMAX = (T + L - 1) / L;           // rows that can hold column j
-            int slot = pos + j;
-            if (slot >= L) slot -= L;
-            float line = rb[slot];
-            float xs[KMAX];
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-                if (128 * r + 127 + k * L < T) xs[k] = s[j + k * L];            // row k is complete for this trip
-                else if (128 * r + k * L < T) xs[k] = (j + k * L < T) ? s[j + k * L] : 0.0f;
-            }
-#pragma unroll
-            for (int k = 0; k < KMAX; ++k) {
-                if (128 * r + 127 + k * L < T) {
-                    const float yo = fmaf(-g, xs[k], line);
-                    s[j + k * L] = yo;
-                    line = fmaf(g, yo, xs[k]);
-                } else if (128 * r + k * L < T) {
-                    if (j + k * L < T) {
-                        const float yo = fmaf(-g, xs[k], line);
-                        s[j + k * L] = yo;
-                        line = fmaf(g, yo, xs[k]);
-                    }
-                }
-            }
-            rb[slot] = line;
+        for (int j = 0; j < 4; ++j) {
+            constexpr int M = C::M;
+            const int e = M + j;                            // element 4u + e: plane e&3, index u + (e>>2)
+            y[j] = *reinterpret_cast<const float *>(rb + (e & 3) * C::PS + s + 4 * (e >> 2));
         }
     }
 }
 
-template <int TOPO, int K>
-__device__ __forceinline__ void aesrv_allpass(float *S, float *rings, int ch, int j0, int pos, float g)
+template <int L>
+__device__ __forceinline__ void aesrv_comb_write(char *rb, int s, const float (&nb)[4])
+{
+    using C = AesrvComb<L>;
+    if constexpr (C::KIND == 0) {
+        *reinterpret_cast<float4 *>(rb + s) = make_float4(nb[0], nb[1], nb[2], nb[3]);
+    } else if constexpr (C::KIND == 2) {
+        *reinterpret_cast<float2 *>(rb + s) = make_float2(nb[0], nb[1]);
+        *reinterpret_cast<float2 *>(rb + C::PS + s) = make_float2(nb[2], nb[3]);
+        if (s == 0) *reinterpret_cast<float2 *>(rb + C::NSLOT * 8) = make_float2(nb[0], nb[1]);    // guard of plane 0
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) *reinterpret_cast<float *>(rb + j * C::PS + s) = nb[j];
+        if (s == 0) {
+#pragma unroll
+            for (int j = 0; j < C::M; ++j) *reinterpret_cast<float *>(rb + j * C::PS + C::NSLOT * 4) = nb[j];
+        }
+    }
+}
+
+// all-pass walk over one channel's tile `s` (T samples) by NTH threads: column j of the tile, seen as
+// rows of L samples, is one serial chain  y = line - g*x,  line' = x + g*y  (reverb.py:48-67) down the
+// rows; the chain's state enters from / leaves to the ring (length L, phase `pos` = tile start mod L).
+// A thread walks NC columns (j0 + NTH*(r0 + c)) at once: the chains are independent, and two FFMA
+// chains in flight is what the walkers' 32 registers allow (a single chain left them latency-bound at
+// 0.08 instructions per cycle, ncu r2d).
+template <int L, int NTH, int R0, int NCOL>
+__device__ __forceinline__ void aesrv_walk_cols(float *s, float *rb, int pos, int j0, float g)
 {
     constexpr int T = AES_NT * 4;
-    if (ch == 0) aesrv_walk<aesf_topo_ap(TOPO, 0, K)>(S, rings + aesf_topo_ap_off(TOPO, 0, K), pos, j0, g);
-    else         aesrv_walk<aesf_topo_ap(TOPO, 1, K)>(S + T, rings + aesf_topo_ap_off(TOPO, 1, K), pos, j0, g);
+    constexpr int KMAX = (T + L - 1) / L;                   // rows that can hold a column
+    int slot[NCOL];
+    float line[NCOL];
+    float *p[NCOL];
+    bool act[NCOL];
+#pragma unroll
+    for (int c = 0; c < NCOL; ++c) {
+        const int j = j0 + NTH * (R0 + c);
+        act[c] = (NTH * (R0 + c + 1) <= L) || j < L;        // compile-time true when the whole trip fits
+        const int jj = act[c] ? j : 0;                      // idle lanes shadow column 0 without storing
+        slot[c] = pos + jj;
+        if (slot[c] >= L) slot[c] -= L;
+        line[c] = rb[slot[c]];
+        p[c] = s + jj;
+    }
+#pragma unroll
+    for (int k0 = 0; k0 < KMAX; k0 += 4) {                  // loads of four rows ahead of their serial chains
+        float xs[NCOL][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int c = 0; c < NCOL; ++c) {
+                const int k = k0 + u;
+                if (k < KMAX) {
+                    if ((L - 1) + k * L < T) xs[c][u] = p[c][k * L];                 // row k is complete
+                    else xs[c][u] = (p[c] - s) + k * L < T ? p[c][k * L] : 0.0f;
+                }
+            }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int c = 0; c < NCOL; ++c) {
+                const int k = k0 + u;
+                if (k < KMAX) {
+                    const float yo = fmaf(-g, xs[c][u], line[c]);
+                    if ((L - 1) + k * L < T) {              // complete row: only idle lanes must not store
+                        if (act[c]) p[c][k * L] = yo;
+                        line[c] = fmaf(g, yo, xs[c][u]);
+                    } else if ((p[c] - s) + k * L < T) {    // last row: the column may end above it
+                        if (act[c]) p[c][k * L] = yo;
+                        line[c] = fmaf(g, yo, xs[c][u]);
+                    }
+                }
+            }
+    }
+#pragma unroll
+    for (int c = 0; c < NCOL; ++c)
+        if (act[c]) rb[slot[c]] = line[c];
+}
+
+// columns j0, j0 + NTH, ... of a ring of L samples, two at a time; a warp whose lanes all lie beyond the
+// last, partial trip walks its remaining column alone
+template <int L, int NTH>
+__device__ __forceinline__ void aesrv_walk(float *s, float *rb, int pos, int j0, float g)
+{
+    constexpr int NTRIP = (L + NTH - 1) / NTH;
+    aes_static_for<0, NTRIP / 2>([&](auto ir) {
+        constexpr int r0 = 2 * decltype(ir)::value;
+        constexpr bool second_partial = NTH * (r0 + 2) > L;
+        if (!second_partial || (j0 & ~31) + NTH * (r0 + 1) < L) aesrv_walk_cols<L, NTH, r0, 2>(s, rb, pos, j0, g);
+        else aesrv_walk_cols<L, NTH, r0, 1>(s, rb, pos, j0, g);
+    });
+    if constexpr ((NTRIP & 1) != 0) {
+        if ((j0 & ~31) + NTH * (NTRIP - 1) < L) aesrv_walk_cols<L, NTH, NTRIP - 1, 1>(s, rb, pos, j0, g);
+    }
 }
 
 template <int TOPO, int PRE, int PM>
@@ -92,50 +209,152 @@ __device__ void aes_rv_body(const FastArgs &a)
 {
     constexpr int FR = 4, T = AES_NT * FR, NC = 4;
     constexpr int SR = PRE == AESRV_PRE_NONE ? 0 : 1;      // index of the reverb stage
+    constexpr int LNS = T + 8;                              // staged line samples per channel (T + 4 used)
     static_assert(TOPO == AESF_TOPO_48K || TOPO == AESF_TOPO_44K, "compile-time reverb topology only");
     static_assert(!(PRE == AESRV_PRE_BIQUAD && PM != 0), "biquad + pre-delay is not instantiated (the biquad output only exists in phase 2)");
     AES_DYN_SMEM(float, smem);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, i0 = FR * tid;
-    const int wch = tid >> 7, wj0 = tid & 127;              // all-pass walks: threads 0..127 left, 128..255 right
-    float *const rings = smem + 4 * T;
-    const int foff = (4 * T + a.smem_floats + 3) & ~3;
+    const int tid = threadIdx.x;
+    float *const rings = smem + 2 * AESRV_NXS * T;
+    const int foff = (2 * AESRV_NXS * T + a.smem_floats + 3) & ~3;
     float *const wt = smem + foff;                          // [8 warps][2 ch][4 combs] warp totals of the comb one-poles
     float *const cst = wt + 64;                             // [2 parity][8] one-pole values carried across tiles
     double *const wtot = reinterpret_cast<double *>(cst + 16);  // biquad: [8 warps][2 ch][2]
     double *const bst = wtot + 32;                          // biquad: [2 parity][8] DF-I state carried across tiles
+    float *const LN = reinterpret_cast<float *>(bst + 16);  // [2 parity][2 ch][LNS] staged feedback-delay line samples
+    unsigned long long *const mbar = reinterpret_cast<unsigned long long *>(LN + (PRE == AESRV_PRE_DELAY ? 4 * LNS : 0));
     float *const gscr = a.scratch + (long long)blockIdx.x * a.scratch_floats;
-
     const FastStage &rs = a.st[SR];
-    const float h = rs.h, hw = rs.hp[5], apg = rs.a, rdry = rs.dry, rwet = rs.wet;
+    const int N = (int)a.N;                                 // the host routes clips of 2^31 frames or more elsewhere
+    const int ntiles = (N + T - 1) / T;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int i = 0; i < AESRV_NXS; ++i) aes_mbar_init(mbar + i, 1);
+        aes_mbar_init_fence();
+    }
+    // (the first __syncthreads of the clip loop orders the init before any use)
+
+    if (tid >= AES_NT) {
+        // =========================== walker warps ===========================
+        aes_setmaxnreg_dec<AESRV_REGS_WALK>();
+        const int wt_id = tid - AES_NT;                     // 0..127
+        const int ch = wt_id >> 6, j0 = wt_id & 63;
+        const bool issuer = wt_id == 0;
+        const float apg = rs.a;
+        constexpr int L1_0 = aesf_topo_ap(TOPO, 0, 0), L1_1 = aesf_topo_ap(TOPO, 1, 0);
+        constexpr int L2_0 = aesf_topo_ap(TOPO, 0, 1), L2_1 = aesf_topo_ap(TOPO, 1, 1);
+        const int apL1 = ch ? L1_1 : L1_0, apI1 = ch ? T % L1_1 : T % L1_0;
+        const int apL2 = ch ? L2_1 : L2_0, apI2 = ch ? T % L2_1 : T % L2_0;
+        float *const ring1 = rings + (ch ? aesf_topo_ap_off(TOPO, 1, 0) : aesf_topo_ap_off(TOPO, 0, 0));
+        float *const ring2 = rings + (ch ? aesf_topo_ap_off(TOPO, 1, 1) : aesf_topo_ap_off(TOPO, 0, 1));
+        int q = 0;                                          // buffer of the tile being walked; never reset
+        for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
+            {   // fresh all-pass lines (the comb warps clear theirs): the all-pass rings follow the comb rings
+                constexpr int ap0 = aesf_topo_ap_off(TOPO, 0, 0);
+                for (int i = ap0 + wt_id; i < a.smem_floats; i += AESRV_NW) rings[i] = 0.0f;
+            }
+            __syncthreads();
+            const bool clip_staged = a.in_fmt == AESK_F32_STEREO && ((b * a.N) & 1) == 0;
+            const float *const xin = reinterpret_cast<const float *>(a.x) + 2 * (b * a.N);
+            int lnbase[2] = { 0, 0 };                       // thread 0's aligned line read base of the tile staged next
+            if constexpr (PRE == AESRV_PRE_DELAY) {
+#pragma unroll
+                for (int c2 = 0; c2 < 2; ++c2) {
+                    int w0;
+                    aesf_line_init<FR>(a.st[0].ring[c2][0], 0, w0, lnbase[c2]);
+                }
+            }
+            // hand the tile starting at frame f0 to the TMA: input frames into buffer qq, line samples into LN[pp]
+            auto issue_tile = [&](int f0, int qq, int pp) {
+                unsigned long long *bar = mbar + qq;
+                // generic-proxy accesses (line stores; loads / stores of the tile buffer) before the copies
+                if (PRE == AESRV_PRE_DELAY) aes_fence_proxy_async();
+                aes_fence_proxy_async_smem();
+                aes_mbar_expect(bar, (unsigned)(T * 8 + (PRE == AESRV_PRE_DELAY ? 2 * (T + 4) * 4 : 0)));
+                aes_bulk_g2s(smem + qq * 2 * T, xin + 2 * (long long)f0, T * 8, bar, aes_policy_evict_first());
+                if constexpr (PRE == AESRV_PRE_DELAY) {
+                    const unsigned long long keep = aes_policy_evict_last();
+#pragma unroll
+                    for (int c2 = 0; c2 < 2; ++c2) {
+                        const FRing rg = a.st[0].ring[c2][0];
+                        const int a0 = lnbase[c2];
+                        const float *rb = gscr + rg.off;
+                        float *dst = LN + (pp * 2 + c2) * LNS;
+                        const int n1 = (rg.len - a0) < (T + 4) ? (rg.len - a0) : (T + 4);
+                        aes_bulk_g2s(dst, rb + a0, (unsigned)n1 * 4, bar, keep);
+                        if (n1 < T + 4) aes_bulk_g2s(dst + n1, rb, (unsigned)(T + 4 - n1) * 4, bar, keep);   // the ring wraps
+                        lnbase[c2] = aesf_adv(a0, rg.tinc, rg.len);
+                    }
+                }
+#ifdef AES_CPU_EMU
+                aes_mbar_complete_emu(bar);
+#endif
+            };
+            // tiles 0 and 1 right away; tile i+2 once the comb warps are through with tile i (its buffer, tile
+            // i-2's, was read last before that, and every line sample the copy needs has been stored)
+            if (issuer && clip_staged) {
+                if (N >= T) issue_tile(0, q, 0);
+                if (N >= 2 * T) issue_tile(T, (q + 1) & (AESRV_NXS - 1), 1);
+            }
+            int pos1 = 0, pos2 = 0;                         // all-pass ring phases of the tile being walked
+            for (int it = 0; it < ntiles; ++it) {
+                const int par = it & 1;
+                float *const S = smem + q * 2 * T + ch * T;
+                aes_bar_sync(AESRV_BAR_FULL + par, AESRV_NT);
+                if (issuer && clip_staged && N - it * T >= 3 * T)
+                    issue_tile((it + 2) * T, (q + 2) & (AESRV_NXS - 1), par);
+                if (ch == 0) aesrv_walk<L1_0, 64>(S, ring1, pos1, j0, apg);
+                else         aesrv_walk<L1_1, 64>(S, ring1, pos1, j0, apg);
+                aes_bar_sync(AESRV_BAR_CHAN + ch, 64);
+                if (ch == 0) aesrv_walk<L2_0, 64>(S, ring2, pos2, j0, apg);
+                else         aesrv_walk<L2_1, 64>(S, ring2, pos2, j0, apg);
+                aes_bar_arrive(AESRV_BAR_DONE + par, AESRV_NT);
+                pos1 = aesf_adv(pos1, apI1, apL1);
+                pos2 = aesf_adv(pos2, apI2, apL2);
+                q = (q + 1) & (AESRV_NXS - 1);
+            }
+            __syncthreads();                                // (matches the comb warps' clip-end barrier)
+        }
+        return;
+    }
+
+    // =========================== comb warps ===========================
+    aes_setmaxnreg_inc<AESRV_REGS_COMB>();
+    const int lane = tid & 31, warp = tid >> 5, i0 = FR * tid;
+    // feedback-delay lines of this CTA.  Kept in registers on purpose: left alone, ptxas re-derives
+    // blockIdx * scratch_floats + offset in 64 bits in front of every line store (ten instructions each).
+    float *gl0 = gscr + (PRE == AESRV_PRE_DELAY ? a.st[0].ring[0][0].off : 0);
+    float *gl1 = gscr + (PRE == AESRV_PRE_DELAY ? a.st[0].ring[1][0].off : 0);
+#ifndef AES_CPU_EMU
+    asm volatile("" : "+l"(gl0), "+l"(gl1));
+#endif
+    const float h = rs.h, hw = rs.hp[5], rdry = rs.dry, rwet = rs.wet;
     const int nscan = rs.nscan, nxw = rs.nxw;
     const float hl = a.lane_tab[(SR * 32 + lane) * FAST_LANE_STRIDE];       // h^(FR*lane)
     // where this warp finds the one-pole values entering its first frame: the previous warp's totals,
     // or (warp 0) the values carried from the previous tile, by tile parity
     const float *const cp0 = warp == 0 ? cst : wt + (warp - 1) * 8;
     const float *const cp1 = warp == 0 ? cst + 8 : wt + (warp - 1) * 8;
-    constexpr int apT1_0 = T % aesf_topo_ap(TOPO, 0, 0), apT1_1 = T % aesf_topo_ap(TOPO, 1, 0);
-    constexpr int apT2_0 = T % aesf_topo_ap(TOPO, 0, 1), apT2_1 = T % aesf_topo_ap(TOPO, 1, 1);
-    const int apL1 = wch ? aesf_topo_ap(TOPO, 1, 0) : aesf_topo_ap(TOPO, 0, 0), apI1 = wch ? apT1_1 : apT1_0;
-    const int apL2 = wch ? aesf_topo_ap(TOPO, 1, 1) : aesf_topo_ap(TOPO, 0, 1), apI2 = wch ? apT2_1 : apT2_0;
 
-    ChainArgs io;                                           // tile I/O helpers are shared with the generic kernel
+    ChainArgs io;                                           // ragged / odd-format tile I/O is shared with the generic kernel
     io.x = a.x; io.y = a.y; io.N = a.N; io.in_fmt = a.in_fmt; io.out_fmt = a.out_fmt;
-    const int N = (int)a.N;                                 // the host routes clips of 2^31 frames or more elsewhere
-    const int ntiles = (N + T - 1) / T;
+    int q = 0;                                              // tile buffer of the current tile; never reset
+    unsigned phbits = 0;                                    // parity of the next wait on each buffer's mbarrier
 
     for (long long b = blockIdx.x; b < a.B; b += gridDim.x) {
-        {   // fresh lines, carried values and ring phases at every clip start (core.py:123-129 re-prepares)
+        {   // fresh lines and carried values at every clip start (core.py:123-129 re-prepares)
+            constexpr int ap0 = aesf_topo_ap_off(TOPO, 0, 0);           // comb rings come first (aes_plan_build.h)
             float4 *r4 = reinterpret_cast<float4 *>(rings);
             const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int i = tid; i < (a.smem_floats + 3) / 4; i += AES_NT) r4[i] = z4;
+            for (int i = tid; i < ap0 / 4; i += AES_NT) r4[i] = z4;
             if (tid < 16) cst[tid] = 0.0f;
             if (PRE == AESRV_PRE_BIQUAD && tid < 8) { bst[tid] = a.init[0][tid]; bst[8 + tid] = a.init[0][tid]; }
         }
-        int wb[2][NC];                                      // comb slots: BYTE offset of this thread's float4 in the ring
-#pragma unroll
-        for (int ch = 0; ch < 2; ++ch)
-#pragma unroll
-            for (int cc = 0; cc < NC; ++cc) wb[ch][cc] = 4 * i0;
+        int wb[2][NC];                                      // comb slots: this thread's float4 slot, in its ring's slot bytes
+        aes_static_for<0, 2 * NC>([&](auto ic) {
+            constexpr int ch = decltype(ic)::value / NC, cc = decltype(ic)::value % NC;
+            wb[ch][cc] = tid * AesrvComb<aesf_topo_comb(TOPO, ch, cc)>::SB;
+        });
         int dw[2] = { 0, 0 }, da[2] = { 0, 0 };             // feedback-delay line: write slot, aligned read base
         if constexpr (PRE == AESRV_PRE_DELAY) {
 #pragma unroll
@@ -146,20 +365,12 @@ __device__ void aes_rv_body(const FastArgs &a)
 #pragma unroll
             for (int ch = 0; ch < 2; ++ch) aesf_line_init<FR>(rs.pre[ch], i0, pw[ch], pa[ch]);
         }
-        int pos1 = 0, pos2 = 0;                             // all-pass ring phases of the tile the walks work on
         __syncthreads();
 
-        const bool fast_in = a.in_fmt == AESK_F32_STEREO && ((b * a.N) & 1) == 0;
-        const float *const xin = reinterpret_cast<const float *>(a.x) + 2 * (b * a.N);
-        float4 pfx0, pfx1;                                  // next tile's 4 stereo frames of this thread
-        float4 lnA[2], lnB[2];                              // next tile's feedback-delay line samples
-        pfx0 = pfx1 = lnA[0] = lnA[1] = lnB[0] = lnB[1] = make_float4(0.f, 0.f, 0.f, 0.f);
-        bool pf_ok = false;                                 // pfx holds the coming tile
-        if (fast_in && N >= T) {
-            pfx0 = aes_ldg_v4(xin + 2 * i0);
-            pfx1 = aes_ldg_v4(xin + 2 * i0 + 4);
-            pf_ok = true;
-        }
+        // a tile goes through TMA staging when it is full, 16-byte aligned and plain f32 stereo
+        const bool clip_staged = a.in_fmt == AESK_F32_STEREO && ((b * a.N) & 1) == 0;
+        const bool fast_out = a.out_fmt == AESK_F32_STEREO && ((b * a.N) & 1) == 0;
+        float *yp = reinterpret_cast<float *>(a.y) + 2 * (b * a.N) + 2 * i0 - 2 * T;      // this thread's frames of tile i-1
         float vprev[2][FR];                                 // dry signal at the reverb input, tile i-1
 #pragma unroll
         for (int ch = 0; ch < 2; ++ch)
@@ -172,17 +383,26 @@ __device__ void aes_rv_body(const FastArgs &a)
             const int n0 = it * T;
             const int rem = N - n0;
             const int len = rem < T ? rem : T;
-            float *const Sc = smem + par * 2 * T;           // this tile's buffer
-            float *const Sp = smem + (par ^ 1) * 2 * T;     // tile i-1's
-            float v[2][FR], y[2][NC][FR], e[2][NC];
-            double bq_yz[2][FR], bq_e1[2], bq_e2[2];
+            float *const Sc = smem + q * 2 * T;             // this tile's buffer: staged input, then the comb sum
+            float *const Sp = smem + ((q + AESRV_NXS - 1) & (AESRV_NXS - 1)) * 2 * T;    // tile i-1's: its wet signal
+            const bool staged = clip_staged && len == T;
+            float v[2][FR];
 
-            // ---------------- phase 1 ----------------
-            if (has_prev) aesrv_allpass<TOPO, 0>(Sp, rings, wch, wj0, pos1, apg);
             if (has_cur) {
-                if (pf_ok) {
-                    v[0][0] = pfx0.x; v[1][0] = pfx0.y; v[0][1] = pfx0.z; v[1][1] = pfx0.w;
-                    v[0][2] = pfx1.x; v[1][2] = pfx1.y; v[0][3] = pfx1.z; v[1][3] = pfx1.w;
+                float y[2][NC][FR], e[2][NC];
+                double bq_yz[2][FR], bq_e1[2], bq_e2[2];
+                // ---------------- phase 1 ----------------
+                if (staged) {
+                    aes_mbar_wait_parity(mbar + q, (phbits >> q) & 1u);
+                    phbits ^= 1u << q;
+                    // interleaved L R L R ..., 32 bytes per thread: two 128-bit loads at a 32-byte lane stride
+                    // conflict 2-way, so lanes 4..7 of every eight take their halves in the other order
+                    const float *sx = Sc + 2 * i0;
+                    const int sw = (tid >> 2) & 1;
+                    const float4 ta = aes_lds_v4(sx + 4 * sw), tb = aes_lds_v4(sx + 4 * (sw ^ 1));
+                    const float4 t0 = sw ? tb : ta, t1 = sw ? ta : tb;
+                    v[0][0] = t0.x; v[1][0] = t0.y; v[0][1] = t0.z; v[1][1] = t0.w;
+                    v[0][2] = t1.x; v[1][2] = t1.y; v[0][3] = t1.z; v[1][3] = t1.w;
                 } else {
                     aes_load_frames<FR>(io, b, n0, len, tid, v);            // ragged / unaligned / non-f32 tiles
                 }
@@ -195,15 +415,19 @@ __device__ void aes_rv_body(const FastArgs &a)
                         const FRing rg = ds.ring[ch][0];
                         const int m = ((rg.lag + 3) & ~3) - rg.lag;
                         float line[FR];
-                        if (!pf_ok || it == 0) {                            // nothing was fetched ahead for this tile
-                            const float *rb = gscr + rg.off;
-                            int b0 = da[ch] + 4;
-                            b0 = b0 >= rg.len ? b0 - rg.len : b0;
-                            lnA[ch] = aes_ldg_v4(rb + da[ch]);
-                            lnB[ch] = aes_ldg_v4(rb + b0);
+                        if (staged) {
+                            // line samples staged by TMA: [i0 + m, i0 + m + FR) of the staged span
+                            const float *sp = LN + (par * 2 + ch) * LNS + i0 + m;
+                            if (m == 0) {
+                                const float4 A = aes_lds_v4(sp);
+                                line[0] = A.x; line[1] = A.y; line[2] = A.z; line[3] = A.w;
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < FR; ++j) line[j] = sp[j];
+                            }
+                        } else {
+                            aesf_read<FR, 1>(ch ? gl1 : gl0, da[ch], m, rg.len, line);
                         }
-                        if (m == 0) { line[0] = lnA[ch].x; line[1] = lnA[ch].y; line[2] = lnA[ch].z; line[3] = lnA[ch].w; }
-                        else aesf_select4<FR>(lnA[ch], lnB[ch], m, line);
                         if (n0 < rg.lag) {                                  // only the first tiles of a clip: zero history
 #pragma unroll
                             for (int j = 0; j < FR; ++j)
@@ -216,7 +440,7 @@ __device__ void aes_rv_body(const FastArgs &a)
                             nb[j] = fmaf(line[j], fb, x);
                             v[ch][j] = aes_mix_clip(dry, x, wet, line[j]);
                         }
-                        aes_stv<FR>(gscr + rg.off + dw[ch], nb);
+                        aes_stv<FR>((ch ? gl1 : gl0) + dw[ch], nb);
                     }
                 }
                 if constexpr (PRE == AESRV_PRE_BIQUAD) {
@@ -259,17 +483,15 @@ __device__ void aes_rv_body(const FastArgs &a)
                 }
                 // damped combs (reverb.py:33-46) on u = lp/(1-h): delayed ring reads, one-pole over the
                 // thread's 4 samples from zero, Kogge-Stone over the warp, lane 31 publishes the warp total
+                aes_static_for<0, 2 * NC>([&](auto ic) {
+                    constexpr int ch = decltype(ic)::value / NC, cc = decltype(ic)::value % NC;
+                    aesrv_comb_read<aesf_topo_comb(TOPO, ch, cc)>(
+                        reinterpret_cast<const char *>(rings + aesf_topo_comb_off(TOPO, ch, cc)), wb[ch][cc], y[ch][cc]);
+                    float u = y[ch][cc][0];
 #pragma unroll
-                for (int ch = 0; ch < 2; ++ch)
-#pragma unroll
-                    for (int cc = 0; cc < NC; ++cc) {
-                        const int L = aesf_topo_comb(TOPO, ch, cc), rlen = (L + 3) & ~3;
-                        aesf_comb_read<FR>(rings + aesf_topo_comb_off(TOPO, ch, cc), wb[ch][cc], rlen - L, rlen, y[ch][cc]);
-                        float u = y[ch][cc][0];
-#pragma unroll
-                        for (int j = 1; j < FR; ++j) u = fmaf(h, u, y[ch][cc][j]);
-                        e[ch][cc] = u;
-                    }
+                    for (int j = 1; j < FR; ++j) u = fmaf(h, u, y[ch][cc][j]);
+                    e[ch][cc] = u;
+                });
 #pragma unroll 1
                 for (int s = 0; s < nscan; ++s) {
                     const float m = rs.hp[s];
@@ -290,12 +512,9 @@ __device__ void aes_rv_body(const FastArgs &a)
 #pragma unroll
                     for (int ch = 0; ch < 2; ++ch) aes_stv<FR>(rings + rs.pre[ch].off + pw[ch], v[ch]);
                 }
-            }
-            __syncthreads();
+                aes_bar_sync(AESRV_BAR_COMB, AES_NT);
 
-            // ---------------- phase 2 ----------------
-            if (has_prev) aesrv_allpass<TOPO, 1>(Sp, rings, wch, wj0, pos2, apg);
-            if (has_cur) {
+                // ---------------- phase 2 ----------------
                 if constexpr (PRE == AESRV_PRE_BIQUAD) {
                     const FastStage &bs = a.st[0];
                     const double b1 = bs.bq[1], b2 = bs.bq[2], a1 = bs.bq[3], a2 = bs.bq[4];
@@ -356,11 +575,11 @@ __device__ void aes_rv_body(const FastArgs &a)
                 float *const cnext = cst + (par ^ 1) * 8;
                 const int u0 = warp > nxw ? warp - nxw : 0;
                 float sum[2][FR];
-#pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
+                aes_static_for<0, 2>([&](auto ich) {
+                    constexpr int ch = decltype(ich)::value;
                     float uend[NC];
-#pragma unroll
-                    for (int cc = 0; cc < NC; ++cc) {
+                    aes_static_for<0, NC>([&](auto icc) {
+                        constexpr int cc = decltype(icc)::value;
                         const float ex = __shfl_up_sync(0xffffffffu, e[ch][cc], 1);
                         float C;
                         if (nxw == 1) {                                  // usual case: h^(32*FR) < 2^-32
@@ -379,18 +598,21 @@ __device__ void aes_rv_body(const FastArgs &a)
                             if (cc == 0) sum[ch][j] = y[ch][0][j];      // reverb.py:235-241: sum starts at 0
                             else sum[ch][j] = __fadd_rn(sum[ch][j], y[ch][cc][j]);
                         }
-                        aes_stv<FR>(reinterpret_cast<float *>(reinterpret_cast<char *>(rings + aesf_topo_comb_off(TOPO, ch, cc)) + wb[ch][cc]), nb);
+                        aesrv_comb_write<aesf_topo_comb(TOPO, ch, cc)>(
+                            reinterpret_cast<char *>(rings + aesf_topo_comb_off(TOPO, ch, cc)), wb[ch][cc], nb);
                         uend[cc] = u;
-                    }
+                    });
                     if (tid == AES_NT - 1) aes_stv<4>(cnext + ch * 4, uend);
-                }
+                });
                 aes_stv<FR>(Sc + i0, sum[0]);
                 aes_stv<FR>(Sc + T + i0, sum[1]);
+                aes_bar_arrive(AESRV_BAR_FULL + par, AESRV_NT);             // the walkers take the tile from here
             }
-            __syncthreads();
 
-            // ---------------- phase 3 ----------------
+            // ---------------- phase 3: tile i-1 comes back from the walkers ----------------
             if (has_prev) {
+                // (also the barrier between this tile's ring writes and the next tile's ring reads)
+                aes_bar_sync(AESRV_BAR_DONE + (par ^ 1), AESRV_NT);
                 float o[2][FR];
                 aes_ldv_sp<FR, 0>(Sp + i0, o[0]);
                 aes_ldv_sp<FR, 0>(Sp + T + i0, o[1]);
@@ -398,23 +620,26 @@ __device__ void aes_rv_body(const FastArgs &a)
                 for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
                     for (int j = 0; j < FR; ++j) o[ch][j] = aes_mix_clip(rdry, vprev[ch][j], rwet, o[ch][j]);
-                const int rp = N - (n0 - T);
-                aes_store_frames<FR>(io, b, n0 - T, rp < T ? rp : T, tid, o);
-                pos1 = aesf_adv(pos1, apI1, apL1);
-                pos2 = aesf_adv(pos2, apI2, apL2);
-            }
+                if (fast_out && rem >= 0) {                 // tile i-1 was a full one
+                    __stcs(reinterpret_cast<float4 *>(yp), make_float4(o[0][0], o[1][0], o[0][1], o[1][1]));
+                    __stcs(reinterpret_cast<float4 *>(yp) + 1, make_float4(o[0][2], o[1][2], o[0][3], o[1][3]));
+                } else {
+                    aes_store_frames<FR>(io, b, n0 - T, rem + T < T ? rem + T : T, tid, o);
+                }
+            } else {
+                aes_bar_sync(AESRV_BAR_COMB, AES_NT);       // first tile: nothing to wait for, but the ring writes still
+            }                                               // have to be ordered before the next tile's reads
+            yp += 2 * T;
             if (has_cur) {
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
                     for (int j = 0; j < FR; ++j) vprev[ch][j] = v[ch][j];
-#pragma unroll
-                for (int ch = 0; ch < 2; ++ch)
-#pragma unroll
-                    for (int cc = 0; cc < NC; ++cc) {
-                        const int rlen = (aesf_topo_comb(TOPO, ch, cc) + 3) & ~3;
-                        wb[ch][cc] = aesf_adv(wb[ch][cc], 4 * (T % rlen), 4 * rlen);
-                    }
+                aes_static_for<0, 2 * NC>([&](auto ic) {
+                    constexpr int ch = decltype(ic)::value / NC, cc = decltype(ic)::value % NC;
+                    using CR = AesrvComb<aesf_topo_comb(TOPO, ch, cc)>;
+                    wb[ch][cc] = aesf_adv(wb[ch][cc], CR::TINC, CR::WRAP);
+                });
                 if constexpr (PM != 0) {
 #pragma unroll
                     for (int ch = 0; ch < 2; ++ch) {
@@ -422,38 +647,20 @@ __device__ void aes_rv_body(const FastArgs &a)
                         pa[ch] = aesf_adv(pa[ch], rs.pre[ch].tinc, rs.pre[ch].len);
                     }
                 }
-                // loads for tile i+1: a whole phase (and the next tile's first all-pass walk) ahead of their use
-                const bool next_full = rem >= 2 * T;
-                pf_ok = fast_in && next_full;
-                if (pf_ok) {
-                    const float *p = xin + 2 * (n0 + T + i0);
-                    pfx0 = aes_ldg_v4(p);
-                    pfx1 = aes_ldg_v4(p + 4);
-                }
                 if constexpr (PRE == AESRV_PRE_DELAY) {
-                    const FastStage &ds = a.st[0];
 #pragma unroll
                     for (int ch = 0; ch < 2; ++ch) {
-                        const FRing rg = ds.ring[ch][0];
+                        const FRing rg = a.st[0].ring[ch][0];
                         dw[ch] = aesf_adv(dw[ch], rg.tinc, rg.len);
                         da[ch] = aesf_adv(da[ch], rg.tinc, rg.len);
-                        if (pf_ok) {
-                            const float *rb = gscr + rg.off;
-                            lnA[ch] = aes_ldg_v4(rb + da[ch]);
-                            if (((rg.lag + 3) & ~3) != rg.lag) {
-                                int b0 = da[ch] + 4;
-                                b0 = b0 >= rg.len ? b0 - rg.len : b0;
-                                lnB[ch] = aes_ldg_v4(rb + b0);
-                            }
-                        }
                     }
                 }
+                q = (q + 1) & (AESRV_NXS - 1);
             }
         }
         if (PRE == AESRV_PRE_BIQUAD && a.state_out != nullptr) {
-            __syncthreads();
-            // carried scalars of the biquad (stage 0) at the end of the clip: written by the last tile
-            // into the parity opposite to its own, i.e. opposite to the drain iteration's too
+            // carried scalars of the biquad (stage 0) at the end of the clip: written by the last tile into the
+            // parity opposite to its own (every comb warp is past the DONE barrier behind that write)
             if (tid < 8) a.state_out[b * 32 + tid] = bst[(ntiles & 1) * 8 + tid];
         }
         __syncthreads();                                    // the next clip re-initialises rings and carried values
@@ -462,7 +669,7 @@ __device__ void aes_rv_body(const FastArgs &a)
 
 #ifndef AES_CPU_EMU
 template <int TOPO, int PRE, int PM>
-__global__ void __launch_bounds__(AES_NT, 2) aes_rv_kernel(const __grid_constant__ FastArgs a)
+__global__ void __launch_bounds__(AESRV_NT, 2) aes_rv_kernel(const __grid_constant__ FastArgs a)
 {
     aes_rv_body<TOPO, PRE, PM>(a);
 }

@@ -57,6 +57,8 @@ struct Cta {
     std::vector<int> w_count; std::vector<unsigned> w_gen;
     std::vector<uint64_t> slot;       // nthreads x 4 values
     std::vector<char> smem;
+    // named barriers (bar.sync / bar.arrive id, count): arrivals so far and completed generations
+    int nb_count[16] = {}; unsigned nb_gen[16] = {};
 };
 extern Cta *g_cta;
 extern thread_local int dummy;
@@ -65,6 +67,18 @@ inline void block_barrier() {
     Cta &c = *g_cta; unsigned gen = c.bar_gen;
     if (++c.bar_count == c.nthreads) { c.bar_count = 0; ++c.bar_gen; return; }
     while (c.bar_gen == gen) yield();
+}
+// bar.sync id, n: wait until n threads have arrived (by sync or arrive); bar.arrive id, n: count, do not wait
+inline void named_sync(int id, int n) {
+    Cta &c = *g_cta; unsigned gen = c.nb_gen[id];
+    if (++c.nb_count[id] == n) { c.nb_count[id] = 0; ++c.nb_gen[id]; return; }
+    if (c.nb_count[id] > n) { std::fprintf(stderr, "emu: named barrier %d over-subscribed\n", id); std::abort(); }
+    while (c.nb_gen[id] == gen) yield();
+}
+inline void named_arrive(int id, int n) {
+    Cta &c = *g_cta;
+    if (++c.nb_count[id] == n) { c.nb_count[id] = 0; ++c.nb_gen[id]; }
+    else if (c.nb_count[id] > n) { std::fprintf(stderr, "emu: named barrier %d over-subscribed\n", id); std::abort(); }
 }
 inline void warp_barrier() {
     Cta &c = *g_cta; int w = c.cur >> 5; unsigned gen = c.w_gen[w];

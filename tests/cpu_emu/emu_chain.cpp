@@ -58,7 +58,7 @@ int emu_chain_run(const aes_stage_desc *stages, int n, int fs, const void *x, in
                 g_last_topo = sh.topo;
                 fa.x = x; fa.y = y; fa.B = B; fa.N = N; fa.scratch = scratch.data(); fa.lane_tab = lane_tab;
                 fa.state_out = state_out; fa.in_fmt = in_fmt; fa.out_fmt = out_fmt;
-                emu::launch(sh.fn, &fa, grid, AES_NT, aes_rv_smem_bytes(plan.smem_floats));
+                emu::launch(sh.fn, &fa, grid, AESRV_NT, aes_rv_smem_bytes(plan.smem_floats, rv_pre));
                 g_last_fast = 2;
                 return 0;
             }

@@ -120,7 +120,8 @@ def test_final_state_of_filter_and_gate_matches_oracle():
         assert np.max(np.abs(got - filt.state.astype(np.float64))) < 1e-6 * max(1.0, np.abs(filt.state).max())
 
 
-RV_PRESETS = ("Rain Delay", "Cathedral", "Guitar Filter")     # chains ending in the default reverb
+RV_PRESETS = ("Rain Delay", "Cathedral")     # chains ending in the default reverb that take aes_rv_kernel by default
+RV_FORCED = ("Guitar Filter",)               # ... and with AES_RV_BIQUAD=1 (slower on the GPU: registers)
 
 
 @pytest.mark.parametrize("name", NATIVE)
@@ -147,12 +148,13 @@ def test_specialised_and_generic_kernels_agree_with_oracle(name, monkeypatch):
             check(y[b], want[b], exact=(name == "Slapback Echo"), what=(name, which, b))
 
 
-@pytest.mark.parametrize("name", RV_PRESETS)
+@pytest.mark.parametrize("name", RV_PRESETS + RV_FORCED)
 @pytest.mark.parametrize("fs", [48000, 44100])
-@pytest.mark.parametrize("n", [1, 777, 1024, 2048, 3100, 19000])
-def test_pipelined_reverb_kernel_tile_edges(name, fs, n):
+@pytest.mark.parametrize("n", [1, 777, 1024, 2048, 3100, 4096, 5000, 19000])
+def test_pipelined_reverb_kernel_tile_edges(name, fs, n, monkeypatch):
     """aes_rv_kernel.cuh works one tile behind itself (all-pass walks, mix and store of tile i-1 in the
     phases of tile i): clips of less than one tile, exact multiples and ragged tails, two clips per CTA."""
+    monkeypatch.setenv("AES_RV_BIQUAD", "1")
     cfg = synth.PRESETS[name]
     x = synth.batch(77, 3, n, fs=fs)
     y = emu.run(emu.resolved_descs(cfg, fs, n, 2), fs, x, grid=2)
@@ -161,9 +163,10 @@ def test_pipelined_reverb_kernel_tile_edges(name, fs, n):
         check(y[b], orc.run_file_path(cfg, x[b], fs), what=(name, fs, n, b))
 
 
-def test_pipelined_reverb_kernel_formats_and_final_biquad_state():
+def test_pipelined_reverb_kernel_formats_and_final_biquad_state(monkeypatch):
     """Mono / int16 input and int16 output through the pipelined kernel, and the biquad's DF-I state at
     the end of the clip (what a later streamed block continues from)."""
+    monkeypatch.setenv("AES_RV_BIQUAD", "1")
     cfg = synth.PRESETS["Guitar Filter"]
     n = 5000
     x = synth.clip(9, n, 1)
