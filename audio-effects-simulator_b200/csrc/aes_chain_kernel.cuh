@@ -99,7 +99,13 @@ __device__ __forceinline__ float4 aes_ldg_v4(const float *p)
     asm volatile("ld.global.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
+// 128-bit store to GLOBAL memory through a pointer whose address space the compiler cannot see
+__device__ __forceinline__ void aes_stg_v4(float *p, const float (&v)[4])
+{
+    asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]) : "memory");
+}
 #else
+static inline void aes_stg_v4(float *p, const float (&v)[4]) { *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]); }
 static inline float4 aes_lds_v4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 static inline float4 aes_ldg_v4(const float *p) { return *reinterpret_cast<const float4 *>(p); }
 #endif

@@ -149,6 +149,25 @@ static inline void aes_fence_proxy_async_all() {}
 static inline void aes_fence_proxy_async_smem() {}
 #endif
 
+// ---- packed f32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2, one issue slot for two lanes' worth) ------
+// Each component rounds exactly like the scalar __fmaf_rn / __fadd_rn / __fmul_rn (no contraction).
+#ifndef AES_CPU_EMU
+__device__ __forceinline__ float2 aes_fma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 aes_add2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 aes_mul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+#else
+static inline float2 aes_fma2(float2 a, float2 b, float2 c) { return make_float2(std::fmaf(a.x, b.x, c.x), std::fmaf(a.y, b.y, c.y)); }
+static inline float2 aes_add2(float2 a, float2 b) { return make_float2(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y)); }
+static inline float2 aes_mul2(float2 a, float2 b) { return make_float2(__fmul_rn(a.x, b.x), __fmul_rn(a.y, b.y)); }
+#endif
+// clip(dry*x + wet*w) for two samples: products and sum separately rounded like numpy (see aes_mix_clip)
+__device__ __forceinline__ void aes_mix_clip2(float dry, float2 x, float wet, float2 w, float &o0, float &o1)
+{
+    const float2 t = aes_add2(aes_mul2(make_float2(dry, dry), x), aes_mul2(make_float2(wet, wet), w));
+    o0 = aes_clip1(t.x);
+    o1 = aes_clip1(t.y);
+}
+
 // ---- named barriers and per-role register budgets (warp-specialised kernels) ---------------------
 #ifndef AES_CPU_EMU
 __device__ __forceinline__ void aes_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }

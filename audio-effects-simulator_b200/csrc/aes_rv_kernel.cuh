@@ -43,9 +43,14 @@ __device__ __forceinline__ void aes_static_for(F &&f)
 
 // CTA: 8 "comb" warps (threads 0..255: frames in registers, everything but the all-passes) and
 // 4 "walker" warps (threads 256..383: the two all-pass stages of tile i-1 -- two warps per channel --
-// and the TMA copies of tile i+2).  The register file is split with setmaxnreg: 104 + 32 registers.
+// and the TMA copies of tile i+2).  The register file is split with setmaxnreg: 104 + 32 registers
+// (384 threads x 80 at launch = 256 x 104 + 128 x 32).  Measured alternative (ncu r2j): eight walker
+// warps with 24 registers take the walkers off the critical path (comb warps wait 3.6 % instead of 10 %)
+// but the kernel as a whole gets slower, 268 against 293 Gsamples/s -- issue slots and the shared-memory
+// pipe are the budget, and twice the walker warps spend more of both.
 #define AESRV_NT 384
 #define AESRV_NW 128
+#define AESRV_NWC 64                // walkers per channel
 #define AESRV_REGS_COMB 104
 #define AESRV_REGS_WALK 32
 #define AESRV_NXS 4                 // tile buffers (8 KB each): TMA input -> comb sum -> all-pass output
@@ -53,7 +58,7 @@ __device__ __forceinline__ void aes_static_for(F &&f)
 #define AESRV_BAR_COMB 1            // the comb warps between their two phases (256 threads)
 #define AESRV_BAR_FULL 2            // +parity: comb sum of a tile is in its buffer (comb warps arrive, walkers wait)
 #define AESRV_BAR_DONE 4            // +parity: all-pass output of a tile is in its buffer (walkers arrive, comb warps wait)
-#define AESRV_BAR_CHAN 6            // +channel: the 64 walkers of one channel between the two all-passes
+#define AESRV_BAR_CHAN 6            // +channel: the walkers of one channel between the two all-passes
 
 // shared memory (floats): XS[4][2][T] | rings[smem_floats] | wt[8][8] | cst[2][8] | f64: wtot[32] | bst[2][8] |
 //                         LN[2][2][T+8] (feedback-delay shapes only) | 4 mbarriers
@@ -171,6 +176,8 @@ __device__ __forceinline__ void aesrv_walk_cols(float *s, float *rb, int pos, in
             for (int c = 0; c < NCOL; ++c) {
                 const int k = k0 + u;
                 if (k < KMAX) {
+                    // (carrying line' = g*line + (1-g*g)*x -- one dependent FFMA per row instead of two -- changed
+                    // nothing: the walkers wait on shared-memory loads, not on the FFMA chain; ncu r2i)
                     const float yo = fmaf(-g, xs[c][u], line[c]);
                     if ((L - 1) + k * L < T) {              // complete row: only idle lanes must not store
                         if (act[c]) p[c][k * L] = yo;
@@ -238,8 +245,9 @@ __device__ void aes_rv_body(const FastArgs &a)
         // =========================== walker warps ===========================
         aes_setmaxnreg_dec<AESRV_REGS_WALK>();
         const int wt_id = tid - AES_NT;                     // 0..127
-        const int ch = wt_id >> 6, j0 = wt_id & 63;
-        const bool issuer = wt_id == 0;
+        const int ch = wt_id / AESRV_NWC, j0 = wt_id % AESRV_NWC;
+        const bool issuer = wt_id == 32;                    // a channel's second warp walks one all-pass-2 column, its first
+                                                            // two: the TMA bookkeeping goes to a warp with time to spare
         const float apg = rs.a;
         constexpr int L1_0 = aesf_topo_ap(TOPO, 0, 0), L1_1 = aesf_topo_ap(TOPO, 1, 0);
         constexpr int L2_0 = aesf_topo_ap(TOPO, 0, 1), L2_1 = aesf_topo_ap(TOPO, 1, 1);
@@ -303,11 +311,11 @@ __device__ void aes_rv_body(const FastArgs &a)
                 aes_bar_sync(AESRV_BAR_FULL + par, AESRV_NT);
                 if (issuer && clip_staged && N - it * T >= 3 * T)
                     issue_tile((it + 2) * T, (q + 2) & (AESRV_NXS - 1), par);
-                if (ch == 0) aesrv_walk<L1_0, 64>(S, ring1, pos1, j0, apg);
-                else         aesrv_walk<L1_1, 64>(S, ring1, pos1, j0, apg);
-                aes_bar_sync(AESRV_BAR_CHAN + ch, 64);
-                if (ch == 0) aesrv_walk<L2_0, 64>(S, ring2, pos2, j0, apg);
-                else         aesrv_walk<L2_1, 64>(S, ring2, pos2, j0, apg);
+                if (ch == 0) aesrv_walk<L1_0, AESRV_NWC>(S, ring1, pos1, j0, apg);
+                else         aesrv_walk<L1_1, AESRV_NWC>(S, ring1, pos1, j0, apg);
+                aes_bar_sync(AESRV_BAR_CHAN + ch, AESRV_NWC);
+                if (ch == 0) aesrv_walk<L2_0, AESRV_NWC>(S, ring2, pos2, j0, apg);
+                else         aesrv_walk<L2_1, AESRV_NWC>(S, ring2, pos2, j0, apg);
                 aes_bar_arrive(AESRV_BAR_DONE + par, AESRV_NT);
                 pos1 = aesf_adv(pos1, apI1, apL1);
                 pos2 = aesf_adv(pos2, apI2, apL2);
@@ -378,19 +386,24 @@ __device__ void aes_rv_body(const FastArgs &a)
             for (int j = 0; j < FR; ++j) vprev[ch][j] = 0.0f;
 
         int par = 0;
-        for (int it = 0; it <= ntiles; ++it, par ^= 1) {
-            const bool has_cur = it < ntiles, has_prev = it > 0;
+        // One iteration: phases 1 and 2 of tile `it`, phase 3 of tile it-1.  FAST is the steady state -- a full,
+        // TMA-staged tile with a full tile behind it, past the delay's first lap, f32 stereo out, the usual
+        // one-warp carry reach -- where every flag below is a compile-time constant; the general
+        // instantiation serves the first tiles, the ragged tail, the drain iteration and odd formats.
+        auto tile_iter = [&](auto fast_tag, const int it) {
+            constexpr bool FAST = decltype(fast_tag)::value;
+            const bool has_cur = FAST || it < ntiles, has_prev = FAST || it > 0;
             const int n0 = it * T;
             const int rem = N - n0;
-            const int len = rem < T ? rem : T;
+            const int len = FAST ? T : (rem < T ? rem : T);
             float *const Sc = smem + q * 2 * T;             // this tile's buffer: staged input, then the comb sum
             float *const Sp = smem + ((q + AESRV_NXS - 1) & (AESRV_NXS - 1)) * 2 * T;    // tile i-1's: its wet signal
-            const bool staged = clip_staged && len == T;
+            const bool staged = FAST || (clip_staged && len == T);
             float v[2][FR];
 
             if (has_cur) {
                 float y[2][NC][FR], e[2][NC];
-                double bq_yz[2][FR], bq_e1[2], bq_e2[2];
+                [[maybe_unused]] double bq_yz[2][FR], bq_e1[2], bq_e2[2];
                 // ---------------- phase 1 ----------------
                 if (staged) {
                     aes_mbar_wait_parity(mbar + q, (phbits >> q) & 1u);
@@ -428,19 +441,20 @@ __device__ void aes_rv_body(const FastArgs &a)
                         } else {
                             aesf_read<FR, 1>(ch ? gl1 : gl0, da[ch], m, rg.len, line);
                         }
-                        if (n0 < rg.lag) {                                  // only the first tiles of a clip: zero history
+                        if (!FAST && n0 < rg.lag) {                         // only the first tiles of a clip: zero history
 #pragma unroll
                             for (int j = 0; j < FR; ++j)
                                 if (n0 + i0 + j < rg.lag) line[j] = 0.0f;
                         }
                         float nb[FR];
 #pragma unroll
-                        for (int j = 0; j < FR; ++j) {
-                            const float x = v[ch][j];
-                            nb[j] = fmaf(line[j], fb, x);
-                            v[ch][j] = aes_mix_clip(dry, x, wet, line[j]);
+                        for (int j = 0; j < FR; j += 2) {                   // two frames per packed instruction
+                            const float2 x = make_float2(v[ch][j], v[ch][j + 1]), ln = make_float2(line[j], line[j + 1]);
+                            const float2 n2 = aes_fma2(ln, make_float2(fb, fb), x);
+                            nb[j] = n2.x; nb[j + 1] = n2.y;
+                            aes_mix_clip2(dry, x, wet, ln, v[ch][j], v[ch][j + 1]);
                         }
-                        aes_stv<FR>((ch ? gl1 : gl0) + dw[ch], nb);
+                        aes_stg_v4((ch ? gl1 : gl0) + dw[ch], nb);
                     }
                 }
                 if constexpr (PRE == AESRV_PRE_BIQUAD) {
@@ -582,7 +596,7 @@ __device__ void aes_rv_body(const FastArgs &a)
                         constexpr int cc = decltype(icc)::value;
                         const float ex = __shfl_up_sync(0xffffffffu, e[ch][cc], 1);
                         float C;
-                        if (nxw == 1) {                                  // usual case: h^(32*FR) < 2^-32
+                        if (FAST || nxw == 1) {                          // usual case: h^(32*FR) < 2^-32
                             C = Cin[ch][cc];
                         } else {
                             C = u0 == 0 ? cst[par * 8 + ch * 4 + cc] : 0.0f;
@@ -592,11 +606,18 @@ __device__ void aes_rv_body(const FastArgs &a)
                         const float gs = rs.gs[ch][cc];
                         float nb[FR];
 #pragma unroll
-                        for (int j = 0; j < FR; ++j) {
-                            u = fmaf(h, u, y[ch][cc][j]);
-                            nb[j] = fmaf(gs, u, pre[ch][j]);            // buf[n] = x + g*(1-h)*u
-                            if (cc == 0) sum[ch][j] = y[ch][0][j];      // reverb.py:235-241: sum starts at 0
-                            else sum[ch][j] = __fadd_rn(sum[ch][j], y[ch][cc][j]);
+                        for (int j = 0; j < FR; j += 2) {                   // the one-pole is serial, the rest packs in pairs
+                            const float ua = fmaf(h, u, y[ch][cc][j]);
+                            u = fmaf(h, ua, y[ch][cc][j + 1]);
+                            const float2 n2 = aes_fma2(make_float2(gs, gs), make_float2(ua, u),
+                                                       make_float2(pre[ch][j], pre[ch][j + 1]));   // buf[n] = x + g*(1-h)*u
+                            nb[j] = n2.x; nb[j + 1] = n2.y;
+                            if (cc == 0) { sum[ch][j] = y[ch][0][j]; sum[ch][j + 1] = y[ch][0][j + 1]; }   // reverb.py:235-241: sum starts at 0
+                            else {
+                                const float2 s2 = aes_add2(make_float2(sum[ch][j], sum[ch][j + 1]),
+                                                           make_float2(y[ch][cc][j], y[ch][cc][j + 1]));
+                                sum[ch][j] = s2.x; sum[ch][j + 1] = s2.y;
+                            }
                         }
                         aesrv_comb_write<aesf_topo_comb(TOPO, ch, cc)>(
                             reinterpret_cast<char *>(rings + aesf_topo_comb_off(TOPO, ch, cc)), wb[ch][cc], nb);
@@ -619,8 +640,10 @@ __device__ void aes_rv_body(const FastArgs &a)
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch)
 #pragma unroll
-                    for (int j = 0; j < FR; ++j) o[ch][j] = aes_mix_clip(rdry, vprev[ch][j], rwet, o[ch][j]);
-                if (fast_out && rem >= 0) {                 // tile i-1 was a full one
+                    for (int j = 0; j < FR; j += 2)
+                        aes_mix_clip2(rdry, make_float2(vprev[ch][j], vprev[ch][j + 1]), rwet,
+                                      make_float2(o[ch][j], o[ch][j + 1]), o[ch][j], o[ch][j + 1]);
+                if (FAST || (fast_out && rem >= 0)) {       // tile i-1 was a full one
                     __stcs(reinterpret_cast<float4 *>(yp), make_float4(o[0][0], o[1][0], o[0][1], o[1][1]));
                     __stcs(reinterpret_cast<float4 *>(yp) + 1, make_float4(o[0][2], o[1][2], o[0][3], o[1][3]));
                 } else {
@@ -657,6 +680,18 @@ __device__ void aes_rv_body(const FastArgs &a)
                 }
                 q = (q + 1) & (AESRV_NXS - 1);
             }
+        };
+        // first tile the fast instantiation may take: behind tile 0 and behind the feedback delay's first lap
+        int it_fast = 1;
+        if constexpr (PRE == AESRV_PRE_DELAY) {
+            const int lmax = a.st[0].ring[0][0].lag > a.st[0].ring[1][0].lag ? a.st[0].ring[0][0].lag : a.st[0].ring[1][0].lag;
+            it_fast = (lmax + T - 1) / T;
+        }
+        const bool fast_clip = clip_staged && fast_out && nxw == 1;
+        const int nfull = N / T;                            // tiles 0 .. nfull-1 are full
+        for (int it = 0; it <= ntiles; ++it, par ^= 1) {
+            if (fast_clip && it >= it_fast && it < nfull) tile_iter(std::true_type{}, it);
+            else tile_iter(std::false_type{}, it);
         }
         if (PRE == AESRV_PRE_BIQUAD && a.state_out != nullptr) {
             // carried scalars of the biquad (stage 0) at the end of the clip: written by the last tile into the
