@@ -47,7 +47,12 @@ __device__ __forceinline__ void aes_static_for(F &&f)
 // (384 threads x 80 at launch = 256 x 104 + 128 x 32).  Measured alternative (ncu r2j): eight walker
 // warps with 24 registers take the walkers off the critical path (comb warps wait 3.6 % instead of 10 %)
 // but the kernel as a whole gets slower, 268 against 293 Gsamples/s -- issue slots and the shared-memory
-// pipe are the budget, and twice the walker warps spend more of both.
+// pipe are the budget, and twice the walker warps spend more of both.  Also measured: walks vectorised
+// over adjacent columns (64- / 128-bit accesses for even ring lengths, r2k): fewer instructions, but the
+// work concentrates in a quarter of the threads and the walkers' critical path grows, 271;  a 96 + 48
+// register split with four interleaved columns per walker (r2l): the walkers get 30 % faster and the bare
+// reverb gains 1 % (307), but the feedback-delay shape spills in the comb warps, 265;  four columns in 32
+// registers (r2m): 286.
 #define AESRV_NT 384
 #define AESRV_NW 128
 #define AESRV_NWC 64                // walkers per channel
@@ -363,10 +368,13 @@ __device__ void aes_rv_body(const FastArgs &a)
             constexpr int ch = decltype(ic)::value / NC, cc = decltype(ic)::value % NC;
             wb[ch][cc] = tid * AesrvComb<aesf_topo_comb(TOPO, ch, cc)>::SB;
         });
-        int dw[2] = { 0, 0 }, da[2] = { 0, 0 };             // feedback-delay line: write slot, aligned read base
+        int dw[2] = { 0, 0 };                               // feedback-delay line: write slot of this thread's frames
         if constexpr (PRE == AESRV_PRE_DELAY) {
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) aesf_line_init<FR>(a.st[0].ring[ch][0], i0, dw[ch], da[ch]);
+            for (int ch = 0; ch < 2; ++ch) {
+                int a0;
+                aesf_line_init<FR>(a.st[0].ring[ch][0], i0, dw[ch], a0);
+            }
         }
         int pw[2] = { 0, 0 }, pa[2] = { 0, 0 };             // reverb pre-delay line
         if constexpr (PM != 0) {
@@ -439,7 +447,9 @@ __device__ void aes_rv_body(const FastArgs &a)
                                 for (int j = 0; j < FR; ++j) line[j] = sp[j];
                             }
                         } else {
-                            aesf_read<FR, 1>(ch ? gl1 : gl0, da[ch], m, rg.len, line);
+                            int a0 = dw[ch] - ((rg.lag + 3) & ~3);          // aligned read base: lag4 behind the write slot
+                            if (a0 < 0) a0 += rg.len;
+                            aesf_read<FR, 1>(ch ? gl1 : gl0, a0, m, rg.len, line);
                         }
                         if (!FAST && n0 < rg.lag) {                         // only the first tiles of a clip: zero history
 #pragma unroll
@@ -675,7 +685,6 @@ __device__ void aes_rv_body(const FastArgs &a)
                     for (int ch = 0; ch < 2; ++ch) {
                         const FRing rg = a.st[0].ring[ch][0];
                         dw[ch] = aesf_adv(dw[ch], rg.tinc, rg.len);
-                        da[ch] = aesf_adv(da[ch], rg.tinc, rg.len);
                     }
                 }
                 q = (q + 1) & (AESRV_NXS - 1);
