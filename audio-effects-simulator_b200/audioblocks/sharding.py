@@ -59,6 +59,27 @@ def gather_clips(y_local, total: int, dst: int | None = 0, group=None):
     return full.view(orig_dtype) if as_bytes else full
 
 
+def all_gather_pcm(y_local, out=None, group=None):
+    """Gather equal-sized int16 PCM shards (n_local, frames, 2) of every rank into one preallocated
+    (world * n_local, frames, 2) tensor with a single all_gather_into_tensor: no padding, no list of
+    per-rank tensors, no concatenation.  NCCL has no 16-bit integer type, so the PCM travels as bytes.
+    `out` may be passed to reuse the destination (bench.py double-buffers it to overlap the gather of
+    one chunk with the compute of the next).  Shards must have the same shape on every rank
+    (`shard_range` of a batch that the world size divides, or a fixed chunk size)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    if y_local.dtype != torch.int16:
+        raise TypeError("all_gather_pcm gathers int16 PCM (quantise on the device first: out_fmt I16)")
+    y_local = y_local.contiguous()
+    if out is None:
+        out = torch.empty((world * y_local.shape[0],) + tuple(y_local.shape[1:]), dtype=torch.int16, device=y_local.device)
+    elif out.dtype != torch.int16 or out.numel() != world * y_local.numel() or not out.is_contiguous():
+        raise ValueError("out must be a contiguous int16 tensor of world x the local shard")
+    dist.all_gather_into_tensor(out.view(torch.uint8).reshape(-1), y_local.view(torch.uint8).reshape(-1), group=group)
+    return out
+
+
 def max_over_ranks(seconds: float, device=None, group=None) -> float:
     """Timing reduction used by bench.py: the slowest rank defines the step."""
     import torch

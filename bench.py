@@ -4,15 +4,20 @@
     python bench.py --gpus N --steps K --warmup W            # B200 arm (this repo)
     python bench.py --impl reference --gpus N --steps K ...  # reference arm: the CPU algorithm on host cores
 
-A "step" is one pass of the fused preset chain over one batch of synthetic 48 kHz
-stereo clips that is already resident in HBM (`value`), and the same batch pushed
-through the reference-facing host-buffer call with H2D/D2H inside the timed region
-(`e2e`).  1 sample = one float32 value of one channel of output (SURVEY 8d);
-algorithmic traffic is 8 bytes per sample (read once, write once).
-
-Under torchrun (N>1) every rank processes its own shard of clips (no data-path
-collective: clips are independent), times it with CUDA events, and rank 0 reports
-total samples / max-over-ranks time ("scaling": "weak").
+Default workload = BASELINE configs[4]: 8192 synthetic 10 s 48 kHz stereo clips, batch-sharded
+over the N ranks (STRONG scaling: 8192 / N clips per GPU).  A "step" is one pass of the fused
+'Rain Delay' preset chain over the rank's shard, already resident in HBM (`value`, `roofline`).
+The same line carries
+  * `sweep`: every preset of app.py:41-71 over the same shard, one at a time and all six at once
+    on separate streams (per-preset and aggregate Msamples/s);
+  * `e2e`: a bounded sample of the shard pushed through the reference-facing host-buffer call with
+    H2D/D2H inside the timed region, next to a copy-only ceiling of the same bytes;
+  * `gather` (N > 1): the int16 results of a bounded sample gathered over NCCL, alone and
+    overlapped with the next chunk's compute;
+  * `cpu_baseline` (N = 1): the unmodified reference (numba) on the box's host cores, and the C port.
+1 sample = one float32 value of one channel of output; algorithmic traffic is 8 bytes
+per sample (read once, write once).  No data-path collective: clips are independent.
+`--clips K` switches to K clips per GPU (weak scaling) for side experiments.
 """
 from __future__ import annotations
 
@@ -41,11 +46,17 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--preset", default="Rain Delay")
-    ap.add_argument("--clips", type=int, default=1184, help="clips per GPU (default 8 per SM: whole clips for every resident CTA)")
+    ap.add_argument("--total-clips", type=int, default=8192, help="clips in the whole job, sharded over the ranks (BASELINE configs[4])")
+    ap.add_argument("--clips", type=int, default=0, help="clips PER GPU instead (weak scaling; side experiments)")
     ap.add_argument("--seconds", type=float, default=10.0, help="clip length")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-clips", type=int, default=1184, help="bounded sample of the shard for the end-to-end / copy-ceiling legs")
+    ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--sweep-steps", type=int, default=2)
+    ap.add_argument("--no-gather", action="store_true")
+    ap.add_argument("--gather-clips", type=int, default=512, help="clips per rank in the NCCL gather leg")
     ap.add_argument("--cpu-clips", type=int, default=0, help="clips in the CPU baseline sample (0 = auto)")
     return ap.parse_args()
 
@@ -131,11 +142,28 @@ def chain_config(name):
     return EXTRA_CHAINS[name]
 
 
-def workload(args):
-    return {"workload": f"'{args.preset}' preset chain (app.py:41-71) on {args.clips} synthetic "
-                        f"{args.seconds:g} s 48 kHz stereo float32 clips per GPU (BASELINE configs[4]-style shard)",
-            "preset": args.preset, "clips_per_gpu": args.clips, "frames_per_clip": int(args.seconds * FS),
-            "sample_rate": FS, "l2": "inputs larger than L2 (no flush needed)", "parallelism": "clip-sharded"}
+def shard_of(args, rank, world):
+    """(clips of this rank, clips of the whole job, scaling mode)."""
+    if args.clips > 0:
+        return args.clips, args.clips * world, "weak"
+    from audioblocks.sharding import shard_range
+    lo, hi = shard_range(args.total_clips, rank, world)
+    return hi - lo, args.total_clips, "strong"
+
+
+def workload(args, world=1):
+    n_frames = int(args.seconds * FS)
+    if args.clips > 0:
+        what = f"{args.clips} synthetic {args.seconds:g} s 48 kHz stereo float32 clips per GPU (weak scaling; side experiment)"
+        return {"workload": f"'{args.preset}' preset chain (app.py:41-71) on {what}", "preset": args.preset,
+                "clips_per_gpu": args.clips, "frames_per_clip": n_frames, "sample_rate": FS,
+                "l2": "inputs larger than L2 (no flush needed)", "parallelism": "clip-sharded"}
+    return {"workload": f"BASELINE configs[4]: {args.total_clips} synthetic {args.seconds:g} s 48 kHz stereo float32 clips, "
+                        f"batch-sharded over the GPUs (strong scaling); headline = '{args.preset}' preset chain "
+                        f"(app.py:41-71), `sweep` = every preset over the same shard",
+            "preset": args.preset, "total_clips": args.total_clips, "clips_per_gpu": args.total_clips // max(1, world),
+            "frames_per_clip": n_frames, "sample_rate": FS, "l2": "inputs larger than L2 (no flush needed)",
+            "parallelism": f"clip-sharded x{world}"}
 
 
 # ------------------------------------------------------------------ reference arm / CPU baseline
@@ -166,33 +194,62 @@ def cpu_run(preset, n_clips, n_frames, threads, reps=1):
     return x.size / best / 1e6, best
 
 
+def reference_pool(preset, n_frames, cores):
+    """The unmodified reference package on `cores` worker processes (baseline/ref_runner.py), or None when
+    it is not installed under baseline/_ref or the chain uses a block the reference does not have."""
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    import ref_runner
+    cfg = chain_config(preset)
+    if not ref_runner.available() or not ref_runner.supports(cfg):
+        return None
+    try:
+        return ref_runner.Pool(cfg, FS, n_frames, cores)
+    except Exception as e:                                  # numba missing, worker crash: fall back to the port
+        print(f"bench.py: reference package unavailable ({e}); timing the C port", file=sys.stderr)
+        return None
+
+
 def reference_arm(args):
-    """The reference's own algorithm on the box's host cores.  The reference is pure
-    Python+numba and cannot travel to the GPU box, so this times the C port under
-    oracle/ (kind "port"), one clip per thread like the reference's single-threaded
-    kernels, on all host threads."""
+    """The reference's own implementation on the box's host cores: the UNMODIFIED numba package from
+    baseline/_ref, one clip per worker process like its single-threaded kernels (kind "reference");
+    the C port under oracle/ when the package is absent or the chain has blocks it lacks (kind "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", "1"))
     cores = os.cpu_count() or 1
     n_frames = int(args.seconds * FS)
-    n_clips = args.cpu_clips or max(cores, min(20 * cores, 512))      # same sample as the B200 arm's cpu_baseline
-    cpu_run(args.preset, cores, n_frames, cores)
+    pool = reference_pool(args.preset, n_frames, cores)
     times = []
-    for _ in range(args.warmup):
-        cpu_run(args.preset, n_clips, n_frames, cores)
-    for _ in range(args.steps):
-        _, dt = cpu_run(args.preset, n_clips, n_frames, cores)
-        times.append(dt)
+    if pool is not None:
+        kind, per_worker = "reference", 4                   # ~0.1 s per 10 s clip and core: ~0.4 s per step
+        n_clips = per_worker * cores
+        for _ in range(max(1, args.warmup)):
+            pool.run(1)
+        for _ in range(args.steps):
+            _, dt = pool.run(per_worker)
+            times.append(dt)
+        pool.close()
+        sample = f"{n_clips} clips x {args.seconds:g} s per step, {cores} worker processes (unmodified reference, numba)"
+    else:
+        kind = "port"
+        n_clips = args.cpu_clips or max(cores, min(20 * cores, 512))
+        cpu_run(args.preset, cores, n_frames, cores)
+        for _ in range(args.warmup):
+            cpu_run(args.preset, n_clips, n_frames, cores)
+        for _ in range(args.steps):
+            _, dt = cpu_run(args.preset, n_clips, n_frames, cores)
+            times.append(dt)
+        sample = f"{n_clips} clips x {args.seconds:g} s per step on {cores} threads (C port of the reference, one clip per thread)"
     total = sum(times)
     value = n_clips * n_frames * 2 * len(times) / total / 1e6
-    sample = f"{n_clips} clips x {args.seconds:g} s per step on {cores} threads (one clip per thread)"
+    _, _, scaling = shard_of(args, 0, world) if args.clips > 0 else (0, 0, "strong")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, len(times)),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": workload(args),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload(args, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -278,6 +335,185 @@ def synth_device(torch, n_clips, n_frames, first_clip, device):
     return x
 
 
+PRESET_ORDER = ("Robot Voice", "Cathedral", "Slapback Echo", "Clean Noise Removal", "Guitar Filter", "Rain Delay")
+
+
+def timed_steps(torch, stream, barrier, fn, steps):
+    """K launches of fn() on `stream`, one CUDA-event pair per step; returns (total ms, per-step ms)."""
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    barrier()
+    ev[0].record(stream)
+    for k in range(steps):
+        fn()
+        ev[k + 1].record(stream)
+    barrier()
+    return ev[0].elapsed_time(ev[-1]), [ev[k].elapsed_time(ev[k + 1]) for k in range(steps)]
+
+
+def max_ms(torch, dist, world, dev, ms):
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sweep_leg(args, torch, dist, _native, file_chain, x, y, B, n_frames, world, dev, barrier, peak):
+    """Every preset of app.py:41-71 over this rank's shard (BASELINE configs[4]): each one alone, then all six
+    at once on separate streams so that the partial last wave of one preset's launch is filled by the others."""
+    import synth
+    res, pipes, keep = {}, {}, []
+    stream = torch.cuda.current_stream()
+    tmp = None
+    samples_rank = B * n_frames * 2
+    for name in PRESET_ORDER:
+        chain = file_chain(synth.PRESETS[name], FS, channels_in=2)
+        pipe, plans = chain.device_pipeline(n_frames)
+        keep.append(plans)
+        pipes[name] = pipe
+        if pipe.n_segments > 1 and tmp is None:
+            tmp = torch.empty_like(y)
+        tp = tmp.data_ptr() if tmp is not None else y.data_ptr()
+        run = lambda pipe=pipe, tp=tp: pipe(x.data_ptr(), y.data_ptr(), tp, B, stream.cuda_stream)
+        run()                                                   # warm-up (plans allocate their scratch here)
+        tot, _ = timed_steps(torch, stream, barrier, run, args.sweep_steps)
+        ms = max_ms(torch, dist, world, dev, tot) / args.sweep_steps
+        v = world * samples_rank / (ms * 1e-3) / 1e6
+        res[name] = {"ms": ms, "value": v, "frac_of_hbm_roofline": (v / world) * 8e6 / 1e9 / peak}
+    # all six concurrently, chunked so that six output chunks fit beside the shard
+    chunk = min(B, 1184)
+    streams = [torch.cuda.Stream(device=dev) for _ in PRESET_ORDER]
+    outs = [torch.empty((chunk, n_frames, 2), dtype=torch.float32, device=dev) for _ in PRESET_ORDER]
+    tmps = {n: torch.empty((chunk, n_frames, 2), dtype=torch.float32, device=dev)
+            for n in PRESET_ORDER if pipes[n].n_segments > 1}
+    fsz = n_frames * 2 * 4
+
+    def all_at_once():
+        for b0 in range(0, B, chunk):
+            nb = min(chunk, B - b0)
+            for k, name in enumerate(PRESET_ORDER):
+                tp = tmps[name].data_ptr() if name in tmps else outs[k].data_ptr()
+                pipes[name](x.data_ptr() + b0 * fsz, outs[k].data_ptr(), tp, nb, streams[k].cuda_stream)
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    all_at_once()
+    barrier()
+    e0.record(stream)
+    for st in streams:
+        st.wait_stream(stream)
+    for _ in range(args.sweep_steps):
+        all_at_once()
+    for st in streams:
+        stream.wait_stream(st)
+    e1.record(stream)
+    barrier()
+    ms = max_ms(torch, dist, world, dev, e0.elapsed_time(e1)) / args.sweep_steps
+    seq_ms = sum(r["ms"] for r in res.values())
+    out = {"presets": res, "steps": args.sweep_steps,
+           "one_at_a_time": {"ms": seq_ms, "value": 6 * world * samples_rank / (seq_ms * 1e-3) / 1e6},
+           "six_streams": {"ms": ms, "value": 6 * world * samples_rank / (ms * 1e-3) / 1e6, "chunk_clips": chunk},
+           "unit": UNIT, "samples": "6 presets x the whole job's clips x frames x 2 channels per pass"}
+    for plans in keep:
+        for p in plans:
+            p.close()
+    del outs, tmps, tmp
+    return out
+
+
+def copy_ceiling(torch, dist, world, dev, barrier, xh, yh, reps):
+    """What the PCIe path alone delivers: H2D of `xh` and D2H into `yh` (pinned, same bytes as the end-to-end
+    leg), both directions at once on two streams, all ranks at the same time, no kernel."""
+    xd = torch.empty(xh.shape, dtype=torch.from_numpy(xh[:1]).dtype, device=dev)
+    yd = torch.empty(yh.shape, dtype=torch.from_numpy(yh[:1]).dtype, device=dev)
+    tx, ty = torch.from_numpy(xh), torch.from_numpy(yh)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    def once():
+        with torch.cuda.stream(s1):
+            xd.copy_(tx, non_blocking=True)
+        with torch.cuda.stream(s2):
+            ty.copy_(yd, non_blocking=True)
+    once()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        once()
+    torch.cuda.synchronize()
+    dt = max_ms(torch, dist, world, dev, (time.perf_counter() - t0) * 1e3) * 1e-3 / reps
+    return {"h2d_gbs_per_gpu": xh.nbytes / dt / 1e9, "d2h_gbs_per_gpu": yh.nbytes / dt / 1e9, "seconds": dt,
+            "pinned": bool(tx.is_pinned() and ty.is_pinned())}
+
+
+def gather_leg(args, torch, dist, _native, plan, x, B, n_frames, rank, world, dev, barrier):
+    """NCCL over NVLink, used only to gather results (north_star): int16 PCM of a bounded sample per rank,
+    all_gather_into_tensor into a preallocated buffer -- alone, and with chunk k's gather on a side stream
+    while chunk k+1 is computed."""
+    from audioblocks.sharding import all_gather_pcm
+    Bg = min(B, args.gather_clips)
+    t = torch.tensor([Bg], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    Bg = int(t.item())
+    nchunk = 4
+    per = max(1, Bg // nchunk)
+    Bg = per * nchunk
+    stream = torch.cuda.current_stream()
+    comm = torch.cuda.Stream(device=dev)
+    yq = [torch.empty((per, n_frames, 2), dtype=torch.int16, device=dev) for _ in range(2)]
+    full = [torch.empty((world * per, n_frames, 2), dtype=torch.int16, device=dev) for _ in range(2)]
+    fsz = n_frames * 2 * 4
+
+    def compute(k):
+        plan.run_device(x.data_ptr() + k * per * fsz, _native.FMT_F32_STEREO, yq[k & 1].data_ptr(), _native.FMT_I16_STEREO,
+                        per, n_frames, stream.cuda_stream)
+
+    def gather(k, st):
+        with torch.cuda.stream(st):
+            all_gather_pcm(yq[k & 1], out=full[k & 1])
+
+    for k in range(2):                                      # warm-up: communicator, plan scratch
+        compute(k)
+        gather(k, stream)
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    # (1) gather alone
+    barrier()
+    e[0].record(stream)
+    for k in range(nchunk):
+        gather(k, stream)
+    e[1].record(stream)
+    barrier()
+    g_ms = max_ms(torch, dist, world, dev, e[0].elapsed_time(e[1]))
+    # (2) compute alone, (3) compute of chunk k+1 overlapped with the gather of chunk k
+    barrier()
+    e[0].record(stream)
+    for k in range(nchunk):
+        compute(k)
+    e[1].record(stream)
+    barrier()
+    c_ms = max_ms(torch, dist, world, dev, e[0].elapsed_time(e[1]))
+    done = [torch.cuda.Event() for _ in range(nchunk)]
+    freed = [torch.cuda.Event() for _ in range(nchunk)]
+    barrier()
+    e[2].record(stream)
+    for k in range(nchunk):
+        if k >= 2:
+            stream.wait_event(freed[k - 2])                 # the gather of chunk k-2 has read this buffer
+        compute(k)
+        done[k].record(stream)
+        comm.wait_event(done[k])
+        gather(k, comm)
+        freed[k].record(comm)
+    stream.wait_stream(comm)
+    e[3].record(stream)
+    barrier()
+    o_ms = max_ms(torch, dist, world, dev, e[2].elapsed_time(e[3]))
+    recv = (world - 1) * Bg * n_frames * 2 * 2              # bytes every rank receives from its peers
+    same = bool(torch.equal(full[(nchunk - 1) & 1][rank * per:(rank + 1) * per], yq[(nchunk - 1) & 1]))
+    return {"clips_per_rank": Bg, "chunks": nchunk, "dtype": "int16 PCM (as bytes)", "collective": "all_gather_into_tensor",
+            "bytes_received_per_rank": recv, "ms": g_ms, "gbs": recv / (g_ms * 1e-3) / 1e9,
+            "busbw_gbs": recv / (g_ms * 1e-3) / 1e9,   # all-gather: bus bandwidth = received bytes / time
+            "compute_only_ms": c_ms, "compute_plus_gather_overlapped_ms": o_ms,
+            "gather_hidden_frac": max(0.0, min(1.0, (c_ms + g_ms - o_ms) / g_ms)) if g_ms > 0 else None,
+            "own_shard_round_trips": same}
+
+
 def b200_arm(args):
     import numpy as np
     import torch
@@ -310,9 +546,12 @@ def b200_arm(args):
         clocks.start()              # nvidia-smi takes a while to start: launch it before the data is built
 
     if args.preset == "c4-convreverb":
+        if args.clips <= 0:
+            args.clips = 256
         return conv_arm(args, torch, dist, _native, rank, world, local, dev)
     n_frames = int(args.seconds * FS)
-    B = args.clips
+    B, total_clips, scaling = shard_of(args, rank, world)
+    first_clip = rank * B if args.clips > 0 else __import__("audioblocks.sharding", fromlist=["shard_range"]).shard_range(args.total_clips, rank, world)[0]
     cfg = chain_config(args.preset)
     chain = file_chain(cfg, FS, channels_in=2)            # build@1024 + warm-up, as engine.py:86-99
     pipe, plans = chain.device_pipeline(n_frames)         # re-prepared at the file's frame count
@@ -321,7 +560,7 @@ def b200_arm(args):
     info = plan.info() if fused else {"tile_frames": None, "smem_bytes": None, "ctas_per_sm": None,
                                       "kernel": f"{pipe.n_segments} segments (whole-clip FFT block between fused runs)"}
 
-    x = synth_device(torch, B, n_frames, rank * B, dev)
+    x = synth_device(torch, B, n_frames, first_clip, dev)
     y = torch.empty_like(x)
     tmp = torch.empty_like(x) if pipe.n_segments > 1 else y
     stream = torch.cuda.current_stream()
@@ -341,7 +580,7 @@ def b200_arm(args):
     barrier()
     launches0 = L.aes_launch_count()
     # timing rule: inputs larger than L2, or L2 flushed between timed iterations.  The default workload
-    # (9 GB per step) is the former; a side workload that fits the 126 MB L2 (one 60 s clip: 46 MB)
+    # (tens of GB per step) is the former; a side workload that fits the 126 MB L2 (one 60 s clip: 46 MB)
     # gets a 256 MB buffer written before every timed step, and the steps are timed one by one.
     l2_fits = B * n_frames * 16 < 2 * 126e6
     if l2_fits:
@@ -355,50 +594,61 @@ def b200_arm(args):
             step()
             evb[k].record(stream)
         barrier()
-        launches = L.aes_launch_count() - launches0
         per_launch_ms = [eva[k].elapsed_time(evb[k]) for k in range(args.steps)]
         total_ms = sum(per_launch_ms)
         del flush
     else:
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-        barrier()
-        ev[0].record(stream)
-        for k in range(args.steps):
-            step()
-            ev[k + 1].record(stream)
-        barrier()
-        launches = L.aes_launch_count() - launches0
-        total_ms = ev[0].elapsed_time(ev[-1])
-        per_launch_ms = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+        total_ms, per_launch_ms = timed_steps(torch, stream, barrier, step, args.steps)
+    launches = L.aes_launch_count() - launches0
     clk = clocks.stop(t_load0, time.time()) if rank == 0 else None
+    total_ms = max_ms(torch, dist, world, dev, total_ms)
 
-    # parity spot check of the timed buffers (first clip of this rank) against the oracle
+    # parity of the timed buffers against the oracle: the FIRST and the LAST clip of this rank's shard, whole clips
     parity = None
     if rank == 0 and not args.no_cpu:
         from oracle import oracle as orc
-        n_chk = min(n_frames, 96000)
-        xs = x[0, :n_chk].cpu().numpy()
-        want = orc.run_file_path(cfg, np.ascontiguousarray(xs), FS)
-        got = y[0, :n_chk].cpu().numpy()
-        mx, snr = synth.err_stats(got, want)
-        parity = {"max_abs_err": mx, "snr_db": snr if np.isfinite(snr) else None, "frames": n_chk}
+        worst, wsnr = 0.0, float("inf")
+        which = sorted({0, B - 1})
+        for b in which:
+            xs = np.ascontiguousarray(x[b].cpu().numpy())
+            want = orc.run_file_path(cfg, xs, FS)
+            mx, snr = synth.err_stats(y[b].cpu().numpy(), want)
+            worst, wsnr = max(worst, mx), min(wsnr, snr)
+        parity = {"max_abs_err": worst, "snr_db": wsnr if np.isfinite(wsnr) else None, "clips": which, "frames": n_frames,
+                  "bar": "max-abs 1e-5 of full scale, SNR 100 dB (north_star)"}
+
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+
+    # ---- every preset over the same shard
+    sweep = None
+    if not args.no_sweep and args.clips <= 0 and args.preset == "Rain Delay":
+        sweep = sweep_leg(args, torch, dist, _native, file_chain, x, y, B, n_frames, world, dev, barrier, peak)
+
+    # ---- results gathered over NCCL (N > 1 only)
+    gather = None
+    if world > 1 and fused and not args.no_gather:
+        gather = gather_leg(args, torch, dist, _native, plan, x, B, n_frames, rank, world, dev, barrier)
 
     # ---- end to end through the host-buffer call (pinned host memory, H2D + D2H timed)
     e2e = None
+    Be = min(B, args.e2e_clips)
     if not args.no_e2e and not fused:
-        xh = _native.pinned_empty((B, n_frames, 2), np.float32)
-        yh = np.empty((B, n_frames, 2), np.float32)
-        torch.from_numpy(xh).copy_(x)
+        xh = _native.pinned_empty((Be, n_frames, 2), np.float32)
+        yh = np.empty((Be, n_frames, 2), np.float32)
+        torch.from_numpy(xh).copy_(x[:Be])
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             file_chain(cfg, FS, channels_in=2).process_batch(xh, yh)
         e2e_s = time.perf_counter() - t0
-        e2e = {"value": world * B * n_frames * 2 * args.e2e_steps / e2e_s / 1e6, "unit": UNIT,
+        e2e = {"value": world * Be * n_frames * 2 * args.e2e_steps / e2e_s / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": int(xh.nbytes), "d2h_bytes_per_step": int(yh.nbytes), "steps": args.e2e_steps,
                "api": "EffectsChain.process_batch (host buffers, one H2D/D2H per chain segment)"}
     elif not args.no_e2e:
-        Be = B
         xh = _native.pinned_empty((Be, n_frames, 2), np.float32)
         yh = _native.pinned_empty((Be, n_frames, 2), np.float32)
         torch.from_numpy(xh).copy_(x[:Be])
@@ -410,16 +660,20 @@ def b200_arm(args):
         for _ in range(args.e2e_steps):
             plan.run_host(xh, fmt, yh, fmt, Be, n_frames)
         torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
+        e2e_s = max_ms(torch, dist, world, dev, (time.perf_counter() - t0) * 1e3) * 1e-3
         e2e_ok = bool(np.array_equal(yh[0, :4096], y[0, :4096].cpu().numpy()))
-        t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * Be * n_frames * 2 * args.e2e_steps / float(t.item()) / 1e6, "unit": UNIT,
+        e2e = {"value": world * Be * n_frames * 2 * args.e2e_steps / e2e_s / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": int(xh.nbytes), "d2h_bytes_per_step": int(yh.nbytes),
                "steps": args.e2e_steps, "matches_device_path": e2e_ok,
+               "sample": f"{Be} clips of the shard per GPU and step (bounded: pinned host memory)",
                "host_cpus_bound_to_gpu_node": len(numa_cpus) if numa_cpus else None,
                "api": "EffectsChain.prepare_batch(...).run_host -> aes_chain_process_host (pinned host buffers)"}
+        ceil = copy_ceiling(torch, dist, world, dev, barrier, xh, yh, args.e2e_steps)
+        ceil["value"] = world * Be * n_frames * 2 / ceil["seconds"] / 1e6
+        ceil["unit"] = UNIT
+        ceil["what"] = "cudaMemcpyAsync H2D + D2H of the same pinned bytes, both directions at once, all ranks at once, no kernel"
+        e2e["copy_ceiling"] = ceil
+        e2e["frac_of_copy_ceiling"] = e2e["value"] / ceil["value"]
         # the same call fed like the WAV-file route feeds it (engine.py:78-84,104-105): int16 stereo
         # PCM in (down-mixed on the device), int16 stereo PCM out -- half the PCIe bytes per frame
         xq = _native.pinned_empty((Be, n_frames, 2), np.int16)
@@ -431,30 +685,23 @@ def b200_arm(args):
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
             plan.run_host(xq, _native.FMT_I16_DOWNMIX, yq, _native.FMT_I16_STEREO, Be, n_frames)
-        t = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        pcm_s = float(t.item())
-        e2e["pcm16_file_route"] = {"value": world * Be * n_frames * 2 * args.e2e_steps / pcm_s / 1e6, "unit": UNIT,
-                                   "h2d_bytes_per_step": int(xq.nbytes), "d2h_bytes_per_step": int(yq.nbytes)}
+        pcm_s = max_ms(torch, dist, world, dev, (time.perf_counter() - t0) * 1e3) * 1e-3
+        pceil = copy_ceiling(torch, dist, world, dev, barrier, xq, yq, args.e2e_steps)
+        pv = world * Be * n_frames * 2 * args.e2e_steps / pcm_s / 1e6
+        pcv = world * Be * n_frames * 2 / pceil["seconds"] / 1e6
+        e2e["pcm16_file_route"] = {"value": pv, "unit": UNIT, "h2d_bytes_per_step": int(xq.nbytes), "d2h_bytes_per_step": int(yq.nbytes),
+                                   "copy_ceiling": {"value": pcv, "h2d_gbs_per_gpu": pceil["h2d_gbs_per_gpu"], "d2h_gbs_per_gpu": pceil["d2h_gbs_per_gpu"]},
+                                   "frac_of_copy_ceiling": pv / pcv}
         del xh, yh, xq, yq
 
-    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
-
     if rank == 0:
-        samples_per_step = world * B * n_frames * 2
+        samples_per_step = world * B * n_frames * 2 if scaling == "weak" else total_clips * n_frames * 2
         value = samples_per_step * args.steps / (total_ms * 1e-3) / 1e6
-        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-        if os.path.exists(peaks_path):
-            peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         k_ms = sum(per_launch_ms) / len(per_launch_ms)
         achieved = B * n_frames * 2 * 8 / (k_ms * 1e-3) / 1e9
-        traffic, traffic_src = NCU_DRAM_TRAFFIC.get((args.preset, B, n_frames), (None, None))
+        traffic, traffic_src = NCU_DRAM_TRAFFIC.get((args.preset, n_frames), (None, None))
+        if traffic is not None:
+            traffic = traffic * B                            # recorded per clip: the capture ran another batch size
         kernel = info["kernel"]
         if args.preset == "c2-biquad-cascade" and info["ctas_per_sm"] and not os.environ.get("AES_NO_SCAN") and \
                 B < info["ctas_per_sm"] * torch.cuda.get_device_properties(0).multi_processor_count:
@@ -464,9 +711,9 @@ def b200_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {**workload(args), "tile_frames": info["tile_frames"], "smem_bytes_per_cta": info["smem_bytes"],
-                       "ctas_per_sm": info["ctas_per_sm"],
+            "scaling": scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {**workload(args, world), "clips_this_rank": B, "tile_frames": info["tile_frames"],
+                       "smem_bytes_per_cta": info["smem_bytes"], "ctas_per_sm": info["ctas_per_sm"],
                        **({"l2": "fits L2: a 256 MB buffer is written before every timed step, steps timed one by one"}
                           if l2_fits else {})},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -476,14 +723,29 @@ def b200_arm(args):
                          "launch_ms": k_ms},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clk, "parity": parity,
         }
+        if sweep is not None:
+            line["sweep"] = sweep
+        if gather is not None:
+            line["gather"] = gather
         if not args.no_cpu and world == 1:          # the CPU baseline is reported at N = 1 only
             cores = os.cpu_count() or 1
             n_cpu = args.cpu_clips or max(cores, min(20 * cores, 512))     # ~20 s of CPU work on all threads
             v, dt = cpu_run(args.preset, n_cpu, n_frames, cores, reps=2)
             numpy_fft = any(c["type"] in ("spectral", "convreverb") for c in cfg)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1 if numpy_fft else cores, "kind": "port",
-                                    "sample": (f"2 clips x {args.seconds:g} s, 1 thread (numpy FFT block), {dt:.2f} s" if numpy_fft
-                                               else f"{n_cpu} clips x {args.seconds:g} s, {cores} threads, {dt:.2f} s")}
+            port = {"value": v, "unit": UNIT, "cores": 1 if numpy_fft else cores, "kind": "port",
+                    "sample": (f"2 clips x {args.seconds:g} s, 1 thread (numpy FFT block), {dt:.2f} s" if numpy_fft
+                               else f"{n_cpu} clips x {args.seconds:g} s, {cores} threads, {dt:.2f} s")}
+            line["cpu_baseline"] = port
+            pool = reference_pool(args.preset, n_frames, cores)
+            if pool is not None:                    # the unmodified reference (numba), one clip per worker process
+                pool.run(1)
+                per_worker = 8
+                rv, rdt = pool.run(per_worker)
+                pool.close()
+                line["cpu_baseline"] = {"value": rv, "unit": UNIT, "cores": cores, "kind": "reference",
+                                        "sample": f"{per_worker * cores} clips x {args.seconds:g} s, {cores} worker processes "
+                                                  f"(unmodified reference package, numba), {rdt:.2f} s",
+                                        "c_port_same_box": port}
         print(json.dumps(line))
     for p in plans:
         p.close()
@@ -493,8 +755,9 @@ def b200_arm(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum of the chain kernel, per launch, from the committed
 # `ncu --set full` capture of exactly this workload: (preset, clips per GPU, frames per clip) -> bytes
+# (the capture ran 1184 clips per launch; stored per clip so that any shard size can quote it)
 NCU_DRAM_TRAFFIC = {
-    ("Rain Delay", 1184, 480000): (4.613200e9 + 5.971754e9, "profiles/r1o_ncu_chain_kernel.csv"),
+    ("Rain Delay", 480000): ((4.657284e9 + 5.812085e9) / 1184, "profiles/r2i_ncu_rv_kernel.csv (1184 clips per launch, scaled to this shard)"),
 }
 
 

@@ -52,6 +52,11 @@ def _worker(rank, world, port, total, n):
         q = (np.clip(y, -1, 1) * 32767).astype(np.int16)
         qfull = sharding.gather_clips(torch.from_numpy(q), total, dst=None)      # int16 PCM travels as bytes
         assert qfull.dtype == torch.int16 and torch.equal(qfull[lo:hi], torch.from_numpy(q))
+        if total % world == 0:                                # equal shards: the single-collective path bench.py times
+            qall = sharding.all_gather_pcm(torch.from_numpy(q))
+            assert qall.shape == (total, n, 2) and torch.equal(qall, qfull)
+            again = sharding.all_gather_pcm(torch.from_numpy(q), out=qall)
+            assert again is qall and torch.equal(again, qfull)
         slow = sharding.max_over_ranks(1.0 + rank)
         assert slow == float(world)
         assert every.shape == (total, n, 2)
@@ -69,3 +74,7 @@ def _worker(rank, world, port, total, n):
 
 def test_two_rank_shard_process_gather_gloo():
     mp.spawn(_worker, args=(2, _free_port(), 5, 3000), nprocs=2, join=True)
+
+
+def test_two_rank_equal_shards_all_gather_into_tensor_gloo():
+    mp.spawn(_worker, args=(2, _free_port(), 4, 2500), nprocs=2, join=True)
