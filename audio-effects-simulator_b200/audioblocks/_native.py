@@ -29,7 +29,10 @@ class StageDesc(C.Structure):
 
 
 class AesimError(RuntimeError):
-    pass
+    code = 0
+
+
+ERR_UNSUPPORTED = -4        # AES_ERR_UNSUPPORTED: valid in the reference, not on the whole-clip kernels
 
 
 _lib = None
@@ -97,7 +100,9 @@ def lib() -> C.CDLL:
 
 def check(rc: int):
     if rc != 0:
-        raise AesimError(f"aesim error {rc}: {lib().aes_last_error().decode(errors='replace')}")
+        err = AesimError(f"aesim error {rc}: {lib().aes_last_error().decode(errors='replace')}")
+        err.code = rc
+        raise err
 
 
 def desc_array(descs):

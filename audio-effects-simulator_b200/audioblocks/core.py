@@ -115,6 +115,7 @@ class NativeEffect(Effect):
     _stale = False          # a whole-clip call consumed the lines without writing them back
     _n_total = 0            # frames processed since prepare()
     _blob = None            # device memory of the delay lines (streaming path), allocated lazily
+    _replay = None          # input + pre-call state of the last whole-clip call (see _replay_whole_clip)
 
     def _stages(self, frames: int) -> list:
         raise NotImplementedError
@@ -132,6 +133,7 @@ class NativeEffect(Effect):
         self._stale = False
         self._n_total = 0
         self._blob_zero = True
+        self._replay = None
 
     def _stream_desc(self, frames: int):
         descs = self._stages(frames)
@@ -175,15 +177,69 @@ class NativeEffect(Effect):
         if self._stale:
             raise _native.AesimError(
                 f"{type(self).__name__}: a whole-clip call left the delay lines behind (they are not written "
-                "back); call prepare() before streaming further blocks through this effect")
+                "back) and its input was too large to keep for a replay; call prepare() before streaming "
+                "further blocks through this effect")
 
     def process_into(self, x_in: np.ndarray, out: np.ndarray) -> None:
         run_native([self], self._sr, x_in, out)
 
 
+# A whole-clip call keeps a copy of its input (up to this many floats) so that a caller who goes on
+# processing block after block at the same size -- legal in the reference, whose rings carry over
+# (core.py:123-161) -- can be served: the block is replayed through the streaming kernel first.
+REPLAY_MAX_FLOATS = 64 << 20
+
+_SNAP_TYPES = (int, float, bool, str, type(None), tuple)
+
+
+def _snapshot(fx):
+    """Host-visible scalar state of an effect (write pointers, phasors, gains, filter memories)."""
+    snap = {}
+    for k, v in fx.__dict__.items():
+        if k in ("_blob", "_replay"):
+            continue
+        if isinstance(v, _SNAP_TYPES):
+            snap[k] = v
+        elif isinstance(v, np.ndarray):
+            snap[k] = v.copy()
+    return snap
+
+
+def _stream_block(effects, x, y, silent):
+    per_fx = []
+    for fx in effects:
+        fx._require_usable()
+        per_fx.append(fx._stream_desc(x.shape[0]))
+    arr = _native.desc_array([d for ds in per_fx for d in ds])
+    _native.stream_process(arr, x, y)
+    k = 0
+    for fx, ds in zip(effects, per_fx):
+        fx._absorb(arr[k], x.shape[0], silent)
+        k += len(ds)
+
+
+def _replay_whole_clip(effects):
+    """The lines a whole-clip call left behind are not written back by its kernels.  When another block
+    follows without a prepare(), rebuild them: restore every effect's state from before that call and
+    push the kept input through the streaming kernel (slow, exact, and only on this path)."""
+    group = getattr(effects[0], "_replay", None)
+    if group is None or group["ids"] != [id(fx) for fx in effects] or any(getattr(fx, "_replay", None) is not group for fx in effects):
+        return False
+    for fx, snap in zip(effects, group["snaps"]):
+        for k, v in snap.items():
+            setattr(fx, k, v.copy() if isinstance(v, np.ndarray) else v)
+        fx._stale = False
+        fx._blob_zero = True                    # fresh lines, as they were before the whole-clip call
+        fx._replay = None
+    x = group["x"]
+    _stream_block(effects, x, np.empty((x.shape[0], 2), np.float32), not x.any())
+    return True
+
+
 def run_native(effects, sample_rate, x_in: np.ndarray, out: np.ndarray):
     """One block of (frames, channels) host arrays through a run of native effects: one fused
-    whole-clip launch when the block is long and the lines are fresh, else the streaming kernel."""
+    whole-clip launch when the block is long and the lines are fresh, else the streaming kernel
+    (also when the whole-clip kernels do not support the chain, e.g. comb lines shorter than a tile)."""
     frames = x_in.shape[0]
     x = np.ascontiguousarray(x_in, np.float32)
     if x.shape[1] not in (1, 2):
@@ -192,15 +248,28 @@ def run_native(effects, sample_rate, x_in: np.ndarray, out: np.ndarray):
         raise ValueError("output block must be (frames, 2)")
     y = out if (out.dtype == np.float32 and out.flags.c_contiguous) else np.empty((frames, 2), np.float32)
     silent = not x.any()
+    if frames > 0 and any(fx._stale for fx in effects):
+        _replay_whole_clip(effects)             # (if it cannot, _require_usable below says why)
     whole = frames >= WHOLE_CLIP_MIN_FRAMES and not any(fx._dirty or fx._stale for fx in effects)
-    if frames == 0:
-        pass
-    elif whole:
+    plan = None
+    if whole:
+        snaps = [_snapshot(fx) for fx in effects]
         descs = []
         for fx in effects:
             descs.extend(fx._stages(frames))
+        try:
+            plan = _native.ChainPlan(descs, sample_rate)
+        except _native.AesimError as e:
+            if e.code != _native.ERR_UNSUPPORTED:
+                raise
+            for fx, snap in zip(effects, snaps):    # e.g. an 8 kHz reverb: its shortest comb is 235 samples
+                for k, v in snap.items():
+                    setattr(fx, k, v)
+            whole = False
+    if frames == 0:
+        pass
+    elif whole:
         fmt_in = _native.FMT_F32_MONO if x.shape[1] == 1 else _native.FMT_F32_STEREO
-        plan = _native.ChainPlan(descs, sample_rate)
         try:
             plan.run_host(x, fmt_in, y, _native.FMT_F32_STEREO, 1, frames)
             finals = [plan.final_state(s) for s in range(len(descs))]
@@ -208,17 +277,13 @@ def run_native(effects, sample_rate, x_in: np.ndarray, out: np.ndarray):
             plan.close()
         for fx, final in zip(effects, finals):          # one stage per effect
             fx._advance(frames, silent, final)
+        if not silent and x.size <= REPLAY_MAX_FLOATS:
+            group = {"x": x.copy() if x is x_in or np.shares_memory(x, x_in) else x, "snaps": snaps,
+                     "ids": [id(fx) for fx in effects]}
+            for fx in effects:
+                fx._replay = group
     else:
-        per_fx = []
-        for fx in effects:
-            fx._require_usable()
-            per_fx.append(fx._stream_desc(frames))
-        arr = _native.desc_array([d for ds in per_fx for d in ds])
-        _native.stream_process(arr, x, y)
-        k = 0
-        for fx, ds in zip(effects, per_fx):
-            fx._absorb(arr[k], frames, silent)
-            k += len(ds)
+        _stream_block(effects, x, y, silent)
     if y is not out:
         out[:, :] = y
 
@@ -391,6 +456,32 @@ class EffectsChain:
         run.n_segments = len(steps)
         return run, plans
 
+    @staticmethod
+    def _stream_batch(seg, data, dst):
+        """Batch through the streaming kernel, one clip at a time, every clip from the same freshly
+        prepared state (chains the whole-clip kernels refuse); formats converted on the host like
+        engine.py:78-84 / :104-105."""
+        snaps = [_snapshot(fx) for fx in seg]
+        for b in range(data.shape[0]):
+            for fx, snap in zip(seg, snaps):
+                for k, v in snap.items():
+                    setattr(fx, k, v.copy() if isinstance(v, np.ndarray) else v)
+                fx._dirty = fx._stale = False
+                fx._blob_zero = True
+            xb = data[b]
+            if xb.dtype == np.int16:                 # int16 -> /32768 -> mean over channels, exact in f32
+                xb = ((xb[:, :1].astype(np.int32) + xb[:, 1:2].astype(np.int32)).astype(np.float32) * np.float32(1.0 / 65536.0))
+            xb = np.ascontiguousarray(xb, np.float32)
+            yb = dst[b] if dst.dtype == np.float32 else np.empty((xb.shape[0], 2), np.float32)
+            _stream_block(seg, xb, yb, not xb.any())
+            if dst.dtype == np.int16:
+                dst[b] = (np.clip(yb, -1.0, 1.0) * np.float32(32767.0)).astype(np.int16)
+        for fx, snap in zip(seg, snaps):             # a batch leaves the chain as it found it
+            for k, v in snap.items():
+                setattr(fx, k, v)
+            fx._dirty = fx._stale = False
+            fx._blob_zero = True
+
     def process_batch(self, x: np.ndarray, out: np.ndarray | None = None) -> np.ndarray:
         """x: (B, frames, 1|2) float32 host array (or (B, frames, 2) int16 PCM, which is
         down-mixed like engine.py:78-84) -> (B, frames, 2) float32 or int16 (if `out`
@@ -434,11 +525,19 @@ class EffectsChain:
                 else:
                     dst = np.empty((B, frames, 2), np.int16 if (last and want_i16) else np.float32)
                 fmt_out = _native.FMT_I16_STEREO if dst.dtype == np.int16 else _native.FMT_F32_STEREO
-                plan = _native.ChainPlan(descs, self.sr)
                 try:
-                    plan.run_host(np.ascontiguousarray(data), fmt_in, dst, fmt_out, B, frames)
-                finally:
-                    plan.close()
+                    plan = _native.ChainPlan(descs, self.sr)
+                except _native.AesimError as err:
+                    if err.code != _native.ERR_UNSUPPORTED:
+                        raise
+                    plan = None                      # e.g. comb lines shorter than a tile (8 kHz): stream clip by clip
+                if plan is None:
+                    self._stream_batch(seg, data, dst)
+                else:
+                    try:
+                        plan.run_host(np.ascontiguousarray(data), fmt_in, dst, fmt_out, B, frames)
+                    finally:
+                        plan.close()
                 data = dst
             else:
                 if data.dtype == np.int16 or data.shape[2] != 2:      # down-mix / fan out through an empty chain

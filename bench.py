@@ -689,9 +689,19 @@ def b200_arm(args):
         pceil = copy_ceiling(torch, dist, world, dev, barrier, xq, yq, args.e2e_steps)
         pv = world * Be * n_frames * 2 * args.e2e_steps / pcm_s / 1e6
         pcv = world * Be * n_frames * 2 / pceil["seconds"] / 1e6
-        e2e["pcm16_file_route"] = {"value": pv, "unit": UNIT, "h2d_bytes_per_step": int(xq.nbytes), "d2h_bytes_per_step": int(yq.nbytes),
-                                   "copy_ceiling": {"value": pcv, "h2d_gbs_per_gpu": pceil["h2d_gbs_per_gpu"], "d2h_gbs_per_gpu": pceil["d2h_gbs_per_gpu"]},
-                                   "frac_of_copy_ceiling": pv / pcv}
+        # Headline = the WAV-file route's own formats (engine.py:78-84 reads int16 PCM and down-mixes it,
+        # engine.py:104-110 writes int16 PCM): 4 bytes in + 4 bytes out per stereo frame.  The float32-buffer
+        # variant (8 + 8 bytes per frame, what EffectsChain.process takes) is kept beside it.
+        f32 = {k: e2e[k] for k in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step", "copy_ceiling",
+                                   "frac_of_copy_ceiling", "matches_device_path")}
+        e2e.update({"value": pv, "h2d_bytes_per_step": int(xq.nbytes), "d2h_bytes_per_step": int(yq.nbytes),
+                    "formats": "int16 stereo PCM in (down-mixed on the device like engine.py:81-84), int16 stereo PCM out "
+                               "(clip, x32767, truncate like engine.py:104-105)",
+                    "copy_ceiling": {"value": pcv, "unit": UNIT, "h2d_gbs_per_gpu": pceil["h2d_gbs_per_gpu"],
+                                     "d2h_gbs_per_gpu": pceil["d2h_gbs_per_gpu"], "pinned": pceil["pinned"],
+                                     "what": ceil["what"]},
+                    "frac_of_copy_ceiling": pv / pcv, "f32_buffers": f32})
+        e2e.pop("matches_device_path", None)
         del xh, yh, xq, yq
 
     if rank == 0:
@@ -762,6 +772,10 @@ NCU_DRAM_TRAFFIC = {
 
 
 def main():
+    # exactly ONE line on stdout: libraries that print there (NCCL's version banner) go to stderr instead
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    sys.stdout = real_stdout
     args = parse()
     if args.impl == "reference":
         reference_arm(args)

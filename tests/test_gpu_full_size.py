@@ -1,0 +1,107 @@
+"""Parity at BASELINE.json's full sizes (the `-m gpu` tier): the sm_100a build behind the C ABI against
+the CPU oracle on whole clips of the benchmark's own dimensions -- not excerpts, not properties.
+
+  * configs[1]: ONE 60 s 48 kHz stereo clip (2 880 000 frames) through the LP / HP / BP / peaking cascade;
+  * configs[2] and every preset of app.py:41-71 on 10 s clips (480 000 frames) inside a 1184-clip batch
+    (four waves of the 296 resident CTAs): the FIRST four and the LAST four clips are distinct and checked
+    against the oracle over their whole length -- the last ones sit in the grid-stride tail -- and every
+    clip in between is a copy that must come out bit-identical to its source;
+  * configs[3]: one full 30 s clip through the IR-convolution reverb with the 3 s IR.
+The bar is north_star's: max-abs 1e-5 of full scale and SNR above 100 dB; bit-exact where the path is
+index-only (Slapback Echo, fb = 0).
+"""
+import numpy as np
+import pytest
+
+import synth
+
+pytestmark = pytest.mark.gpu
+
+FP_TOL = 1e-5
+FS = 48000
+
+C2 = [{"type": "filter", "params": {"filter_type": 0, "cutoff_hz": 8000, "q": 0.707}},
+      {"type": "filter", "params": {"filter_type": 1, "cutoff_hz": 80, "q": 0.707}},
+      {"type": "filter", "params": {"filter_type": 2, "cutoff_hz": 1000, "q": 0.8}},
+      {"type": "filter", "params": {"filter_type": 3, "cutoff_hz": 1000, "q": 1.0, "gain_db": 6.0}}]
+C3 = [{"type": "distortion", "params": {"drive": 4.0}},
+      {"type": "octaver", "params": {"semitones": -12, "mix": 0.5}},
+      {"type": "delay", "params": {"delay_ms": 120, "feedback": 0.3, "offset_ms": 10}}]
+CHAINS = dict(synth.PRESETS)
+CHAINS["c3-dist-octaver-delay"] = C3
+
+
+@pytest.fixture(scope="module")
+def ab():
+    import audioblocks
+    from audioblocks import _native
+    _native.lib()                                  # fail loudly if the CUDA library is missing
+    return audioblocks
+
+
+@pytest.fixture(scope="module")
+def orc():
+    from oracle import oracle
+    return oracle
+
+
+def check(got, want, exact=False, what=""):
+    mx, snr = synth.err_stats(got, want)
+    if exact:
+        assert np.array_equal(got, want), (what, mx)
+    scale = max(1.0, float(np.max(np.abs(want))))
+    assert mx <= FP_TOL * scale and snr >= 100.0, (what, mx, snr)
+
+
+def test_c2_one_60_s_clip_through_the_biquad_cascade(ab, orc):
+    """BASELINE configs[1] as written: 2 880 000 frames, the time-parallel scan (one clip < resident CTAs)."""
+    from audioblocks.engine import file_chain
+    n = FS * 60
+    x = synth.clip(1, n, 2)
+    y = file_chain(C2, FS, channels_in=2).process_batch(x[None])[0]
+    check(y, orc.run_file_path(C2, x, FS), what="c2 60 s")
+
+
+@pytest.fixture(scope="module")
+def big_batch():
+    """1184 clips x 480 000 frames x 2: clips 0..3 and 1180..1183 distinct, the rest copies of 0..3."""
+    n, B = FS * 10, 1184
+    heads = synth.batch(200, 4, n)
+    tails = synth.batch(300, 4, n)
+    x = np.empty((B, n, 2), np.float32)
+    for b in range(B - 4):
+        x[b] = heads[b % 4]
+    x[B - 4:] = tails
+    return x
+
+
+@pytest.mark.parametrize("name", sorted(CHAINS))
+def test_full_size_batch_first_and_last_clips(ab, orc, big_batch, name):
+    from audioblocks.engine import file_chain
+    cfg = CHAINS[name]
+    x = big_batch
+    B = x.shape[0]
+    y = file_chain(cfg, FS, channels_in=2).process_batch(x)
+    idx = [0, 1, 2, 3, B - 4, B - 3, B - 2, B - 1]
+    if any(c["type"] == "spectral" for c in cfg):
+        want = [orc.run_file_path(cfg, x[b], FS) for b in idx]           # numpy-FFT block: no C batch driver
+    else:
+        want = orc.run_batch_c(cfg, np.ascontiguousarray(x[idx]), FS, threads=8)
+    for k, b in enumerate(idx):
+        check(y[b], want[k], exact=(name == "Slapback Echo"), what=(name, b))
+    # copies of a clip are bit-identical wherever they sit in the batch (every wave, every CTA)
+    for k in range(4):
+        same = (y[k:B - 4:4] == y[k]).all(axis=(1, 2))
+        assert same.all(), (name, k, int(np.argmin(same)))
+
+
+def test_c4_one_30_s_clip_through_the_convolution_reverb(ab, orc):
+    """BASELINE configs[3] clip size: 1 440 000 frames, 3 s synthetic IR (144 000 taps); float64
+    fftconvolve oracle (parity unpinned by the reference: it has no convolution reverb)."""
+    ir = orc.synthetic_ir(144000)
+    n = FS * 30
+    x = synth.clip(7, n, 2)
+    y = ab.ConvolutionReverbEffect(ir, mix_dry=0.7, mix_wet=0.5).process_batch(x[None])[0]
+    want = np.zeros_like(x)
+    orc.OConvReverb(ir, 0.7, 0.5).process_into(x, want)
+    check(y, want, what="c4 30 s")

@@ -399,19 +399,69 @@ def test_engine_process_wav_file_websocket_reply(ab, orc):
     assert np.max(np.abs(np.array(reply["original_samples"], np.float32) - mono[:, 0])) == 0.0
 
 
-def test_second_block_through_used_delay_lines_fails_loudly(ab):
-    """Whole-clip kernels start from freshly prepared lines; continuing a clip in a second call
-    without prepare() must raise rather than silently drop the tail."""
-    from audioblocks import _native
+@pytest.mark.parametrize("name", NATIVE)
+def test_blocks_of_whole_clip_size_continue_the_clip_like_the_reference(ab, orc, name):
+    """The reference carries its rings from call to call at ANY block size (core.py:123-161).  Here the
+    first long block takes the whole-clip kernels, which do not write their lines back; when a second
+    block follows without prepare(), the first is replayed through the streaming kernel and the clip
+    goes on -- results as if it had been one call (block-wise processing with blocks of 2048
+    frames or more used to raise on the second block)."""
+    from audioblocks.engine import file_chain
+    cfg = synth.PRESETS[name]
+    bs, nblk = 4096, 3
+    x = synth.clip(21, bs * nblk, 2)
+    chain = file_chain(cfg, 48000, channels_in=2, blocksize=bs)       # built and warmed at the block size: no re-prepare
+    got = np.zeros((bs * nblk, 2), np.float32)
+    for k in range(nblk):
+        chain.process(x[k * bs:(k + 1) * bs], got[k * bs:(k + 1) * bs])
+    ref = orc.build_chain(cfg, 48000, ci=2, bs=bs)
+    ref.warmup()
+    want = np.zeros_like(got)
+    for k in range(nblk):
+        ref.process(x[k * bs:(k + 1) * bs], want[k * bs:(k + 1) * bs])
+    check(got, want, exact=(name == "Slapback Echo"), what=name)
+
+
+def test_single_effect_second_block_and_reprepare(ab, orc):
     fx = ab.StereoDelayEffect()
     fx.prepare(48000, 2, 2, 4096)
-    x = synth.clip(1, 4096, 2)
-    out = np.zeros_like(x)
-    fx.process_into(x, out)
-    with pytest.raises(_native.AesimError, match=r"call prepare\(\)"):
-        fx.process_into(x, out)
-    fx.prepare(48000, 2, 2, 4096)
-    fx.process_into(x, out)
+    x = synth.batch(1, 2, 4096)
+    out = np.zeros((2, 4096, 2), np.float32)
+    fx.process_into(x[0], out[0])
+    fx.process_into(x[1], out[1])                           # continues the lines of the first block
+    o = orc.ODelay()
+    o.prepare(48000, 2, 2, 4096)
+    want = np.zeros_like(out)
+    o.process_into(x[0], want[0])
+    o.process_into(x[1], want[1])
+    check(out.reshape(-1, 2), want.reshape(-1, 2), what="second block")
+    fx.prepare(48000, 2, 2, 4096)                           # fresh lines again
+    fx.process_into(x[1], out[1])
+    o.prepare(48000, 2, 2, 4096)
+    o.process_into(x[1], want[1])
+    check(out[1], want[1], what="after prepare")
+
+
+@pytest.mark.parametrize("fs", [8000, 192000])
+def test_sample_rates_the_whole_clip_kernels_refuse_fall_back_to_streaming(ab, orc, fs):
+    """At 8 kHz the default reverb's shortest comb is 235 samples (< the smallest tile), at 192 kHz its
+    rings exceed shared memory: aes_chain_plan_create answers AES_ERR_UNSUPPORTED and the host side
+    takes the streaming kernel instead of raising (such files never got a reply)."""
+    from audioblocks.engine import file_chain
+    cfg = synth.PRESETS["Rain Delay"]
+    n = 9000 if fs == 8000 else 20000
+    x = synth.clip(5, n, 1, fs)
+    got = np.zeros((n, 2), np.float32)
+    file_chain(cfg, fs, channels_in=1).process(x, got)
+    check(got, orc.run_file_path(cfg, x, fs), what=("file", fs))
+    xb = synth.batch(6, 3, n, 2, fs)
+    yb = file_chain(cfg, fs, channels_in=2).process_batch(xb)
+    for b in range(3):
+        check(yb[b], orc.run_file_path(cfg, xb[b], fs), what=("batch", fs, b))
+    q = np.zeros((3, n, 2), np.int16)
+    file_chain(cfg, fs, channels_in=2).process_batch(xb, q)
+    wq = (np.clip(yb, -1.0, 1.0) * np.float32(32767.0)).astype(np.int16)
+    assert np.array_equal(q, wq)
 
 
 @pytest.mark.parametrize("name", NATIVE)
