@@ -411,7 +411,7 @@ __device__ void aes_rv_body(const FastArgs &a)
 
             if (has_cur) {
                 float y[2][NC][FR], e[2][NC];
-                [[maybe_unused]] double bq_yz[2][FR], bq_e1[2], bq_e2[2];
+                [[maybe_unused]] double bq_e1[2], bq_e2[2];
                 // ---------------- phase 1 ----------------
                 if (staged) {
                     aes_mbar_wait_parity(mbar + q, (phbits >> q) & 1u);
@@ -468,7 +468,7 @@ __device__ void aes_rv_body(const FastArgs &a)
                     }
                 }
                 if constexpr (PRE == AESRV_PRE_BIQUAD) {
-                    // transposed DF-II from zero state, outputs kept (filter.py:8-40; see aes_fast_kernel.cuh)
+                    // transposed DF-II from zero state: only the chunk's end state is kept (filter.py:8-40; see aes_fast_kernel.cuh)
                     const FastStage &bs = a.st[0];
                     const double b0 = bs.bq[0], b1 = bs.bq[1], b2 = bs.bq[2], a1 = bs.bq[3], a2 = bs.bq[4];
 #pragma unroll
@@ -480,9 +480,8 @@ __device__ void aes_rv_body(const FastArgs &a)
                             const double yy = fma(b0, xj, s1);
                             s1 = fma(b1, xj, fma(-a1, yy, s2));
                             s2 = fma(b2, xj, -a2 * yy);
-                            bq_yz[ch][j] = yy;
                         }
-                        bq_e1[ch] = s1; bq_e2[ch] = s2;
+                        bq_e1[ch] = s1; bq_e2[ch] = s2;             // (outputs are recomputed in phase 2: registers)
                     }
                     const int bq_nscan = bs.nscan;
                     for (int s = 0; s < bq_nscan; ++s) {
@@ -561,18 +560,24 @@ __device__ void aes_rv_body(const FastArgs &a)
                         }
                         double x1 = __shfl_up_sync(0xffffffffu, bq_e1[ch], 1), x2 = __shfl_up_sync(0xffffffffu, bq_e2[ch], 1);
                         if (lane == 0) { x1 = 0.0; x2 = 0.0; }
-                        const double S1 = fma(l0, C1, fma(l2, C2, x1));
-                        const double S2 = fma(l1, C1, fma(l3, C2, x2));
+                        double s1 = fma(l0, C1, fma(l2, C2, x1));           // state entering this thread's chunk
+                        double s2 = fma(l1, C1, fma(l3, C2, x2));
+                        const double b0 = bs.bq[0];
 #pragma unroll
                         for (int j = 0; j < FR; ++j) {
-                            const double yy = j == 0 ? bq_yz[ch][0] + S1 : fma(bs.bq_row[j][0], S1, fma(bs.bq_row[j][1], S2, bq_yz[ch][j]));
+                            // the recurrence again, from the true state (keeping the zero-state outputs of phase 1
+                            // across the barrier cost 16 registers the comb warps do not have)
+                            const double xj = (double)v[ch][j];
+                            const double yy = fma(b0, xj, s1);
+                            s1 = fma(b1, xj, fma(-a1, yy, s2));
+                            s2 = fma(b2, xj, -a2 * yy);
                             if (len == T) {
                                 if (j >= FR - 2 && tid == AES_NT - 1) {
-                                    sout[4 * ch + (FR - 1 - j)] = (double)v[ch][j]; sout[4 * ch + 2 + (FR - 1 - j)] = yy;
+                                    sout[4 * ch + (FR - 1 - j)] = xj; sout[4 * ch + 2 + (FR - 1 - j)] = yy;
                                 }
                             } else {
-                                if (i0 + j == len - 1) { sout[4 * ch + 0] = (double)v[ch][j]; sout[4 * ch + 2] = yy; }
-                                if (i0 + j == len - 2) { sout[4 * ch + 1] = (double)v[ch][j]; sout[4 * ch + 3] = yy; }
+                                if (i0 + j == len - 1) { sout[4 * ch + 0] = xj; sout[4 * ch + 2] = yy; }
+                                if (i0 + j == len - 2) { sout[4 * ch + 1] = xj; sout[4 * ch + 3] = yy; }
                             }
                             v[ch][j] = (float)yy;
                         }

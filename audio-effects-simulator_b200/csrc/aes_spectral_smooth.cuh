@@ -1,0 +1,366 @@
+// aes_spectral_smooth.cuh -- SpectralFilter transforms for frame lengths M = n1 * n2 whose factors are
+// 2, 3 and 5 only (BASELINE's whole-file frame: 960 000 = 960 x 1000), without Bluestein.
+//
+// The chirp-z path (aes_spectral.cuh) serves ANY M with four power-of-two FFTs of P >= 2M-1 points per
+// transform pair: 21 passes over a 16.8 MB buffer for M = 960 000.  When M is smooth the DFT is done
+// directly as a four-step (n1 x n2) transform in three kernels, 46 MB of traffic per pair of clips:
+//
+//   K1  columns:  for a tile of C adjacent columns b, load x[a*n2 + b] (a = 0..n1-1; straight from the
+//                 clips / analysis frames: window, pairing z = f0 + i*f1, zero half), n1-point DIF FFTs
+//                 in shared memory, times W_M^(b*k1), store Y[k1][b]
+//   K2  row pairs: rows k1 and n1-k1 together (they hold bins k and M-k): n2-point DIF FFTs, the
+//                 conjugate-symmetry split into the two clips' spectra, the spectral gate
+//                 (spectral.py:66-73), recombination, n2-point inverse DIT FFTs, times W_M^(-b*k1)
+//                 -- the spectrum never leaves shared memory
+//   K3  columns:  n1-point inverse DIT FFTs, 1/M, real part -> clip / frame 2p, imaginary -> 2p+1
+//
+// Shared-memory FFTs are in-place mixed radix (4, 2, 3, 5): decimation in frequency forward, which
+// leaves X[k] at the digit-reversed position, and decimation in time inverse, which takes that
+// order; the gate and the global stores translate indices, no permutation pass exists.  Twiddles
+// come from tables built in double precision at plan creation (w_n^j per FFT length; W_M^t as a
+// product of a 1024-entry and an M/1024-entry table).
+#pragma once
+#include "aes_spectral.cuh"
+
+#define AESM_MAX_STAGES 12
+#define AESM_NT 256
+#define AESM_C 8                    // columns per K1 / K3 tile
+
+struct SmoothDiv { unsigned mul; unsigned d; };     // x / d for x * d < 2^32:  __umulhi(x, mul)
+
+struct SmoothFft {
+    int n, ns;
+    int r[AESM_MAX_STAGES];         // radices in DIF order
+    int len[AESM_MAX_STAGES];       // sub-transform length entering stage i (len[0] = n)
+    SmoothDiv dm[AESM_MAX_STAGES];  // division by m_i = len[i] / r[i]
+};
+
+struct SmoothArgs {
+    SmoothFft f1, f2;               // column (n1) and row (n2) transforms
+    cpx *buf;                       // [np][n1][n2] work buffer
+    const cpx *tw1, *tw2;           // w_n1^j, w_n2^j
+    const cpx *twlo, *twhi;         // W_M^t = twhi[t >> 10] * twlo[t & 1023]
+    const float *frames;            // [nf][M] analysis frames (mode 1) or null
+    const float *window;            // [M] Hann window or null
+    const float *clips;             // [nf][N][2] stereo clips (mode 2: frame = [zeros(N), mean * window[N:]])
+    float *mask;                    // [nf][M/2+1] smoothed mask in/out, or null: starts at ones, not kept
+    float *out;                     // [nf][M] (mode 1)
+    float *yclips;                  // [nf][N][2] (mode 2): first N samples, both channels
+    long long M;
+    int n1, n2, np, nf;             // np = ceil(nf / 2) transform pairs
+    int mode;                       // 1 frames -> out, 2 clips -> yclips
+    float thr, red, alpha;
+};
+
+#ifdef AES_CPU_EMU
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+#endif
+__device__ __forceinline__ unsigned aesm_div(unsigned x, const SmoothDiv &d) { return d.d == 1 ? x : __umulhi(x, d.mul); }
+
+__device__ __forceinline__ cpx aesm_cmulc(cpx a, cpx w, bool conj_w)
+{
+    cpx r;
+    if (!conj_w) { r.x = a.x * w.x - a.y * w.y; r.y = a.x * w.y + a.y * w.x; }
+    else         { r.x = a.x * w.x + a.y * w.y; r.y = a.y * w.x - a.x * w.y; }
+    return r;
+}
+
+// small DFTs in registers; INV conjugates the roots of unity
+template <int R, bool INV> __device__ __forceinline__ void aesm_dft(cpx (&a)[R])
+{
+    if (R == 2) {
+        const cpx u = a[0], v = a[1 % R];
+        a[0] = c_add(u, v); a[1 % R] = c_sub(u, v);
+    } else if (R == 4) {
+        const cpx s0 = c_add(a[0], a[2 % R]), d0 = c_sub(a[0], a[2 % R]);
+        const cpx s1 = c_add(a[1 % R], a[3 % R]), d1 = c_sub(a[1 % R], a[3 % R]);
+        cpx jd; jd.x = d1.y; jd.y = -d1.x;                  // -i * d1
+        if (INV) { jd.x = -jd.x; jd.y = -jd.y; }            // +i * d1
+        a[0] = c_add(s0, s1); a[2 % R] = c_sub(s0, s1);
+        a[1 % R] = c_add(d0, jd); a[3 % R] = c_sub(d0, jd);
+    } else if (R == 3) {
+        const float s = 0.86602540378443864676f;
+        const cpx t1 = c_add(a[1 % R], a[2 % R]);
+        cpx t2; t2.x = a[0].x - 0.5f * t1.x; t2.y = a[0].y - 0.5f * t1.y;
+        const cpx t3 = c_sub(a[1 % R], a[2 % R]);
+        cpx jt; jt.x = s * t3.y; jt.y = -s * t3.x;          // -i * s * t3
+        if (INV) { jt.x = -jt.x; jt.y = -jt.y; }
+        a[0] = c_add(a[0], t1);
+        a[1 % R] = c_add(t2, jt); a[2 % R] = c_sub(t2, jt);
+    } else {
+        static_assert(R == 2 || R == 3 || R == 4 || R == 5, "");
+        const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
+        const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
+        const cpx t1 = c_add(a[1 % R], a[4 % R]), t2 = c_add(a[2 % R], a[3 % R]);
+        const cpx t3 = c_sub(a[1 % R], a[4 % R]), t4 = c_sub(a[2 % R], a[3 % R]);
+        cpx m1, m2, q1, q2;
+        m1.x = a[0].x + c1 * t1.x + c2 * t2.x; m1.y = a[0].y + c1 * t1.y + c2 * t2.y;
+        m2.x = a[0].x + c2 * t1.x + c1 * t2.x; m2.y = a[0].y + c2 * t1.y + c1 * t2.y;
+        q1.x = s1 * t3.x + s2 * t4.x; q1.y = s1 * t3.y + s2 * t4.y;
+        q2.x = s2 * t3.x - s1 * t4.x; q2.y = s2 * t3.y - s1 * t4.y;
+        cpx j1, j2;                                         // -i * q
+        j1.x = q1.y; j1.y = -q1.x; j2.x = q2.y; j2.y = -q2.x;
+        if (INV) { j1.x = -j1.x; j1.y = -j1.y; j2.x = -j2.x; j2.y = -j2.y; }
+        a[0].x += t1.x + t2.x; a[0].y += t1.y + t2.y;
+        a[1 % R] = c_add(m1, j1); a[4 % R] = c_sub(m1, j1);
+        a[2 % R] = c_add(m2, j2); a[3 % R] = c_sub(m2, j2);
+    }
+}
+
+// One in-place stage over S sequences held in shared memory: element e of sequence q sits at
+// s[q * qs + e * es].  DIF (forward):  out_d[p] = (sum_j a_j w_R^(jd)) * w_len^(p*d) -> block d of the
+// sub-transform;  DIT (inverse): the transpose with conjugated roots.
+template <int R, bool INV>
+__device__ __forceinline__ void aesm_stage(cpx *s, int S, SmoothDiv divS, int qs, int es, const SmoothFft &f, int i, const cpx *tw)
+{
+    const int len = f.len[i], m = len / R, nbf = f.n / R, tstep = f.n / len;
+    for (unsigned e = threadIdx.x; e < (unsigned)(S * nbf); e += AESM_NT) {
+        const unsigned fi = aesm_div(e, divS), q = e - fi * S;          // sequences fastest: adjacent columns, adjacent words
+        const unsigned blk = aesm_div(fi, f.dm[i]), p = fi - blk * m;
+        cpx *base = s + q * qs + (blk * len + p) * es;
+        cpx a[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) a[j] = base[j * m * es];
+        if (INV) {
+#pragma unroll
+            for (int d = 1; d < R; ++d) a[d] = aesm_cmulc(a[d], tw[p * d * tstep], true);
+        }
+        aesm_dft<R, INV>(a);
+        if (!INV) {
+#pragma unroll
+            for (int d = 1; d < R; ++d) a[d] = aesm_cmulc(a[d], tw[p * d * tstep], false);
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) base[j * m * es] = a[j];
+    }
+}
+
+template <bool INV>
+__device__ __forceinline__ void aesm_fft(cpx *s, int S, SmoothDiv divS, int qs, int es, const SmoothFft &f, const cpx *tw)
+{
+    for (int k = 0; k < f.ns; ++k) {
+        const int i = INV ? f.ns - 1 - k : k;
+        switch (f.r[i]) {
+        case 4: aesm_stage<4, INV>(s, S, divS, qs, es, f, i, tw); break;
+        case 2: aesm_stage<2, INV>(s, S, divS, qs, es, f, i, tw); break;
+        case 3: aesm_stage<3, INV>(s, S, divS, qs, es, f, i, tw); break;
+        default: aesm_stage<5, INV>(s, S, divS, qs, es, f, i, tw); break;
+        }
+        __syncthreads();
+    }
+}
+
+// position of output index k after the DIF stages (mixed-radix digit reversal)
+__device__ __forceinline__ int aesm_rev(int k, const SmoothFft &f)
+{
+    int pos = 0, len = f.n;
+    for (int i = 0; i < f.ns; ++i) {
+        const int r = f.r[i], d = k % r;
+        k /= r; len /= r;
+        pos += d * len;
+    }
+    return pos;
+}
+
+// W_M^t (t in [0, M)) or its conjugate
+__device__ __forceinline__ cpx aesm_wM(const SmoothArgs &a, long long t, bool conj_w)
+{
+    const cpx w = aesm_cmulc(a.twhi[t >> 10], a.twlo[t & 1023], false);
+    cpx r = w;
+    if (conj_w) r.y = -r.y;
+    return r;
+}
+
+// sample n of the analysis frame of real frame `fr` (or 0 when the pair has no second frame)
+__device__ __forceinline__ float aesm_sample(const SmoothArgs &a, int fr, long long n)
+{
+    if (fr >= a.nf) return 0.0f;
+    if (a.mode == 2) {
+        const long long N = a.M / 2;
+        if (n < N) return 0.0f;
+        const float2 f = reinterpret_cast<const float2 *>(a.clips)[(long long)fr * N + (n - N)];
+        return __fmul_rn(__fmul_rn(__fadd_rn(f.x, f.y), 0.5f), a.window[n]);     // np.mean, then * window, in f32
+    }
+    const float v = a.frames[(long long)fr * a.M + n];
+    return a.window != nullptr ? __fmul_rn(v, a.window[n]) : v;
+}
+
+// ---- K1: column FFTs ---------------------------------------------------------------------------------
+__device__ void aesm_cols_fwd_body(const SmoothArgs &a)
+{
+    AES_DYN_SMEM(cpx, s);                                   // [n1][C]
+    const int n1 = a.n1, n2 = a.n2, tiles = (n2 + AESM_C - 1) / AESM_C;
+    SmoothDiv divC; divC.d = AESM_C; divC.mul = 0x20000000u;        // x / 8
+    for (long long w = blockIdx.x; w < (long long)a.np * tiles; w += gridDim.x) {
+        const int p = (int)(w / tiles), b0 = (int)(w % tiles) * AESM_C;
+        for (int e = threadIdx.x; e < n1 * AESM_C; e += AESM_NT) {
+            const int row = e / AESM_C, c = e % AESM_C, b = b0 + c;
+            cpx z; z.x = 0.f; z.y = 0.f;
+            if (b < n2) {
+                const long long n = (long long)row * n2 + b;
+                z.x = aesm_sample(a, 2 * p, n);
+                z.y = aesm_sample(a, 2 * p + 1, n);
+            }
+            s[e] = z;
+        }
+        __syncthreads();
+        aesm_fft<false>(s, AESM_C, divC, 1, AESM_C, a.f1, a.tw1);
+        cpx *dst = a.buf + (long long)p * a.M;
+        for (int e = threadIdx.x; e < n1 * AESM_C; e += AESM_NT) {
+            const int k1 = e / AESM_C, c = e % AESM_C, b = b0 + c;
+            if (b < n2) {
+                const cpx v = s[aesm_rev(k1, a.f1) * AESM_C + c];
+                dst[(long long)k1 * n2 + b] = c_mul(v, aesm_wM(a, ((long long)b * k1) % a.M, false));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- K2: row pairs: forward rows, gate, inverse rows -------------------------------------------------
+__device__ __forceinline__ cpx aesm_gate_one(cpx X, float *maskp, bool self_conj, const SmoothArgs &a)
+{
+    const float mag = sqrtf(X.x * X.x + X.y * X.y);
+    const float cur = mag > a.thr ? 1.0f : a.red;               // spectral.py:68
+    const float prev = maskp != nullptr ? *maskp : 1.0f;
+    const float m = a.alpha * prev + (1.0f - a.alpha) * cur;    // spectral.py:71
+    if (maskp != nullptr) *maskp = m;
+    cpx Pk; Pk.x = X.x * m; Pk.y = X.y * m;                     // mag * mask * exp(i*phase)
+    if (self_conj) Pk.y = 0.f;                                  // irfft ignores the imaginary part of DC / Nyquist
+    return Pk;
+}
+
+__device__ void aesm_rows_body(const SmoothArgs &a)
+{
+    AES_DYN_SMEM(cpx, s);                                   // [2][n2]: row k1, row n1 - k1
+    const int n1 = a.n1, n2 = a.n2, half = n1 / 2 + 1;      // row pairs per transform: k1 = 0 .. n1/2
+    const long long nbins = a.M / 2 + 1;
+    SmoothDiv div2; div2.d = 2; div2.mul = 0x80000000u;
+    SmoothDiv div1; div1.d = 1; div1.mul = 0;
+    for (long long w = blockIdx.x; w < (long long)a.np * half; w += gridDim.x) {
+        const int p = (int)(w / half), k1 = (int)(w % half), k1b = (n1 - k1) % n1;
+        const bool self = k1 == k1b;                        // rows 0 and n1/2 pair with themselves
+        const int S = self ? 1 : 2;
+        cpx *rowA = a.buf + (long long)p * a.M + (long long)k1 * n2;
+        cpx *rowB = a.buf + (long long)p * a.M + (long long)k1b * n2;
+        for (int e = threadIdx.x; e < n2; e += AESM_NT) {
+            s[e] = rowA[e];
+            if (!self) s[n2 + e] = rowB[e];
+        }
+        __syncthreads();
+        aesm_fft<false>(s, S, self ? div1 : div2, n2, 1, a.f2, a.tw2);
+        // bins: k = k1 + n1*k2 (row A, column k2)  <->  M - k = k1b + n1*k2b (row B, column k2b)
+        const bool two = 2 * p + 1 < a.nf;
+        for (int k2 = threadIdx.x; k2 < n2; k2 += AESM_NT) {
+            const long long k = k1 + (long long)n1 * k2;
+            const int k2b = k1 == 0 ? (n2 - k2) % n2 : n2 - 1 - k2;
+            const long long km = (long long)k1b + (long long)n1 * k2b;          // = (M - k) mod M
+            if (self && km < k) continue;                   // each unordered pair once
+            const int ia = aesm_rev(k2, a.f2), ib = (self ? 0 : n2) + aesm_rev(k2b, a.f2);
+            const cpx Zk = s[ia], Zm = s[ib];
+            const long long kk = k <= km ? k : km;          // the rfft bin this pair is
+            cpx X0, X1;                                     // rfft bin of frame 2p / 2p+1 at index k
+            X0.x = 0.5f * (Zk.x + Zm.x); X0.y = 0.5f * (Zk.y - Zm.y);
+            X1.x = 0.5f * (Zk.y + Zm.y); X1.y = 0.5f * (Zm.x - Zk.x);
+            if (k > km) { X0.y = -X0.y; X1.y = -X1.y; }    // we hold bin M-kk: its spectrum value is the conjugate
+            const bool sc = k == km;
+            float *m0 = a.mask != nullptr ? a.mask + (long long)(2 * p) * nbins + kk : nullptr;
+            float *m1 = a.mask != nullptr ? a.mask + (long long)(2 * p + 1) * nbins + kk : nullptr;
+            const cpx P0 = aesm_gate_one(X0, m0, sc, a);
+            cpx P1; P1.x = 0.f; P1.y = 0.f;
+            if (two) P1 = aesm_gate_one(X1, m1, sc, a);
+            // W = P0full + i*P1full: W[kk] = P0 + i*P1, W[M-kk] = conj(P0) + i*conj(P1)
+            cpx Wlo, Whi;
+            Wlo.x = P0.x - P1.y; Wlo.y = P0.y + P1.x;
+            Whi.x = P0.x + P1.y; Whi.y = P1.x - P0.y;
+            s[ia] = k <= km ? Wlo : Whi;
+            if (!sc) s[ib] = k <= km ? Whi : Wlo;
+        }
+        __syncthreads();
+        aesm_fft<true>(s, S, self ? div1 : div2, n2, 1, a.f2, a.tw2);
+        for (int e = threadIdx.x; e < n2; e += AESM_NT) {
+            rowA[e] = c_mul(s[e], aesm_wM(a, ((long long)e * k1) % a.M, true));
+            if (!self) rowB[e] = c_mul(s[n2 + e], aesm_wM(a, ((long long)e * k1b) % a.M, true));
+        }
+        __syncthreads();
+    }
+}
+
+// ---- K3: inverse column FFTs, outputs --------------------------------------------------------------------
+__device__ void aesm_cols_inv_body(const SmoothArgs &a)
+{
+    AES_DYN_SMEM(cpx, s);
+    const int n1 = a.n1, n2 = a.n2, tiles = (n2 + AESM_C - 1) / AESM_C;
+    const float inv = 1.0f / (float)a.M;
+    const long long N = a.M / 2;
+    SmoothDiv divC; divC.d = AESM_C; divC.mul = 0x20000000u;
+    for (long long w = blockIdx.x; w < (long long)a.np * tiles; w += gridDim.x) {
+        const int p = (int)(w / tiles), b0 = (int)(w % tiles) * AESM_C;
+        const cpx *src = a.buf + (long long)p * a.M;
+        for (int e = threadIdx.x; e < n1 * AESM_C; e += AESM_NT) {
+            const int k1 = e / AESM_C, c = e % AESM_C, b = b0 + c;
+            cpx z; z.x = 0.f; z.y = 0.f;
+            if (b < n2) z = src[(long long)k1 * n2 + b];
+            s[aesm_rev(k1, a.f1) * AESM_C + c] = z;
+        }
+        __syncthreads();
+        aesm_fft<true>(s, AESM_C, divC, 1, AESM_C, a.f1, a.tw1);
+        const bool two = 2 * p + 1 < a.nf;
+        for (int e = threadIdx.x; e < n1 * AESM_C; e += AESM_NT) {
+            const int row = e / AESM_C, c = e % AESM_C, b = b0 + c;
+            if (b >= n2) continue;
+            const long long n = (long long)row * n2 + b;
+            const cpx v = s[e];
+            if (a.mode == 2) {
+                if (n < N) {                                // the block emits the first N samples, both channels
+                    const float y0 = v.x * inv, y1 = v.y * inv;
+                    reinterpret_cast<float2 *>(a.yclips)[(long long)(2 * p) * N + n] = make_float2(y0, y0);
+                    if (two) reinterpret_cast<float2 *>(a.yclips)[(long long)(2 * p + 1) * N + n] = make_float2(y1, y1);
+                }
+            } else {
+                a.out[(long long)(2 * p) * a.M + n] = v.x * inv;
+                if (two) a.out[(long long)(2 * p + 1) * a.M + n] = v.y * inv;
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---- host: factorisation -----------------------------------------------------------------------------------
+static inline bool aesm_build_fft(int n, SmoothFft *f)
+{
+    f->n = n; f->ns = 0;
+    int rem = n, len = n;
+    const int order[4] = { 4, 2, 3, 5 };
+    for (int oi = 0; oi < 4; ++oi) {
+        const int r = order[oi];
+        while (rem % r == 0 && rem > 1) {
+            if (f->ns >= AESM_MAX_STAGES) return false;
+            f->r[f->ns] = r; f->len[f->ns] = len;
+            const unsigned m = (unsigned)(len / r);
+            f->dm[f->ns].d = m;
+            f->dm[f->ns].mul = m == 1 ? 0u : (unsigned)(0x100000000ULL / m) + 1u;
+            ++f->ns; rem /= r; len /= r;
+        }
+    }
+    return rem == 1;
+}
+
+// n1 x n2 = M with both factors {2,3,5}-smooth, n1 even, and small enough for shared memory;
+// the most balanced such split, or false
+static inline bool aesm_split(long long M, int *n1, int *n2)
+{
+    const int max1 = 2048, max2 = 4096;
+    long long best = -1;
+    for (long long a = 2; a <= max1 && a <= M; a += 2) {
+        if (M % a) continue;
+        const long long b = M / a;
+        if (b > max2 || b < 2) continue;
+        SmoothFft t1, t2;
+        if (!aesm_build_fft((int)a, &t1) || !aesm_build_fft((int)b, &t2)) continue;
+        if ((unsigned long long)a * AESM_C * (unsigned long long)b >= 0x80000000ULL) continue;
+        const long long score = a > b ? a - b : b - a;
+        if (best < 0 || score < best) { best = score; *n1 = (int)a; *n2 = (int)b; }
+    }
+    return best >= 0;
+}
