@@ -28,7 +28,7 @@
 #define AESC_KT 256         // bins per MAC tile
 #define AESC_JB 8           // output blocks per MAC chunk
 
-struct cpx { float x, y; };
+struct alignas(8) cpx { float x, y; };      // one 64-bit load / store per element
 
 __device__ __forceinline__ cpx c_mul(cpx a, cpx b) { cpx r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r; }
 

@@ -2,12 +2,29 @@
 #include <algorithm>
 #include <math.h>
 #include <new>
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
 #include "aes_common.h"
 #include "aes_chain_kernel.cuh"      // AES_DYN_SMEM
 #include "aes_spectral.cuh"
+#include "aes_spectral_smooth.cuh"
+
+__global__ void __launch_bounds__(AESM_NTC) aesm_cols_fwd_kernel(const __grid_constant__ SmoothArgs a) { aesm_cols_fwd_body(a); }
+__global__ void __launch_bounds__(AESM_NT, 5) aesm_rows_kernel(const __grid_constant__ SmoothArgs a) { aesm_rows_body(a); }
+__global__ void __launch_bounds__(AESM_NT) aesm_cols_inv_kernel(const __grid_constant__ SmoothArgs a) { aesm_cols_inv_body(a); }
+// tables of the smooth path, in double: W_M^j (j < 1024), W_M^(1024 j), np.hanning(M)
+__global__ void aesm_tables_kernel(cpx *twlo, cpx *twhi, long long nhi, float *window, long long M)
+{
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    auto w = [](double num, double den) { double sn, cs; sincospi(-2.0 * num / den, &sn, &cs); cpx c; c.x = (float)cs; c.y = (float)sn; return c; };
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < M; e += stride) {
+        window[e] = (float)(0.5 - 0.5 * cospi(2.0 * (double)e / (double)(M - 1)));
+        if (e < 1024) twlo[e] = w((double)e, (double)M);
+        if (e < nhi) twhi[e] = w((double)(e * 1024), (double)M);
+    }
+}
 
 __global__ void aess_load_kernel(const __grid_constant__ SpecArgs a) { aess_load_body(a); }
 template <int R, int IN, int OUT>
@@ -80,6 +97,12 @@ struct aes_spectral_plan {
     float *d_window = nullptr;
     void *d_work = nullptr;          // buf | frames | mask | out | (x | y for the clip entry)
     size_t work_cap = 0;
+    // frame lengths n1 * n2 with factors 2, 3, 5 only skip Bluestein (aes_spectral_smooth.cuh)
+    bool smooth = false;
+    int n1 = 0, n2 = 0;
+    SmoothFft f1, f2;
+    cpx *d_stw = nullptr;            // stage twiddles of f1 | of f2 | twlo [1024] | twhi [ceil(M / 1024)]
+    int *d_rev = nullptr;            // rev1 [n1] | rev2 [n2]
 };
 
 static int spec_grid(const aes_spectral_plan *pl) { return pl->sms * 8; }
@@ -160,10 +183,39 @@ static int spec_process(const aes_spectral_plan *pl, SpecArgs a, cudaStream_t st
     return 0;
 }
 
+static SmoothArgs smooth_args(const aes_spectral_plan *pl)
+{
+    SmoothArgs a; memset(&a, 0, sizeof a);
+    a.f1 = pl->f1; a.f2 = pl->f2; a.n1 = pl->n1; a.n2 = pl->n2; a.M = (int)pl->M;
+    a.tw1 = pl->d_stw; a.tw2 = a.tw1 + pl->f1.tsize; a.twlo = a.tw2 + pl->f2.tsize; a.twhi = a.twlo + 1024;
+    a.rev1 = pl->d_rev; a.rev2 = pl->d_rev + pl->n1;
+    a.window = pl->d_window;
+    return a;
+}
+
+// the three passes of the four-step path; a.buf / frames / clips / outputs set by the caller
+static int smooth_process(const aes_spectral_plan *pl, const SmoothArgs &a, cudaStream_t st)
+{
+    const long long tiles = (long long)a.np * ((a.n2 + AESM_C - 1) / AESM_C), rows = (long long)a.np * (a.n1 / 2 + 1);
+    const size_t sm_c = (size_t)a.n1 * AESM_C * sizeof(cpx), sm_r = (size_t)2 * a.n2 * sizeof(cpx);
+    const int per_sm_c = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)220 * 1024 / (sm_c + 1024)));
+    const int per_sm_r = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)220 * 1024 / (sm_r + 1024)));
+    const unsigned gc = (unsigned)std::min<long long>(tiles, (long long)pl->sms * per_sm_c);
+    const unsigned gr = (unsigned)std::min<long long>(rows, (long long)pl->sms * per_sm_r);
+    aesm_cols_fwd_kernel<<<gc, AESM_NTC, sm_c, st>>>(a);
+    aesm_rows_kernel<<<gr, AESM_NT, sm_r, st>>>(a);
+    aesm_cols_inv_kernel<<<gc, AESM_NT, sm_c, st>>>(a);       // 512 threads: 50 registers leave 2 CTAs per SM (3.1 ms against 1.8)
+    aes_count_launch(); aes_count_launch(); aes_count_launch();
+    AES_CUDA(cudaGetLastError());
+    return 0;
+}
+
 AES_EXPORT int aes_spectral_plan_destroy(aes_spectral_plan *pl)
 {
     if (!pl) return 0;
     cudaDeviceSynchronize();                        // launches on the caller's streams may still use the buffers
+    spec_free(pl->d_stw);
+    spec_free(pl->d_rev);
     spec_free(pl->d_vhat);
     spec_free(pl->d_chirp);
     spec_free(pl->d_tw1k);
@@ -183,8 +235,33 @@ AES_EXPORT int aes_spectral_plan_create(int64_t frame_len, aes_spectral_plan **o
     long long P = 1024; int L = 10;
     while (P < 2 * M - 1) { P <<= 1; ++L; }
     pl->M = M; pl->P = P; pl->L = L;
+    pl->smooth = !getenv("AES_SPECTRAL_BLUESTEIN") && aesm_split(M, &pl->n1, &pl->n2);
     int rc = [&]() -> int {
         aes_device_sm_count(&pl->sms);
+        if (pl->smooth) {
+            aesm_build_fft(pl->n1, &pl->f1); aesm_build_fft(pl->n2, &pl->f2);
+            const long long nhi = (M + 1023) / 1024;
+            int ra;
+            const int nst = pl->f1.tsize + pl->f2.tsize;
+            if ((ra = spec_alloc((void **)&pl->d_stw, (size_t)(nst + 1024 + nhi) * sizeof(cpx)))) return ra;
+            std::vector<cpx> stw((size_t)nst + 1);
+            aesm_fill_twiddles(pl->f1, stw.data()); aesm_fill_twiddles(pl->f2, stw.data() + pl->f1.tsize);
+            AES_CUDA(cudaMemcpy(pl->d_stw, stw.data(), (size_t)nst * sizeof(cpx), cudaMemcpyHostToDevice));
+            if ((ra = spec_alloc((void **)&pl->d_window, (size_t)M * sizeof(float)))) return ra;
+            if ((ra = spec_alloc((void **)&pl->d_rev, (size_t)(pl->n1 + pl->n2) * sizeof(int)))) return ra;
+            std::vector<int> rev((size_t)pl->n1 + pl->n2);
+            for (int k = 0; k < pl->n1; ++k) rev[k] = aesm_rev(k, pl->f1);
+            for (int k = 0; k < pl->n2; ++k) rev[pl->n1 + k] = aesm_rev(k, pl->f2);
+            AES_CUDA(cudaMemcpy(pl->d_rev, rev.data(), rev.size() * sizeof(int), cudaMemcpyHostToDevice));
+            const int sm_c = pl->n1 * AESM_C * (int)sizeof(cpx), sm_r = 2 * pl->n2 * (int)sizeof(cpx);
+            AES_CUDA(cudaFuncSetAttribute(aesm_cols_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_c));
+            AES_CUDA(cudaFuncSetAttribute(aesm_cols_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_c));
+            AES_CUDA(cudaFuncSetAttribute(aesm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_r));
+            aesm_tables_kernel<<<spec_grid(pl), 256>>>(pl->d_stw + nst, pl->d_stw + nst + 1024, nhi, pl->d_window, M);
+            aes_count_launch();
+            AES_CUDA(cudaDeviceSynchronize());
+            return 0;
+        }
         std::vector<cpx> tw1k(512);
         for (int q = 0; q < 512; ++q) { const double ang = -2.0 * M_PI * q / 1024.0; tw1k[q].x = (float)cos(ang); tw1k[q].y = (float)sin(ang); }
         int ra;
@@ -231,10 +308,24 @@ AES_EXPORT int aes_spectral_frames_host(aes_spectral_plan *pl, const float *in_b
     AES_REQUIRE(pl != nullptr && in_buffers != nullptr && mask != nullptr && y != nullptr, "NULL argument");
     if (n_frames <= 0) return 0;
     const long long M = pl->M, nbins = M / 2 + 1;
-    const size_t s_buf = al256((size_t)pl->P * sizeof(cpx)), s_fr = al256((size_t)M * 4), s_mk = al256((size_t)nbins * 4);
+    const size_t s_buf = al256((size_t)(pl->smooth ? M : pl->P) * sizeof(cpx)), s_fr = al256((size_t)M * 4), s_mk = al256((size_t)nbins * 4);
     int rc = spec_reserve(pl, s_buf + 2 * s_fr + s_mk);
     if (rc) return rc;
     char *w = (char *)pl->d_work;
+    if (pl->smooth) {
+        SmoothArgs sa = smooth_args(pl);
+        float *d_fr = (float *)(w + s_buf), *d_out = (float *)(w + s_buf + s_fr), *d_mask = (float *)(w + s_buf + 2 * s_fr);
+        sa.buf = (cpx *)w; sa.frames = d_fr; sa.out = d_out; sa.mask = d_mask; sa.mode = 1; sa.np = 1; sa.nf = 1;
+        sa.thr = (float)thresh_lin; sa.red = (float)reduction; sa.alpha = (float)alpha;
+        for (int f = 0; f < n_frames; ++f) {
+            AES_CUDA(cudaMemcpy(d_fr, in_buffers + (size_t)f * M, (size_t)M * 4, cudaMemcpyHostToDevice));
+            AES_CUDA(cudaMemcpy(d_mask, mask + (size_t)f * nbins, (size_t)nbins * 4, cudaMemcpyHostToDevice));
+            if ((rc = smooth_process(pl, sa, nullptr))) return rc;
+            AES_CUDA(cudaMemcpy(y + (size_t)f * M, d_out, (size_t)M * 4, cudaMemcpyDeviceToHost));
+            AES_CUDA(cudaMemcpy(mask + (size_t)f * nbins, d_mask, (size_t)nbins * 4, cudaMemcpyDeviceToHost));
+        }
+        return 0;
+    }
     SpecArgs a; memset(&a, 0, sizeof a);
     a.buf = (cpx *)w; a.frames = (float *)(w + s_buf); a.out = (float *)(w + s_buf + s_fr); a.mask = (float *)(w + s_buf + 2 * s_fr);
     a.vhat = pl->d_vhat; a.chirp = pl->d_chirp; a.twP = nullptr; a.tw1k = pl->d_tw1k;
@@ -262,6 +353,26 @@ AES_EXPORT int aes_spectral_run(aes_spectral_plan *pl, const float *x, float *y,
     AES_REQUIRE(x != nullptr && y != nullptr, "NULL device buffer");
     AES_REQUIRE(pl->M == 2 * n_frames, "plan frame length %lld != 2 * n_frames", pl->M);
     const long long M = pl->M, nbins = M / 2 + 1;
+    if (pl->smooth) {
+        // one M-point complex buffer per pair of clips is all the state there is; the default chunk keeps
+        // it L2-sized so the three passes hand the spectrum over on chip (AES_SPECTRAL_CHUNK_MB overrides)
+        const char *env = getenv("AES_SPECTRAL_CHUNK_MB");
+        const size_t budget_s = (size_t)(env ? std::max(1, atoi(env)) : 64) << 20, pair = (size_t)M * sizeof(cpx);
+        const int64_t pairs_all = (n_clips + 1) / 2;
+        const int64_t cp = std::max<int64_t>(1, std::min<int64_t>(pairs_all, (int64_t)(budget_s / pair)));
+        int rcs = spec_reserve(pl, pair * (size_t)cp);
+        if (rcs) return rcs;
+        SmoothArgs sa = smooth_args(pl);
+        sa.buf = (cpx *)pl->d_work; sa.mode = 2;
+        sa.thr = (float)thresh_lin; sa.red = (float)reduction; sa.alpha = (float)alpha;
+        for (int64_t p0 = 0; p0 < pairs_all; p0 += cp) {
+            const int64_t c0 = 2 * p0, nc = std::min<int64_t>(2 * cp, n_clips - c0);
+            sa.clips = x + (size_t)c0 * n_frames * 2; sa.yclips = y + (size_t)c0 * n_frames * 2;
+            sa.nf = (int)nc; sa.np = (int)((nc + 1) / 2);
+            if ((rcs = smooth_process(pl, sa, (cudaStream_t)stream))) return rcs;
+        }
+        return 0;
+    }
     // per clip: half a transform buffer (two clips share one), frame, output, mask
     const size_t per = al256((size_t)pl->P * sizeof(cpx)) / 2 + 2 * al256((size_t)M * 4) + al256((size_t)nbins * 4);
     const size_t budget = (size_t)8 << 30;

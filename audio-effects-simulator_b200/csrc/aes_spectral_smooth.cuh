@@ -23,7 +23,8 @@
 #include "aes_spectral.cuh"
 
 #define AESM_MAX_STAGES 12
-#define AESM_NT 256
+#define AESM_NT 256                 // threads of the row-pair kernel
+#define AESM_NTC 512                // threads of the forward column kernel (61 KB tiles: 3 CTAs per SM, 48 warps)
 #define AESM_C 8                    // columns per K1 / K3 tile
 
 struct SmoothDiv { unsigned mul; unsigned d; };     // x / d for x * d < 2^32:  __umulhi(x, mul)
@@ -33,20 +34,23 @@ struct SmoothFft {
     int r[AESM_MAX_STAGES];         // radices in DIF order
     int len[AESM_MAX_STAGES];       // sub-transform length entering stage i (len[0] = n)
     SmoothDiv dm[AESM_MAX_STAGES];  // division by m_i = len[i] / r[i]
+    int toff[AESM_MAX_STAGES];      // stage twiddles T_i[(d-1) * m_i + p] = w_len^(p*d) start here in the plan's table
+    int tsize;                      // entries of all stages (stages with m = 1 have none)
 };
 
 struct SmoothArgs {
     SmoothFft f1, f2;               // column (n1) and row (n2) transforms
     cpx *buf;                       // [np][n1][n2] work buffer
-    const cpx *tw1, *tw2;           // w_n1^j, w_n2^j
+    const cpx *tw1, *tw2;           // per-stage twiddles of the two transforms (SmoothFft::toff)
     const cpx *twlo, *twhi;         // W_M^t = twhi[t >> 10] * twlo[t & 1023]
+    const int *rev1, *rev2;         // position of output index k after the DIF stages (mixed-radix digit reversal)
     const float *frames;            // [nf][M] analysis frames (mode 1) or null
     const float *window;            // [M] Hann window or null
     const float *clips;             // [nf][N][2] stereo clips (mode 2: frame = [zeros(N), mean * window[N:]])
     float *mask;                    // [nf][M/2+1] smoothed mask in/out, or null: starts at ones, not kept
     float *out;                     // [nf][M] (mode 1)
     float *yclips;                  // [nf][N][2] (mode 2): first N samples, both channels
-    long long M;
+    int M;                          // frame length (n1 * n2 <= 2^23)
     int n1, n2, np, nf;             // np = ceil(nf / 2) transform pairs
     int mode;                       // 1 frames -> out, 2 clips -> yclips
     float thr, red, alpha;
@@ -78,6 +82,25 @@ template <int R, bool INV> __device__ __forceinline__ void aesm_dft(cpx (&a)[R])
         if (INV) { jd.x = -jd.x; jd.y = -jd.y; }            // +i * d1
         a[0] = c_add(s0, s1); a[2 % R] = c_sub(s0, s1);
         a[1 % R] = c_add(d0, jd); a[3 % R] = c_sub(d0, jd);
+    } else if (R == 8) {
+        const float h = 0.70710678118654752440f;
+        cpx b[4], c[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { b[j] = c_add(a[j], a[(j + 4) % R]); c[j] = c_sub(a[j], a[(j + 4) % R]); }
+        cpx t;                                              // c[j] *= w8^j (conjugated for the inverse)
+        if (!INV) {
+            t.x = h * (c[1].x + c[1].y); t.y = h * (c[1].y - c[1].x); c[1] = t;
+            t.x = c[2].y; t.y = -c[2].x; c[2] = t;
+            t.x = h * (c[3].y - c[3].x); t.y = -h * (c[3].x + c[3].y); c[3] = t;
+        } else {
+            t.x = h * (c[1].x - c[1].y); t.y = h * (c[1].x + c[1].y); c[1] = t;
+            t.x = -c[2].y; t.y = c[2].x; c[2] = t;
+            t.x = -h * (c[3].x + c[3].y); t.y = h * (c[3].x - c[3].y); c[3] = t;
+        }
+        aesm_dft<4, INV>(b);
+        aesm_dft<4, INV>(c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { a[(2 * k) % R] = b[k]; a[(2 * k + 1) % R] = c[k]; }
     } else if (R == 3) {
         const float s = 0.86602540378443864676f;
         const cpx t1 = c_add(a[1 % R], a[2 % R]);
@@ -88,7 +111,7 @@ template <int R, bool INV> __device__ __forceinline__ void aesm_dft(cpx (&a)[R])
         a[0] = c_add(a[0], t1);
         a[1 % R] = c_add(t2, jt); a[2 % R] = c_sub(t2, jt);
     } else {
-        static_assert(R == 2 || R == 3 || R == 4 || R == 5, "");
+        static_assert(R == 2 || R == 3 || R == 4 || R == 5 || R == 8, "");
         const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;
         const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;
         const cpx t1 = c_add(a[1 % R], a[4 % R]), t2 = c_add(a[2 % R], a[3 % R]);
@@ -113,22 +136,23 @@ template <int R, bool INV> __device__ __forceinline__ void aesm_dft(cpx (&a)[R])
 template <int R, bool INV>
 __device__ __forceinline__ void aesm_stage(cpx *s, int S, SmoothDiv divS, int qs, int es, const SmoothFft &f, int i, const cpx *tw)
 {
-    const int len = f.len[i], m = len / R, nbf = f.n / R, tstep = f.n / len;
-    for (unsigned e = threadIdx.x; e < (unsigned)(S * nbf); e += AESM_NT) {
+    const int len = f.len[i], m = len / R, nbf = f.n / R;
+    const cpx *__restrict__ T = tw + f.toff[i];
+    for (unsigned e = threadIdx.x; e < (unsigned)(S * nbf); e += blockDim.x) {
         const unsigned fi = aesm_div(e, divS), q = e - fi * S;          // sequences fastest: adjacent columns, adjacent words
         const unsigned blk = aesm_div(fi, f.dm[i]), p = fi - blk * m;
         cpx *base = s + q * qs + (blk * len + p) * es;
         cpx a[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) a[j] = base[j * m * es];
-        if (INV) {
+        if (INV && m > 1) {
 #pragma unroll
-            for (int d = 1; d < R; ++d) a[d] = aesm_cmulc(a[d], tw[p * d * tstep], true);
+            for (int d = 1; d < R; ++d) a[d] = aesm_cmulc(a[d], T[(d - 1) * m + p], true);
         }
         aesm_dft<R, INV>(a);
-        if (!INV) {
+        if (!INV && m > 1) {
 #pragma unroll
-            for (int d = 1; d < R; ++d) a[d] = aesm_cmulc(a[d], tw[p * d * tstep], false);
+            for (int d = 1; d < R; ++d) a[d] = aesm_cmulc(a[d], T[(d - 1) * m + p], false);
         }
 #pragma unroll
         for (int j = 0; j < R; ++j) base[j * m * es] = a[j];
@@ -141,6 +165,7 @@ __device__ __forceinline__ void aesm_fft(cpx *s, int S, SmoothDiv divS, int qs, 
     for (int k = 0; k < f.ns; ++k) {
         const int i = INV ? f.ns - 1 - k : k;
         switch (f.r[i]) {
+        case 8: aesm_stage<8, INV>(s, S, divS, qs, es, f, i, tw); break;
         case 4: aesm_stage<4, INV>(s, S, divS, qs, es, f, i, tw); break;
         case 2: aesm_stage<2, INV>(s, S, divS, qs, es, f, i, tw); break;
         case 3: aesm_stage<3, INV>(s, S, divS, qs, es, f, i, tw); break;
@@ -150,8 +175,8 @@ __device__ __forceinline__ void aesm_fft(cpx *s, int S, SmoothDiv divS, int qs, 
     }
 }
 
-// position of output index k after the DIF stages (mixed-radix digit reversal)
-__device__ __forceinline__ int aesm_rev(int k, const SmoothFft &f)
+// position of output index k after the DIF stages (mixed-radix digit reversal); host side, tabulated per plan
+static inline int aesm_rev(int k, const SmoothFft &f)
 {
     int pos = 0, len = f.n;
     for (int i = 0; i < f.ns; ++i) {
@@ -163,7 +188,7 @@ __device__ __forceinline__ int aesm_rev(int k, const SmoothFft &f)
 }
 
 // W_M^t (t in [0, M)) or its conjugate
-__device__ __forceinline__ cpx aesm_wM(const SmoothArgs &a, long long t, bool conj_w)
+__device__ __forceinline__ cpx aesm_wM(const SmoothArgs &a, int t, bool conj_w)
 {
     const cpx w = aesm_cmulc(a.twhi[t >> 10], a.twlo[t & 1023], false);
     cpx r = w;
@@ -172,17 +197,16 @@ __device__ __forceinline__ cpx aesm_wM(const SmoothArgs &a, long long t, bool co
 }
 
 // sample n of the analysis frame of real frame `fr` (or 0 when the pair has no second frame)
-__device__ __forceinline__ float aesm_sample(const SmoothArgs &a, int fr, long long n)
+__device__ __forceinline__ float aesm_sample(const SmoothArgs &a, int fr, int n, float w)
 {
     if (fr >= a.nf) return 0.0f;
     if (a.mode == 2) {
-        const long long N = a.M / 2;
+        const int N = a.M / 2;
         if (n < N) return 0.0f;
         const float2 f = reinterpret_cast<const float2 *>(a.clips)[(long long)fr * N + (n - N)];
-        return __fmul_rn(__fmul_rn(__fadd_rn(f.x, f.y), 0.5f), a.window[n]);     // np.mean, then * window, in f32
+        return __fmul_rn(__fmul_rn(__fadd_rn(f.x, f.y), 0.5f), w);      // np.mean, then * window, in f32
     }
-    const float v = a.frames[(long long)fr * a.M + n];
-    return a.window != nullptr ? __fmul_rn(v, a.window[n]) : v;
+    return __fmul_rn(a.frames[(long long)fr * a.M + n], w);
 }
 
 // ---- K1: column FFTs ---------------------------------------------------------------------------------
@@ -193,24 +217,25 @@ __device__ void aesm_cols_fwd_body(const SmoothArgs &a)
     SmoothDiv divC; divC.d = AESM_C; divC.mul = 0x20000000u;        // x / 8
     for (long long w = blockIdx.x; w < (long long)a.np * tiles; w += gridDim.x) {
         const int p = (int)(w / tiles), b0 = (int)(w % tiles) * AESM_C;
-        for (int e = threadIdx.x; e < n1 * AESM_C; e += AESM_NT) {
+        for (int e = threadIdx.x; e < n1 * AESM_C; e += blockDim.x) {
             const int row = e / AESM_C, c = e % AESM_C, b = b0 + c;
             cpx z; z.x = 0.f; z.y = 0.f;
-            if (b < n2) {
-                const long long n = (long long)row * n2 + b;
-                z.x = aesm_sample(a, 2 * p, n);
-                z.y = aesm_sample(a, 2 * p + 1, n);
+            if (b < n2 && (a.mode != 2 || 2 * row >= n1)) {          // whole-clip frames: the first half is zeros
+                const int n = row * n2 + b;
+                const float wn = a.window != nullptr ? a.window[n] : 1.0f;
+                z.x = aesm_sample(a, 2 * p, n, wn);
+                z.y = aesm_sample(a, 2 * p + 1, n, wn);
             }
             s[e] = z;
         }
         __syncthreads();
         aesm_fft<false>(s, AESM_C, divC, 1, AESM_C, a.f1, a.tw1);
         cpx *dst = a.buf + (long long)p * a.M;
-        for (int e = threadIdx.x; e < n1 * AESM_C; e += AESM_NT) {
+        for (int e = threadIdx.x; e < n1 * AESM_C; e += blockDim.x) {
             const int k1 = e / AESM_C, c = e % AESM_C, b = b0 + c;
             if (b < n2) {
-                const cpx v = s[aesm_rev(k1, a.f1) * AESM_C + c];
-                dst[(long long)k1 * n2 + b] = c_mul(v, aesm_wM(a, ((long long)b * k1) % a.M, false));
+                const cpx v = s[a.rev1[k1] * AESM_C + c];
+                dst[k1 * n2 + b] = c_mul(v, aesm_wM(a, b * k1, false));       // b * k1 < n2 * n1 = M
             }
         }
         __syncthreads();
@@ -234,7 +259,7 @@ __device__ void aesm_rows_body(const SmoothArgs &a)
 {
     AES_DYN_SMEM(cpx, s);                                   // [2][n2]: row k1, row n1 - k1
     const int n1 = a.n1, n2 = a.n2, half = n1 / 2 + 1;      // row pairs per transform: k1 = 0 .. n1/2
-    const long long nbins = a.M / 2 + 1;
+    const int nbins = a.M / 2 + 1;
     SmoothDiv div2; div2.d = 2; div2.mul = 0x80000000u;
     SmoothDiv div1; div1.d = 1; div1.mul = 0;
     for (long long w = blockIdx.x; w < (long long)a.np * half; w += gridDim.x) {
@@ -243,7 +268,7 @@ __device__ void aesm_rows_body(const SmoothArgs &a)
         const int S = self ? 1 : 2;
         cpx *rowA = a.buf + (long long)p * a.M + (long long)k1 * n2;
         cpx *rowB = a.buf + (long long)p * a.M + (long long)k1b * n2;
-        for (int e = threadIdx.x; e < n2; e += AESM_NT) {
+        for (int e = threadIdx.x; e < n2; e += blockDim.x) {
             s[e] = rowA[e];
             if (!self) s[n2 + e] = rowB[e];
         }
@@ -251,14 +276,14 @@ __device__ void aesm_rows_body(const SmoothArgs &a)
         aesm_fft<false>(s, S, self ? div1 : div2, n2, 1, a.f2, a.tw2);
         // bins: k = k1 + n1*k2 (row A, column k2)  <->  M - k = k1b + n1*k2b (row B, column k2b)
         const bool two = 2 * p + 1 < a.nf;
-        for (int k2 = threadIdx.x; k2 < n2; k2 += AESM_NT) {
-            const long long k = k1 + (long long)n1 * k2;
-            const int k2b = k1 == 0 ? (n2 - k2) % n2 : n2 - 1 - k2;
-            const long long km = (long long)k1b + (long long)n1 * k2b;          // = (M - k) mod M
+        for (int k2 = threadIdx.x; k2 < n2; k2 += blockDim.x) {
+            const int k = k1 + n1 * k2;
+            const int k2b = k1 == 0 ? (k2 == 0 ? 0 : n2 - k2) : n2 - 1 - k2;
+            const int km = k1b + n1 * k2b;                  // = (M - k) mod M
             if (self && km < k) continue;                   // each unordered pair once
-            const int ia = aesm_rev(k2, a.f2), ib = (self ? 0 : n2) + aesm_rev(k2b, a.f2);
+            const int ia = a.rev2[k2], ib = (self ? 0 : n2) + a.rev2[k2b];
             const cpx Zk = s[ia], Zm = s[ib];
-            const long long kk = k <= km ? k : km;          // the rfft bin this pair is
+            const int kk = k <= km ? k : km;                // the rfft bin this pair is
             cpx X0, X1;                                     // rfft bin of frame 2p / 2p+1 at index k
             X0.x = 0.5f * (Zk.x + Zm.x); X0.y = 0.5f * (Zk.y - Zm.y);
             X1.x = 0.5f * (Zk.y + Zm.y); X1.y = 0.5f * (Zm.x - Zk.x);
@@ -278,9 +303,9 @@ __device__ void aesm_rows_body(const SmoothArgs &a)
         }
         __syncthreads();
         aesm_fft<true>(s, S, self ? div1 : div2, n2, 1, a.f2, a.tw2);
-        for (int e = threadIdx.x; e < n2; e += AESM_NT) {
-            rowA[e] = c_mul(s[e], aesm_wM(a, ((long long)e * k1) % a.M, true));
-            if (!self) rowB[e] = c_mul(s[n2 + e], aesm_wM(a, ((long long)e * k1b) % a.M, true));
+        for (int e = threadIdx.x; e < n2; e += blockDim.x) {
+            rowA[e] = c_mul(s[e], aesm_wM(a, e * k1, true));
+            if (!self) rowB[e] = c_mul(s[n2 + e], aesm_wM(a, e * k1b, true));
         }
         __syncthreads();
     }
@@ -292,24 +317,24 @@ __device__ void aesm_cols_inv_body(const SmoothArgs &a)
     AES_DYN_SMEM(cpx, s);
     const int n1 = a.n1, n2 = a.n2, tiles = (n2 + AESM_C - 1) / AESM_C;
     const float inv = 1.0f / (float)a.M;
-    const long long N = a.M / 2;
+    const int N = a.M / 2;
     SmoothDiv divC; divC.d = AESM_C; divC.mul = 0x20000000u;
     for (long long w = blockIdx.x; w < (long long)a.np * tiles; w += gridDim.x) {
         const int p = (int)(w / tiles), b0 = (int)(w % tiles) * AESM_C;
         const cpx *src = a.buf + (long long)p * a.M;
-        for (int e = threadIdx.x; e < n1 * AESM_C; e += AESM_NT) {
+        for (int e = threadIdx.x; e < n1 * AESM_C; e += blockDim.x) {
             const int k1 = e / AESM_C, c = e % AESM_C, b = b0 + c;
             cpx z; z.x = 0.f; z.y = 0.f;
-            if (b < n2) z = src[(long long)k1 * n2 + b];
-            s[aesm_rev(k1, a.f1) * AESM_C + c] = z;
+            if (b < n2) z = src[k1 * n2 + b];
+            s[a.rev1[k1] * AESM_C + c] = z;
         }
         __syncthreads();
         aesm_fft<true>(s, AESM_C, divC, 1, AESM_C, a.f1, a.tw1);
         const bool two = 2 * p + 1 < a.nf;
-        for (int e = threadIdx.x; e < n1 * AESM_C; e += AESM_NT) {
+        for (int e = threadIdx.x; e < n1 * AESM_C; e += blockDim.x) {
             const int row = e / AESM_C, c = e % AESM_C, b = b0 + c;
             if (b >= n2) continue;
-            const long long n = (long long)row * n2 + b;
+            const int n = row * n2 + b;
             const cpx v = s[e];
             if (a.mode == 2) {
                 if (n < N) {                                // the block emits the first N samples, both channels
@@ -329,10 +354,10 @@ __device__ void aesm_cols_inv_body(const SmoothArgs &a)
 // ---- host: factorisation -----------------------------------------------------------------------------------
 static inline bool aesm_build_fft(int n, SmoothFft *f)
 {
-    f->n = n; f->ns = 0;
+    f->n = n; f->ns = 0; f->tsize = 0;
     int rem = n, len = n;
-    const int order[4] = { 4, 2, 3, 5 };
-    for (int oi = 0; oi < 4; ++oi) {
+    const int order[5] = { 8, 4, 2, 3, 5 };     // odd radices last: their unit-stride last stage is bank-conflict free
+    for (int oi = 0; oi < 5; ++oi) {
         const int r = order[oi];
         while (rem % r == 0 && rem > 1) {
             if (f->ns >= AESM_MAX_STAGES) return false;
@@ -340,10 +365,27 @@ static inline bool aesm_build_fft(int n, SmoothFft *f)
             const unsigned m = (unsigned)(len / r);
             f->dm[f->ns].d = m;
             f->dm[f->ns].mul = m == 1 ? 0u : (unsigned)(0x100000000ULL / m) + 1u;
+            f->toff[f->ns] = f->tsize;
+            if (m > 1) f->tsize += (r - 1) * (int)m;
             ++f->ns; rem /= r; len /= r;
         }
     }
     return rem == 1;
+}
+
+// stage twiddles of one transform, in double (host; a few thousand entries)
+static inline void aesm_fill_twiddles(const SmoothFft &f, cpx *t)
+{
+    for (int i = 0; i < f.ns; ++i) {
+        const int r = f.r[i], len = f.len[i], m = len / r;
+        if (m == 1) continue;
+        for (int d = 1; d < r; ++d)
+            for (int p = 0; p < m; ++p) {
+                const double ang = -2.0 * 3.14159265358979323846 * (double)(((long long)p * d) % len) / (double)len;
+                t[f.toff[i] + (d - 1) * m + p].x = (float)cos(ang);
+                t[f.toff[i] + (d - 1) * m + p].y = (float)sin(ang);
+            }
+    }
 }
 
 // n1 x n2 = M with both factors {2,3,5}-smooth, n1 even, and small enough for shared memory;

@@ -225,3 +225,41 @@ int emu_spectral_frames(const float *frames, float *mask, float *y, long long M,
     if (!fuse) emu::launch(sp_store, &l, 4, 256, 0);
     return 0;
 }
+
+// ---- smooth-length SpectralFilter path (aes_spectral_smooth.cuh) on the emulator ------------------
+#include "../../audio-effects-simulator_b200/csrc/aes_spectral_smooth.cuh"
+static void sm_k1(void *p) { aesm_cols_fwd_body(*reinterpret_cast<SmoothArgs *>(p)); }
+static void sm_k2(void *p) { aesm_rows_body(*reinterpret_cast<SmoothArgs *>(p)); }
+static void sm_k3(void *p) { aesm_cols_inv_body(*reinterpret_cast<SmoothArgs *>(p)); }
+
+// mode 1: frames [nf][M] raw (window applied when `window` != null), mask [nf][M/2+1] or null, y [nf][M]
+// mode 2: frames = clips [nf][M/2][2], y = [nf][M/2][2]; returns 1 when M has no smooth split
+extern "C" __attribute__((visibility("default")))
+int emu_spectral_smooth(int mode, const float *frames, const float *window, float *mask, float *y, long long M, int nf,
+                        float thr, float red, float alpha, int *n1_out, int *n2_out)
+{
+    int n1 = 0, n2 = 0;
+    if (!aesm_split(M, &n1, &n2)) return 1;
+    if (n1_out) *n1_out = n1;
+    if (n2_out) *n2_out = n2;
+    SmoothArgs a; memset(&a, 0, sizeof a);
+    aesm_build_fft(n1, &a.f1); aesm_build_fft(n2, &a.f2);
+    const long long nhi = (M + 1023) / 1024;
+    std::vector<cpx> tw1((size_t)a.f1.tsize + 1), tw2((size_t)a.f2.tsize + 1), twlo(1024), twhi((size_t)nhi), buf((size_t)((nf + 1) / 2) * M);
+    auto fill = [](std::vector<cpx> &t, double step, double denom) {
+        for (size_t j = 0; j < t.size(); ++j) { const double ang = -2.0 * M_PI * (double)j * step / denom; t[j].x = (float)cos(ang); t[j].y = (float)sin(ang); }
+    };
+    aesm_fill_twiddles(a.f1, tw1.data()); aesm_fill_twiddles(a.f2, tw2.data()); fill(twlo, 1.0, (double)M); fill(twhi, 1024.0, (double)M);
+    std::vector<int> rev1(n1), rev2(n2);
+    for (int k = 0; k < n1; ++k) rev1[k] = aesm_rev(k, a.f1);
+    for (int k = 0; k < n2; ++k) rev2[k] = aesm_rev(k, a.f2);
+    a.rev1 = rev1.data(); a.rev2 = rev2.data();
+    a.buf = buf.data(); a.tw1 = tw1.data(); a.tw2 = tw2.data(); a.twlo = twlo.data(); a.twhi = twhi.data();
+    a.window = window; a.mask = mask; a.M = (int)M; a.n1 = n1; a.n2 = n2; a.nf = nf; a.np = (nf + 1) / 2; a.mode = mode;
+    a.thr = thr; a.red = red; a.alpha = alpha;
+    if (mode == 2) { a.clips = frames; a.yclips = y; } else { a.frames = frames; a.out = y; }
+    emu::launch(sm_k1, &a, 3, AESM_NTC, (size_t)n1 * AESM_C * sizeof(cpx));
+    emu::launch(sm_k2, &a, 3, AESM_NT, (size_t)2 * n2 * sizeof(cpx));
+    emu::launch(sm_k3, &a, 3, AESM_NT, (size_t)n1 * AESM_C * sizeof(cpx));
+    return 0;
+}
