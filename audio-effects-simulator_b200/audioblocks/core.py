@@ -166,6 +166,18 @@ class NativeEffect(Effect):
         if not silent:
             self._dirty = True
 
+    def _at_rest(self) -> bool:
+        """Nothing in this effect's memory can make sound: a silent block comes out silent."""
+        return not (self._dirty or self._stale)
+
+    def _rest_block(self, frames: int):
+        """State after a silent block through an effect at rest, in closed form (no launch): the
+        parameters took their per-block smoothing step in _stages(); lines stay zero."""
+        self._absorb_rest(frames)
+
+    def _absorb_rest(self, frames: int):
+        self._n_total += frames
+
     def _require_fresh(self):
         if self._dirty or self._stale:
             raise _native.AesimError(
@@ -206,6 +218,14 @@ def _snapshot(fx):
 
 
 def _stream_block(effects, x, y, silent):
+    if silent and all(fx._at_rest() for fx in effects):
+        # the reference's warm-up (engine.py:96-99: two zero blocks) and any silent stretch: zero in,
+        # zero out; only write pointers, phasors, gate gain and the smoothed parameters move
+        for fx in effects:
+            fx._stages(x.shape[0])
+            fx._rest_block(x.shape[0])
+        y[...] = 0.0
+        return
     per_fx = []
     for fx in effects:
         fx._require_usable()

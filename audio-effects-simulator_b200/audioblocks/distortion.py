@@ -30,3 +30,9 @@ class DistortionEffect(NativeEffect):
 
     def _absorb(self, desc, frames, silent):
         pass
+
+    def _at_rest(self):
+        return True
+
+    def _rest_block(self, frames):
+        pass

@@ -72,6 +72,9 @@ class FilterEffect(NativeEffect):
                 d.p[8 + 4 * c + k] = float(row[k])
         return [d]
 
+    def _at_rest(self):
+        return not self._state.any()        # zero DF-I memories: zero in, zero out, memories stay zero
+
     def _absorb(self, desc, frames, silent):
         self._n_total += frames
         for c in range(self._state.shape[0]):

@@ -45,6 +45,21 @@ class NoiseGateEffect(NativeEffect):
         self._n_total += frames
         self._gain_state = float(desc.p[3])
 
+    def _at_rest(self):
+        return True                 # the only memory is the gain; silence times any gain is silence
+
+    def _rest_block(self, frames):
+        # level 0 never exceeds the threshold: the gain releases towards 0 (gate.py:33-40)
+        self._n_total += frames
+        g, k = self._gain_state, 1.0 - self._rel_now
+        if g != 0.0:
+            if frames <= 8192:
+                for _ in range(frames):
+                    g = k * g
+            else:
+                g *= k ** frames
+        self._gain_state = g
+
     def _advance(self, frames, silent, final=None):
         self._n_total += frames
         if final is not None:

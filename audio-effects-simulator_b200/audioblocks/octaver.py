@@ -53,6 +53,9 @@ class OctaverEffect(NativeEffect):
         if not silent:
             self._dirty = True
 
+    def _rest_block(self, frames):
+        self._advance(frames, True)         # write pointer and phasor move, the ring stays zero
+
     def _advance(self, frames, silent, final=None):
         self._n_total += frames
         self.w = (self.w + frames) % self.size

@@ -6,8 +6,9 @@ latency.  hop follows the chain's block size (spectral.py:30-42), so on the whol
 frame is 2N samples long and the block emits the zero-padded half of a single frame -- near
 silence; that quirk is reproduced, not fixed.
 
-The transforms run on the GPU (csrc/aes_spectral.cuh: Bluestein chirp-z over power-of-two
-FFTs, any frame length); the buffer shifting and the overlap-add bookkeeping around them are
+The transforms run on the GPU: frame lengths whose factors are 2, 3 and 5 (BASELINE's 960 000) as a
+four-step mixed-radix FFT with the gate fused between the row transforms (csrc/aes_spectral_smooth.cuh),
+any other length by Bluestein's chirp-z over power-of-two FFTs (csrc/aes_spectral.cuh); the buffer shifting and the overlap-add bookkeeping around them are
 the same few numpy lines as in the reference.  There is no CPU fallback for the transforms."""
 from __future__ import annotations
 
@@ -65,10 +66,16 @@ class SpectralFilter(Effect):
             self.in_buffer[-hop:] = (x_in[:, 0] + x_in[:, 1]) * np.float32(0.5)
         else:
             self.in_buffer[-hop:] = np.mean(x_in, axis=1)
-        mask = self.mask_smooth[None, :].copy()
-        y = self._plan(self.n_fft).frames_host(self.in_buffer[None, :].copy(), mask, thr, red, float(self.alpha_param))
-        self.mask_smooth = mask[0]
-        self.out_accum += y[0]
+        if not self.in_buffer.any():
+            # an all-zero frame (the warm-up blocks, silent stretches): every bin is under the threshold,
+            # the mask relaxes towards `reduction` (spectral.py:68-71) and the frame adds nothing
+            a = np.float32(self.alpha_param)
+            self.mask_smooth = a * self.mask_smooth + (np.float32(1.0) - a) * np.float32(red)
+        else:
+            mask = self.mask_smooth[None, :].copy()
+            y = self._plan(self.n_fft).frames_host(self.in_buffer[None, :].copy(), mask, thr, red, float(self.alpha_param))
+            self.mask_smooth = mask[0]
+            self.out_accum += y[0]
         for c in range(out.shape[1]):
             out[:, c] = self.out_accum[:hop]
         self.out_accum[:-hop] = self.out_accum[hop:]

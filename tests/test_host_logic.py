@@ -102,6 +102,45 @@ def test_octaver_warmup_phase_leaks_into_the_file():
     assert d.p[0] == 0.5333333333333231
 
 
+def test_warmup_of_a_chain_at_rest_launches_nothing(monkeypatch):
+    """engine.py:96-99 pushes two zero blocks through the fresh chain.  Zero in, zero out: the state they
+    leave (write pointers, phasor, gate gain, smoothed parameters, spectral mask) is advanced on the host."""
+    def boom(*a, **k):
+        raise AssertionError("the warm-up of a chain at rest must not reach the library")
+    monkeypatch.setattr(_native, "stream_process", boom)
+    monkeypatch.setattr(_native, "ChainPlan", boom)
+    monkeypatch.setattr(_native, "SpectralPlan", boom)
+    cfg = [{"type": "filter", "params": {"filter_type": 1, "cutoff_hz": 80}},
+           {"type": "octaver", "params": {"semitones": -12, "mix": 1.0}},
+           {"type": "gate", "params": {"threshold_db": -30}},
+           {"type": "delay", "params": {"delay_ms": 100}},
+           {"type": "spectral", "params": {"reduction": 0.25, "smoothing": 0.8}},
+           {"type": "reverb", "params": {}}]
+    chain = ab.EffectsChain(48000, 1, 2, 1024)
+    for c in cfg:
+        fx = make_effect(c)
+        assert fx is not None, c
+        chain.add(fx)
+    gate = chain.effects[2]
+    gate._gain_state = 0.5
+    chain.warmup()
+    octv, spec = chain.effects[1], chain.effects[4]
+    assert (octv.size, octv.w, octv.phasor) == (1920, 128, 0.5333333333333231)        # SURVEY 3.1 [probe]
+    k = 1.0 - gate._calc_coeff(100.0)
+    g = 0.5
+    for _ in range(2048):
+        g = k * g
+    assert gate._gain_state == g
+    assert all(fx._n_total == 2048 for fx in chain.effects if hasattr(fx, "_n_total"))
+    m = np.float32(1.0)
+    for _ in range(2):
+        m = np.float32(0.8) * m + (np.float32(1.0) - np.float32(0.8)) * np.float32(0.25)
+    assert spec.mask_smooth.shape == (1025,) and np.all(spec.mask_smooth == m)
+    out = np.ones((1024, 2), np.float32)
+    chain.process(np.zeros((1024, 1), np.float32), out)
+    assert not out.any()
+
+
 def test_filter_and_gate_constants_match_oracle():
     for t, fc, q in [(0, 1000.0, 0.707), (1, 80.0, 0.707), (2, 800.0, 0.8), (0, 20.0, 10.0)]:
         fx, o = ab.FilterEffect(t, fc, q), orc.OFilter(t, fc, q)
@@ -142,10 +181,11 @@ def test_no_cpu_fallback_without_a_device():
         pytest.skip("a CUDA device is present")
     chain = ab.EffectsChain(48000, 1, 2, 1024)
     chain.add(ab.StereoDelayEffect())
+    # (signal, not silence: a silent block through a chain at rest is zeros by construction and launches nothing)
     with pytest.raises(_native.AesimError):
-        chain.process(np.zeros((1024, 1), np.float32), np.zeros((1024, 2), np.float32))
+        chain.process(np.full((1024, 1), 0.25, np.float32), np.zeros((1024, 2), np.float32))
     with pytest.raises(_native.AesimError):
-        ab.SpectralFilter().process_into(np.zeros((8, 2), np.float32), np.zeros((8, 2), np.float32))
+        ab.SpectralFilter().process_into(np.full((8, 2), 0.25, np.float32), np.zeros((8, 2), np.float32))
     with pytest.raises(_native.AesimError):
         ab.ConvolutionReverbEffect(np.ones((4, 2), np.float32)).process_into(np.zeros((8, 2), np.float32),
                                                                                np.zeros((8, 2), np.float32))
