@@ -4,6 +4,7 @@
 #include <new>
 #include <stdlib.h>
 #include <string.h>
+#include <string>
 #include <vector>
 
 #include "aes_common.h"
@@ -78,13 +79,21 @@ struct aes_chain_plan {
     double *d_state = nullptr;                  // final carried scalars of a single-clip host call
     double h_state[16 * AES_MAX_STAGES];
     bool state_valid = false;
+    // A chain no kernel was specialised for, cut at stage boundaries into runs that are (the signal is
+    // f32 between stages in every kernel, so the cut changes no bit): launched back to back, in place
+    // on the output buffer.  Empty when the whole chain has its own kernel or no cut helps.
+    std::vector<aes_chain_plan *> seg;
+    std::vector<int> seg_first;                 // first stage of each segment
 };
+
+static int plan_create(const aes_stage_desc *stages, int n_stages, int sample_rate, aes_chain_plan **out, bool allow_split);
 
 template <int K>
 static int configure_kernel(aes_chain_plan *pl)
 {
-    AES_CUDA(cudaFuncSetAttribute(aes_chain_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)pl->smem_bytes));
+    // (the attribute belongs to the kernel, not to the plan: always the limit, so that a later, smaller plan
+    //  does not take a live plan's launch size away)
+    AES_CUDA(cudaFuncSetAttribute(aes_chain_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_SMEM_LIMIT));
     int occ = 0;
     AES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, aes_chain_kernel<K>, AES_NT, pl->smem_bytes));
     if (occ < 1) { aes_set_error("chain kernel does not fit on an SM"); return AES_ERR_UNSUPPORTED; }
@@ -100,6 +109,21 @@ static int launch_chain(aes_chain_plan *pl, const void *x, int in_fmt, void *y, 
                         bool allow_scan = true)
 {
     if (B <= 0 || N <= 0) return 0;
+    if (!pl->seg.empty()) {
+        // segment k reads what segment k-1 wrote: f32 stereo, in the output buffer itself when that is the
+        // caller's format (every kernel reads a tile before it writes it), else in a stream-ordered temporary
+        float *mid = (float *)y;
+        if (out_fmt != AES_FMT_F32_STEREO) AES_CUDA(cudaMallocAsync((void **)&mid, (size_t)B * N * 2 * sizeof(float), st));
+        int rc = 0;
+        for (size_t k = 0; k < pl->seg.size() && !rc; ++k) {
+            const bool first = k == 0, last = k + 1 == pl->seg.size();
+            rc = launch_chain(pl->seg[k], first ? x : mid, first ? in_fmt : AES_FMT_F32_STEREO, last ? y : mid,
+                              last ? out_fmt : AES_FMT_F32_STEREO, B, N, scratch, st,
+                              state_out ? state_out + 16 * pl->seg_first[k] : nullptr, allow_scan);
+        }
+        if (mid != (float *)y) cudaFreeAsync(mid, st);
+        return rc;
+    }
     if (pl->bq_ok && allow_scan && (B < pl->grid_max || getenv("AES_FORCE_SCAN")) && in_fmt == AES_FMT_F32_STEREO && out_fmt == AES_FMT_F32_STEREO &&
         !getenv("AES_NO_SCAN")) {
         // fewer clips than resident CTAs: go parallel in time (one CTA per 1024-frame tile)
@@ -186,6 +210,11 @@ static int check_formats(int in_fmt, int out_fmt)
 AES_EXPORT int aes_chain_plan_create(const aes_stage_desc *stages, int n_stages, int sample_rate,
                                      aes_chain_plan **out)
 {
+    return plan_create(stages, n_stages, sample_rate, out, true);
+}
+
+static int plan_create(const aes_stage_desc *stages, int n_stages, int sample_rate, aes_chain_plan **out, bool allow_split)
+{
     AES_REQUIRE(out != nullptr, "plan out-pointer is NULL");
     AES_REQUIRE(n_stages == 0 || stages != nullptr, "stages is NULL");
     aes_chain_plan *pl = new (std::nothrow) aes_chain_plan();
@@ -212,7 +241,7 @@ AES_EXPORT int aes_chain_plan_create(const aes_stage_desc *stages, int n_stages,
                 const size_t rv_smem = aes_rv_smem_bytes(pl->host.smem_floats, rv_pre);
                 for (const RvShape &sh : g_rv_shapes) {
                     if (sh.topo != topo || sh.pre != rv_pre || sh.pm != rv_pm || rv_smem > AES_SMEM_LIMIT) continue;
-                    AES_CUDA(cudaFuncSetAttribute(sh.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rv_smem));
+                    AES_CUDA(cudaFuncSetAttribute(sh.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_SMEM_LIMIT));
                     int occ = 0;
                     AES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sh.fn, AESRV_NT, rv_smem));
                     if (occ < 1) break;
@@ -229,7 +258,7 @@ AES_EXPORT int aes_chain_plan_create(const aes_stage_desc *stages, int n_stages,
             for (const FastShape &sh : g_fast_shapes) {      // compile-time topologies come first
                 if (memcmp(sh.c, codes, sizeof codes) != 0 || fast_smem > AES_SMEM_LIMIT) continue;
                 if (sh.topo != AESF_TOPO_NONE && sh.topo != topo) continue;
-                AES_CUDA(cudaFuncSetAttribute(sh.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fast_smem));
+                AES_CUDA(cudaFuncSetAttribute(sh.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, AES_SMEM_LIMIT));
                 int occ = 0;
                 AES_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sh.fn, AES_NT, fast_smem));
                 if (occ < 1) break;
@@ -271,6 +300,37 @@ AES_EXPORT int aes_chain_plan_create(const aes_stage_desc *stages, int n_stages,
         }
         AES_CUDA(cudaMalloc(&pl->d_state, sizeof pl->h_state));
         AES_CUDA(cudaMemset(pl->d_state, 0, sizeof pl->h_state));
+        // no kernel for the whole chain: cut it into the longest runs that have one
+        if (allow_split && !pl->fast_fn && !pl->bq_ok && n_stages > 1 && !getenv("AES_NO_SPLIT")) {
+            int i = 0, n_fast = 0;
+            while (i < n_stages) {
+                aes_chain_plan *best = nullptr;
+                int blen = 0;
+                for (int len = std::min<int>(AESF_MAX_STAGES, n_stages - i); len >= 1 && !best; --len) {
+                    aes_chain_plan *sp = nullptr;
+                    if (plan_create(stages + i, len, sample_rate, &sp, false) != 0) continue;
+                    if (sp->fast_fn || len == 1) { best = sp; blen = len; }
+                    else aes_chain_plan_destroy(sp);
+                }
+                if (!best) break;
+                n_fast += best->fast_fn != nullptr;
+                pl->seg.push_back(best); pl->seg_first.push_back(i);
+                i += blen;
+            }
+            // each launch is another trip through HBM, yet four of them still run a 5-stage chain twice as fast
+            // as the interpreter (profiles/README.md, r2q)
+            const char *env = getenv("AES_SPLIT_MAX");
+            const size_t max_seg = env ? (size_t)atoi(env) : 8;
+            if (i < n_stages || n_fast == 0 || pl->seg.size() > max_seg) {
+                for (aes_chain_plan *sp : pl->seg) aes_chain_plan_destroy(sp);
+                pl->seg.clear(); pl->seg_first.clear();
+            } else {
+                for (aes_chain_plan *sp : pl->seg) {    // one scratch and one grid bound serve every segment
+                    pl->host.scratch_floats = std::max(pl->host.scratch_floats, sp->host.scratch_floats);
+                    pl->grid_max = std::max(pl->grid_max, sp->grid_max);
+                }
+            }
+        }
         return 0;
     }();
     if (rc) { aes_chain_plan_destroy(pl); return rc; }
@@ -281,6 +341,7 @@ AES_EXPORT int aes_chain_plan_create(const aes_stage_desc *stages, int n_stages,
 AES_EXPORT int aes_chain_plan_destroy(aes_chain_plan *pl)
 {
     if (!pl) return 0;
+    for (aes_chain_plan *sp : pl->seg) aes_chain_plan_destroy(sp);
     if (pl->dev) cudaFree(pl->dev);
     if (pl->scratch) cudaFree(pl->scratch);
     if (pl->d_state) cudaFree(pl->d_state);
@@ -306,6 +367,15 @@ AES_EXPORT int aes_chain_plan_info(const aes_chain_plan *pl, int *tile_frames, i
 AES_EXPORT const char *aes_chain_plan_kernel_name(const aes_chain_plan *pl)
 {
     if (!pl) return "";
+    if (!pl->seg.empty()) {
+        static thread_local std::string name;
+        name = "split:";
+        for (size_t k = 0; k < pl->seg.size(); ++k) {
+            name += k ? " | " : " ";
+            name += std::to_string(pl->seg[k]->host.n_stages) + "x " + aes_chain_plan_kernel_name(pl->seg[k]);
+        }
+        return name.c_str();
+    }
     if (pl->rv) return "aes_rv_kernel<pipelined reverb chain>";
     return pl->fast_fn ? "aes_fast_kernel<FR=4, shape-specialised>" : "aes_chain_kernel<generic interpreter>";
 }

@@ -11,9 +11,9 @@
 #include "aes_spectral.cuh"
 #include "aes_spectral_smooth.cuh"
 
-__global__ void __launch_bounds__(AESM_NTC) aesm_cols_fwd_kernel(const __grid_constant__ SmoothArgs a) { aesm_cols_fwd_body(a); }
-__global__ void __launch_bounds__(AESM_NT, 5) aesm_rows_kernel(const __grid_constant__ SmoothArgs a) { aesm_rows_body(a); }
-__global__ void __launch_bounds__(AESM_NT) aesm_cols_inv_kernel(const __grid_constant__ SmoothArgs a) { aesm_cols_inv_body(a); }
+template <int SHAPE> __global__ void __launch_bounds__(AESM_NTC) aesm_cols_fwd_kernel(const __grid_constant__ SmoothArgs a) { aesm_cols_fwd_body<SHAPE>(a); }
+template <int SHAPE> __global__ void __launch_bounds__(AESM_NT, 5) aesm_rows_kernel(const __grid_constant__ SmoothArgs a) { aesm_rows_body<SHAPE>(a); }
+template <int SHAPE> __global__ void __launch_bounds__(AESM_NT) aesm_cols_inv_kernel(const __grid_constant__ SmoothArgs a) { aesm_cols_inv_body<SHAPE>(a); }
 // tables of the smooth path, in double: W_M^j (j < 1024), W_M^(1024 j), np.hanning(M)
 __global__ void aesm_tables_kernel(cpx *twlo, cpx *twhi, long long nhi, float *window, long long M)
 {
@@ -99,7 +99,7 @@ struct aes_spectral_plan {
     size_t work_cap = 0;
     // frame lengths n1 * n2 with factors 2, 3, 5 only skip Bluestein (aes_spectral_smooth.cuh)
     bool smooth = false;
-    int n1 = 0, n2 = 0;
+    int n1 = 0, n2 = 0, static_shape = 0;
     SmoothFft f1, f2;
     cpx *d_stw = nullptr;            // stage twiddles of f1 | of f2 | twlo [1024] | twhi [ceil(M / 1024)]
     int *d_rev = nullptr;            // rev1 [n1] | rev2 [n2]
@@ -202,9 +202,15 @@ static int smooth_process(const aes_spectral_plan *pl, const SmoothArgs &a, cuda
     const int per_sm_r = (int)std::max<size_t>(1, std::min<size_t>(8, (size_t)220 * 1024 / (sm_r + 1024)));
     const unsigned gc = (unsigned)std::min<long long>(tiles, (long long)pl->sms * per_sm_c);
     const unsigned gr = (unsigned)std::min<long long>(rows, (long long)pl->sms * per_sm_r);
-    aesm_cols_fwd_kernel<<<gc, AESM_NTC, sm_c, st>>>(a);
-    aesm_rows_kernel<<<gr, AESM_NT, sm_r, st>>>(a);
-    aesm_cols_inv_kernel<<<gc, AESM_NT, sm_c, st>>>(a);       // 512 threads: 50 registers leave 2 CTAs per SM (3.1 ms against 1.8)
+    if (pl->static_shape == AESM_SHAPE_960x1000) {
+        aesm_cols_fwd_kernel<AESM_SHAPE_960x1000><<<gc, AESM_NTC, sm_c, st>>>(a);
+        aesm_rows_kernel<AESM_SHAPE_960x1000><<<gr, AESM_NT, sm_r, st>>>(a);
+        aesm_cols_inv_kernel<AESM_SHAPE_960x1000><<<gc, AESM_NT, sm_c, st>>>(a);
+    } else {
+        aesm_cols_fwd_kernel<0><<<gc, AESM_NTC, sm_c, st>>>(a);
+        aesm_rows_kernel<0><<<gr, AESM_NT, sm_r, st>>>(a);
+        aesm_cols_inv_kernel<0><<<gc, AESM_NT, sm_c, st>>>(a);      // 512 threads: 50 registers leave 2 CTAs per SM (3.1 ms against 1.8)
+    }
     aes_count_launch(); aes_count_launch(); aes_count_launch();
     AES_CUDA(cudaGetLastError());
     return 0;
@@ -253,10 +259,14 @@ AES_EXPORT int aes_spectral_plan_create(int64_t frame_len, aes_spectral_plan **o
             for (int k = 0; k < pl->n1; ++k) rev[k] = aesm_rev(k, pl->f1);
             for (int k = 0; k < pl->n2; ++k) rev[pl->n1 + k] = aesm_rev(k, pl->f2);
             AES_CUDA(cudaMemcpy(pl->d_rev, rev.data(), rev.size() * sizeof(int), cudaMemcpyHostToDevice));
-            const int sm_c = pl->n1 * AESM_C * (int)sizeof(cpx), sm_r = 2 * pl->n2 * (int)sizeof(cpx);
-            AES_CUDA(cudaFuncSetAttribute(aesm_cols_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_c));
-            AES_CUDA(cudaFuncSetAttribute(aesm_cols_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_c));
-            AES_CUDA(cudaFuncSetAttribute(aesm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_r));
+            // (kernel attributes, not plan ones: always the limit, plans of other frame lengths may be alive)
+            pl->static_shape = getenv("AES_SPECTRAL_GENERIC") ? 0 : aesm_static_shape(pl->f1, pl->f2);
+            AES_CUDA(cudaFuncSetAttribute(aesm_cols_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            AES_CUDA(cudaFuncSetAttribute(aesm_cols_inv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            AES_CUDA(cudaFuncSetAttribute(aesm_rows_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            AES_CUDA(cudaFuncSetAttribute(aesm_cols_fwd_kernel<AESM_SHAPE_960x1000>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            AES_CUDA(cudaFuncSetAttribute(aesm_cols_inv_kernel<AESM_SHAPE_960x1000>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+            AES_CUDA(cudaFuncSetAttribute(aesm_rows_kernel<AESM_SHAPE_960x1000>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             aesm_tables_kernel<<<spec_grid(pl), 256>>>(pl->d_stw + nst, pl->d_stw + nst + 1024, nhi, pl->d_window, M);
             aes_count_launch();
             AES_CUDA(cudaDeviceSynchronize());

@@ -175,6 +175,70 @@ __device__ __forceinline__ void aesm_fft(cpx *s, int S, SmoothDiv divS, int qs, 
     }
 }
 
+// ---- the same stages with every size a compile-time constant (BASELINE's 960 000 = 960 x 1000): the
+// index arithmetic of the run-time version (about half of its instructions) folds into immediates
+template <int R, bool INV, int LEN, int NTOT, int S, int QS, int ES, int NT, int TOFF>
+__device__ __forceinline__ void aesm_stage_c(cpx *s, const cpx *__restrict__ tw)
+{
+    constexpr int m = LEN / R, nbf = NTOT / R, total = S * nbf;
+    const cpx *__restrict__ T = tw + TOFF;
+#pragma unroll
+    for (int e0 = 0; e0 < total; e0 += NT) {
+        const int e = e0 + (int)threadIdx.x;
+        if (e0 + NT > total && e >= total) break;
+        const int fi = e / S, q = e % S;
+        const int blk = fi / m, p = fi % m;
+        cpx *base = s + q * QS + (blk * LEN + p) * ES;
+        cpx a[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) a[j] = base[j * m * ES];
+        if (INV && m > 1) {
+#pragma unroll
+            for (int d = 1; d < R; ++d) a[d] = aesm_cmulc(a[d], T[(d - 1) * m + p], true);
+        }
+        aesm_dft<R, INV>(a);
+        if (!INV && m > 1) {
+#pragma unroll
+            for (int d = 1; d < R; ++d) a[d] = aesm_cmulc(a[d], T[(d - 1) * m + p], false);
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) base[j * m * ES] = a[j];
+    }
+}
+
+// four stages R0..R3 of an N-point transform (the order aesm_build_fft picks: 8s, 4s, 2s, 3s, 5s)
+template <bool INV, int N, int S, int QS, int ES, int NT, int R0, int R1, int R2, int R3>
+__device__ __forceinline__ void aesm_fft_c(cpx *s, const cpx *__restrict__ tw)
+{
+    constexpr int L0 = N, L1 = L0 / R0, L2 = L1 / R1, L3 = L2 / R2;
+    static_assert(L3 == R3, "radices must multiply to N");
+    constexpr int T0 = 0;
+    constexpr int T1 = T0 + (L0 / R0 > 1 ? (R0 - 1) * (L0 / R0) : 0);
+    constexpr int T2 = T1 + (L1 / R1 > 1 ? (R1 - 1) * (L1 / R1) : 0);
+    constexpr int T3 = T2 + (L2 / R2 > 1 ? (R2 - 1) * (L2 / R2) : 0);
+    if (!INV) {
+        aesm_stage_c<R0, INV, L0, N, S, QS, ES, NT, T0>(s, tw); __syncthreads();
+        aesm_stage_c<R1, INV, L1, N, S, QS, ES, NT, T1>(s, tw); __syncthreads();
+        aesm_stage_c<R2, INV, L2, N, S, QS, ES, NT, T2>(s, tw); __syncthreads();
+        aesm_stage_c<R3, INV, L3, N, S, QS, ES, NT, T3>(s, tw); __syncthreads();
+    } else {
+        aesm_stage_c<R3, INV, L3, N, S, QS, ES, NT, T3>(s, tw); __syncthreads();
+        aesm_stage_c<R2, INV, L2, N, S, QS, ES, NT, T2>(s, tw); __syncthreads();
+        aesm_stage_c<R1, INV, L1, N, S, QS, ES, NT, T1>(s, tw); __syncthreads();
+        aesm_stage_c<R0, INV, L0, N, S, QS, ES, NT, T0>(s, tw); __syncthreads();
+    }
+}
+
+// SHAPE 1: n1 = 960 = 8*8*3*5, n2 = 1000 = 8*5*5*5
+#define AESM_SHAPE_960x1000 1
+static inline int aesm_static_shape(const SmoothFft &f1, const SmoothFft &f2)
+{
+    const int r1[4] = { 8, 8, 3, 5 }, r2[4] = { 8, 5, 5, 5 };
+    if (f1.n != 960 || f2.n != 1000 || f1.ns != 4 || f2.ns != 4) return 0;
+    for (int i = 0; i < 4; ++i) if (f1.r[i] != r1[i] || f2.r[i] != r2[i]) return 0;
+    return AESM_SHAPE_960x1000;
+}
+
 // position of output index k after the DIF stages (mixed-radix digit reversal); host side, tabulated per plan
 static inline int aesm_rev(int k, const SmoothFft &f)
 {
@@ -210,10 +274,11 @@ __device__ __forceinline__ float aesm_sample(const SmoothArgs &a, int fr, int n,
 }
 
 // ---- K1: column FFTs ---------------------------------------------------------------------------------
+template <int SHAPE>
 __device__ void aesm_cols_fwd_body(const SmoothArgs &a)
 {
     AES_DYN_SMEM(cpx, s);                                   // [n1][C]
-    const int n1 = a.n1, n2 = a.n2, tiles = (n2 + AESM_C - 1) / AESM_C;
+    const int n1 = SHAPE == AESM_SHAPE_960x1000 ? 960 : a.n1, n2 = SHAPE == AESM_SHAPE_960x1000 ? 1000 : a.n2, tiles = (n2 + AESM_C - 1) / AESM_C;
     SmoothDiv divC; divC.d = AESM_C; divC.mul = 0x20000000u;        // x / 8
     for (long long w = blockIdx.x; w < (long long)a.np * tiles; w += gridDim.x) {
         const int p = (int)(w / tiles), b0 = (int)(w % tiles) * AESM_C;
@@ -229,7 +294,8 @@ __device__ void aesm_cols_fwd_body(const SmoothArgs &a)
             s[e] = z;
         }
         __syncthreads();
-        aesm_fft<false>(s, AESM_C, divC, 1, AESM_C, a.f1, a.tw1);
+        if (SHAPE == AESM_SHAPE_960x1000) aesm_fft_c<false, 960, AESM_C, 1, AESM_C, AESM_NTC, 8, 8, 3, 5>(s, a.tw1);
+        else aesm_fft<false>(s, AESM_C, divC, 1, AESM_C, a.f1, a.tw1);
         cpx *dst = a.buf + (long long)p * a.M;
         for (int e = threadIdx.x; e < n1 * AESM_C; e += blockDim.x) {
             const int k1 = e / AESM_C, c = e % AESM_C, b = b0 + c;
@@ -255,10 +321,11 @@ __device__ __forceinline__ cpx aesm_gate_one(cpx X, float *maskp, bool self_conj
     return Pk;
 }
 
+template <int SHAPE>
 __device__ void aesm_rows_body(const SmoothArgs &a)
 {
     AES_DYN_SMEM(cpx, s);                                   // [2][n2]: row k1, row n1 - k1
-    const int n1 = a.n1, n2 = a.n2, half = n1 / 2 + 1;      // row pairs per transform: k1 = 0 .. n1/2
+    const int n1 = SHAPE == AESM_SHAPE_960x1000 ? 960 : a.n1, n2 = SHAPE == AESM_SHAPE_960x1000 ? 1000 : a.n2, half = n1 / 2 + 1;      // row pairs per transform: k1 = 0 .. n1/2
     const int nbins = a.M / 2 + 1;
     SmoothDiv div2; div2.d = 2; div2.mul = 0x80000000u;
     SmoothDiv div1; div1.d = 1; div1.mul = 0;
@@ -273,7 +340,10 @@ __device__ void aesm_rows_body(const SmoothArgs &a)
             if (!self) s[n2 + e] = rowB[e];
         }
         __syncthreads();
-        aesm_fft<false>(s, S, self ? div1 : div2, n2, 1, a.f2, a.tw2);
+        if (SHAPE == AESM_SHAPE_960x1000) {
+            if (self) aesm_fft_c<false, 1000, 1, 1000, 1, AESM_NT, 8, 5, 5, 5>(s, a.tw2);
+            else aesm_fft_c<false, 1000, 2, 1000, 1, AESM_NT, 8, 5, 5, 5>(s, a.tw2);
+        } else aesm_fft<false>(s, S, self ? div1 : div2, n2, 1, a.f2, a.tw2);
         // bins: k = k1 + n1*k2 (row A, column k2)  <->  M - k = k1b + n1*k2b (row B, column k2b)
         const bool two = 2 * p + 1 < a.nf;
         for (int k2 = threadIdx.x; k2 < n2; k2 += blockDim.x) {
@@ -302,7 +372,10 @@ __device__ void aesm_rows_body(const SmoothArgs &a)
             if (!sc) s[ib] = k <= km ? Whi : Wlo;
         }
         __syncthreads();
-        aesm_fft<true>(s, S, self ? div1 : div2, n2, 1, a.f2, a.tw2);
+        if (SHAPE == AESM_SHAPE_960x1000) {
+            if (self) aesm_fft_c<true, 1000, 1, 1000, 1, AESM_NT, 8, 5, 5, 5>(s, a.tw2);
+            else aesm_fft_c<true, 1000, 2, 1000, 1, AESM_NT, 8, 5, 5, 5>(s, a.tw2);
+        } else aesm_fft<true>(s, S, self ? div1 : div2, n2, 1, a.f2, a.tw2);
         for (int e = threadIdx.x; e < n2; e += blockDim.x) {
             rowA[e] = c_mul(s[e], aesm_wM(a, e * k1, true));
             if (!self) rowB[e] = c_mul(s[n2 + e], aesm_wM(a, e * k1b, true));
@@ -312,10 +385,11 @@ __device__ void aesm_rows_body(const SmoothArgs &a)
 }
 
 // ---- K3: inverse column FFTs, outputs --------------------------------------------------------------------
+template <int SHAPE>
 __device__ void aesm_cols_inv_body(const SmoothArgs &a)
 {
     AES_DYN_SMEM(cpx, s);
-    const int n1 = a.n1, n2 = a.n2, tiles = (n2 + AESM_C - 1) / AESM_C;
+    const int n1 = SHAPE == AESM_SHAPE_960x1000 ? 960 : a.n1, n2 = SHAPE == AESM_SHAPE_960x1000 ? 1000 : a.n2, tiles = (n2 + AESM_C - 1) / AESM_C;
     const float inv = 1.0f / (float)a.M;
     const int N = a.M / 2;
     SmoothDiv divC; divC.d = AESM_C; divC.mul = 0x20000000u;
@@ -329,7 +403,8 @@ __device__ void aesm_cols_inv_body(const SmoothArgs &a)
             s[a.rev1[k1] * AESM_C + c] = z;
         }
         __syncthreads();
-        aesm_fft<true>(s, AESM_C, divC, 1, AESM_C, a.f1, a.tw1);
+        if (SHAPE == AESM_SHAPE_960x1000) aesm_fft_c<true, 960, AESM_C, 1, AESM_C, AESM_NT, 8, 8, 3, 5>(s, a.tw1);
+        else aesm_fft<true>(s, AESM_C, divC, 1, AESM_C, a.f1, a.tw1);
         const bool two = 2 * p + 1 < a.nf;
         for (int e = threadIdx.x; e < n1 * AESM_C; e += blockDim.x) {
             const int row = e / AESM_C, c = e % AESM_C, b = b0 + c;

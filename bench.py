@@ -357,6 +357,22 @@ def max_ms(torch, dist, world, dev, ms):
     return float(t.item())
 
 
+UNLISTED_CHAINS = {
+    "filter>delay>reverb": [
+        {"type": "filter", "params": {"filter_type": 0, "cutoff_hz": 4000, "q": 0.707}},
+        {"type": "delay", "params": {"delay_ms": 250, "feedback": 0.35, "mix_wet": 0.5, "mix_dry": 1.0, "offset_ms": 15}},
+        {"type": "reverb", "params": {"rt60_s": 1.5, "mix_wet": 0.3, "mix_dry": 0.9}},
+    ],
+    "gate>filter>octaver>delay>reverb": [
+        {"type": "gate", "params": {"threshold_db": -45, "attack_ms": 5, "release_ms": 150}},
+        {"type": "filter", "params": {"filter_type": 1, "cutoff_hz": 120, "q": 0.707}},
+        {"type": "octaver", "params": {"semitones": 7, "mix": 0.4}},
+        {"type": "delay", "params": {"delay_ms": 180, "feedback": 0.25, "mix_wet": 0.4, "mix_dry": 1.0, "offset_ms": 5}},
+        {"type": "reverb", "params": {"rt60_s": 1.2, "mix_wet": 0.25, "mix_dry": 0.9}},
+    ],
+}
+
+
 def sweep_leg(args, torch, dist, _native, file_chain, x, y, B, n_frames, world, dev, barrier, peak):
     """Every preset of app.py:41-71 over this rank's shard (BASELINE configs[4]): each one alone, then all six
     at once on separate streams so that the partial last wave of one preset's launch is filled by the others."""
@@ -379,6 +395,21 @@ def sweep_leg(args, torch, dist, _native, file_chain, x, y, B, n_frames, world, 
         ms = max_ms(torch, dist, world, dev, tot) / args.sweep_steps
         v = world * samples_rank / (ms * 1e-3) / 1e6
         res[name] = {"ms": ms, "value": v, "frac_of_hbm_roofline": (v / world) * 8e6 / 1e9 / peak}
+    # chains a user may build that no kernel was specialised for (app.py:396-482 builds arbitrary ones):
+    # what the generic interpreter kernel costs next to the listed shapes
+    unlisted = {}
+    for name, cfg in UNLISTED_CHAINS.items():
+        chain = file_chain(cfg, FS, channels_in=2)
+        pipe, plans = chain.device_pipeline(n_frames)
+        keep.append(plans)
+        run = lambda pipe=pipe: pipe(x.data_ptr(), y.data_ptr(), (tmp if tmp is not None else y).data_ptr(), B, stream.cuda_stream)
+        run()
+        tot, _ = timed_steps(torch, stream, barrier, run, args.sweep_steps)
+        ms = max_ms(torch, dist, world, dev, tot) / args.sweep_steps
+        v = world * samples_rank / (ms * 1e-3) / 1e6
+        unlisted[name] = {"ms": ms, "value": v, "frac_of_hbm_roofline": (v / world) * 8e6 / 1e9 / peak,
+                          "stages": [c["type"] for c in cfg],
+                          "kernels": [p.info()["kernel"] for p in plans if hasattr(p, "info")]}
     # all six concurrently, chunked so that six output chunks fit beside the shard
     chunk = min(B, 1184)
     streams = [torch.cuda.Stream(device=dev) for _ in PRESET_ORDER]
@@ -411,6 +442,7 @@ def sweep_leg(args, torch, dist, _native, file_chain, x, y, B, n_frames, world, 
     out = {"presets": res, "steps": args.sweep_steps,
            "one_at_a_time": {"ms": seq_ms, "value": 6 * world * samples_rank / (seq_ms * 1e-3) / 1e6},
            "six_streams": {"ms": ms, "value": 6 * world * samples_rank / (ms * 1e-3) / 1e6, "chunk_clips": chunk},
+           "unlisted_chains": unlisted,
            "unit": UNIT, "samples": "6 presets x the whole job's clips x frames x 2 channels per pass"}
     for plans in keep:
         for p in plans:

@@ -228,9 +228,9 @@ int emu_spectral_frames(const float *frames, float *mask, float *y, long long M,
 
 // ---- smooth-length SpectralFilter path (aes_spectral_smooth.cuh) on the emulator ------------------
 #include "../../audio-effects-simulator_b200/csrc/aes_spectral_smooth.cuh"
-static void sm_k1(void *p) { aesm_cols_fwd_body(*reinterpret_cast<SmoothArgs *>(p)); }
-static void sm_k2(void *p) { aesm_rows_body(*reinterpret_cast<SmoothArgs *>(p)); }
-static void sm_k3(void *p) { aesm_cols_inv_body(*reinterpret_cast<SmoothArgs *>(p)); }
+template <int SHAPE> static void sm_k1(void *p) { aesm_cols_fwd_body<SHAPE>(*reinterpret_cast<SmoothArgs *>(p)); }
+template <int SHAPE> static void sm_k2(void *p) { aesm_rows_body<SHAPE>(*reinterpret_cast<SmoothArgs *>(p)); }
+template <int SHAPE> static void sm_k3(void *p) { aesm_cols_inv_body<SHAPE>(*reinterpret_cast<SmoothArgs *>(p)); }
 
 // mode 1: frames [nf][M] raw (window applied when `window` != null), mask [nf][M/2+1] or null, y [nf][M]
 // mode 2: frames = clips [nf][M/2][2], y = [nf][M/2][2]; returns 1 when M has no smooth split
@@ -258,8 +258,9 @@ int emu_spectral_smooth(int mode, const float *frames, const float *window, floa
     a.window = window; a.mask = mask; a.M = (int)M; a.n1 = n1; a.n2 = n2; a.nf = nf; a.np = (nf + 1) / 2; a.mode = mode;
     a.thr = thr; a.red = red; a.alpha = alpha;
     if (mode == 2) { a.clips = frames; a.yclips = y; } else { a.frames = frames; a.out = y; }
-    emu::launch(sm_k1, &a, 3, AESM_NTC, (size_t)n1 * AESM_C * sizeof(cpx));
-    emu::launch(sm_k2, &a, 3, AESM_NT, (size_t)2 * n2 * sizeof(cpx));
-    emu::launch(sm_k3, &a, 3, AESM_NT, (size_t)n1 * AESM_C * sizeof(cpx));
+    const bool st = aesm_static_shape(a.f1, a.f2) == AESM_SHAPE_960x1000;       // the compile-time 960 x 1000 kernels
+    emu::launch(st ? sm_k1<AESM_SHAPE_960x1000> : sm_k1<0>, &a, 3, AESM_NTC, (size_t)n1 * AESM_C * sizeof(cpx));
+    emu::launch(st ? sm_k2<AESM_SHAPE_960x1000> : sm_k2<0>, &a, 3, AESM_NT, (size_t)2 * n2 * sizeof(cpx));
+    emu::launch(st ? sm_k3<AESM_SHAPE_960x1000> : sm_k3<0>, &a, 3, AESM_NT, (size_t)n1 * AESM_C * sizeof(cpx));
     return 0;
 }

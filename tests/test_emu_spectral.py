@@ -67,8 +67,10 @@ def test_smooth_lengths_gated_roundtrip(M, nb):
         assert np.max(np.abs(y[b] - want)) < 2e-6, (M, b, n1.value, n2.value)
 
 
-@pytest.mark.parametrize("N,nb", [(48, 1), (300, 2), (4800, 3)])
-def test_smooth_whole_clip_mode_reads_clips_and_emits_first_half(N, nb):
+# the last: BASELINE's frame on the compile-time 960 x 1000 kernels, threshold in the middle of the magnitude
+# distribution (a handful of the 480 001 bins sit within rounding of it and flip: 1.5e-5 each at most)
+@pytest.mark.parametrize("N,nb,thr,tol", [(48, 1, 0.5, 2e-6), (300, 2, 0.5, 2e-6), (4800, 3, 0.5, 2e-6), (480000, 2, 80.0, 1e-4)])
+def test_smooth_whole_clip_mode_reads_clips_and_emits_first_half(N, nb, thr, tol):
     """mode 2 = the file route's single whole-clip block: frame = [zeros(N), mean(x) * hanning(2N)[N:]],
     fresh mask of ones (not kept), output = first N samples on both channels (spectral.py:30-42, 80-100)"""
     L = emu.lib()
@@ -78,7 +80,7 @@ def test_smooth_whole_clip_mode_reads_clips_and_emits_first_half(N, nb):
     x = (0.3 * rng.standard_normal((nb, N, 2))).astype(np.float32)
     win = np.hanning(M).astype(np.float32)
     y = np.full((nb, N, 2), 7.0, np.float32)
-    thr, red, alpha = 0.5, 0.1, 0.8
+    red, alpha = 0.1, 0.8
     assert L.emu_spectral_smooth(2, x.ctypes.data, win.ctypes.data, None, y.ctypes.data, M, nb, thr, red, alpha, None, None) == 0
     for b in range(nb):
         mono = ((x[b, :, 0] + x[b, :, 1]) * np.float32(0.5)) * win[N:]
@@ -86,7 +88,9 @@ def test_smooth_whole_clip_mode_reads_clips_and_emits_first_half(N, nb):
         X = np.fft.rfft(fr)
         m = alpha * 1.0 + (1 - alpha) * np.where(np.abs(X) > thr, 1.0, red)
         want = np.fft.irfft(X * m, M)[:N]
-        assert np.max(np.abs(y[b, :, 0] - want)) < 2e-6 and np.array_equal(y[b, :, 0], y[b, :, 1]), (N, b)
+        assert 0.2 < np.mean(np.abs(X) > thr) < 0.8 or N < 100000
+        assert np.max(np.abs(y[b, :, 0] - want)) < tol and np.array_equal(y[b, :, 0], y[b, :, 1]), (N, b)
+        assert np.sqrt(np.mean((y[b, :, 0] - want) ** 2)) < 2e-6
 
 
 def test_non_smooth_length_has_no_split():

@@ -211,6 +211,59 @@ def test_generic_interpreter_kernel_matches_too(ab, orc, name, monkeypatch):
         check(y[b], orc.run_file_path(cfg, x[b], 48000), exact=(name == "Slapback Echo"), what=(name, b))
 
 
+UNLISTED = {
+    "filter>delay>reverb": [
+        {"type": "filter", "params": {"filter_type": 0, "cutoff_hz": 4000, "q": 0.707}},
+        {"type": "delay", "params": {"delay_ms": 250, "feedback": 0.35, "mix_wet": 0.5, "mix_dry": 1.0, "offset_ms": 15}},
+        {"type": "reverb", "params": {"rt60_s": 1.5, "mix_wet": 0.3, "mix_dry": 0.9}}],
+    "octaver>reverb": [
+        {"type": "octaver", "params": {"semitones": 7, "mix": 0.4}},
+        {"type": "reverb", "params": {"rt60_s": 1.2, "mix_wet": 0.25, "mix_dry": 0.9}}],
+    "delay>gate>delay": [
+        {"type": "delay", "params": {"delay_ms": 80, "feedback": 0.5, "mix_wet": 0.5, "mix_dry": 1.0, "offset_ms": 0}},
+        {"type": "gate", "params": {"threshold_db": -35, "attack_ms": 5, "release_ms": 80}},
+        {"type": "delay", "params": {"delay_ms": 300, "feedback": 0.2, "mix_wet": 0.4, "mix_dry": 1.0, "offset_ms": 20}}],
+}
+
+
+@pytest.mark.parametrize("name", sorted(UNLISTED))
+@pytest.mark.parametrize("in_fmt,out_fmt", [("f32_stereo", "f32"), ("f32_mono", "i16"), ("i16", "i16")])
+def test_chains_without_their_own_kernel_run_as_runs_of_specialised_ones(ab, orc, name, in_fmt, out_fmt, monkeypatch):
+    """A chain no kernel was instantiated for is cut at stage boundaries into runs that have one
+    (aes_chain.cu, plan_create): every kernel hands float32 from stage to stage, so the cut itself changes
+    nothing; the result agrees with the generic interpreter to the kernels' own rounding and sits within
+    the parity bar of the oracle."""
+    from audioblocks import _native
+    from audioblocks.engine import file_chain
+    cfg = UNLISTED[name]
+    n, B = 70000, 5
+    x = synth.batch(60, B, n, 1 if in_fmt == "f32_mono" else 2)
+    if in_fmt == "i16":
+        xin, fi = (np.clip(x, -1, 1) * 32767).astype(np.int16), _native.FMT_I16_DOWNMIX
+    else:
+        xin, fi = x, (_native.FMT_F32_MONO if in_fmt == "f32_mono" else _native.FMT_F32_STEREO)
+    fo, odt = (_native.FMT_I16_STEREO, np.int16) if out_fmt == "i16" else (_native.FMT_F32_STEREO, np.float32)
+
+    def run():
+        ch = file_chain(cfg, 48000, channels_in=1 if in_fmt != "f32_stereo" else 2)
+        plan = ch.prepare_batch(n)
+        y = np.zeros((B, n, 2), odt)
+        plan.run_host(xin, fi, y, fo, B, n)
+        kern = plan.info()["kernel"]
+        plan.close()
+        return y, kern
+    y_split, k_split = run()
+    monkeypatch.setenv("AES_NO_SPLIT", "1")
+    y_whole, k_whole = run()
+    assert k_split.startswith("split:") and "generic" in k_whole, (k_split, k_whole)
+    # (the specialised reverb kernels sum their comb recurrences as scans: ulp-level differences to the interpreter)
+    d = np.max(np.abs(y_split.astype(np.float64) - y_whole.astype(np.float64)))
+    assert d <= (1 if out_fmt == "i16" else 2e-6), d
+    if in_fmt == "f32_stereo" and "gate" not in name:      # (a gate behind a float block: see test_fuzz_chains.check)
+        for b in (0, B - 1):
+            check(y_split[b], orc.run_file_path(cfg, x[b], 48000), what=(name, b))
+
+
 def test_time_parallel_scan_equals_batch_kernel_on_a_single_clip(ab, orc, monkeypatch):
     """One long clip through biquads takes the decoupled-look-back scan kernel
     (aes_biquad_scan.cuh); forcing the one-CTA-per-clip kernel must give the same audio,
