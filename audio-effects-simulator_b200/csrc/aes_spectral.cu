@@ -11,7 +11,7 @@
 #include "aes_spectral.cuh"
 #include "aes_spectral_smooth.cuh"
 
-template <int SHAPE> __global__ void __launch_bounds__(AESM_NTC) aesm_cols_fwd_kernel(const __grid_constant__ SmoothArgs a) { aesm_cols_fwd_body<SHAPE>(a); }
+template <int SHAPE> __global__ void __launch_bounds__(AESM_NTC, 3) aesm_cols_fwd_kernel(const __grid_constant__ SmoothArgs a) { aesm_cols_fwd_body<SHAPE>(a); }
 template <int SHAPE> __global__ void __launch_bounds__(AESM_NT, 5) aesm_rows_kernel(const __grid_constant__ SmoothArgs a) { aesm_rows_body<SHAPE>(a); }
 template <int SHAPE> __global__ void __launch_bounds__(AESM_NT) aesm_cols_inv_kernel(const __grid_constant__ SmoothArgs a) { aesm_cols_inv_body<SHAPE>(a); }
 // tables of the smooth path, in double: W_M^j (j < 1024), W_M^(1024 j), np.hanning(M)
@@ -364,10 +364,11 @@ AES_EXPORT int aes_spectral_run(aes_spectral_plan *pl, const float *x, float *y,
     AES_REQUIRE(pl->M == 2 * n_frames, "plan frame length %lld != 2 * n_frames", pl->M);
     const long long M = pl->M, nbins = M / 2 + 1;
     if (pl->smooth) {
-        // one M-point complex buffer per pair of clips is all the state there is; the default chunk keeps
-        // it L2-sized so the three passes hand the spectrum over on chip (AES_SPECTRAL_CHUNK_MB overrides)
+        // one M-point complex buffer per pair of clips is all the state there is.  Chunks of up to 4 GB of it:
+        // L2-sized chunks (64 MB, so that the three passes hand the spectrum over on chip) measured 15 % slower,
+        // the partial last wave of every small launch costs more than the DRAM trips (AES_SPECTRAL_CHUNK_MB overrides)
         const char *env = getenv("AES_SPECTRAL_CHUNK_MB");
-        const size_t budget_s = (size_t)(env ? std::max(1, atoi(env)) : 64) << 20, pair = (size_t)M * sizeof(cpx);
+        const size_t budget_s = (size_t)(env ? std::max(1, atoi(env)) : 4096) << 20, pair = (size_t)M * sizeof(cpx);
         const int64_t pairs_all = (n_clips + 1) / 2;
         const int64_t cp = std::max<int64_t>(1, std::min<int64_t>(pairs_all, (int64_t)(budget_s / pair)));
         int rcs = spec_reserve(pl, pair * (size_t)cp);
