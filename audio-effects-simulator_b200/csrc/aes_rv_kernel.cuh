@@ -52,7 +52,11 @@ __device__ __forceinline__ void aes_static_for(F &&f)
 // work concentrates in a quarter of the threads and the walkers' critical path grows, 271;  a 96 + 48
 // register split with four interleaved columns per walker (r2l): the walkers get 30 % faster and the bare
 // reverb gains 1 % (307), but the feedback-delay shape spills in the comb warps, 265;  four columns in 32
-// registers (r2m): 286.
+// registers (r2m): 286.  The L1 data pipe is the binding resource (ncu r2i: l1tex data-pipe wavefronts 88 % of peak;
+// 1781 wavefronts per tile against ~1024 for rings + I/O alone, the rest are the tile hand-offs between the
+// warp roles and the TMA's own shared-memory writes, ~229 per tile for 16.4 KB).  Two placements of the staged line
+// samples were measured against the plain 16-byte aligned one (r2t, r2u): at the 128-byte phase of their global
+// source, and 128-byte aligned destinations; both RAISED the copy's shared-memory wavefronts (288 per tile) and cost 3 %.
 #define AESRV_NT 384
 #define AESRV_NW 128
 #define AESRV_NWC 64                // walkers per channel
