@@ -14,3 +14,4 @@ from .distortion import DistortionEffect
 from .convreverb import ConvolutionReverbEffect
 from .engine import AudioEngine, SAMPLE_RATE
 from . import sharding
+from . import analysis

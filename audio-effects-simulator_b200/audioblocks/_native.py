@@ -87,6 +87,8 @@ def lib() -> C.CDLL:
         L.aes_spectral_run.argtypes = [vp, vp, vp, i64, i64, C.c_double, C.c_double, C.c_double, vp]
         L.aes_spectral_process_host.argtypes = [vp, vp, vp, i64, i64, C.c_double, C.c_double, C.c_double]
         L.aes_stream_process_host.argtypes = [C.POINTER(StageDesc), ci, vp, ci, vp, i64]
+        L.aes_spectrum_chroma.argtypes = [vp, vp, i64, i64, ci, C.c_double, vp, vp, vp, vp, vp]
+        L.aes_spectrum_chroma_host.argtypes = [vp, vp, i64, i64, ci, C.c_double, vp, vp, vp, vp]
         for fn in (L.aes_json_float_list, L.aes_json_stereo_mean_list):
             fn.restype = i64
             fn.argtypes = [vp, i64, vp, i64, ci]
@@ -268,7 +270,8 @@ class SpectralPlan:
 
 
 def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
-    """A numpy array over page-locked host memory (freed with the array)."""
+    """A numpy array over page-locked host memory, freed when the array and every view of it are gone
+    (the owner rides on the ctypes buffer numpy keeps as the array's base)."""
     dtype = np.dtype(dtype)
     n = int(np.prod(shape)) * dtype.itemsize
     p = C.c_void_p()
@@ -281,11 +284,8 @@ def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
         def __del__(self):
             try: lib().aes_host_free(self.ptr)
             except Exception: pass
-    _OWNERS[arr.ctypes.data] = _Owner(p)
+    buf._aes_owner = _Owner(p)
     return arr
-
-
-_OWNERS: dict = {}
 
 
 def json_float_list(x: np.ndarray, stereo_mean: bool = False, threads: int = 0) -> str:

@@ -7,329 +7,462 @@
 // Parity is checked against a float64 numpy restatement in the test tree (parity unpinned by the
 // reference).
 //
-// Uniformly partitioned overlap-save in the frequency domain, blocks of BK = N/2 frames and
-// FFTs of N = 2^LOG2N points that live entirely in shared memory:
-//   K1  fft_blocks : z = xL + i*xR -- an interleaved stereo frame IS a complex number -- so ONE
-//                    complex FFT per block carries both channels;  Z[clip][j][.] (bit-reversed)
-//   K2  mac        : W_j = sum_p  A_p * Z_{j-p} + B_p * conj(Z_{j-p}[N-k])   per bin,
-//                    A_p = (HL_p + HR_p)/2, B_p = (HL_p - HR_p)/2 fold the two real IRs back into
-//                    the packed spectrum; the IR partitions of a 256-bin tile are staged once
-//                    per CTA in shared memory and reused for every clip and block of the CTA
-//   K3  ifft_mix   : inverse FFT, keep the last BK samples (overlap-save), real = yL, imag = yR,
-//                    dry/wet mix and clip, written as stereo frames.
-// Forward transforms are decimation-in-frequency (natural in, bit-reversed out), the inverse
-// is decimation-in-time (bit-reversed in, natural out); the MAC works in bit-reversed index
-// space, where the mirror bin N-k of physical index i is a reversal inside i's power-of-two
-// band: i' = 3*2^m - 1 - i for 2^m <= i < 2^(m+1) (i' = i for i < 2) -- contiguous, coalesced.
+// Uniformly partitioned overlap-save in the frequency domain, blocks of BK = N/2 frames, FFTs of
+// N = R*R*R/2 points (R = 32: 16384, R = 16: 2048, R = 8: 256):
+//   K1  fwd   : z = xL + i*xR -- an interleaved stereo frame IS a complex number -- so ONE complex
+//               FFT per block carries both channels; the two real spectra are separated before the
+//               store:  S[k] = XL[k], S[N-k] = XR[k] (0 < k < N/2), natural bin order; the four real
+//               values XL[0], XL[N/2], XR[0], XR[N/2] go to S[0], S[N/2], S[N], S[N+1] (imaginary part
+//               0), so every bin of the product is one ordinary complex multiplication;
+//               rows of NS = N + 32 entries, [clip][block][NS]
+//   K2  mac   : per bin a FIR over the block index, W_j = sum_p H_p * S_{j-p}, with the IR
+//               partitions laid out like S -- ONE complex multiply-add per bin, partition and block
+//               (the packed form A_p Z + B_p conj(Z[N-k]) of the first revision needed two and read
+//               every spectrum twice).  A thread owns one bin: the PC partition values of its bin sit
+//               in registers, PC accumulators rotate over the output blocks, so every spectrum is
+//               read once and every product spectrum written once.  The IR tiles ([PC][256 bins]) are
+//               staged by TMA (cp.async.bulk + mbarrier), double-buffered across the work items of a
+//               persistent CTA.
+//   K3  inv   : Y[k] = YL + i*YR rebuilt in registers, inverse FFT, keep the last BK samples
+//               (overlap-save), real = yL, imag = yR, dry/wet mix and clip, written as stereo frames.
+//
+// The FFT: N = R1*R2*R3 with R1 = R2 = R, R3 = H = R/2, n = n1*R*H + n2*H + n3, k = k1 + R*k2 + R*R*k3,
+// three passes of register-resident radix-R / radix-H DFTs, NT = R*H threads (512 for 16384 points):
+//   forward   pass 1  thread (n2,n3): DFT over n1, input straight from global memory, times W_N^(t*k1)
+//             pass 2  thread (k1,n3): DFT over n2, times W_N^(R*n3*k2)
+//             pass 3  thread kl = k1+R*k2 AND its mirror R*R-kl: two DFTs over n3; a bin k and its
+//                     mirror N-k then sit in the same thread, the L/R separation needs no exchange,
+//                     results go straight to global memory
+//   inverse   the same three passes backwards (pass A from global memory, pass C to global memory).
+// Shared memory is touched twice per transform (two writes + two reads of the 128 KB frame) instead of
+// twelve times in the radix-8 version; both hand-off layouts are padded so that every access of a
+// half-warp covers 32 distinct banks (layout 2: row per k1, one pad every 16; layout 1: row per kl of
+// H+1 entries).
 #pragma once
+#include <type_traits>
 #include "aes_plan.h"
+#include "aes_fast_kernel.cuh"          // cp.async.bulk / mbarrier helpers
 
-#define AESC_NT 1024
-#define AESC_KT 256         // bins per MAC tile
-#define AESC_JB 8           // output blocks per MAC chunk
+#define AESC_MT 256         // bins per MAC tile = threads of the MAC kernel
 
 struct alignas(8) cpx { float x, y; };      // one 64-bit load / store per element
 
 __device__ __forceinline__ cpx c_mul(cpx a, cpx b) { cpx r; r.x = a.x * b.x - a.y * b.y; r.y = a.x * b.y + a.y * b.x; return r; }
-
-#ifdef AES_CPU_EMU
-static inline unsigned __brev(unsigned v)
-{
-    unsigned r = 0;
-    for (int i = 0; i < 32; ++i) r |= ((v >> i) & 1u) << (31 - i);
-    return r;
-}
-#endif
-
-// mirror bin (N - k) mod N in bit-reversed index space
-__device__ __forceinline__ int aesc_mirror(int i)
-{
-    if (i < 2) return i;
-    const int m = 31 - __clz(i);
-    return 3 * (1 << m) - 1 - i;
-}
-
-// In-place FFTs on N = 2^L points in shared memory; tw[q] = exp(-2*pi*i*q/N), q < N/2.
-// Three radix-2 stages are fused per pass (8 elements in registers, one table twiddle per
-// thread and its squares, the rest are the constants of W_8), a radix-4 or radix-2 pass takes
-// the remainder: 14 stages = 5 shared-memory round trips and barriers instead of 14.
-__device__ __forceinline__ cpx c_add(cpx a, cpx b) { cpx r; r.x = a.x + b.x; r.y = a.y + b.y; return r; }
-__device__ __forceinline__ cpx c_sub(cpx a, cpx b) { cpx r; r.x = a.x - b.x; r.y = a.y - b.y; return r; }
+// complex add / subtract as ONE packed instruction (sm_100 FADD2; each half rounds like the scalar add)
+__device__ __forceinline__ cpx c_add(cpx a, cpx b) { const float2 t = aes_add2(make_float2(a.x, a.y), make_float2(b.x, b.y)); cpx r; r.x = t.x; r.y = t.y; return r; }
+__device__ __forceinline__ cpx c_sub(cpx a, cpx b) { const float2 t = aes_add2(make_float2(a.x, a.y), make_float2(-b.x, -b.y)); cpx r; r.x = t.x; r.y = t.y; return r; }
 __device__ __forceinline__ cpx c_sq(cpx a) { cpx r; r.x = a.x * a.x - a.y * a.y; r.y = 2.0f * a.x * a.y; return r; }
+__device__ __forceinline__ cpx c_conj(cpx a) { cpx r; r.x = a.x; r.y = -a.y; return r; }
 __device__ __forceinline__ cpx c_mul_mi(cpx a) { cpx r; r.x = a.y; r.y = -a.x; return r; }     // a * (-i)
 __device__ __forceinline__ cpx c_mul_pi(cpx a) { cpx r; r.x = -a.y; r.y = a.x; return r; }     // a * (+i)
-#define AESC_R2 0.70710678118654752f
 
-// forward, decimation in frequency: natural order in, bit-reversed order out
-template <int L>
-__device__ void aesc_fft_dif(cpx *s, const cpx *__restrict__ tw, int tid)
+// compile-time loop: f(std::integral_constant<int, I>) for I = 0 .. N-1
+template <int I, int N, class F>
+__device__ __forceinline__ void aesc_for(F &&f)
 {
-    constexpr int N = 1 << L;
-    int st = 0;
-    for (; L - st >= 3; st += 3) {
-        const int q = N >> (st + 3);                     // distances 4q, 2q, q
-        for (int it = tid; it < N / 8; it += AESC_NT) {
-            const int r = it & (q - 1);
-            const int base = ((it - r) << 3) + r;
-            cpx v[8];
-#pragma unroll
-            for (int m = 0; m < 8; ++m) v[m] = s[base + m * q];
-            const cpx w1 = tw[r << st], w2 = c_sq(w1), w4 = c_sq(w2);
-            // stage st (distance 4q): twiddle of pair m is w1 * W_8^m
-            {
-                const cpx d0 = c_sub(v[0], v[4]), d1 = c_sub(v[1], v[5]), d2 = c_sub(v[2], v[6]), d3 = c_sub(v[3], v[7]);
-                v[0] = c_add(v[0], v[4]); v[1] = c_add(v[1], v[5]); v[2] = c_add(v[2], v[6]); v[3] = c_add(v[3], v[7]);
-                cpx t1; t1.x = AESC_R2 * (d1.x + d1.y); t1.y = AESC_R2 * (d1.y - d1.x);          // d1 * (1-i)/sqrt2
-                cpx t3; t3.x = AESC_R2 * (d3.y - d3.x); t3.y = -AESC_R2 * (d3.x + d3.y);         // d3 * (-1-i)/sqrt2
-                v[4] = c_mul(d0, w1); v[5] = c_mul(t1, w1); v[6] = c_mul(c_mul_mi(d2), w1); v[7] = c_mul(t3, w1);
-            }
-            // stage st+1 (distance 2q): twiddle w2 * (-i)^(m&1)
-#pragma unroll
-            for (int g = 0; g < 8; g += 4) {
-                const cpx d0 = c_sub(v[g], v[g + 2]), d1 = c_sub(v[g + 1], v[g + 3]);
-                v[g] = c_add(v[g], v[g + 2]); v[g + 1] = c_add(v[g + 1], v[g + 3]);
-                v[g + 2] = c_mul(d0, w2); v[g + 3] = c_mul(c_mul_mi(d1), w2);
-            }
-            // stage st+2 (distance q): twiddle w4
-#pragma unroll
-            for (int g = 0; g < 8; g += 2) {
-                const cpx d = c_sub(v[g], v[g + 1]);
-                v[g] = c_add(v[g], v[g + 1]);
-                v[g + 1] = c_mul(d, w4);
-            }
-#pragma unroll
-            for (int m = 0; m < 8; ++m) s[base + m * q] = v[m];
-        }
-        __syncthreads();
-    }
-    for (; st < L; ++st) {                                // remaining 1 or 2 plain radix-2 stages
-        const int half = N >> (st + 1);
-        for (int b = tid; b < N / 2; b += AESC_NT) {
-            const int pos = b & (half - 1);
-            const int i0 = ((b - pos) << 1) + pos, i1 = i0 + half;
-            const cpx u = s[i0], v = s[i1], w = tw[pos << st];
-            s[i0] = c_add(u, v);
-            s[i1] = c_mul(c_sub(u, v), w);
-        }
-        __syncthreads();
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        aesc_for<I + 1, N>(f);
     }
 }
 
-// inverse, decimation in time: bit-reversed order in, natural order out (unnormalised)
-template <int L>
-__device__ void aesc_ifft_dit(cpx *s, const cpx *__restrict__ tw, int tid)
+__host__ __device__ constexpr int aesc_log2(int n) { return n <= 1 ? 0 : 1 + aesc_log2(n / 2); }
+__host__ __device__ constexpr int aesc_brev(int k, int bits) { return bits == 0 ? 0 : ((k & 1) << (bits - 1)) | aesc_brev(k >> 1, bits - 1); }
+// cos(2 pi e / 32), 0 <= e <= 16
+__host__ __device__ constexpr float aesc_c32(int e)
 {
-    constexpr int N = 1 << L;
-    int st = 0;
-    for (; st < L % 3; ++st) {                            // leading 1 or 2 plain radix-2 stages
-        const int half = 1 << st;
-        for (int b = tid; b < N / 2; b += AESC_NT) {
-            const int pos = b & (half - 1);
-            const int i0 = ((b - pos) << 1) + pos, i1 = i0 + half;
-            cpx w = tw[pos << (L - 1 - st)];
-            w.y = -w.y;
-            const cpx u = s[i0], t = c_mul(s[i1], w);
-            s[i0] = c_add(u, t);
-            s[i1] = c_sub(u, t);
-        }
-        __syncthreads();
+    constexpr float C[9] = {1.0f, 0.98078528040323043f, 0.92387953251128674f, 0.83146961230254524f, 0.70710678118654752f,
+                            0.55557023301960218f, 0.38268343236508978f, 0.19509032201612825f, 0.0f};
+    return e <= 8 ? C[e] : -C[16 - e];
+}
+
+// d * exp(-2 pi i E / 32) (INV: the conjugate), 0 <= E < 16; every constant is an immediate
+template <int E, bool INV>
+__device__ __forceinline__ cpx aesc_mul_w32(cpx d)
+{
+    if constexpr (E == 0) return d;
+    else if constexpr (E == 8) return INV ? c_mul_pi(d) : c_mul_mi(d);
+    else {
+        constexpr float c = aesc_c32(E), s0 = aesc_c32(E <= 8 ? 8 - E : E - 8);      // cos, sin of 2 pi E / 32
+        constexpr float s = INV ? s0 : -s0;
+        cpx r;
+        r.x = d.x * c - d.y * s;
+        r.y = d.x * s + d.y * c;
+        return r;
     }
-    for (; st < L; st += 3) {
-        const int h = 1 << st;                            // distances h, 2h, 4h
-        for (int it = tid; it < N / 8; it += AESC_NT) {
-            const int r = it & (h - 1);
-            const int base = ((it - r) << 3) + r;
-            cpx v[8];
-#pragma unroll
-            for (int m = 0; m < 8; ++m) v[m] = s[base + m * h];
-            cpx v4 = tw[r << (L - 3 - st)];               // exponent r*N/(8h)
-            v4.y = -v4.y;
-            const cpx v2 = c_sq(v4), v1 = c_sq(v2);
-            // stage st (distance h): twiddle v1
-#pragma unroll
-            for (int g = 0; g < 8; g += 2) {
-                const cpx t = c_mul(v[g + 1], v1);
-                v[g + 1] = c_sub(v[g], t);
-                v[g] = c_add(v[g], t);
-            }
-            // stage st+1 (distance 2h): twiddle v2 * (+i)^(m&1)
-#pragma unroll
-            for (int g = 0; g < 8; g += 4) {
-                const cpx t0 = c_mul(v[g + 2], v2), t1 = c_mul_pi(c_mul(v[g + 3], v2));
-                v[g + 2] = c_sub(v[g], t0); v[g] = c_add(v[g], t0);
-                v[g + 3] = c_sub(v[g + 1], t1); v[g + 1] = c_add(v[g + 1], t1);
-            }
-            // stage st+2 (distance 4h): twiddle v4 * conj(W_8)^m
-            {
-                const cpx a0 = c_mul(v[4], v4), a1 = c_mul(v[5], v4), a2 = c_mul(v[6], v4), a3 = c_mul(v[7], v4);
-                cpx t1; t1.x = AESC_R2 * (a1.x - a1.y); t1.y = AESC_R2 * (a1.x + a1.y);          // a1 * (1+i)/sqrt2
-                const cpx t2 = c_mul_pi(a2);
-                cpx t3; t3.x = -AESC_R2 * (a3.x + a3.y); t3.y = AESC_R2 * (a3.x - a3.y);         // a3 * (-1+i)/sqrt2
-                v[4] = c_sub(v[0], a0); v[0] = c_add(v[0], a0);
-                v[5] = c_sub(v[1], t1); v[1] = c_add(v[1], t1);
-                v[6] = c_sub(v[2], t2); v[2] = c_add(v[2], t2);
-                v[7] = c_sub(v[3], t3); v[3] = c_add(v[3], t3);
-            }
-#pragma unroll
-            for (int m = 0; m < 8; ++m) s[base + m * h] = v[m];
+}
+
+// R-point DFT in registers (R <= 32, a power of two): radix-2 decimation in frequency, natural order
+// in, element k of the result at v[aesc_brev(k)]
+template <int R, int HALF, bool INV>
+__device__ __forceinline__ void aesc_dft(cpx (&v)[R])
+{
+    aesc_for<0, R / 2>([&](auto ic) {
+        constexpr int b = decltype(ic)::value, j = b % HALF, g = (b / HALF) * 2 * HALF, e = j * (16 / HALF);
+        const cpx p = v[g + j], q = v[g + j + HALF];
+        v[g + j] = c_add(p, q);
+        v[g + j + HALF] = aesc_mul_w32<e, INV>(c_sub(p, q));
+    });
+    if constexpr (HALF > 1) aesc_dft<R, HALF / 2, INV>(v);
+}
+
+// f(k, X[k] * w^k) for k = 0 .. R-1 in natural order; powers of w as four interleaved chains over w^4
+// (at most R/4 + 2 roundings deep)
+template <int R, class F>
+__device__ __forceinline__ void aesc_emit_tw(const cpx (&v)[R], cpx w, F &&f)
+{
+    constexpr int LG = aesc_log2(R);
+    const cpx w2 = c_sq(w), w3 = c_mul(w2, w), w4 = c_sq(w2);
+    cpx pw[4];
+    pw[0] = w4; pw[1] = w; pw[2] = w2; pw[3] = w3;
+    aesc_for<0, R>([&](auto ic) {
+        constexpr int k = decltype(ic)::value, src = aesc_brev(k, LG);
+        if constexpr (k == 0) f(ic, v[src]);
+        else {
+            if constexpr (k > 4) pw[k & 3] = c_mul(pw[k & 3], w4);
+            f(ic, c_mul(v[src], pw[k & 3]));
         }
+    });
+}
+
+// exp(-2 pi i q / N): from the table, or computed when the caller has none (tw == nullptr)
+__device__ __forceinline__ cpx aesc_tw(const cpx *__restrict__ tw, int q, int N)
+{
+    if (tw) return tw[q];
+    cpx w;
+#ifdef AES_CPU_EMU
+    const double ang = -2.0 * M_PI * (double)q / (double)N;
+    w.x = (float)cos(ang); w.y = (float)sin(ang);
+#else
+    sincospif(-2.0f * (float)q / (float)N, &w.y, &w.x);       // the argument is exact in f32
+#endif
+    return w;
+}
+
+template <int R> struct AescGeo {
+    static constexpr int H = R / 2, N = R * R * H, NT = R * H, BK = N / 2, R2 = R * R;
+    static constexpr int NS = N + 32;                                       // row of separated spectra: N bins + XR[0], XR[N/2] + pad
+    static constexpr int S2 = NT + NT / 16;                                 // layout 2: one row per k1, (n2,n3) padded one per 16
+    static constexpr int L1 = R2 * (H + 1), L2 = R * S2;
+    static constexpr int SMEM_CPX = L1 > L2 ? L1 : L2;
+};
+__device__ __forceinline__ int aesc_pad16(int i) { return i + (i >> 4); }
+
+// L/R separation of a mirror pair: lo = Z[k], hi = Z[N-k] (0 < k < N/2) -> XL[k], XR[k]
+__device__ __forceinline__ void aesc_split(cpx lo, cpx hi, float sc, cpx &xl, cpx &xr)
+{
+    xl.x = sc * (lo.x + hi.x); xl.y = sc * (lo.y - hi.y);
+    xr.x = sc * (lo.y + hi.y); xr.y = sc * (hi.x - lo.x);
+}
+// ... and back: YL, YR -> Y[k] = YL + i YR, Y[N-k] = conj(YL) + i conj(YR)
+__device__ __forceinline__ void aesc_join(cpx yl, cpx yr, cpx &lo, cpx &hi)
+{
+    lo.x = yl.x - yr.y; lo.y = yl.y + yr.x;
+    hi.x = yl.x + yr.y; hi.y = yr.x - yl.y;
+}
+
+// Forward transform of one frame: ld(n) -> z[n] (natural order), st(g, value) receives the separated
+// spectra S[g] (scaled by 2*sc: pass sc = 0.5 for plain spectra).  All NT threads call it.
+template <int R, class LD, class ST>
+__device__ __forceinline__ void aesc_fwd(cpx *s, const cpx *__restrict__ tw, int t, float sc, LD &&ld, ST &&st)
+{
+    using G = AescGeo<R>;
+    constexpr int H = G::H, LGH = aesc_log2(H);
+    {   // pass 1: over n1 (stride NT); thread t = n2*H + n3
+        cpx v[R];
+        aesc_for<0, R>([&](auto ic) { v[decltype(ic)::value] = ld(decltype(ic)::value * G::NT + t); });
+        aesc_dft<R, R / 2, false>(v);
+        const int col = aesc_pad16(t);
+        aesc_emit_tw<R>(v, aesc_tw(tw, t, G::N), [&](auto kc, cpx val) { s[decltype(kc)::value * G::S2 + col] = val; });
+    }
+    __syncthreads();
+    {   // pass 2: over n2 (stride H); thread = (k1, n3)
+        const int k1 = t / H, n3 = t % H;
+        cpx v[R];
+        aesc_for<0, R>([&](auto ic) { v[decltype(ic)::value] = s[k1 * G::S2 + aesc_pad16(decltype(ic)::value * H + n3)]; });
+        __syncthreads();                                    // the layout changes: every read before any write
+        aesc_dft<R, R / 2, false>(v);
+        aesc_emit_tw<R>(v, aesc_tw(tw, R * n3, G::N), [&](auto kc, cpx val) { s[(k1 + R * decltype(kc)::value) * (H + 1) + n3] = val; });
+    }
+    __syncthreads();
+    {   // pass 3: over n3; rows kl = t and its mirror
+        const int kla = t, klb = t ? G::R2 - t : G::R2 / 2;
+        cpx a[H], b[H];
+        aesc_for<0, H>([&](auto ic) {
+            a[decltype(ic)::value] = s[kla * (H + 1) + decltype(ic)::value];
+            b[decltype(ic)::value] = s[klb * (H + 1) + decltype(ic)::value];
+        });
+        aesc_dft<H, H / 2, false>(a);
+        aesc_dft<H, H / 2, false>(b);
+        if (t != 0) {
+            // bin k = t + R2*j of row a pairs with bin N-k = (R2-t) + R2*(H-1-j) of row b
+            aesc_for<0, H>([&](auto jc) {
+                constexpr int j = decltype(jc)::value, jm = H - 1 - j;
+                const cpx za = a[aesc_brev(j, LGH)], zb = b[aesc_brev(jm, LGH)];
+                cpx xl, xr;
+                if constexpr (j < H / 2) { aesc_split(za, zb, sc, xl, xr); st(j * G::R2 + kla, xl); st(jm * G::R2 + klb, xr); }
+                else { aesc_split(zb, za, sc, xl, xr); st(jm * G::R2 + klb, xl); st(j * G::R2 + kla, xr); }
+            });
+        } else {
+            // row 0: bins R2*j, mirror R2*(H-j); DC and Nyquist are real in both channels.  Row R2/2: bins
+            // R2/2 + R2*j, mirror R2/2 + R2*(H-1-j)
+            const cpx dc = a[0], ny = a[aesc_brev(H / 2, LGH)];
+            cpx r;
+            r.y = 0.f;
+            r.x = 2.0f * sc * dc.x; st(0, r);
+            r.x = 2.0f * sc * dc.y; st(G::N, r);
+            r.x = 2.0f * sc * ny.x; st(G::N / 2, r);
+            r.x = 2.0f * sc * ny.y; st(G::N + 1, r);
+            aesc_for<1, H / 2>([&](auto jc) {
+                constexpr int j = decltype(jc)::value;
+                cpx xl, xr;
+                aesc_split(a[aesc_brev(j, LGH)], a[aesc_brev(H - j, LGH)], sc, xl, xr);
+                st(j * G::R2, xl); st((H - j) * G::R2, xr);
+            });
+            aesc_for<0, H / 2>([&](auto jc) {
+                constexpr int j = decltype(jc)::value, jm = H - 1 - j;
+                cpx xl, xr;
+                aesc_split(b[aesc_brev(j, LGH)], b[aesc_brev(jm, LGH)], sc, xl, xr);
+                st(j * G::R2 + klb, xl); st(jm * G::R2 + klb, xr);
+            });
+        }
+    }
+}
+
+// Inverse transform (unnormalised) of separated spectra: ld(g) -> S[g], st(n, y[n]) is called for the
+// second half of the frame only (n >= N/2: overlap-save keeps those); pf(i, n) is called for the same n
+// (i = 0 .. R/2-1) before the last pass, so the caller can have its own operands of st in flight
+template <int R, class LD, class PF, class ST>
+__device__ __forceinline__ void aesc_inv(cpx *s, const cpx *__restrict__ tw, int t, LD &&ld, PF &&pf, ST &&st)
+{
+    using G = AescGeo<R>;
+    constexpr int H = G::H;
+    {   // pass A: over k3; rows kl = t and its mirror, packed spectrum rebuilt on the way in
+        const int kla = t, klb = t ? G::R2 - t : G::R2 / 2;
+        cpx sa[H], sb[H], a[H], b[H];
+        aesc_for<0, H>([&](auto ic) {
+            sa[decltype(ic)::value] = ld(decltype(ic)::value * G::R2 + kla);
+            sb[decltype(ic)::value] = ld(decltype(ic)::value * G::R2 + klb);
+        });
+        if (t != 0) {
+            aesc_for<0, H / 2>([&](auto jc) {
+                constexpr int j = decltype(jc)::value, jm = H - 1 - j;
+                aesc_join(sa[j], sb[jm], a[j], b[jm]);          // lower bin in row a
+                aesc_join(sb[j], sa[jm], b[j], a[jm]);          // lower bin in row b
+            });
+        } else {
+            a[0].x = sa[0].x; a[0].y = ld(G::N).x;
+            a[H / 2].x = sa[H / 2].x; a[H / 2].y = ld(G::N + 1).x;
+            aesc_for<1, H / 2>([&](auto jc) { constexpr int j = decltype(jc)::value; aesc_join(sa[j], sa[H - j], a[j], a[H - j]); });
+            aesc_for<0, H / 2>([&](auto jc) { constexpr int j = decltype(jc)::value; aesc_join(sb[j], sb[H - 1 - j], b[j], b[H - 1 - j]); });
+        }
+        aesc_dft<H, H / 2, true>(a);
+        aesc_dft<H, H / 2, true>(b);
+        aesc_emit_tw<H>(a, c_conj(aesc_tw(tw, kla, G::N)), [&](auto nc, cpx val) { s[kla * (H + 1) + decltype(nc)::value] = val; });
+        aesc_emit_tw<H>(b, c_conj(aesc_tw(tw, klb, G::N)), [&](auto nc, cpx val) { s[klb * (H + 1) + decltype(nc)::value] = val; });
+    }
+    __syncthreads();
+    {   // pass B: over k2; thread = (k1, n3)
+        const int k1 = t / H, n3 = t % H;
+        cpx v[R];
+        aesc_for<0, R>([&](auto ic) { v[decltype(ic)::value] = s[(k1 + R * decltype(ic)::value) * (H + 1) + n3]; });
         __syncthreads();
+        aesc_dft<R, R / 2, true>(v);
+        aesc_emit_tw<R>(v, c_conj(aesc_tw(tw, H * k1, G::N)), [&](auto nc, cpx val) { s[k1 * G::S2 + aesc_pad16(decltype(nc)::value * H + n3)] = val; });
+    }
+    __syncthreads();
+    {   // pass C: over k1; thread t = n2*H + n3
+        constexpr int LG = aesc_log2(R);
+        cpx v[R];
+        const int col = aesc_pad16(t);
+        aesc_for<R / 2, R>([&](auto nc) { constexpr int n1 = decltype(nc)::value; pf(std::integral_constant<int, n1 - R / 2>{}, n1 * G::NT + t); });
+        aesc_for<0, R>([&](auto ic) { v[decltype(ic)::value] = s[decltype(ic)::value * G::S2 + col]; });
+        aesc_dft<R, R / 2, true>(v);
+        aesc_for<R / 2, R>([&](auto nc) {
+            constexpr int n1 = decltype(nc)::value;
+            st(std::integral_constant<int, n1 - R / 2>{}, n1 * G::NT + t, v[aesc_brev(n1, LG)]);
+        });
     }
 }
 
 struct ConvArgs {
     const float *x;         // (B, Nf, 2) f32
     float *y;               // (B, Nf, 2) f32
-    cpx *Z, *W;             // [B][nblk][N] spectra (bit-reversed order)
-    const cpx *A, *Bc;      // [P][N] IR partition spectra (bit-reversed order), 1/N folded in
-    const cpx *tw;          // [N/2]
+    cpx *Z, *W;             // [B][nblk][NS] separated spectra, natural bin order
+    const cpx *H;           // [P][NS] IR partition spectra in the same layout, 1/N folded in; P a multiple of the MAC's PC
+    const cpx *tw;          // [N/2]  exp(-2 pi i q / N)
     long long B, Nf;
     int nblk, P;
     float dry, wet;
 };
 
 // K1: forward FFT of the overlap-save frame [(j-1)*BK, (j+1)*BK) of every clip
-template <int L>
-__device__ void aesc_fft_blocks_body(const ConvArgs &a)
+template <int R>
+__device__ __forceinline__ void aesc_fwd_body(const ConvArgs &a)
 {
-    constexpr int N = 1 << L, BK = N / 2;
+    using G = AescGeo<R>;
     AES_DYN_SMEM(cpx, s);
-    const int tid = threadIdx.x;
     const long long blk = blockIdx.x;
     const long long clip = blk / a.nblk;
     const int j = (int)(blk % a.nblk);
     const cpx *xc = reinterpret_cast<const cpx *>(a.x) + clip * a.Nf;
-    const long long f0 = (long long)(j - 1) * BK;
-    for (int i = tid; i < N; i += AESC_NT) {
-        const long long f = f0 + i;
-        cpx v; v.x = 0.f; v.y = 0.f;
-        if (f >= 0 && f < a.Nf) v = xc[f];
-        s[i] = v;
-    }
-    __syncthreads();
-    aesc_fft_dif<L>(s, a.tw, tid);
-    cpx *zo = a.Z + ((size_t)clip * a.nblk + j) * N;
-    for (int i = tid; i < N; i += AESC_NT) zo[i] = s[i];
+    const long long f0 = (long long)(j - 1) * G::BK;
+    cpx *zo = a.Z + ((size_t)clip * a.nblk + j) * G::NS;
+    const long long Nf = a.Nf;
+    aesc_fwd<R>(s, a.tw, (int)threadIdx.x, 0.5f,
+        [&](int n) { const long long f = f0 + n; cpx v; v.x = 0.f; v.y = 0.f; if (f >= 0 && f < Nf) v = xc[f]; return v; },
+        [&](int g, cpx v) { zo[g] = v; });
 }
 
-// K2: per-bin FIR over the block index with the IR partition spectra
-template <int L>
-__device__ void aesc_mac_body(const ConvArgs &a, int clips_per_cta)
+// IR preparation: partition p of (hL + i*hR), zero-padded to N, through the same transform; 1/N folded in
+template <int R>
+__device__ __forceinline__ void aesc_ir_prep_body(const float *ir, int n_taps, cpx *Hout, const cpx *tw)
 {
-    constexpr int N = 1 << L;
-    AES_DYN_SMEM(cpx, s);                               // A tile [P][KT] | B tile [P][KT]
-    const int tid = threadIdx.x;                        // AESC_KT threads
-    const int ktile = blockIdx.x % (N / AESC_KT);
-    const long long cgrp = blockIdx.x / (N / AESC_KT);
-    const int i = ktile * AESC_KT + tid;                // physical (bit-reversed) bin of this thread
-    const int im = aesc_mirror(i);
-    cpx *sA = s, *sB = s + (size_t)a.P * AESC_KT;
-    for (int p = 0; p < a.P; ++p) {
-        sA[p * AESC_KT + tid] = a.A[(size_t)p * N + i];
-        sB[p * AESC_KT + tid] = a.Bc[(size_t)p * N + i];
-    }
-    __syncthreads();
-    for (long long clip = cgrp * clips_per_cta; clip < a.B && clip < (cgrp + 1) * clips_per_cta; ++clip) {
-        const cpx *zc = a.Z + (size_t)clip * a.nblk * N;
-        cpx *wc = a.W + (size_t)clip * a.nblk * N;
-        for (int j0 = 0; j0 < a.nblk; j0 += AESC_JB) {
-            cpx acc[AESC_JB];
-#pragma unroll
-            for (int u = 0; u < AESC_JB; ++u) { acc[u].x = 0.f; acc[u].y = 0.f; }
-            const int qlo = j0 - a.P + 1 < 0 ? 0 : j0 - a.P + 1;
-            const int qhi = j0 + AESC_JB - 1 < a.nblk - 1 ? j0 + AESC_JB - 1 : a.nblk - 1;
-            for (int q = qlo; q <= qhi; ++q) {
-                const cpx z = zc[(size_t)q * N + i];
-                cpx zm = zc[(size_t)q * N + im];
-                zm.y = -zm.y;
-                const int p0 = j0 - q;                          // partition that maps block q to output j0
-                if (p0 >= 0 && p0 + AESC_JB <= a.P) {
-                    // interior of the window: all JB outputs take this block, partitions p0 .. p0+JB-1
-                    // at constant offsets -- no per-output bounds test or index arithmetic
-                    const cpx *pa = sA + p0 * AESC_KT + tid, *pb = sB + p0 * AESC_KT + tid;
-#pragma unroll
-                    for (int u = 0; u < AESC_JB; ++u) {
-                        const cpx ca = pa[u * AESC_KT], cb = pb[u * AESC_KT];
-                        acc[u].x += ca.x * z.x - ca.y * z.y + cb.x * zm.x - cb.y * zm.y;
-                        acc[u].y += ca.x * z.y + ca.y * z.x + cb.x * zm.y + cb.y * zm.x;
-                    }
-                } else {
-#pragma unroll
-                    for (int u = 0; u < AESC_JB; ++u) {
-                        const int p = p0 + u;
-                        if (p >= 0 && p < a.P) {
-                            const cpx ca = sA[p * AESC_KT + tid], cb = sB[p * AESC_KT + tid];
-                            acc[u].x += ca.x * z.x - ca.y * z.y + cb.x * zm.x - cb.y * zm.y;
-                            acc[u].y += ca.x * z.y + ca.y * z.x + cb.x * zm.y + cb.y * zm.x;
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < AESC_JB; ++u)
-                if (j0 + u < a.nblk) wc[(size_t)(j0 + u) * N + i] = acc[u];
-        }
-    }
+    using G = AescGeo<R>;
+    AES_DYN_SMEM(cpx, s);
+    const int p = blockIdx.x;
+    cpx *ho = Hout + (size_t)p * G::NS;
+    aesc_fwd<R>(s, tw, (int)threadIdx.x, 0.5f / (float)G::N,
+        [&](int n) {
+            const long long tt = (long long)p * G::BK + n;
+            cpx v; v.x = 0.f; v.y = 0.f;
+            if (n < G::BK && tt < n_taps) { v.x = ir[2 * tt]; v.y = ir[2 * tt + 1]; }
+            return v;
+        },
+        [&](int g, cpx v) { ho[g] = v; });
 }
 
 // K3: inverse FFT, overlap-save (keep the last BK samples), dry/wet mix and clip
-template <int L>
-__device__ void aesc_ifft_mix_body(const ConvArgs &a)
+template <int R>
+__device__ __forceinline__ void aesc_inv_body(const ConvArgs &a)
 {
-    constexpr int N = 1 << L, BK = N / 2;
+    using G = AescGeo<R>;
     AES_DYN_SMEM(cpx, s);
-    const int tid = threadIdx.x;
     const long long blk = blockIdx.x;
     const long long clip = blk / a.nblk;
     const int j = (int)(blk % a.nblk);
-    const cpx *wi = a.W + ((size_t)clip * a.nblk + j) * N;
-    for (int i = tid; i < N; i += AESC_NT) s[i] = wi[i];
-    __syncthreads();
-    aesc_ifft_dit<L>(s, a.tw, tid);
+    const cpx *wi = a.W + ((size_t)clip * a.nblk + j) * G::NS;
     const cpx *xc = reinterpret_cast<const cpx *>(a.x) + clip * a.Nf;
     cpx *yc = reinterpret_cast<cpx *>(a.y) + clip * a.Nf;
-    const long long f0 = (long long)j * BK;
-    for (int i = tid; i < BK; i += AESC_NT) {
-        const long long f = f0 + i;
-        if (f < a.Nf) {
-            const cpx dryv = xc[f], wetv = s[BK + i];
-            cpx o;
-            o.x = fminf(fmaxf(__fadd_rn(__fmul_rn(a.dry, dryv.x), __fmul_rn(a.wet, wetv.x)), -1.0f), 1.0f);
-            o.y = fminf(fmaxf(__fadd_rn(__fmul_rn(a.dry, dryv.y), __fmul_rn(a.wet, wetv.y)), -1.0f), 1.0f);
-            yc[f] = o;
-        }
+    const long long f0 = (long long)j * G::BK - G::BK, Nf = a.Nf;
+    const float dry = a.dry, wet = a.wet;
+    cpx dv[R / 2];                                      // the dry frames of this thread's outputs, loaded ahead of the last pass
+    aesc_inv<R>(s, a.tw, (int)threadIdx.x,
+        [&](int g) { return wi[g]; },
+        [&](auto ic, int n) {
+            const long long f = f0 + n;
+            cpx v; v.x = 0.f; v.y = 0.f;
+            if (f < Nf) v = xc[f];
+            dv[decltype(ic)::value] = v;
+        },
+        [&](auto ic, int n, cpx wetv) {
+            const long long f = f0 + n;
+            if (f < Nf) {
+                const cpx dryv = dv[decltype(ic)::value];
+                cpx o;
+                o.x = fminf(fmaxf(__fadd_rn(__fmul_rn(dry, dryv.x), __fmul_rn(wet, wetv.x)), -1.0f), 1.0f);
+                o.y = fminf(fmaxf(__fadd_rn(__fmul_rn(dry, dryv.y), __fmul_rn(wet, wetv.y)), -1.0f), 1.0f);
+                yc[f] = o;
+            }
+        });
+}
+
+// K2: W[j] (+)= sum_{p < PC} H[p0 + p] * S[j - p0 - p] for one bin per thread (NS = row length of the spectra).
+// Persistent CTAs over work items (bin tile, clip group); the item's IR tile [PC][AESC_MT] arrives by TMA in
+// one of two shared buffers while the previous item computes.
+template <int PC>
+__device__ __forceinline__ void aesc_mac_clip(const cpx *__restrict__ zc, cpx *__restrict__ wc, size_t NS, int nq,
+                                              const cpx (&h)[PC], int accumulate)
+{
+    cpx acc[PC];
+#pragma unroll
+    for (int p = 0; p < PC; ++p) { acc[p].x = 0.f; acc[p].y = 0.f; }
+    // input block q = q0 + r adds H[p] * S[q] to output q + p, kept in accumulator (r + p) % PC; output q is
+    // complete after input q
+    auto mac = [&](auto rc, cpx z) {
+        constexpr int r = decltype(rc)::value;
+        aesc_for<0, PC>([&](auto pc) {
+            constexpr int p = decltype(pc)::value, u = (r + p) % PC;
+            acc[u].x = fmaf(-h[p].y, z.y, fmaf(h[p].x, z.x, acc[u].x));
+            acc[u].y = fmaf(h[p].y, z.x, fmaf(h[p].x, z.y, acc[u].y));
+        });
+    };
+    auto out = [&](auto rc, int q) {
+        constexpr int r = decltype(rc)::value;
+        cpx v = acc[r];
+        cpx *dst = wc + (size_t)q * NS;
+        if (accumulate) { const cpx o = *dst; v.x += o.x; v.y += o.y; }
+        *dst = v;
+        acc[r].x = 0.f; acc[r].y = 0.f;
+    };
+    // the spectra stream through in sub-batches of SB blocks: the loads of the next sub-batch are in flight
+    // while this one is multiplied (indices past the end are clamped, their values unused)
+    constexpr int SB = PC % 3 == 0 ? PC / 3 : PC / 2;
+    const int qlast = nq - 1;
+    cpx zn[SB];
+#pragma unroll
+    for (int r = 0; r < SB; ++r) zn[r] = zc[(size_t)(r < qlast ? r : qlast) * NS];
+    for (int q0 = 0; q0 < nq; q0 += PC) {
+        aesc_for<0, PC / SB>([&](auto sc) {
+            constexpr int r0 = decltype(sc)::value * SB;
+            cpx z[SB];
+#pragma unroll
+            for (int r = 0; r < SB; ++r) z[r] = zn[r];
+#pragma unroll
+            for (int r = 0; r < SB; ++r) {
+                const int qn = q0 + r0 + SB + r;
+                zn[r] = zc[(size_t)(qn < qlast ? qn : qlast) * NS];
+            }
+            aesc_for<0, SB>([&](auto rc) {
+                constexpr int r = r0 + decltype(rc)::value;
+                if (q0 + r < nq) { mac(std::integral_constant<int, r>{}, z[decltype(rc)::value]); out(std::integral_constant<int, r>{}, q0 + r); }
+            });
+        });
     }
 }
 
-// IR preparation: FFT of partition p of (hL + i*hR), then A = (HL+HR)/2/N, B = (HL-HR)/2/N
-// with HL[k] = (H[k] + conj(H[N-k]))/2, HR[k] = (H[k] - conj(H[N-k]))/(2i)
-template <int L>
-__device__ void aesc_ir_prep_body(const float *ir, int n_taps, cpx *A, cpx *Bc, const cpx *tw)
+template <int PC>
+__device__ __forceinline__ void aesc_mac_body(const ConvArgs &a, int NS, int p0, int clips_per_item, int accumulate)
 {
-    constexpr int N = 1 << L, BK = N / 2;
-    AES_DYN_SMEM(cpx, s);
-    const int tid = threadIdx.x, p = blockIdx.x;
-    for (int i = tid; i < N; i += AESC_NT) {
-        const long long t = (long long)p * BK + i;
-        cpx v; v.x = 0.f; v.y = 0.f;
-        if (i < BK && t < n_taps) { v.x = ir[2 * t]; v.y = ir[2 * t + 1]; }
-        s[i] = v;
-    }
+    AES_DYN_SMEM(cpx, s);                               // 2 x [PC][MT] IR tiles | 2 mbarriers
+    unsigned long long *bars = reinterpret_cast<unsigned long long *>(s + 2 * PC * AESC_MT);
+    const int tid = threadIdx.x;
+    const int ntiles = (NS + AESC_MT - 1) / AESC_MT;
+    const long long ngroups = (a.B + clips_per_item - 1) / clips_per_item;
+    const long long nitems = (long long)ntiles * ngroups;
+    if (tid == 0) { aes_mbar_init(bars, 1); aes_mbar_init(bars + 1, 1); aes_mbar_init_fence(); }
     __syncthreads();
-    aesc_fft_dif<L>(s, tw, tid);
-    const float sc = 1.0f / (float)N;
-    for (int i = tid; i < N; i += AESC_NT) {
-        const cpx h = s[i];
-        cpx hm = s[aesc_mirror(i)];
-        hm.y = -hm.y;
-        cpx hl, hr;
-        hl.x = 0.5f * (h.x + hm.x); hl.y = 0.5f * (h.y + hm.y);
-        // (h - hm) / (2i) = (-i/2) * (h - hm) = ( (h.y - hm.y)/2 , -(h.x - hm.x)/2 )
-        hr.x = 0.5f * (h.y - hm.y); hr.y = -0.5f * (h.x - hm.x);
-        cpx av, bv;
-        av.x = 0.5f * sc * (hl.x + hr.x); av.y = 0.5f * sc * (hl.y + hr.y);
-        bv.x = 0.5f * sc * (hl.x - hr.x); bv.y = 0.5f * sc * (hl.y - hr.y);
-        A[(size_t)p * N + i] = av;
-        Bc[(size_t)p * N + i] = bv;
+    auto issue = [&](long long item, int buf) {
+        const int tile = (int)(item % ntiles);
+        aes_fence_proxy_async_smem();                   // the buffer was read with ordinary loads before
+        aes_mbar_expect(bars + buf, (unsigned)(PC * AESC_MT * sizeof(cpx)));
+        const unsigned long long keep = aes_policy_evict_last();
+        for (int p = 0; p < PC; ++p)                    // (the last tile runs past its row: H has a tile of slack)
+            aes_bulk_g2s(s + (buf * PC + p) * AESC_MT, a.H + (size_t)(p0 + p) * NS + tile * AESC_MT,
+                         (unsigned)(AESC_MT * sizeof(cpx)), bars + buf, keep);
+#ifdef AES_CPU_EMU
+        aes_mbar_complete_emu(bars + buf);
+#endif
+    };
+    long long item = blockIdx.x;
+    if (tid == 0 && item < nitems) issue(item, 0);
+    const int nq = a.nblk - p0;                         // input blocks that reach an output through this chunk
+    for (unsigned it = 0; item < nitems; item += gridDim.x, ++it) {
+        const int buf = it & 1;
+        if (tid == 0 && item + gridDim.x < nitems) issue(item + gridDim.x, buf ^ 1);
+        aes_mbar_wait(bars + buf, it >> 1);
+        cpx h[PC];
+#pragma unroll
+        for (int p = 0; p < PC; ++p) h[p] = s[(buf * PC + p) * AESC_MT + tid];
+        __syncthreads();                                // every thread holds its values: the buffer may be refilled
+        const int tile = (int)(item % ntiles);
+        const long long grp = item / ntiles;
+        const int g = tile * AESC_MT + tid;
+        long long c1 = (grp + 1) * clips_per_item;
+        if (c1 > a.B) c1 = a.B;
+        if (g < NS)
+            for (long long clip = grp * clips_per_item; clip < c1; ++clip)
+                aesc_mac_clip<PC>(a.Z + (size_t)clip * a.nblk * NS + g, a.W + ((size_t)clip * a.nblk + p0) * NS + g,
+                                  (size_t)NS, nq, h, accumulate);
     }
 }

@@ -193,6 +193,21 @@ int aes_spectral_run(aes_spectral_plan *plan, const float *x, float *y, int64_t 
 int aes_spectral_process_host(aes_spectral_plan *plan, const float *x_host, float *y_host, int64_t n_clips,
                               int64_t n_frames, double thresh_lin, double reduction, double alpha);
 
+/* ---- plot-side analysis (assets/02_custom.js:65-154): what the page computes for every
+ *      plot refresh from the last FFT_SIZE = 16384 samples of the original and of the processed signal
+ *      (02_custom.js:179-184) -- 4-term Blackman-Harris window, FFT, 20*log10(|X|/n_fft + 1e-9) for the
+ *      n_fft/2+1 bins, the 12-bin chromagram of calculateChroma and the peak frequency above 60 Hz.
+ *      a, b: [n_pairs][n_samples] mono float32 signals (the last n_fft samples of each are analysed; b may
+ *      equal a); outputs mag_db / mag_lin [n_pairs][2][n_fft/2+1], chroma [n_pairs][2][12],
+ *      peak_freq [n_pairs][2], index [.][0] = a, [.][1] = b.  n_fft: 16384, 2048 or 256.  Both signals of a
+ *      pair ride through ONE complex transform.  Device pointers / host pointers (mag_lin may be NULL in the
+ *      host entry). */
+int aes_spectrum_chroma(const float *a, const float *b, int64_t n_pairs, int64_t n_samples, int n_fft,
+                        double sample_rate, float *mag_db, float *mag_lin, float *chroma, float *peak_freq,
+                        void *stream);
+int aes_spectrum_chroma_host(const float *a_host, const float *b_host, int64_t n_pairs, int64_t n_samples, int n_fft,
+                             double sample_rate, float *mag_db, float *mag_lin, float *chroma, float *peak_freq);
+
 #ifdef __cplusplus
 }
 #endif

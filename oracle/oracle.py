@@ -525,3 +525,50 @@ def run_batch_c(config, x, fs, threads=1, fast=False):
     y = np.empty_like(x)
     lib(fast).orc_chain_batch(C.cast(ops, C.c_void_p), n, _p(x), _p(y), B, N, threads)
     return y
+
+
+# ---- plot-side analysis (assets/02_custom.js:65-154); float64 like the page's JavaScript ----------------
+def chroma_from_magnitudes(mag, sample_rate, n_fft, threshold_scale=1.0):
+    """assets/02_custom.js:65-106 `calculateChroma`.  `threshold_scale` moves the 15 % gate by a hair so a
+    test can bracket the bins a float32 transform may put on the other side of it."""
+    mag = np.asarray(mag, np.float64)
+    chroma = np.zeros(12)
+    threshold = mag.max() * 0.15 * threshold_scale
+    for k in range(1, len(mag)):
+        freq = k * (sample_rate / n_fft)
+        if freq < 70:
+            continue
+        weighting = 1.0
+        if freq > 800:
+            weighting *= 0.5
+        if freq > 1500:
+            weighting *= 0.1
+        if freq > 5000:
+            continue
+        if mag[k] * weighting < threshold:
+            continue
+        midi = 12 * np.log2(freq / 440) + 69
+        nearest = np.floor(midi + 0.5)                  # Math.round
+        if abs(midi - nearest) > 0.50:
+            continue
+        chroma[(int(nearest) % 12 + 12) % 12] += mag[k] * weighting
+    v = chroma / (chroma.max() + 1e-9)
+    return v * v * v
+
+
+def spectrum_and_chroma(signal, sample_rate, threshold_scale=1.0):
+    """assets/02_custom.js:108-154 `calculateSpectrumAndChroma` on one signal of n_fft samples:
+    (freqs, magnitudesDB, chroma, peakFreq, magnitudesLin)."""
+    x = np.asarray(signal, np.float64)
+    n = len(x)
+    i = np.arange(n)
+    w = (0.35875 - 0.48829 * np.cos(2 * np.pi * i / (n - 1)) + 0.14128 * np.cos(4 * np.pi * i / (n - 1))
+         - 0.01168 * np.cos(6 * np.pi * i / (n - 1)))
+    mag = np.abs(np.fft.fft(x * w)[: n // 2 + 1])
+    freqs = np.arange(n // 2 + 1) * (sample_rate / n)
+    db = 20 * np.log10(mag / n + 1e-9)
+    peak_mag, peak_freq = -np.inf, 0.0
+    for k in range(n // 2 + 1):
+        if freqs[k] > 60 and db[k] > peak_mag:
+            peak_mag, peak_freq = db[k], freqs[k]
+    return freqs, db, chroma_from_magnitudes(mag, sample_rate, n, threshold_scale), peak_freq, mag

@@ -1,0 +1,6 @@
+set -x
+python -m pytest tests -m gpu -x -q -k "conv" 2>&1 | tail -5
+python bench.py --preset c4-convreverb --steps 5 --warmup 3 --no-e2e --no-cpu > gpurun_out/c4_r2x.json 2> gpurun_out/c4_r2x.err
+tail -3 gpurun_out/c4_r2x.err
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:aesc_ --csv --log-file gpurun_out/c4_r2x_launches.csv python bench.py --preset c4-convreverb --steps 2 --warmup 1 --no-e2e --no-cpu > /dev/null 2>&1
+ncu --set full --import-source on --clock-control none -k regex:aesc_ -s 4 -c 3 -o gpurun_out/c4_r2x python bench.py --preset c4-convreverb --steps 2 --warmup 1 --no-e2e --no-cpu > gpurun_out/c4_ncu.log 2>&1

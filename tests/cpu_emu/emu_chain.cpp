@@ -9,6 +9,7 @@
 #include "../../audio-effects-simulator_b200/csrc/aes_rv_build.h"
 #include "../../audio-effects-simulator_b200/csrc/aes_biquad_build.h"
 #include "../../audio-effects-simulator_b200/csrc/aes_convreverb.cuh"
+#include "../../audio-effects-simulator_b200/csrc/aes_analysis.cuh"
 #include "../../audio-effects-simulator_b200/csrc/aes_spectral.cuh"
 
 static char g_err[512];
@@ -131,31 +132,66 @@ int emu_biquad_lookback_depth(int n_stages, const double *coeffs5, int *out)
     return 0;
 }
 
-// ---- IR-convolution reverb (aes_convreverb.cuh) on the emulator, FFT size 2^8 -----------------
-struct ConvLaunch { ConvArgs a; int cpc; const float *ir; int n_taps; cpx *A, *B; const cpx *tw; };
-static void conv_k1(void *p) { aesc_fft_blocks_body<8>(reinterpret_cast<ConvLaunch *>(p)->a); }
-static void conv_k2(void *p) { ConvLaunch *l = reinterpret_cast<ConvLaunch *>(p); aesc_mac_body<8>(l->a, l->cpc); }
-static void conv_k3(void *p) { aesc_ifft_mix_body<8>(reinterpret_cast<ConvLaunch *>(p)->a); }
-static void conv_k0(void *p) { ConvLaunch *l = reinterpret_cast<ConvLaunch *>(p); aesc_ir_prep_body<8>(l->ir, l->n_taps, l->A, l->B, l->tw); }
+// ---- IR-convolution reverb (aes_convreverb.cuh) on the emulator, FFT size 2^8 / 2^11 / 2^14 -----
+struct ConvLaunch { ConvArgs a; int NS, p0, cpi, acc; const float *ir; int n_taps; cpx *H; const cpx *tw; };
+template <int R> static void conv_k0(void *p) { ConvLaunch *l = reinterpret_cast<ConvLaunch *>(p); aesc_ir_prep_body<R>(l->ir, l->n_taps, l->H, l->tw); }
+template <int R> static void conv_k1(void *p) { aesc_fwd_body<R>(reinterpret_cast<ConvLaunch *>(p)->a); }
+template <int PC> static void conv_k2(void *p) { ConvLaunch *l = reinterpret_cast<ConvLaunch *>(p); aesc_mac_body<PC>(l->a, l->NS, l->p0, l->cpi, l->acc); }
+template <int R> static void conv_k3(void *p) { aesc_inv_body<R>(reinterpret_cast<ConvLaunch *>(p)->a); }
 
-extern "C" __attribute__((visibility("default")))
-int emu_convreverb(const float *ir, long long n_taps, const float *x, float *y, long long B, long long Nf,
-                   float dry, float wet)
+template <int R>
+static int emu_conv_run(const float *ir, long long n_taps, const float *x, float *y, long long B, long long Nf,
+                        float dry, float wet, int pc, int mac_grid)
 {
-    constexpr int L = 8, N = 1 << L, BK = N / 2;
+    using G = AescGeo<R>;
+    constexpr int N = G::N, NS = G::NS, BK = G::BK;
     const int P = (int)((n_taps + BK - 1) / BK);
+    const int Ppad = (P + pc - 1) / pc * pc;
     const int nblk = (int)((Nf + BK - 1) / BK);
-    std::vector<cpx> tw(N / 2), A((size_t)P * N), Bc((size_t)P * N), Z((size_t)B * nblk * N), W((size_t)B * nblk * N);
+    std::vector<cpx> tw(N / 2), H((size_t)Ppad * NS + AESC_MT), Z((size_t)B * nblk * NS), W((size_t)B * nblk * NS);
+    for (auto &h : H) { h.x = 0.f; h.y = 0.f; }
+    for (auto &w : W) { w.x = 7.f; w.y = 7.f; }
     for (int q = 0; q < N / 2; ++q) { double ang = -2.0 * M_PI * q / N; tw[q].x = (float)cos(ang); tw[q].y = (float)sin(ang); }
     ConvLaunch l;
-    l.ir = ir; l.n_taps = (int)n_taps; l.A = A.data(); l.B = Bc.data(); l.tw = tw.data(); l.cpc = 2;
-    emu::launch(conv_k0, &l, P, AESC_NT, N * 8);
-    l.a.x = x; l.a.y = y; l.a.Z = Z.data(); l.a.W = W.data(); l.a.A = A.data(); l.a.Bc = Bc.data(); l.a.tw = tw.data();
-    l.a.B = B; l.a.Nf = Nf; l.a.nblk = nblk; l.a.P = P; l.a.dry = dry; l.a.wet = wet;
-    emu::launch(conv_k1, &l, (unsigned)(B * nblk), AESC_NT, N * 8);
-    // N / AESC_KT == 1 tile of 256 bins at this FFT size
-    emu::launch(conv_k2, &l, (unsigned)((N / AESC_KT) * ((B + 1) / 2)), AESC_KT, 2 * P * AESC_KT * 8);
-    emu::launch(conv_k3, &l, (unsigned)(B * nblk), AESC_NT, N * 8);
+    l.ir = ir; l.n_taps = (int)n_taps; l.H = H.data(); l.tw = tw.data(); l.NS = NS; l.cpi = 2;
+    const size_t fft_smem = (size_t)G::SMEM_CPX * sizeof(cpx);
+    emu::launch(conv_k0<R>, &l, P, G::NT, fft_smem);
+    l.a.x = x; l.a.y = y; l.a.Z = Z.data(); l.a.W = W.data(); l.a.H = H.data(); l.a.tw = tw.data();
+    l.a.B = B; l.a.Nf = Nf; l.a.nblk = nblk; l.a.P = Ppad; l.a.dry = dry; l.a.wet = wet;
+    emu::launch(conv_k1<R>, &l, (unsigned)(B * nblk), G::NT, fft_smem);
+    for (int p0 = 0; p0 < Ppad && p0 < nblk; p0 += pc) {
+        l.p0 = p0; l.acc = p0 > 0;
+        emu::launch(pc == 18 ? conv_k2<18> : pc == 9 ? conv_k2<9> : conv_k2<4>, &l, (unsigned)mac_grid, AESC_MT,
+                    (size_t)2 * pc * AESC_MT * sizeof(cpx) + 16);
+    }
+    emu::launch(conv_k3<R>, &l, (unsigned)(B * nblk), G::NT, fft_smem);
+    return 0;
+}
+
+// log2n: 8, 11 or 14; pc: partitions per MAC pass (4, 9, 18); mac_grid: persistent MAC CTAs
+extern "C" __attribute__((visibility("default")))
+int emu_convreverb(const float *ir, long long n_taps, const float *x, float *y, long long B, long long Nf,
+                   float dry, float wet, int log2n, int pc, int mac_grid)
+{
+    if (pc != 4 && pc != 9 && pc != 18) return -1;
+    if (log2n == 8) return emu_conv_run<8>(ir, n_taps, x, y, B, Nf, dry, wet, pc, mac_grid);
+    if (log2n == 11) return emu_conv_run<16>(ir, n_taps, x, y, B, Nf, dry, wet, pc, mac_grid);
+    if (log2n == 14) return emu_conv_run<32>(ir, n_taps, x, y, B, Nf, dry, wet, pc, mac_grid);
+    return -1;
+}
+
+// ---- spectrum / chromagram analysis (aes_analysis.cuh) on the emulator --------------------------
+template <int R> static void ana_k(void *p) { aesa_body<R>(*reinterpret_cast<AnalysisArgs *>(p)); }
+extern "C" __attribute__((visibility("default")))
+int emu_spectrum_chroma(const float *a, const float *b, long long n_pairs, long long n_samples, int n_fft, double fs,
+                        float *db, float *lin, float *chroma, float *peak)
+{
+    AnalysisArgs q;
+    q.a = a; q.b = b; q.db = db; q.lin = lin; q.chroma = chroma; q.peak_freq = peak; q.n_samples = n_samples; q.sample_rate = fs;
+    if (n_fft == 256) emu::launch(ana_k<8>, &q, (unsigned)n_pairs, AescGeo<8>::NT, AescGeo<8>::SMEM_CPX * sizeof(cpx));
+    else if (n_fft == 2048) emu::launch(ana_k<16>, &q, (unsigned)n_pairs, AescGeo<16>::NT, AescGeo<16>::SMEM_CPX * sizeof(cpx));
+    else if (n_fft == 16384) emu::launch(ana_k<32>, &q, (unsigned)n_pairs, AescGeo<32>::NT, AescGeo<32>::SMEM_CPX * sizeof(cpx));
+    else return -1;
     return 0;
 }
 

@@ -20,7 +20,10 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        subprocess.check_call(["make", "-s", "-C", _DIR], stdout=subprocess.DEVNULL)
+        import fcntl
+        with open(os.path.join(_DIR, ".build.lock"), "w") as lk:      # xdist workers build once, one at a time
+            fcntl.flock(lk, fcntl.LOCK_EX)
+            subprocess.check_call(["make", "-s", "-C", _DIR], stdout=subprocess.DEVNULL)
         L = C.CDLL(os.path.join(_DIR, "libaes_emu.so"))
         L.emu_last_error.restype = C.c_char_p
         L.emu_chain_run.argtypes = [C.POINTER(_native.StageDesc), C.c_int, C.c_int, C.c_void_p, C.c_int,
