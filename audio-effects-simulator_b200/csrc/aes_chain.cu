@@ -510,6 +510,8 @@ AES_EXPORT int aes_chain_process_host(aes_chain_plan *pl, const void *x_host, in
     }
     const bool pin_in = is_pinned(x_host), pin_out = is_pinned(y_host);
 
+    // (a lambda so that every early error return passes through the clean-up below)
+    auto pipeline = [&]() -> int {
     int k = 0;
     for (int64_t b0 = 0; b0 < n_clips; b0 += per, ++k) {
         const int64_t nb = std::min<int64_t>(per, n_clips - b0);
@@ -548,6 +550,20 @@ AES_EXPORT int aes_chain_process_host(aes_chain_plan *pl, const void *x_host, in
         if ((rc = drain_slot(cache.slot[i]))) return rc;
     pl->state_valid = (n_clips == 1);
     return 0;
+    };
+    rc = pipeline();
+    if (rc) {
+        // an error left copies in flight into the caller's buffers and staged results pending: wait for every
+        // slot and forget the pending host copies, so that a later call never writes through a stale pointer
+        for (HostSlot &s : cache.slot) {
+            if (s.stream) cudaStreamSynchronize(s.stream);
+            s.pend_dst = nullptr;
+            s.pend_bytes = 0;
+        }
+        cudaGetLastError();
+        pl->state_valid = false;
+    }
+    return rc;
 }
 
 // Carried scalars of stage `stage` after the last single-clip aes_chain_process_host call:

@@ -119,7 +119,7 @@ def conv_arm(args, torch, dist, _native, rank, world, local, dev):
     info = plan.info()
     samples = B * n_frames * 2
     nblk = -(-n_frames // (info["fft_size"] // 2))
-    mac_flops = B * nblk * info["fft_size"] * info["partitions"] * 16.0
+    mac_flops = B * nblk * info["fft_size"] * info["partitions"] * 8.0       # one complex multiply-add per bin, partition and block
     peak = 6547.8
     pp = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pp):
@@ -132,7 +132,7 @@ def conv_arm(args, torch, dist, _native, rank, world, local, dev):
         "config": {"workload": f"IR-convolution reverb, 3 s synthetic IR ({ir.shape[0]} taps), {B} synthetic "
                                f"{args.seconds:g} s 48 kHz stereo clips (BASELINE configs[3])", **info},
         "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                     "kernel": "aesc_fft_blocks + aesc_mac + aesc_ifft_mix", "mac_fp32_tflops": mac_flops / (ms * 1e-3) / 1e12},
+                     "kernel": "aesc_fwd + aesc_mac (TMA-staged IR tiles) + aesc_inv", "mac_fp32_tflops": mac_flops / (ms * 1e-3) / 1e12},
         "gpu_launches": int(L.aes_launch_count() - l0), "parity": {"max_abs_err": mx, "snr_db": snr, "frames": n_chk},
     }))
     plan.close()
@@ -454,6 +454,105 @@ def sweep_leg(args, torch, dist, _native, file_chain, x, y, B, n_frames, world, 
     return out
 
 
+def baseline_configs_leg(args, torch, _native, file_chain, dev, peak):
+    """BASELINE configs[1], [2], [3] at their own sizes and the plot-side analysis, one GPU, inputs
+    resident in HBM, each checked against the oracle: the numbers DESIGN quotes, measured by the default run."""
+    import ctypes as C
+    import numpy as np
+    import synth
+    from oracle import oracle as orc
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def median_ms(run, steps, flush_l2):
+        run()
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(steps):
+            if flush_l2:
+                flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            run()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+        return sorted(ms)[len(ms) // 2]
+
+    def chain_case(name, B, seconds, steps, flush_l2, check):
+        n = int(seconds * FS)
+        cfg = chain_config(name)
+        x = synth_device(torch, B, n, 0, dev)
+        y = torch.empty_like(x)
+        pipe, plans = file_chain(cfg, FS, channels_in=2).device_pipeline(n)
+        ms = median_ms(lambda: pipe(x.data_ptr(), y.data_ptr(), y.data_ptr(), B, sptr), steps, flush_l2)
+        worst, wsnr = 0.0, float("inf")
+        for b in check:
+            want = orc.run_file_path(cfg, np.ascontiguousarray(x[b].cpu().numpy()), FS)
+            mx, snr = synth.err_stats(y[b].cpu().numpy(), want)
+            worst, wsnr = max(worst, mx / max(1.0, float(np.max(np.abs(want))))), min(wsnr, snr)
+        v = B * n * 2 / (ms * 1e-3) / 1e6
+        r = {"clips": B, "seconds": seconds, "ms": ms, "value": v, "unit": UNIT, "frac_of_hbm_roofline": v * 8e6 / 1e9 / peak,
+             "l2": "flushed before every timed launch" if flush_l2 else "inputs larger than L2",
+             "kernels": [p.info()["kernel"] for p in plans if hasattr(p, "info")],
+             "parity": {"max_abs_err": worst, "snr_db": wsnr if np.isfinite(wsnr) else None, "clips": list(check), "frames": n}}
+        for p_ in plans:
+            p_.close()
+        return r
+
+    out = {}
+    c2 = chain_case("c2-biquad-cascade", 1, 60.0, 10, True, [0])
+    c2["us_per_clip"] = c2["ms"] * 1e3
+    out["configs[1] one 60 s clip, LP/HP/BP/peaking biquad cascade"] = c2
+    out["configs[2] 1024 clips x 10 s, distortion > octaver > delay"] = chain_case("c3-dist-octaver-delay", 1024, 10.0, 5, False, [0, 1023])
+
+    # configs[3]: IR-convolution reverb, 3 s IR, 256 clips x 30 s
+    n, B = 30 * FS, 256
+    ir = orc.synthetic_ir(int(3.0 * FS))
+    plan = _native.ConvReverbPlan(ir)
+    x = synth_device(torch, B, n, 0, dev)
+    y = torch.empty_like(x)
+    ms = median_ms(lambda: plan.run_device(x.data_ptr(), y.data_ptr(), B, n, 0.7, 0.5, sptr), 5, False)
+    n_chk = 200000
+    xs = x[0, :n_chk].cpu().numpy()
+    want = np.zeros_like(xs)
+    orc.OConvReverb(ir, 0.7, 0.5).process_into(xs, want)
+    mx, snr = synth.err_stats(y[0, :n_chk].cpu().numpy(), want)
+    info = plan.info()
+    v = B * n * 2 / (ms * 1e-3) / 1e6
+    out["configs[3] 256 clips x 30 s, convolution reverb with a 3 s IR"] = {
+        "clips": B, "seconds": 30.0, "ms": ms, "value": v, "unit": UNIT, "frac_of_hbm_roofline": v * 8e6 / 1e9 / peak, **info,
+        "mac_fp32_tflops": B * -(-n // (info["fft_size"] // 2)) * info["fft_size"] * info["partitions"] * 8.0 / (ms * 1e-3) / 1e12,
+        "kernels": ["aesc_fwd_kernel", "aesc_mac_kernel (TMA-staged IR tiles)", "aesc_inv_kernel"],
+        "parity": {"max_abs_err": mx, "snr_db": snr, "clips": [0], "frames": n_chk, "oracle": "float64 fftconvolve restatement (ours)"}}
+    plan.close()
+    del x, y
+
+    # plot-side analysis (02_custom.js:65-154): 4096 (original, processed) pairs of 16384 samples
+    n_pairs, n_fft = 4096, 16384
+    a = torch.rand(n_pairs, n_fft, device=dev) - 0.5
+    t = torch.arange(n_fft, device=dev, dtype=torch.float32) / FS
+    b = 0.4 * torch.sin(2 * torch.pi * 440.0 * t)[None, :] + 0.1 * a
+    nb = n_fft // 2 + 1
+    db, lin = torch.empty(n_pairs, 2, nb, device=dev), torch.empty(n_pairs, 2, nb, device=dev)
+    ch, pk = torch.empty(n_pairs, 2, 12, device=dev), torch.empty(n_pairs, 2, device=dev)
+    L = _native.lib()
+    ms = median_ms(lambda: _native.check(L.aes_spectrum_chroma(
+        C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), n_pairs, n_fft, n_fft, float(FS), C.c_void_p(db.data_ptr()),
+        C.c_void_p(lin.data_ptr()), C.c_void_p(ch.data_ptr()), C.c_void_p(pk.data_ptr()), C.c_void_p(sptr))), 5, False)
+    _, want_db, want_ch, want_pk, _ = orc.spectrum_and_chroma(b[7].cpu().numpy(), float(FS))
+    got_db = db[7, 1].cpu().numpy()
+    loud = want_db > -80.0
+    out["plot-side spectrum + chromagram, 4096 pairs x 16384 samples"] = {
+        "ms": ms, "spectra_per_s": 2 * n_pairs / (ms * 1e-3), "value": 2 * n_pairs * n_fft / (ms * 1e-3) / 1e6, "unit": UNIT,
+        "kernel": "aesa_kernel (one complex FFT per pair)",
+        "parity": {"max_db_err_above_-80dB": float(np.max(np.abs(got_db[loud] - want_db[loud]))),
+                   "max_chroma_err": float(np.max(np.abs(ch[7, 1].cpu().numpy() - want_ch))),
+                   "peak_freq": [float(pk[7, 1]), float(want_pk)], "oracle": "float64 restatement of the page's JavaScript (ours)"}}
+    return out
+
+
 def copy_ceiling(torch, dist, world, dev, barrier, xh, yh, reps):
     """What the PCIe path alone delivers: H2D of `xh` and D2H into `yh` (pinned, same bytes as the end-to-end
     leg), both directions at once on two streams, all ranks at the same time, no kernel."""
@@ -687,6 +786,11 @@ def b200_arm(args):
     if not args.no_sweep and args.clips <= 0 and args.preset == "Rain Delay":
         sweep = sweep_leg(args, torch, dist, _native, file_chain, x, y, B, n_frames, world, dev, barrier, peak)
 
+    # ---- BASELINE's other configurations at their own sizes (N = 1 only: none of them shards further)
+    others = None
+    if sweep is not None and world == 1 and not args.no_cpu:
+        others = baseline_configs_leg(args, torch, _native, file_chain, dev, peak)
+
     # ---- results gathered over NCCL (N > 1 only)
     gather = None
     if world > 1 and fused and not args.no_gather:
@@ -798,6 +902,8 @@ def b200_arm(args):
             line["sweep"] = sweep
         if gather is not None:
             line["gather"] = gather
+        if others is not None:
+            line["baseline_configs"] = others
         if not args.no_cpu and world == 1:          # the CPU baseline is reported at N = 1 only
             cores = os.cpu_count() or 1
             n_cpu = args.cpu_clips or max(cores, min(20 * cores, 512))     # ~20 s of CPU work on all threads
