@@ -57,6 +57,11 @@ __device__ __forceinline__ void aes_static_for(F &&f)
 // warp roles and the TMA's own shared-memory writes, ~229 per tile for 16.4 KB).  Two placements of the staged line
 // samples were measured against the plain 16-byte aligned one (r2t, r2u): at the 128-byte phase of their global
 // source, and 128-byte aligned destinations; both RAISED the copy's shared-memory wavefronts (288 per tile) and cost 3 %.
+// Also measured (r2aa): the staging as per-thread cp.async (LDGSTS, 16 bytes per copy) issued by the comb warps two
+// tiles ahead, each thread waiting for its own copies ahead of the comb-wide barrier -- no mbarrier, no issuing
+// thread.  268 against 289 Gsamples/s: the copies run through the LSU (925 M against 871 M LSU wavefronts, bank
+// conflicts 144 M against 101 M: 16-byte pieces at a 32-byte lane stride) and add 4 % to the comb warps' instructions,
+// while the TMA's writes bypass the LSU queue altogether.
 #define AESRV_NT 384
 #define AESRV_NW 128
 #define AESRV_NWC 64                // walkers per channel
