@@ -1,6 +1,7 @@
 // aes_chain.cu -- host side of the fused effect chain: plan objects, kernel launch,
 // and the host-buffer entry that pipelines H2D / kernel / D2H over internal streams.
 #include <algorithm>
+#include <math.h>
 #include <new>
 #include <stdlib.h>
 #include <string.h>
@@ -13,6 +14,7 @@
 #include "aes_fast_build.h"
 #include "aes_rv_build.h"
 #include "aes_biquad_build.h"
+#include "aes_biquad_seq.cuh"
 
 #define AES_HOST_SLOTS 4
 
@@ -67,6 +69,11 @@ struct aes_chain_plan {
     double *d_bq_tab = nullptr;                 // lane_pw [8][32][4] | tile_pw [8][256][4]
     void *d_bq_scan = nullptr;                  // agg | inc | flag | ticket, grown on demand
     size_t bq_scan_cap = 0;
+    // sequential recurrence per (clip, segment) for batches of biquad cascades (aes_biquad_seq.cuh)
+    bool bqs_ok = false;
+    BqSeqArgs bqs;
+    long long bqs_warm = -1;                    // frames a segment runs ahead of its first output; -1: the cascade
+                                                // remembers too long, clips are not segmented
     FastArgs fast;                              // flattened descriptors when a specialised kernel fits
     fast_kernel_t fast_fn = nullptr;
     bool rv = false;                            // fast_fn is an aes_rv_kernel instantiation
@@ -101,14 +108,46 @@ static int configure_kernel(aes_chain_plan *pl)
     return 0;
 }
 
-// `allow_scan`: the host pipeline decides on the WHOLE batch whether the time-parallel biquad scan
-// runs, not per sub-batch -- the two kernels agree to an ulp, not bit for bit, and a clip's result
-// must not depend on where in a batch it sits
+// Segments per clip for the sequential batch kernel (persistent threads, one (clip, segment) item at a time): the
+// K that wastes least -- whole rounds of the resident threads, warm-up short against the segment.  0: the kernel
+// does not serve this call.
+static int bqseq_segments(const aes_chain_plan *pl, long long decide_B, long long N, bool in_place)
+{
+    if (!pl->bqs_ok || (N & 1) || getenv("AES_NO_BQSEQ")) return 0;
+    const long long resident = (long long)pl->sm_count * (227 * 1024 / AESQ_SMEM_BYTES) * AESQ_WARPS * 32;
+    const long long least = (long long)pl->sm_count * 2 * 32;
+    long long kmax = 1;
+    if (!in_place && pl->bqs_warm > 0) kmax = std::max<long long>(1, std::min<long long>(N / (4 * pl->bqs_warm), 64));
+    long long best = 1;
+    double best_eff = 0.0;
+    for (long long K = 1; K <= kmax; ++K) {
+        const double rounds = (double)(decide_B * K) / (double)resident;
+        const double seg = (double)N / (double)K;
+        const double eff = rounds / ceil(rounds) * (K > 1 ? seg / (seg + (double)pl->bqs_warm) : 1.0);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = K; }
+    }
+    return decide_B * best >= least ? (int)best : 0;
+}
+
+template <int NS> static void bqseq_launch(const aes_chain_plan *pl, const BqSeqArgs &q, cudaStream_t st)
+{
+    static bool once = [] { return cudaFuncSetAttribute(aes_biquad_seq_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESQ_SMEM_BYTES) == cudaSuccess; }();
+    (void)once;
+    const long long need = (q.B * q.K + AESQ_WARPS * 32 - 1) / (AESQ_WARPS * 32);
+    const long long resident = (long long)pl->sm_count * (227 * 1024 / AESQ_SMEM_BYTES);
+    aes_biquad_seq_kernel<NS><<<(unsigned)std::min(need, resident), AESQ_WARPS * 32, AESQ_SMEM_BYTES, st>>>(q);
+}
+
+// `decide_B`: the batch size kernel choices are made on.  The host pipeline passes the size of the WHOLE batch,
+// not of the sub-batch it launches -- the time-parallel scan, the sequential batch kernel and the tile kernels
+// agree to an ulp, not bit for bit, and a clip's result must not depend on where in a batch it sits.
 static int launch_chain(aes_chain_plan *pl, const void *x, int in_fmt, void *y, int out_fmt,
                         long long B, long long N, float *scratch, cudaStream_t st, double *state_out = nullptr,
-                        bool allow_scan = true)
+                        long long decide_B = -1)
 {
     if (B <= 0 || N <= 0) return 0;
+    if (decide_B < 0) decide_B = B;
+    const bool allow_scan = decide_B < pl->grid_max;
     if (!pl->seg.empty()) {
         // segment k reads what segment k-1 wrote: f32 stereo, in the output buffer itself when that is the
         // caller's format (every kernel reads a tile before it writes it), else in a stream-ordered temporary
@@ -119,10 +158,28 @@ static int launch_chain(aes_chain_plan *pl, const void *x, int in_fmt, void *y, 
             const bool first = k == 0, last = k + 1 == pl->seg.size();
             rc = launch_chain(pl->seg[k], first ? x : mid, first ? in_fmt : AES_FMT_F32_STEREO, last ? y : mid,
                               last ? out_fmt : AES_FMT_F32_STEREO, B, N, scratch, st,
-                              state_out ? state_out + 16 * pl->seg_first[k] : nullptr, allow_scan);
+                              state_out ? state_out + 16 * pl->seg_first[k] : nullptr, decide_B);
         }
         if (mid != (float *)y) cudaFreeAsync(mid, st);
         return rc;
+    }
+    if (state_out == nullptr && in_fmt == AES_FMT_F32_STEREO && out_fmt == AES_FMT_F32_STEREO) {
+        if (const int K = bqseq_segments(pl, decide_B, N, x == y)) {
+            // a batch of biquad cascades: the plain recurrence, one thread per (clip, segment)
+            BqSeqArgs q = pl->bqs;
+            q.x = (const float *)x; q.y = (float *)y; q.B = B; q.N = N; q.K = K;
+            q.warm = K > 1 ? pl->bqs_warm : 0;
+            q.seg = (N / K + AESQ_CH - 1) / AESQ_CH * AESQ_CH;
+            switch (q.n_stages) {
+            case 1: bqseq_launch<1>(pl, q, st); break;
+            case 2: bqseq_launch<2>(pl, q, st); break;
+            case 3: bqseq_launch<3>(pl, q, st); break;
+            default: bqseq_launch<4>(pl, q, st); break;
+            }
+            aes_count_launch();
+            AES_CUDA(cudaGetLastError());
+            return 0;
+        }
     }
     if (pl->bq_ok && allow_scan && (B < pl->grid_max || getenv("AES_FORCE_SCAN")) && in_fmt == AES_FMT_F32_STEREO && out_fmt == AES_FMT_F32_STEREO &&
         !getenv("AES_NO_SCAN")) {
@@ -297,6 +354,19 @@ static int plan_create(const aes_stage_desc *stages, int n_stages, int sample_ra
             AES_CUDA(cudaMalloc(&pl->d_bq_tab, tab_bytes));
             AES_CUDA(cudaMemcpy(pl->d_bq_tab, tab, tab_bytes, cudaMemcpyHostToDevice));
             pl->bq_ok = true;
+            if (n_stages <= AESQ_MAX_STAGES) {
+                memset(&pl->bqs, 0, sizeof pl->bqs);
+                pl->bqs.n_stages = n_stages;
+                pl->bqs_warm = 0;
+                for (int s2 = 0; s2 < n_stages; ++s2) {
+                    for (int i = 0; i < 5; ++i) pl->bqs.bq[s2][i] = co[5 * s2 + i];
+                    for (int i = 0; i < 8; ++i) pl->bqs.init[s2][i] = dfi[8 * s2 + i];
+                    // a stage's memory: the look-back depth of the scan, in tiles (0: longer than its window)
+                    if (pl->bq.st[s2].lb_k == 0) pl->bqs_warm = -1;
+                    else if (pl->bqs_warm >= 0) pl->bqs_warm += (long long)pl->bq.st[s2].lb_k * AESB_T;
+                }
+                pl->bqs_ok = true;
+            }
         }
         AES_CUDA(cudaMalloc(&pl->d_state, sizeof pl->h_state));
         AES_CUDA(cudaMemset(pl->d_state, 0, sizeof pl->h_state));
@@ -531,7 +601,7 @@ AES_EXPORT int aes_chain_process_host(aes_chain_plan *pl, const void *x_host, in
         AES_CUDA(cudaMemcpyAsync(s.d_in, src, (size_t)nb * in_clip, cudaMemcpyHostToDevice, s.stream));
         double *st_out = n_clips == 1 ? pl->d_state : nullptr;
         if ((rc = launch_chain(pl, s.d_in, in_fmt, s.d_out, out_fmt, nb, n_frames, (float *)s.scratch, s.stream, st_out,
-                               n_clips < pl->grid_max))) return rc;
+                               n_clips))) return rc;
         if (st_out)
             AES_CUDA(cudaMemcpyAsync(pl->h_state, pl->d_state, (size_t)pl->host.n_state * sizeof(double),
                                      cudaMemcpyDeviceToHost, s.stream));

@@ -149,22 +149,6 @@ static inline void aes_fence_proxy_async_all() {}
 static inline void aes_fence_proxy_async_smem() {}
 #endif
 
-// ---- cp.async (LDGSTS): 16 bytes per thread global -> shared, no register and no scoreboard slot held while
-// it flies; a thread that reads back only what it copied itself needs no barrier, just wait_group.
-#ifndef AES_CPU_EMU
-__device__ __forceinline__ void aes_cp_async16(void *dst, const void *src, unsigned long long policy)
-{
-    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "l"(policy) : "memory");
-}
-__device__ __forceinline__ void aes_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void aes_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-#else
-static inline void aes_cp_async16(void *dst, const void *src, unsigned long long) { std::memcpy(dst, src, 16); }
-static inline void aes_cp_async_commit() {}
-template <int N> static inline void aes_cp_async_wait() {}
-#endif
-
 // ---- packed f32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2, one issue slot for two lanes' worth) ------
 // Each component rounds exactly like the scalar __fmaf_rn / __fadd_rn / __fmul_rn (no contraction).
 #ifndef AES_CPU_EMU

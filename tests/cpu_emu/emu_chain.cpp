@@ -8,6 +8,7 @@
 #include "../../audio-effects-simulator_b200/csrc/aes_fast_build.h"
 #include "../../audio-effects-simulator_b200/csrc/aes_rv_build.h"
 #include "../../audio-effects-simulator_b200/csrc/aes_biquad_build.h"
+#include "../../audio-effects-simulator_b200/csrc/aes_biquad_seq.cuh"
 #include "../../audio-effects-simulator_b200/csrc/aes_convreverb.cuh"
 #include "../../audio-effects-simulator_b200/csrc/aes_analysis.cuh"
 #include "../../audio-effects-simulator_b200/csrc/aes_spectral.cuh"
@@ -117,6 +118,32 @@ int emu_biquad_scan(const float *x, float *y, long long B, long long N, int n_st
     a.agg = agg.data(); a.inc = inc.data(); a.flag = flag.data(); a.ticket = &ticket;
     a.lane_pw = lane_pw.data(); a.tile_pw = tile_pw.data(); a.final_state = nullptr;
     emu::launch(bq_entry, &a, (unsigned)(B * nt), AESB_NT, AESB_SMEM_DOUBLES * sizeof(double));
+    return 0;
+}
+
+// ---- sequential batch biquad kernel (aes_biquad_seq.cuh): K segments per clip, `warm` frames of warm-up
+template <int NS> static void bqseq_entry(void *p) { aes_biquad_seq_body<NS>(*reinterpret_cast<BqSeqArgs *>(p)); }
+extern "C" __attribute__((visibility("default")))
+int emu_biquad_seq(const float *x, float *y, long long B, long long N, int n_stages, const double *coeffs5,
+                   const double *dfi_state, int K, long long warm, int max_ctas)
+{
+    if (n_stages < 1 || n_stages > AESQ_MAX_STAGES || (N & 1) || K < 1 || warm % AESQ_CH) return -1;
+    static BqSeqArgs q;
+    memset(&q, 0, sizeof q);
+    q.x = x; q.y = y; q.B = B; q.N = N; q.K = K; q.warm = K > 1 ? warm : 0; q.n_stages = n_stages;
+    q.seg = (N / K + AESQ_CH - 1) / AESQ_CH * AESQ_CH;
+    for (int s = 0; s < n_stages; ++s) {
+        for (int i = 0; i < 5; ++i) q.bq[s][i] = coeffs5[5 * s + i];
+        for (int i = 0; i < 8; ++i) q.init[s][i] = dfi_state ? dfi_state[8 * s + i] : 0.0;
+    }
+    unsigned grid = (unsigned)((B * K + AESQ_WARPS * 32 - 1) / (AESQ_WARPS * 32));
+    if (max_ctas > 0 && grid > (unsigned)max_ctas) grid = (unsigned)max_ctas;        // persistent threads take several items
+    switch (n_stages) {
+    case 1: emu::launch(bqseq_entry<1>, &q, grid, AESQ_WARPS * 32, AESQ_SMEM_BYTES); break;
+    case 2: emu::launch(bqseq_entry<2>, &q, grid, AESQ_WARPS * 32, AESQ_SMEM_BYTES); break;
+    case 3: emu::launch(bqseq_entry<3>, &q, grid, AESQ_WARPS * 32, AESQ_SMEM_BYTES); break;
+    default: emu::launch(bqseq_entry<4>, &q, grid, AESQ_WARPS * 32, AESQ_SMEM_BYTES); break;
+    }
     return 0;
 }
 

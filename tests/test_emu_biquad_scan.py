@@ -94,3 +94,79 @@ def test_scan_honours_a_carried_dfi_state():
         cur = out
     mx, snr = synth.err_stats(y[0], cur)
     assert mx <= 1e-5 and snr >= 100.0, (mx, snr)
+
+
+# ---- the sequential batch kernel (csrc/aes_biquad_seq.cuh): one thread per (clip, segment) ----------------
+def seq(x, co, n_stages, K, warm, state=None, max_ctas=0):
+    L = emu.lib()
+    L.emu_biquad_seq.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_void_p, C.c_void_p,
+                                 C.c_int, C.c_longlong, C.c_int]
+    y = np.full_like(x, 7.0)
+    sp = state.ctypes.data if state is not None else None
+    assert L.emu_biquad_seq(x.ctypes.data, y.ctypes.data, x.shape[0], x.shape[1], n_stages, co.ctypes.data, sp, K, warm,
+                            max_ctas) == 0
+    return y
+
+
+@pytest.mark.parametrize("n,K", [(2, 1), (62, 1), (1000, 1), (4096, 1), (50000, 3), (70002, 5)])
+def test_sequential_batch_kernel_matches_the_reference_loop(n, K):
+    """Whole clips per thread (K = 1: the reference's loop itself) and clips cut into segments that warm up over
+    the cascade's memory (the scan's look-back depths); ragged lengths, more threads than one warp."""
+    x = synth.batch(5, 37, n)
+    co = coeffs_of(CASCADE, 48000, n)
+    warm = 1024 * sum(lookback_depth(co, 4))
+    y = seq(x, co, 4, K, warm)
+    for b in (0, 17, 36):
+        want = orc.run_file_path(CASCADE, x[b], 48000)
+        mx, snr = synth.err_stats(y[b], want)
+        assert mx <= 2e-7 * max(1.0, float(np.abs(want).max())) and snr >= 120.0, (n, K, b, mx, snr)
+
+
+@pytest.mark.parametrize("ns", [1, 2, 3])
+def test_sequential_batch_kernel_stage_counts_and_in_place(ns):
+    cfg = CASCADE[:ns]
+    x = synth.batch(6, 3, 3000)
+    co = coeffs_of(cfg, 48000, 3000)
+    L = emu.lib()
+    y = seq(x, co, ns, 1, 0)
+    z = x.copy()
+    assert L.emu_biquad_seq(z.ctypes.data, z.ctypes.data, 3, 3000, ns, co.ctypes.data, None, 1, 0, 0) == 0
+    assert np.array_equal(y, z)                        # in place: every chunk is read before it is written
+    want = orc.run_file_path(cfg, x[1], 48000)
+    assert synth.err_stats(y[1], want)[0] <= 2e-7 * max(1.0, float(np.abs(want).max()))
+
+
+def test_sequential_batch_kernel_honours_a_carried_dfi_state():
+    cfg = CASCADE[:2]
+    x = synth.batch(9, 2, 4000)
+    co = coeffs_of(cfg, 48000, 4000)
+    full = seq(x, co, 2, 1, 0)
+    # the state after the first 1000 frames, computed by the oracle's filters, continues the clip
+    st = np.zeros((2, 8))
+    sig = x[0, :1000].copy()
+    for s, c in enumerate(cfg):
+        f = orc.OFilter(**c["params"])
+        f.prepare(48000, 2, 2, 1000)
+        out = np.zeros_like(sig)
+        f.process_into(sig, out)
+        st[s] = np.asarray(f.state, np.float64).reshape(-1)[:8]
+        sig = out
+    rest = seq(np.ascontiguousarray(x[:1, 1000:]), co, 2, 1, 0, st)
+    # (the reference keeps its state as float32, filter.py:35-40: resuming from it is not the unbroken run to the bit)
+    assert np.max(np.abs(rest[0] - full[0, 1000:])) <= 5e-6
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("ns,n,K", [(4, 1500, 1), (2, 40000, 3), (1, 999 * 2, 1)])
+def test_sequential_batch_kernel_persistent_threads_take_several_items(ns, n, K):
+    """One CTA for 150 (clip, segment) items: every thread runs two or three of them back to back through the same
+    buffer ring and mbarriers (a phase that drifts between items shows up as a hang or as stale data)."""
+    cfg = CASCADE[:ns]
+    x = synth.batch(11, 150 // K, n)
+    co = coeffs_of(cfg, 48000, n)
+    warm = 1024 * sum(lookback_depth(co, ns))
+    y = seq(x, co, ns, K, warm, max_ctas=1)
+    assert np.array_equal(y, seq(x, co, ns, K, warm))                     # same bits as one item per thread
+    for b in (0, x.shape[0] // 2, x.shape[0] - 1):
+        want = orc.run_file_path(cfg, x[b], 48000)
+        assert synth.err_stats(y[b], want)[0] <= 2e-7 * max(1.0, float(np.abs(want).max()))
