@@ -505,6 +505,10 @@ def baseline_configs_leg(args, torch, _native, file_chain, dev, peak):
     c2 = chain_case("c2-biquad-cascade", 1, 60.0, 10, True, [0])
     c2["us_per_clip"] = c2["ms"] * 1e3
     out["configs[1] one 60 s clip, LP/HP/BP/peaking biquad cascade"] = c2
+    c2["kernels"] = ["aes_biquad_scan_kernel (one CTA per 1024-frame tile, truncated look-back)"]
+    c2b = chain_case("c2-biquad-cascade", 2368, 10.0, 5, False, [0, 2367])
+    c2b["kernels"] = ["aes_biquad_seq_kernel (one thread per (clip, segment), the plain recurrence)"]
+    out["configs[1] chain on a batch: 2368 clips x 10 s"] = c2b
     out["configs[2] 1024 clips x 10 s, distortion > octaver > delay"] = chain_case("c3-dist-octaver-delay", 1024, 10.0, 5, False, [0, 1023])
 
     # configs[3]: IR-convolution reverb, 3 s IR, 256 clips x 30 s
