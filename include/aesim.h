@@ -109,7 +109,11 @@ int aes_chain_plan_create(const aes_stage_desc *stages, int n_stages, int sample
 int aes_chain_plan_destroy(aes_chain_plan *plan);
 /* x, y: device pointers.  Fresh block state at the start of every clip (what the
  * chain's re-prepare at the file's frame count produces), except the scalar state
- * carried in the descriptors (octaver phase, gate gain, biquad state). */
+ * carried in the descriptors (octaver phase, gate gain, biquad state).
+ * A plan owns the working memory of its launches (the feedback-delay lines of its CTAs, the scan's
+ * records): launches of ONE plan must be ordered with each other -- the same stream, or events
+ * between streams.  Launches that are to overlap take a plan each (the chain of core.py:123-161 is
+ * not re-entrant either). */
 int aes_chain_run(aes_chain_plan *plan, const void *x, int in_fmt, void *y, int out_fmt,
                   int64_t n_clips, int64_t n_frames, void *stream);
 /* Same call with HOST buffers: stages through pinned memory in sub-batches on
