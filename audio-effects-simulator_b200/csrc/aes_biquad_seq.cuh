@@ -21,7 +21,7 @@
 #include "aes_fast_kernel.cuh"      // cp.async.bulk / mbarrier helpers
 
 #define AESQ_CH 32                              // frames per chunk (16: more warps fit, yet 114 against 167 Gsamples/s)
-#define AESQ_NBUF 4                             // chunk buffers per lane
+#define AESQ_NBUF 3                             // chunk buffers per lane (4: 6 warps per SM, 241 against 320 Gsamples/s; 2: 163)
 #define AESQ_ROW (AESQ_CH * 2 + 4)              // floats per row: 256 bytes + 16 bytes of skew
 #define AESQ_WARPS 2                            // warps per CTA (independent of each other)
 #define AESQ_MAX_STAGES 4

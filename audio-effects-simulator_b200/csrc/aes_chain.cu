@@ -123,7 +123,7 @@ static int bqseq_segments(const aes_chain_plan *pl, long long decide_B, long lon
     const long long resident = (long long)pl->sm_count * (227 * 1024 / AESQ_SMEM_BYTES) * AESQ_WARPS * 32;
     const long long least = (long long)pl->sm_count * 2 * 32;
     long long kmax = 1;
-    if (!in_place && pl->bqs_warm > 0) kmax = std::max<long long>(1, std::min<long long>(N / (4 * pl->bqs_warm), 64));
+    if (!in_place && pl->bqs_warm > 0) kmax = std::max<long long>(1, std::min<long long>(N / (2 * pl->bqs_warm), 64));
     long long best = 1;
     double best_eff = 0.0;
     for (long long K = 1; K <= kmax; ++K) {
