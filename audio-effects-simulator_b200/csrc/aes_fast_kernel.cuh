@@ -517,15 +517,15 @@ __device__ __forceinline__ void aesf_stage(const FastArgs &a, const FCtx &c, SRe
                 if (AESF_PF(CODE) && c.ln_stage != nullptr) {
                     // line samples staged by TMA a tile ago: [i0 + m, i0 + m + FR) of the staged span
                     constexpr int T = AES_NT * FR;
-                    // (no misalignment switch: an unaligned line costs four scalar loads instead)
+                    // (an unaligned line: the two aligned vectors around it and a CTA-uniform select -- four scalar
+                    // loads at a 16-byte lane stride conflict 4-way)
                     const int m = ((rg.lag + 3) & ~3) - rg.lag;
-                    const float *sp = c.ln_stage + ch * (T + 8) + i0 + m;
+                    const float *sp = c.ln_stage + ch * (T + 8) + i0;
+                    const float4 A = aes_lds_v4(sp);
                     if (m == 0) {
-                        const float4 A = aes_lds_v4(sp);
                         line[0] = A.x; line[1 % FR] = A.y; line[2 % FR] = A.z; line[3 % FR] = A.w;
                     } else {
-#pragma unroll
-                        for (int j = 0; j < FR; ++j) line[j] = sp[j];
+                        aesf_select4<FR>(A, aes_lds_v4(sp + 4), m, line);
                     }
                 } else if (AESF_PF(CODE)) {
                     aesf_select4<FR>(lnA[ch], lnB[ch], ((rg.lag + 3) & ~3) - rg.lag, line);
@@ -1039,10 +1039,21 @@ __device__ void aes_fast_body(const FastArgs &a)
                 aes_mbar_wait(bars + q, it_wait >> 1);
                 ++it_wait;
                 const float *sx = stage_x + q * 2 * T + 2 * i0;          // interleaved L R L R ...
+                if constexpr (FR == 4) {
+                    // 32 bytes per thread: two 128-bit loads at a 32-byte lane stride conflict 2-way (ncu r2ad, Robot
+                    // Voice: 8.0 wavefronts per load against 4.0), so lanes 4..7 of every eight take their halves in
+                    // the other order (as aes_rv_kernel does)
+                    const int sw = (c.tid >> 2) & 1;
+                    const float4 ta = aes_lds_v4(sx + 4 * sw), tb = aes_lds_v4(sx + 4 * (sw ^ 1));
+                    const float4 t0 = sw ? tb : ta, t1 = sw ? ta : tb;
+                    v[0][0] = t0.x; v[1][0] = t0.y; v[0][1 % FR] = t0.z; v[1][1 % FR] = t0.w;
+                    v[0][2 % FR] = t1.x; v[1][2 % FR] = t1.y; v[0][3 % FR] = t1.z; v[1][3 % FR] = t1.w;
+                } else {
 #pragma unroll
-                for (int j = 0; j < FR / 2; ++j) {
-                    const float4 t = aes_lds_v4(sx + 4 * j);
-                    v[0][2 * j] = t.x; v[1][2 * j] = t.y; v[0][(2 * j + 1) % FR] = t.z; v[1][(2 * j + 1) % FR] = t.w;
+                    for (int j = 0; j < FR / 2; ++j) {
+                        const float4 t = aes_lds_v4(sx + 4 * j);
+                        v[0][2 * j] = t.x; v[1][2 * j] = t.y; v[0][(2 * j + 1) % FR] = t.z; v[1][(2 * j + 1) % FR] = t.w;
+                    }
                 }
                 c.ln_stage = PS >= 0 ? stage_ln + q * 2 * (T + 8) : nullptr;
             } else {

@@ -157,6 +157,7 @@ __device__ __forceinline__ void aesrv_walk_cols(float *s, float *rb, int pos, in
 {
     constexpr int T = AES_NT * 4;
     constexpr int KMAX = (T + L - 1) / L;                   // rows that can hold a column
+    static_assert(L >= NTH, "an idle lane shadows column j0 < NTH, which has to exist");
     int slot[NCOL];
     float line[NCOL];
     float *p[NCOL];
@@ -165,7 +166,10 @@ __device__ __forceinline__ void aesrv_walk_cols(float *s, float *rb, int pos, in
     for (int c = 0; c < NCOL; ++c) {
         const int j = j0 + NTH * (R0 + c);
         act[c] = (NTH * (R0 + c + 1) <= L) || j < L;        // compile-time true when the whole trip fits
-        const int jj = act[c] ? j : 0;                      // idle lanes shadow column 0 without storing
+        // idle lanes shadow their own trip-0 column without storing: its bank, (j0 + k*L) mod 32, is the one the
+        // lane would have hit anyway.  (Shadowing column 0 put every idle lane on lane 0's bank at another address:
+        // ncu r2ad showed 2.0 wavefronts per load in the partial trips, 34 M excess wavefronts per launch.)
+        const int jj = act[c] ? j : j0;
         slot[c] = pos + jj;
         if (slot[c] >= L) slot[c] -= L;
         line[c] = rb[slot[c]];
@@ -447,13 +451,14 @@ __device__ void aes_rv_body(const FastArgs &a)
                         float line[FR];
                         if (staged) {
                             // line samples staged by TMA: [i0 + m, i0 + m + FR) of the staged span
-                            const float *sp = LN + (par * 2 + ch) * LNS + i0 + m;
+                            // (unaligned: the two aligned vectors around them; scalar loads at a 16-byte lane stride
+                            // would conflict 4-way)
+                            const float *sp = LN + (par * 2 + ch) * LNS + i0;
+                            const float4 A = aes_lds_v4(sp);
                             if (m == 0) {
-                                const float4 A = aes_lds_v4(sp);
                                 line[0] = A.x; line[1] = A.y; line[2] = A.z; line[3] = A.w;
                             } else {
-#pragma unroll
-                                for (int j = 0; j < FR; ++j) line[j] = sp[j];
+                                aesf_select4<FR>(A, aes_lds_v4(sp + 4), m, line);
                             }
                         } else {
                             int a0 = dw[ch] - ((rg.lag + 3) & ~3);          // aligned read base: lag4 behind the write slot
