@@ -14,6 +14,9 @@
 template <int SHAPE> __global__ void __launch_bounds__(AESM_NTC, 3) aesm_cols_fwd_kernel(const __grid_constant__ SmoothArgs a) { aesm_cols_fwd_body<SHAPE>(a); }
 template <int SHAPE> __global__ void __launch_bounds__(AESM_NT, 5) aesm_rows_kernel(const __grid_constant__ SmoothArgs a) { aesm_rows_body<SHAPE>(a); }
 template <int SHAPE> __global__ void __launch_bounds__(AESM_NT) aesm_cols_inv_kernel(const __grid_constant__ SmoothArgs a) { aesm_cols_inv_body<SHAPE>(a); }
+// G row pairs per CTA, CTAS resident CTAs per SM (registers: 65536 / (threads * CTAS))
+template <int G, int CTAS, int PP = 2>
+__global__ void __launch_bounds__(AESR_NT_OF(G), CTAS) aesm_rows10_kernel(const __grid_constant__ SmoothArgs a) { aesm_rows10_body<G, PP>(a); }
 // tables of the smooth path, in double: W_M^j (j < 1024), W_M^(1024 j), np.hanning(M)
 __global__ void aesm_tables_kernel(cpx *twlo, cpx *twhi, long long nhi, float *window, long long M)
 {
@@ -100,6 +103,8 @@ struct aes_spectral_plan {
     // frame lengths n1 * n2 with factors 2, 3, 5 only skip Bluestein (aes_spectral_smooth.cuh)
     bool smooth = false;
     int n1 = 0, n2 = 0, static_shape = 0;
+    int rows10_variant = 0;
+    bool rows10 = false;             // 960 x 1000: the register-resident row-pair kernel (AES_SPECTRAL_ROWS_SMEM=1: the shared-memory one)
     SmoothFft f1, f2;
     cpx *d_stw = nullptr;            // stage twiddles of f1 | of f2 | twlo [1024] | twhi [ceil(M / 1024)]
     int *d_rev = nullptr;            // rev1 [n1] | rev2 [n2]
@@ -190,6 +195,7 @@ static SmoothArgs smooth_args(const aes_spectral_plan *pl)
     a.tw1 = pl->d_stw; a.tw2 = a.tw1 + pl->f1.tsize; a.twlo = a.tw2 + pl->f2.tsize; a.twhi = a.twlo + 1024;
     a.rev1 = pl->d_rev; a.rev2 = pl->d_rev + pl->n1;
     a.window = pl->d_window;
+    a.tw10 = a.twhi + (pl->M + 1023) / 1024;
     return a;
 }
 
@@ -204,7 +210,38 @@ static int smooth_process(const aes_spectral_plan *pl, const SmoothArgs &a, cuda
     const unsigned gr = (unsigned)std::min<long long>(rows, (long long)pl->sms * per_sm_r);
     if (pl->static_shape == AESM_SHAPE_960x1000) {
         aesm_cols_fwd_kernel<AESM_SHAPE_960x1000><<<gc, AESM_NTC, sm_c, st>>>(a);
-        aesm_rows_kernel<AESM_SHAPE_960x1000><<<gr, AESM_NT, sm_r, st>>>(a);
+        if (pl->rows10) {
+            // row pairs 1 .. n1/2 - 1 in registers (aesm_rows10_body); rows 0 and n1/2 pair with themselves
+            const long long items = (long long)a.np * (a.n1 / 2 - 1);
+            auto launch10 = [&](auto gt, auto ct, auto pt) {
+                constexpr int G = decltype(gt)::value, CTAS = decltype(ct)::value, PP = decltype(pt)::value;
+                int per_sm = CTAS;                      // what actually fits beside the shared-memory tables
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, aesm_rows10_kernel<G, CTAS, PP>, AESR_NT_OF(G), AESR_SMEM_OF2(G, PP));
+                if (per_sm < 1) per_sm = 1;
+                const unsigned g10 = (unsigned)std::min<long long>((items + G - 1) / G, (long long)pl->sms * per_sm);
+                aesm_rows10_kernel<G, CTAS, PP><<<g10, AESR_NT_OF(G), AESR_SMEM_OF2(G, PP), st>>>(a);
+            };
+            using std::integral_constant;
+            using I1 = integral_constant<int, 1>; using I2 = integral_constant<int, 2>; using I3 = integral_constant<int, 3>;
+            using I4 = integral_constant<int, 4>; using I5 = integral_constant<int, 5>;
+            // Measured on 2048 clips (r2ai, ms per pass of the whole block): <1,3,2> 23.94, <2,2,2> 24.62, <1,4,2> 23.89,
+            // <1,4,1> 23.70, <2,3,1> 23.98, <1,5,1> (80 registers, 48 bytes of spills) 23.47; the shared-memory
+            // kernel 26.58.  AES_ROWS10_VARIANT picks one of the others for re-measuring.
+            switch (pl->rows10_variant) {
+            case 1: launch10(I2{}, I2{}, I2{}); break;
+            case 2: launch10(I1{}, I4{}, I2{}); break;
+            case 3: launch10(I1{}, I3{}, I2{}); break;
+            case 6: launch10(I2{}, I3{}, I1{}); break;
+            case 7: launch10(I1{}, I5{}, I1{}); break;
+            default: launch10(I1{}, I4{}, I1{}); break;
+            }
+            SmoothArgs b = a;
+            b.rows_self_only = 1;
+            aesm_rows_kernel<AESM_SHAPE_960x1000><<<(unsigned)std::min<long long>(2LL * a.np, gr), AESM_NT, sm_r, st>>>(b);
+            aes_count_launch();
+        } else {
+            aesm_rows_kernel<AESM_SHAPE_960x1000><<<gr, AESM_NT, sm_r, st>>>(a);
+        }
         aesm_cols_inv_kernel<AESM_SHAPE_960x1000><<<gc, AESM_NT, sm_c, st>>>(a);
     } else {
         aesm_cols_fwd_kernel<0><<<gc, AESM_NTC, sm_c, st>>>(a);
@@ -249,7 +286,7 @@ AES_EXPORT int aes_spectral_plan_create(int64_t frame_len, aes_spectral_plan **o
             const long long nhi = (M + 1023) / 1024;
             int ra;
             const int nst = pl->f1.tsize + pl->f2.tsize;
-            if ((ra = spec_alloc((void **)&pl->d_stw, (size_t)(nst + 1024 + nhi) * sizeof(cpx)))) return ra;
+            if ((ra = spec_alloc((void **)&pl->d_stw, (size_t)(nst + 1024 + nhi + AESR_TW_ENTRIES) * sizeof(cpx)))) return ra;
             std::vector<cpx> stw((size_t)nst + 1);
             aesm_fill_twiddles(pl->f1, stw.data()); aesm_fill_twiddles(pl->f2, stw.data() + pl->f1.tsize);
             AES_CUDA(cudaMemcpy(pl->d_stw, stw.data(), (size_t)nst * sizeof(cpx), cudaMemcpyHostToDevice));
@@ -261,6 +298,19 @@ AES_EXPORT int aes_spectral_plan_create(int64_t frame_len, aes_spectral_plan **o
             AES_CUDA(cudaMemcpy(pl->d_rev, rev.data(), rev.size() * sizeof(int), cudaMemcpyHostToDevice));
             // (kernel attributes, not plan ones: always the limit, plans of other frame lengths may be alive)
             pl->static_shape = getenv("AES_SPECTRAL_GENERIC") ? 0 : aesm_static_shape(pl->f1, pl->f2);
+            pl->rows10 = pl->static_shape == AESM_SHAPE_960x1000 && !getenv("AES_SPECTRAL_ROWS_SMEM");
+            if (pl->rows10) {
+                std::vector<cpx> t10(AESR_TW_ENTRIES);
+                aesm_fill_rows10(t10.data());
+                AES_CUDA(cudaMemcpy(pl->d_stw + nst + 1024 + nhi, t10.data(), t10.size() * sizeof(cpx), cudaMemcpyHostToDevice));
+                if (const char *v = getenv("AES_ROWS10_VARIANT")) pl->rows10_variant = atoi(v);
+                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<2, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF2(2, 2)));
+                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF2(1, 2)));
+                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<1, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF2(1, 2)));
+                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<1, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF2(1, 1)));
+                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<2, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF2(2, 1)));
+                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<1, 5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF2(1, 1)));
+            }
             AES_CUDA(cudaFuncSetAttribute(aesm_cols_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             AES_CUDA(cudaFuncSetAttribute(aesm_cols_inv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             AES_CUDA(cudaFuncSetAttribute(aesm_rows_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

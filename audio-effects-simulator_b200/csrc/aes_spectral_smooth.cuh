@@ -54,6 +54,8 @@ struct SmoothArgs {
     int n1, n2, np, nf;             // np = ceil(nf / 2) transform pairs
     int mode;                       // 1 frames -> out, 2 clips -> yclips
     float thr, red, alpha;
+    const cpx *tw10;                // aesm_rows10 twiddles [4][10][100] (960 x 1000 only), see aesm_fill_rows10
+    int rows_self_only;             // aesm_rows_body takes only the rows that pair with themselves (0 and n1/2)
 };
 
 #ifdef AES_CPU_EMU
@@ -282,6 +284,8 @@ __device__ void aesm_cols_fwd_body(const SmoothArgs &a)
     SmoothDiv divC; divC.d = AESM_C; divC.mul = 0x20000000u;        // x / 8
     for (long long w = blockIdx.x; w < (long long)a.np * tiles; w += gridDim.x) {
         const int p = (int)(w / tiles), b0 = (int)(w % tiles) * AESM_C;
+        // (measured, r2ah: the zero half as plain stores and the other half's loads batched four trips ahead of use --
+        // 3.63 -> 4.19 ms, the batch spills at this kernel's 42 registers; the loop below already overlaps across warps)
         for (int e = threadIdx.x; e < n1 * AESM_C; e += blockDim.x) {
             const int row = e / AESM_C, c = e % AESM_C, b = b0 + c;
             cpx z; z.x = 0.f; z.y = 0.f;
@@ -329,8 +333,9 @@ __device__ void aesm_rows_body(const SmoothArgs &a)
     const int nbins = a.M / 2 + 1;
     SmoothDiv div2; div2.d = 2; div2.mul = 0x80000000u;
     SmoothDiv div1; div1.d = 1; div1.mul = 0;
-    for (long long w = blockIdx.x; w < (long long)a.np * half; w += gridDim.x) {
-        const int p = (int)(w / half), k1 = (int)(w % half), k1b = (n1 - k1) % n1;
+    const int per = a.rows_self_only ? 2 : half;            // (the other row pairs went through aesm_rows10_body)
+    for (long long w = blockIdx.x; w < (long long)a.np * per; w += gridDim.x) {
+        const int p = (int)(w / per), k1 = a.rows_self_only ? (int)(w % per) * (n1 / 2) : (int)(w % per), k1b = (n1 - k1) % n1;
         const bool self = k1 == k1b;                        // rows 0 and n1/2 pair with themselves
         const int S = self ? 1 : 2;
         cpx *rowA = a.buf + (long long)p * a.M + (long long)k1 * n2;
@@ -384,6 +389,223 @@ __device__ void aesm_rows_body(const SmoothArgs &a)
     }
 }
 
+// ---- K2 for 960 x 1000, register-resident ------------------------------------------------------------
+// ncu (profiles/r2ad): aesm_rows_kernel is bound by the shared-memory pipe (84 % of its wavefront rate, a quarter of
+// the wavefronts bank conflicts of the digit-reversed gate sweep and of the radix-5 stages): 22 shared-memory
+// accesses per element and transform pair (4 stages x load + store, forward and inverse, plus the gate).  Here a
+// row of 1000 = 10 x 10 x 10 is transformed in three radix-10 passes held in registers, 100 threads per row with
+// 10 elements each, two exchanges through shared memory per transform (8 accesses per element in all):
+//
+//   n = 100 n1 + 10 n2 + n3,  k = k1 + 10 k2 + 100 k3
+//   pass A  thread (n2, n3) = n mod 100:  DFT-10 over n1 -> k1, times w_100^(n2 k1)
+//   pass B  thread (k1, n3):              DFT-10 over n2 -> k2, times w_1000^(n3 (k1 + 10 k2))
+//   pass C  thread (k1, k2):              DFT-10 over n3 -> k3:  the thread holds columns k1 + 10 k2 + 100 k3
+//
+// The gate pairs bin k of row k1 (column c) with bin M - k, which is column 999 - c of row n1 - k1 (k1 != 0, n1/2:
+// those two rows pair with themselves and stay with aesm_rows_body).  A thread therefore runs row A as thread u and
+// row B as thread 99 - u: after pass C it holds columns {kA + 100 k3} of row A and {99 - kA + 100 k3'} of row B, i.e.
+// every partner pair (k3' = 9 - k3) sits in its own registers and the gate touches no memory.  The inverse runs the
+// three passes backwards with conjugated roots and leaves thread (n2, n3) with x[100 n1 + n mod 100]: global loads
+// and stores are 800 contiguous bytes per n1.  Exchange layouts (a thread writes 10 values at one stride and another
+// reads 10 at another; both sides hit 16 distinct 8-byte banks per half-warp):
+//   exchange 1  (k1, n2, n3) at 106 k1 + 10 n2 + n3      writer lanes: consecutive;  reader lanes: 106 = 10 (mod 16)
+//   exchange 2  (k1, k2, n3) at n3 + 10 k1 + 113 k2      writer lanes: consecutive;  reader lanes: 113 = 1  (mod 16)
+// Two buffers per row alternate, so an exchange costs one CTA barrier.  Twiddles come from four [10][100] tables
+// (thread index fastest: conflict-free), built in double on the host and copied into shared memory once per CTA
+// (ncu r2af, tables read through L1: 36 % of the stall samples on the long scoreboard).  The four-step factor of
+// the output, W_M^(-b k1) with b = 100 j + u, is W_M^(-u k1) -- one table look-up per thread and row -- times
+// W_M^(-100 j k1), ten values per row that ten threads look up and everyone reads as a broadcast.
+#define AESR_P1 106
+#define AESR_P2 113
+#define AESR_ROWBUF 1136            // cpx per exchange buffer: max(10 * 106, 10 * 113), rounded up to 128 bytes
+#define AESR_G 2                    // row pairs per CTA (default; the kernel is a template on it)
+#define AESR_NT_OF(G) ((100 * (G) + 31) / 32 * 32)
+#define AESR_TW_ENTRIES 4000
+// exchange buffers | the four twiddle tables | W_M^(-100 j k1) of the two rows of every pair, by item parity
+#define AESR_SMEM_OF2(G, PP) (((G) * 2 * (PP) * AESR_ROWBUF + AESR_TW_ENTRIES + (G) * 2 * 2 * 10) * (int)sizeof(cpx))
+#define AESR_SMEM_OF(G) AESR_SMEM_OF2(G, 2)
+#define AESR_NT AESR_NT_OF(AESR_G)
+#define AESR_SMEM_BYTES AESR_SMEM_OF(AESR_G)
+
+// host: t[0][k1][u] = w_100^(n2 k1), u = 10 n2 + n3;          t[1][k2][u] = w_1000^(n3 (k1 + 10 k2)), u = 10 k1 + n3;
+//       t[2][n3][u] = conj w_1000^(n3 (k1 + 10 k2)), u = 10 k1 + k2;   t[3][n2][u] = conj w_100^(n2 k1), u = 10 k1 + n3
+static inline void aesm_fill_rows10(cpx *t)
+{
+    const double tp = 2.0 * 3.14159265358979323846;
+    for (int j = 0; j < 10; ++j)
+        for (int u = 0; u < 100; ++u) {
+            const int hi = u / 10, lo = u % 10;
+            const double ang[4] = { -tp * (double)((hi * j) % 100) / 100.0,              // n2 = hi, k1 = j
+                                    -tp * (double)((lo * (hi + 10 * j)) % 1000) / 1000.0, // k1 = hi, n3 = lo, k2 = j
+                                    tp * (double)((j * (hi + 10 * lo)) % 1000) / 1000.0,  // k1 = hi, k2 = lo, n3 = j
+                                    tp * (double)((j * hi) % 100) / 100.0 };             // k1 = hi, n2 = j
+            for (int q = 0; q < 4; ++q) {
+                t[(q * 10 + j) * 100 + u].x = (float)cos(ang[q]);
+                t[(q * 10 + j) * 100 + u].y = (float)sin(ang[q]);
+            }
+        }
+}
+
+// DFT-10 as Good-Thomas 2 x 5 (no twiddles inside): n = (5 na + 2 nb) mod 10, k = (5 ka + 6 kb) mod 10
+template <bool INV> __device__ __forceinline__ void aesm_dft10(cpx (&a)[10])
+{
+    cpx e[5], o[5];
+#pragma unroll
+    for (int nb = 0; nb < 5; ++nb) {
+        const cpx u = a[(2 * nb) % 10], v = a[(5 + 2 * nb) % 10];
+        e[nb] = c_add(u, v); o[nb] = c_sub(u, v);
+    }
+    aesm_dft<5, INV>(e);
+    aesm_dft<5, INV>(o);
+#pragma unroll
+    for (int kb = 0; kb < 5; ++kb) { a[(6 * kb) % 10] = e[kb]; a[(5 + 6 * kb) % 10] = o[kb]; }
+}
+
+// PP = 2: two exchange buffers per row alternate (one barrier per exchange);  PP = 1: one buffer, a second barrier
+// between an exchange's loads and the next exchange's stores, half the exchange memory (more CTAs per SM)
+template <int G, int PP = 2>
+__device__ void aesm_rows10_body(const SmoothArgs &a)
+{
+    AES_DYN_SMEM(cpx, s);                                   // [G][row A, row B][PP][AESR_ROWBUF]
+    constexpr int n1 = 960, n2 = 1000, NP = n1 / 2 - 1;     // row pairs k1 = 1 .. 479 per transform
+    const int M = n1 * n2;
+    const int tid = threadIdx.x, g = tid / 100, u = tid - 100 * g, uB = 99 - u;
+    const int hi = u / 10, lo = u - 10 * hi, hiB = 9 - hi, loB = 9 - lo;
+    cpx *const A0 = s + (size_t)(g < G ? g : 0) * 2 * PP * AESR_ROWBUF, *const A1 = A0 + (PP - 1) * AESR_ROWBUF;
+    cpx *const B0 = A0 + PP * AESR_ROWBUF, *const B1 = B0 + (PP - 1) * AESR_ROWBUF;
+    cpx *const tws = s + (size_t)G * 2 * PP * AESR_ROWBUF;
+    const cpx *const t1f = tws, *const t2f = tws + 1000, *const t2i = tws + 2000, *const t1i = tws + 3000;
+    cpx *const vj = tws + AESR_TW_ENTRIES + (g < G ? g : 0) * 40;       // [parity][row A, row B][10]
+    for (int i = tid; i < AESR_TW_ENTRIES; i += blockDim.x) tws[i] = a.tw10[i];
+    __syncthreads();
+    const int nbins = M / 2 + 1;
+    const long long total = (long long)a.np * NP, groups = (total + G - 1) / G;
+    int par = 0;
+    for (long long w = blockIdx.x; w < groups; w += gridDim.x, par ^= 1) {
+        const long long item = w * G + g;
+        const bool live = g < G && item < total;
+        const int p = live ? (int)(item / NP) : 0, k1r = live ? 1 + (int)(item % NP) : 1, k1b = n1 - k1r;
+        cpx *const rowA = a.buf + (long long)p * M + (long long)k1r * n2;
+        cpx *const rowB = a.buf + (long long)p * M + (long long)k1b * n2;
+        cpx A[10], B[10];
+        cpx baseA, baseB;
+        baseA.x = baseA.y = baseB.x = baseB.y = 0.f;
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < 10; ++j) { A[j] = rowA[100 * j + u]; B[j] = rowB[100 * j + uB]; }
+            // (read behind the fourth barrier; the slot of the other parity may still be in use by a thread that has
+            // not left the previous item)
+            if (u < 10) {
+                vj[par * 20 + u] = aesm_wM(a, 100 * u * k1r, true);
+                vj[par * 20 + 10 + u] = aesm_wM(a, 100 * u * k1b, true);
+            }
+            baseA = aesm_wM(a, u * k1r, true);
+            baseB = aesm_wM(a, uB * k1b, true);
+            aesm_dft10<false>(A);
+            aesm_dft10<false>(B);
+#pragma unroll
+            for (int k = 1; k < 10; ++k) {
+                A[k] = c_mul(A[k], t1f[k * 100 + u]);
+                B[k] = c_mul(B[k], t1f[k * 100 + uB]);
+            }
+#pragma unroll
+            for (int k = 0; k < 10; ++k) { A0[AESR_P1 * k + u] = A[k]; B0[AESR_P1 * k + uB] = B[k]; }
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < 10; ++j) { A[j] = A0[AESR_P1 * hi + 10 * j + lo]; B[j] = B0[AESR_P1 * hiB + 10 * j + loB]; }
+        }
+        if (PP == 1) __syncthreads();                       // every thread holds its values: the buffer is free
+        if (live) {
+            aesm_dft10<false>(A);
+            aesm_dft10<false>(B);
+#pragma unroll
+            for (int k = 0; k < 10; ++k) {
+                A[k] = c_mul(A[k], t2f[k * 100 + u]);
+                B[k] = c_mul(B[k], t2f[k * 100 + uB]);
+            }
+#pragma unroll
+            for (int k = 0; k < 10; ++k) { A1[u + AESR_P2 * k] = A[k]; B1[uB + AESR_P2 * k] = B[k]; }
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < 10; ++j) { A[j] = A1[j + 10 * hi + AESR_P2 * lo]; B[j] = B1[j + 10 * hiB + AESR_P2 * loB]; }
+        }
+        if (PP == 1) __syncthreads();                       // every thread holds its values: the buffer is free
+        if (live) {
+            aesm_dft10<false>(A);
+            aesm_dft10<false>(B);
+            // A[k3] = column kA + 100 k3 of row k1r, B[k3] = column 99 - kA + 100 k3 of row n1 - k1r
+            const int kA = hi + 10 * lo;
+            const bool two = 2 * p + 1 < a.nf;
+#pragma unroll
+            for (int k3 = 0; k3 < 10; ++k3) {
+                const int k = k1r + n1 * (kA + 100 * k3), km = M - k;
+                const cpx Zk = A[k3], Zm = B[9 - k3];
+                const int kk = k <= km ? k : km;            // the rfft bin this pair is
+                cpx X0, X1;                                 // rfft bin of frame 2p / 2p+1 at index k (see aesm_rows_body)
+                X0.x = 0.5f * (Zk.x + Zm.x); X0.y = 0.5f * (Zk.y - Zm.y);
+                X1.x = 0.5f * (Zk.y + Zm.y); X1.y = 0.5f * (Zm.x - Zk.x);
+                if (k > km) { X0.y = -X0.y; X1.y = -X1.y; }
+                float *m0 = a.mask != nullptr ? a.mask + (long long)(2 * p) * nbins + kk : nullptr;
+                float *m1 = a.mask != nullptr ? a.mask + (long long)(2 * p + 1) * nbins + kk : nullptr;
+                const cpx P0 = aesm_gate_one(X0, m0, false, a);
+                cpx P1; P1.x = 0.f; P1.y = 0.f;
+                if (two) P1 = aesm_gate_one(X1, m1, false, a);
+                cpx Wlo, Whi;
+                Wlo.x = P0.x - P1.y; Wlo.y = P0.y + P1.x;
+                Whi.x = P0.x + P1.y; Whi.y = P1.x - P0.y;
+                A[k3] = k <= km ? Wlo : Whi;
+                B[9 - k3] = k <= km ? Whi : Wlo;
+            }
+            aesm_dft10<true>(A);
+            aesm_dft10<true>(B);
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+                A[j] = c_mul(A[j], t2i[j * 100 + u]);
+                B[j] = c_mul(B[j], t2i[j * 100 + uB]);
+            }
+#pragma unroll
+            for (int j = 0; j < 10; ++j) { A0[j + 10 * hi + AESR_P2 * lo] = A[j]; B0[j + 10 * hiB + AESR_P2 * loB] = B[j]; }
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < 10; ++j) { A[j] = A0[u + AESR_P2 * j]; B[j] = B0[uB + AESR_P2 * j]; }
+        }
+        if (PP == 1) __syncthreads();                       // every thread holds its values: the buffer is free
+        if (live) {
+            aesm_dft10<true>(A);
+            aesm_dft10<true>(B);
+#pragma unroll
+            for (int j = 1; j < 10; ++j) {
+                A[j] = c_mul(A[j], t1i[j * 100 + u]);
+                B[j] = c_mul(B[j], t1i[j * 100 + uB]);
+            }
+#pragma unroll
+            for (int j = 0; j < 10; ++j) { A1[AESR_P1 * hi + 10 * j + lo] = A[j]; B1[AESR_P1 * hiB + 10 * j + loB] = B[j]; }
+        }
+        __syncthreads();
+        if (live) {
+#pragma unroll
+            for (int j = 0; j < 10; ++j) { A[j] = A1[AESR_P1 * j + u]; B[j] = B1[AESR_P1 * j + uB]; }
+        }
+        if (PP == 1) __syncthreads();                       // every thread holds its values: the buffer is free
+        if (live) {
+            aesm_dft10<true>(A);
+            aesm_dft10<true>(B);
+#pragma unroll
+            for (int j = 0; j < 10; ++j) {
+                rowA[100 * j + u] = c_mul(A[j], c_mul(vj[par * 20 + j], baseA));
+                rowB[100 * j + uB] = c_mul(B[j], c_mul(vj[par * 20 + 10 + j], baseB));
+            }
+        }
+        // (the next item's first stores go to the buffers last read ahead of the fourth barrier)
+    }
+}
+
 // ---- K3: inverse column FFTs, outputs --------------------------------------------------------------------
 template <int SHAPE>
 __device__ void aesm_cols_inv_body(const SmoothArgs &a)
@@ -396,6 +618,7 @@ __device__ void aesm_cols_inv_body(const SmoothArgs &a)
     for (long long w = blockIdx.x; w < (long long)a.np * tiles; w += gridDim.x) {
         const int p = (int)(w / tiles), b0 = (int)(w % tiles) * AESM_C;
         const cpx *src = a.buf + (long long)p * a.M;
+        // (measured, r2ah: six trips' loads batched ahead of their stores -- 128 registers, 2 CTAs per SM, 2.64 -> 3.56 ms)
         for (int e = threadIdx.x; e < n1 * AESM_C; e += blockDim.x) {
             const int k1 = e / AESM_C, c = e % AESM_C, b = b0 + c;
             cpx z; z.x = 0.f; z.y = 0.f;

@@ -93,6 +93,36 @@ def test_smooth_whole_clip_mode_reads_clips_and_emits_first_half(N, nb, thr, tol
         assert np.sqrt(np.mean((y[b, :, 0] - want) ** 2)) < 2e-6
 
 
+@pytest.mark.parametrize("one_buffer", [False, True])
+def test_register_resident_row_pairs_with_a_kept_mask_and_an_odd_frame_count(one_buffer, monkeypatch):
+    """BASELINE's frame length in frame mode (mask read and written, three frames: the last transform pair has one):
+    aesm_rows10_body for row pairs 1..479 plus aesm_rows_body for the two self-paired rows.  A zero threshold keeps
+    every bin on the `mag > thr` side (no bins flipping on rounding), so the bar is the transform's own accuracy."""
+    if one_buffer:
+        monkeypatch.setenv("AES_EMU_ROWS10_ONE_BUFFER", "1")      # two row pairs per CTA, one exchange buffer per row
+    else:
+        monkeypatch.delenv("AES_EMU_ROWS10_ONE_BUFFER", raising=False)
+    L = emu.lib()
+    L.emu_spectral_smooth.argtypes = SMOOTH_ARGS
+    M, nb = 960000, 3
+    rng = np.random.default_rng(5)
+    raw = (0.3 * rng.standard_normal((nb, M))).astype(np.float32)
+    win = np.hanning(M).astype(np.float32)
+    mask0 = rng.uniform(0.1, 1.0, (nb, M // 2 + 1)).astype(np.float32)
+    mask = mask0.copy()
+    y = np.zeros((nb, M), np.float32)
+    thr, red, alpha = 0.0, 0.1, 0.8
+    assert L.emu_spectral_smooth(1, raw.ctypes.data, win.ctypes.data, mask.ctypes.data, y.ctypes.data, M, nb, thr, red, alpha,
+                                 None, None) == 0
+    for b in range(nb):
+        X = np.fft.rfft((raw[b] * win).astype(np.float64))
+        m = alpha * mask0[b] + (1 - alpha) * np.where(np.abs(X) > thr, 1.0, red)
+        want = np.fft.irfft(X * m, M)
+        assert np.max(np.abs(mask[b] - m)) < 1e-6, b
+        assert np.max(np.abs(y[b] - want)) < 4e-6, b
+        assert np.sqrt(np.mean((y[b] - want) ** 2)) < 5e-7, b
+
+
 def test_non_smooth_length_has_no_split():
     L = emu.lib()
     L.emu_spectral_smooth.argtypes = SMOOTH_ARGS
