@@ -15,8 +15,8 @@ template <int SHAPE> __global__ void __launch_bounds__(AESM_NTC, 3) aesm_cols_fw
 template <int SHAPE> __global__ void __launch_bounds__(AESM_NT, 5) aesm_rows_kernel(const __grid_constant__ SmoothArgs a) { aesm_rows_body<SHAPE>(a); }
 template <int SHAPE> __global__ void __launch_bounds__(AESM_NT) aesm_cols_inv_kernel(const __grid_constant__ SmoothArgs a) { aesm_cols_inv_body<SHAPE>(a); }
 // G row pairs per CTA, CTAS resident CTAs per SM (registers: 65536 / (threads * CTAS))
-template <int G, int CTAS, int PP = 2>
-__global__ void __launch_bounds__(AESR_NT_OF(G), CTAS) aesm_rows10_kernel(const __grid_constant__ SmoothArgs a) { aesm_rows10_body<G, PP>(a); }
+template <int G, int CTAS, int PP = 2, int PF = 0>
+__global__ void __launch_bounds__(AESR_NT_OF(G), CTAS) aesm_rows10_kernel(const __grid_constant__ SmoothArgs a) { aesm_rows10_body<G, PP, PF>(a); }
 // tables of the smooth path, in double: W_M^j (j < 1024), W_M^(1024 j), np.hanning(M)
 __global__ void aesm_tables_kernel(cpx *twlo, cpx *twhi, long long nhi, float *window, long long M)
 {
@@ -213,27 +213,32 @@ static int smooth_process(const aes_spectral_plan *pl, const SmoothArgs &a, cuda
         if (pl->rows10) {
             // row pairs 1 .. n1/2 - 1 in registers (aesm_rows10_body); rows 0 and n1/2 pair with themselves
             const long long items = (long long)a.np * (a.n1 / 2 - 1);
-            auto launch10 = [&](auto gt, auto ct, auto pt) {
-                constexpr int G = decltype(gt)::value, CTAS = decltype(ct)::value, PP = decltype(pt)::value;
+            auto launch10 = [&](auto gt, auto ct, auto pt, auto ft) {
+                constexpr int G = decltype(gt)::value, CTAS = decltype(ct)::value, PP = decltype(pt)::value, PF = decltype(ft)::value;
                 int per_sm = CTAS;                      // what actually fits beside the shared-memory tables
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, aesm_rows10_kernel<G, CTAS, PP>, AESR_NT_OF(G), AESR_SMEM_OF2(G, PP));
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, aesm_rows10_kernel<G, CTAS, PP, PF>, AESR_NT_OF(G), AESR_SMEM_OF3(G, PP, PF));
                 if (per_sm < 1) per_sm = 1;
                 const unsigned g10 = (unsigned)std::min<long long>((items + G - 1) / G, (long long)pl->sms * per_sm);
-                aesm_rows10_kernel<G, CTAS, PP><<<g10, AESR_NT_OF(G), AESR_SMEM_OF2(G, PP), st>>>(a);
+                aesm_rows10_kernel<G, CTAS, PP, PF><<<g10, AESR_NT_OF(G), AESR_SMEM_OF3(G, PP, PF), st>>>(a);
             };
             using std::integral_constant;
+            using I0 = integral_constant<int, 0>;
             using I1 = integral_constant<int, 1>; using I2 = integral_constant<int, 2>; using I3 = integral_constant<int, 3>;
             using I4 = integral_constant<int, 4>; using I5 = integral_constant<int, 5>;
             // Measured on 2048 clips (r2ai, ms per pass of the whole block): <1,3,2> 23.94, <2,2,2> 24.62, <1,4,2> 23.89,
             // <1,4,1> 23.70, <2,3,1> 23.98, <1,5,1> (80 registers, 48 bytes of spills) 23.47; the shared-memory
-            // kernel 26.58.  AES_ROWS10_VARIANT picks one of the others for re-measuring.
+            // kernel 26.58.  With the next item's rows fetched by bulk copies (r2ak): <1,4,1> 23.34, <1,3,2> 24.19,
+            // <2,2,1> 22.91 -- the shipped one.  AES_ROWS10_VARIANT picks one of the others for re-measuring.
             switch (pl->rows10_variant) {
-            case 1: launch10(I2{}, I2{}, I2{}); break;
-            case 2: launch10(I1{}, I4{}, I2{}); break;
-            case 3: launch10(I1{}, I3{}, I2{}); break;
-            case 6: launch10(I2{}, I3{}, I1{}); break;
-            case 7: launch10(I1{}, I5{}, I1{}); break;
-            default: launch10(I1{}, I4{}, I1{}); break;
+            case 1: launch10(I2{}, I2{}, I2{}, I0{}); break;
+            case 2: launch10(I1{}, I4{}, I2{}, I0{}); break;
+            case 3: launch10(I1{}, I3{}, I2{}, I0{}); break;
+            case 6: launch10(I2{}, I3{}, I1{}, I0{}); break;
+            case 7: launch10(I1{}, I5{}, I1{}, I0{}); break;
+            case 8: launch10(I1{}, I4{}, I1{}, I1{}); break;
+            case 9: launch10(I1{}, I3{}, I2{}, I1{}); break;
+            case 5: launch10(I1{}, I4{}, I1{}, I0{}); break;
+            default: launch10(I2{}, I2{}, I1{}, I1{}); break;
             }
             SmoothArgs b = a;
             b.rows_self_only = 1;
@@ -304,12 +309,15 @@ AES_EXPORT int aes_spectral_plan_create(int64_t frame_len, aes_spectral_plan **o
                 aesm_fill_rows10(t10.data());
                 AES_CUDA(cudaMemcpy(pl->d_stw + nst + 1024 + nhi, t10.data(), t10.size() * sizeof(cpx), cudaMemcpyHostToDevice));
                 if (const char *v = getenv("AES_ROWS10_VARIANT")) pl->rows10_variant = atoi(v);
-                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<2, 2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF2(2, 2)));
-                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<1, 4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF2(1, 2)));
-                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<1, 3, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF2(1, 2)));
-                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<1, 4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF2(1, 1)));
-                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<2, 3, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF2(2, 1)));
-                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<1, 5, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF2(1, 1)));
+                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<2, 2, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF3(2, 2, 0)));
+                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<1, 4, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF3(1, 2, 0)));
+                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<1, 3, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF3(1, 2, 0)));
+                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<1, 4, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF3(1, 1, 0)));
+                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<2, 3, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF3(2, 1, 0)));
+                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<1, 5, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF3(1, 1, 0)));
+                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<1, 4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF3(1, 1, 1)));
+                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<1, 3, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF3(1, 2, 1)));
+                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<2, 2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF3(2, 1, 1)));
             }
             AES_CUDA(cudaFuncSetAttribute(aesm_cols_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
             AES_CUDA(cudaFuncSetAttribute(aesm_cols_inv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -424,6 +424,8 @@ __device__ void aesm_rows_body(const SmoothArgs &a)
 // exchange buffers | the four twiddle tables | W_M^(-100 j k1) of the two rows of every pair, by item parity
 #define AESR_SMEM_OF2(G, PP) (((G) * 2 * (PP) * AESR_ROWBUF + AESR_TW_ENTRIES + (G) * 2 * 2 * 10) * (int)sizeof(cpx))
 #define AESR_SMEM_OF(G) AESR_SMEM_OF2(G, 2)
+// ... | PF: the next item's two rows, fetched by bulk copies under this item's passes, and one mbarrier per pair
+#define AESR_SMEM_OF3(G, PP, PF) (AESR_SMEM_OF2(G, PP) + (PF) * ((G) * 2 * 1000 * (int)sizeof(cpx) + (G) * 8 + 8))
 #define AESR_NT AESR_NT_OF(AESR_G)
 #define AESR_SMEM_BYTES AESR_SMEM_OF(AESR_G)
 
@@ -463,7 +465,10 @@ template <bool INV> __device__ __forceinline__ void aesm_dft10(cpx (&a)[10])
 
 // PP = 2: two exchange buffers per row alternate (one barrier per exchange);  PP = 1: one buffer, a second barrier
 // between an exchange's loads and the next exchange's stores, half the exchange memory (more CTAs per SM)
-template <int G, int PP = 2>
+// PF: the rows of the CTA's next item are fetched into shared memory by two 8000-byte bulk copies (issued by one
+// thread per pair behind the first barrier, when every thread has taken this item's rows into registers) instead of
+// ten 8-byte loads per thread and row at the top of the item -- ncu r2ag: 20 % of the stall samples waited there.
+template <int G, int PP = 2, int PF = 0>
 __device__ void aesm_rows10_body(const SmoothArgs &a)
 {
     AES_DYN_SMEM(cpx, s);                                   // [G][row A, row B][PP][AESR_ROWBUF]
@@ -476,10 +481,27 @@ __device__ void aesm_rows10_body(const SmoothArgs &a)
     cpx *const tws = s + (size_t)G * 2 * PP * AESR_ROWBUF;
     const cpx *const t1f = tws, *const t2f = tws + 1000, *const t2i = tws + 2000, *const t1i = tws + 3000;
     cpx *const vj = tws + AESR_TW_ENTRIES + (g < G ? g : 0) * 40;       // [parity][row A, row B][10]
+    cpx *const stg = tws + AESR_TW_ENTRIES + G * 40 + (g < G ? g : 0) * 2000;      // [row A, row B][1000]
+    unsigned long long *const mbar = reinterpret_cast<unsigned long long *>(tws + AESR_TW_ENTRIES + G * 40 + G * 2000) + (g < G ? g : 0);
     for (int i = tid; i < AESR_TW_ENTRIES; i += blockDim.x) tws[i] = a.tw10[i];
+    if (PF && g < G && u == 0) { aes_mbar_init(mbar, 1); aes_mbar_init_fence(); }
     __syncthreads();
     const int nbins = M / 2 + 1;
     const long long total = (long long)a.np * NP, groups = (total + G - 1) / G;
+    // hand the rows of item `it` to the copy engine (one thread per pair)
+    auto fetch = [&](long long it) {
+        const int pp = (int)(it / NP), kr = 1 + (int)(it % NP);
+        const cpx *ra = a.buf + (long long)pp * M + (long long)kr * n2, *rb = a.buf + (long long)pp * M + (long long)(n1 - kr) * n2;
+        aes_fence_proxy_async_smem();                       // the staging rows were read with ordinary loads
+        aes_mbar_expect(mbar, 2 * 1000 * (unsigned)sizeof(cpx));
+        aes_bulk_g2s(stg, ra, 1000 * (unsigned)sizeof(cpx), mbar, aes_policy_evict_first());
+        aes_bulk_g2s(stg + 1000, rb, 1000 * (unsigned)sizeof(cpx), mbar, aes_policy_evict_first());
+#ifdef AES_CPU_EMU
+        aes_mbar_complete_emu(mbar);
+#endif
+    };
+    if (PF && g < G && u == 0 && (long long)blockIdx.x * G + g < total) fetch((long long)blockIdx.x * G + g);
+    unsigned uses = 0;                                      // items this pair has taken from its staging rows
     int par = 0;
     for (long long w = blockIdx.x; w < groups; w += gridDim.x, par ^= 1) {
         const long long item = w * G + g;
@@ -491,8 +513,15 @@ __device__ void aesm_rows10_body(const SmoothArgs &a)
         cpx baseA, baseB;
         baseA.x = baseA.y = baseB.x = baseB.y = 0.f;
         if (live) {
+            if (PF) {
+                aes_mbar_wait(mbar, uses);
+                ++uses;
 #pragma unroll
-            for (int j = 0; j < 10; ++j) { A[j] = rowA[100 * j + u]; B[j] = rowB[100 * j + uB]; }
+                for (int j = 0; j < 10; ++j) { A[j] = stg[100 * j + u]; B[j] = stg[1000 + 100 * j + uB]; }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 10; ++j) { A[j] = rowA[100 * j + u]; B[j] = rowB[100 * j + uB]; }
+            }
             // (read behind the fourth barrier; the slot of the other parity may still be in use by a thread that has
             // not left the previous item)
             if (u < 10) {
@@ -512,6 +541,7 @@ __device__ void aesm_rows10_body(const SmoothArgs &a)
             for (int k = 0; k < 10; ++k) { A0[AESR_P1 * k + u] = A[k]; B0[AESR_P1 * k + uB] = B[k]; }
         }
         __syncthreads();
+        if (PF && g < G && u == 0 && (w + gridDim.x) * G + g < total) fetch((w + gridDim.x) * G + g);
         if (live) {
 #pragma unroll
             for (int j = 0; j < 10; ++j) { A[j] = A0[AESR_P1 * hi + 10 * j + lo]; B[j] = B0[AESR_P1 * hiB + 10 * j + loB]; }

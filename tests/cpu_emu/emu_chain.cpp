@@ -295,7 +295,7 @@ template <int SHAPE> static void sm_k1(void *p) { aesm_cols_fwd_body<SHAPE>(*rei
 template <int SHAPE> static void sm_k2(void *p) { aesm_rows_body<SHAPE>(*reinterpret_cast<SmoothArgs *>(p)); }
 template <int SHAPE> static void sm_k3(void *p) { aesm_cols_inv_body<SHAPE>(*reinterpret_cast<SmoothArgs *>(p)); }
 static void sm_k2_rows10(void *p) { aesm_rows10_body<1, 2>(*reinterpret_cast<SmoothArgs *>(p)); }
-static void sm_k2_rows10_one_buffer(void *p) { aesm_rows10_body<2, 1>(*reinterpret_cast<SmoothArgs *>(p)); }
+static void sm_k2_rows10_one_buffer(void *p) { aesm_rows10_body<2, 1, 1>(*reinterpret_cast<SmoothArgs *>(p)); }    // + bulk-copy prefetch
 
 // mode 1: frames [nf][M] raw (window applied when `window` != null), mask [nf][M/2+1] or null, y [nf][M]
 // mode 2: frames = clips [nf][M/2][2], y = [nf][M/2][2]; returns 1 when M has no smooth split
@@ -331,7 +331,7 @@ int emu_spectral_smooth(int mode, const float *frames, const float *window, floa
         aesm_fill_rows10(t10.data());
         a.tw10 = t10.data();
         // (one pair per CTA with alternating exchange buffers, or AES_EMU_ROWS10_ONE_BUFFER: two pairs per CTA, one buffer)
-        if (getenv("AES_EMU_ROWS10_ONE_BUFFER")) emu::launch(sm_k2_rows10_one_buffer, &a, 2, AESR_NT_OF(2), AESR_SMEM_OF2(2, 1));
+        if (getenv("AES_EMU_ROWS10_ONE_BUFFER")) emu::launch(sm_k2_rows10_one_buffer, &a, 2, AESR_NT_OF(2), AESR_SMEM_OF3(2, 1, 1));
         else emu::launch(sm_k2_rows10, &a, 3, AESR_NT_OF(1), AESR_SMEM_OF2(1, 2));
         a.rows_self_only = 1;
         emu::launch(sm_k2<AESM_SHAPE_960x1000>, &a, 2, AESM_NT, (size_t)2 * n2 * sizeof(cpx));

@@ -105,3 +105,30 @@ def test_c4_one_30_s_clip_through_the_convolution_reverb(ab, orc):
     want = np.zeros_like(x)
     orc.OConvReverb(ir, 0.7, 0.5).process_into(x, want)
     check(y, want, what="c4 30 s")
+
+
+@pytest.mark.parametrize("B", [3, 2])
+def test_spectral_filter_on_full_10_s_clips_with_partial_gating(ab, orc, B):
+    """The whole-file SpectralFilter at BASELINE's clip length (frame 960 000 = 960 x 1000: the compile-time
+    four-step kernels and the register-resident row-pair kernel, `aesm_rows10_body`) with clips scaled so that
+    about half of the bins fall under the gate.  On the presets' own levels every bin passes and the block's
+    output -- the zero half of the frame -- is rounding noise, which checks nothing; here it is the leakage of
+    the gated bins, far above it.  Clips travel two per complex transform (B = 3: the last one alone, louder
+    partner inside the first pair).  A bin whose magnitude sits on the threshold may flip between the f32
+    device FFT and numpy's (each flip moves the output by ~|X| * 0.9 / M), so the bar is relative: 1 % of the
+    output's peak and 2 % of its RMS; a pairing or index mix-up is an error of order one."""
+    from audioblocks.engine import file_chain
+    cfg = [{"type": "spectral", "params": {"threshold_db": -40.0, "reduction": 0.1, "smoothing": 0.5}}]
+    n = FS * 10
+    # the synthetic clip's median bin magnitude is 37.5 at this length: 2.7e-4 puts it on the -40 dB threshold
+    x = synth.batch(77, B, n) * np.float32(2.7e-4)
+    x[0] *= np.float32(1.6)                         # a louder partner inside the first pair (73 % of its bins pass)
+    y = file_chain(cfg, FS, channels_in=2).process_batch(x)
+    for b in range(B):
+        want = orc.run_file_path(cfg, x[b], FS)
+        peak = float(np.max(np.abs(want)))
+        rms = float(np.sqrt(np.mean(want.astype(np.float64) ** 2)))
+        assert peak > 1e-7 and rms > 0.0, (B, b, peak)          # the case really exercises the gate
+        err = y[b].astype(np.float64) - want
+        assert np.max(np.abs(err)) <= 1e-2 * peak, (B, b, peak, float(np.max(np.abs(err))))
+        assert np.sqrt(np.mean(err ** 2)) <= 2e-2 * rms, (B, b, rms, float(np.sqrt(np.mean(err ** 2))))
