@@ -224,20 +224,16 @@ static int smooth_process(const aes_spectral_plan *pl, const SmoothArgs &a, cuda
             using std::integral_constant;
             using I0 = integral_constant<int, 0>;
             using I1 = integral_constant<int, 1>; using I2 = integral_constant<int, 2>; using I3 = integral_constant<int, 3>;
-            using I4 = integral_constant<int, 4>; using I5 = integral_constant<int, 5>;
+            using I4 = integral_constant<int, 4>;
             // Measured on 2048 clips (r2ai, ms per pass of the whole block): <1,3,2> 23.94, <2,2,2> 24.62, <1,4,2> 23.89,
             // <1,4,1> 23.70, <2,3,1> 23.98, <1,5,1> (80 registers, 48 bytes of spills) 23.47; the shared-memory
             // kernel 26.58.  With the next item's rows fetched by bulk copies (r2ak): <1,4,1> 23.34, <1,3,2> 24.19,
-            // <2,2,1> 22.91 -- the shipped one.  AES_ROWS10_VARIANT picks one of the others for re-measuring.
+            // <2,2,1> 22.91 -- the shipped one.  AES_ROWS10_VARIANT = 3, 5, 8 picks <1,3,2>, <1,4,1> (no prefetch) or
+            // <1,4,1> with it for re-measuring; the other shapes are no longer instantiated.
             switch (pl->rows10_variant) {
-            case 1: launch10(I2{}, I2{}, I2{}, I0{}); break;
-            case 2: launch10(I1{}, I4{}, I2{}, I0{}); break;
             case 3: launch10(I1{}, I3{}, I2{}, I0{}); break;
-            case 6: launch10(I2{}, I3{}, I1{}, I0{}); break;
-            case 7: launch10(I1{}, I5{}, I1{}, I0{}); break;
-            case 8: launch10(I1{}, I4{}, I1{}, I1{}); break;
-            case 9: launch10(I1{}, I3{}, I2{}, I1{}); break;
             case 5: launch10(I1{}, I4{}, I1{}, I0{}); break;
+            case 8: launch10(I1{}, I4{}, I1{}, I1{}); break;
             default: launch10(I2{}, I2{}, I1{}, I1{}); break;
             }
             SmoothArgs b = a;
@@ -309,14 +305,9 @@ AES_EXPORT int aes_spectral_plan_create(int64_t frame_len, aes_spectral_plan **o
                 aesm_fill_rows10(t10.data());
                 AES_CUDA(cudaMemcpy(pl->d_stw + nst + 1024 + nhi, t10.data(), t10.size() * sizeof(cpx), cudaMemcpyHostToDevice));
                 if (const char *v = getenv("AES_ROWS10_VARIANT")) pl->rows10_variant = atoi(v);
-                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<2, 2, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF3(2, 2, 0)));
-                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<1, 4, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF3(1, 2, 0)));
                 AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<1, 3, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF3(1, 2, 0)));
                 AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<1, 4, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF3(1, 1, 0)));
-                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<2, 3, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF3(2, 1, 0)));
-                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<1, 5, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF3(1, 1, 0)));
                 AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<1, 4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF3(1, 1, 1)));
-                AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<1, 3, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF3(1, 2, 1)));
                 AES_CUDA(cudaFuncSetAttribute(aesm_rows10_kernel<2, 2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, AESR_SMEM_OF3(2, 1, 1)));
             }
             AES_CUDA(cudaFuncSetAttribute(aesm_cols_fwd_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
