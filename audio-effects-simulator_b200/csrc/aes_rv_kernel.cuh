@@ -389,10 +389,14 @@ __device__ void aes_rv_body(const FastArgs &a)
                 aesf_line_init<FR>(a.st[0].ring[ch][0], i0, dw[ch], a0);
             }
         }
-        int pw[2] = { 0, 0 }, pa[2] = { 0, 0 };             // reverb pre-delay line
+        // reverb pre-delay line: write slot of this thread's frames.  One slot serves both channels (their lines have
+        // one lag and one period) and the read slot is derived at its use: the Cathedral shape spilled 32 bytes into
+        // the tile loop with the four slots and both channels' delayed frames live at once (ncu-less evidence: the
+        // same reverb without a pre-delay ran at 324 against 248 Gsamples/s, profiles/tools/time_reverb_predelay.py).
+        int pw = 0;
         if constexpr (PM != 0) {
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch) aesf_line_init<FR>(rs.pre[ch], i0, pw[ch], pa[ch]);
+            int a0;
+            aesf_line_init<FR>(rs.pre[0], i0, pw, a0);
         }
         __syncthreads();
 
@@ -547,7 +551,7 @@ __device__ void aes_rv_body(const FastArgs &a)
                 if constexpr (PM != 0) {
                     // pre-delay line (reverb.py:11-31): written here, read behind the barrier
 #pragma unroll
-                    for (int ch = 0; ch < 2; ++ch) aes_stv<FR>(rings + rs.pre[ch].off + pw[ch], v[ch]);
+                    for (int ch = 0; ch < 2; ++ch) aes_stv<FR>(rings + rs.pre[ch].off + pw, v[ch]);
                 }
                 aes_bar_sync(AESRV_BAR_COMB, AES_NT);
 
@@ -598,19 +602,10 @@ __device__ void aes_rv_body(const FastArgs &a)
                         if (len == 1 && tid == 0) { sout[4 * ch + 1] = cx1; sout[4 * ch + 3] = cy1; }
                     }
                 }
-                float pre[2][FR];
-                if constexpr (PM == 0) {
-#pragma unroll
-                    for (int ch = 0; ch < 2; ++ch)
-#pragma unroll
-                        for (int j = 0; j < FR; ++j) pre[ch][j] = v[ch][j];
-                } else {
-#pragma unroll
-                    for (int ch = 0; ch < 2; ++ch) {
-                        const FRing rg = rs.pre[ch];
-                        // (the line lives in the zero-initialised ring area: no first-lap check)
-                        aesf_read<FR, 0>(rings + rg.off, pa[ch], ((rg.lag + 3) & ~3) - rg.lag, rg.len, pre[ch]);
-                    }
+                [[maybe_unused]] int pa = 0;                        // pre-delay line: aligned read base, lag4 behind the write slot
+                if constexpr (PM != 0) {
+                    pa = pw - ((rs.pre[0].lag + 3) & ~3);
+                    if (pa < 0) pa += rs.pre[0].len;
                 }
                 const float *const cp = par ? cp1 : cp0;
                 const float4 Ca = aes_lds_v4(cp), Cb = aes_lds_v4(cp + 4);
@@ -621,6 +616,15 @@ __device__ void aes_rv_body(const FastArgs &a)
                 aes_static_for<0, 2>([&](auto ich) {
                     constexpr int ch = decltype(ich)::value;
                     float uend[NC];
+                    float pre[FR];                                  // the reverb's input: the dry frames, or their pre-delayed copies
+                    if constexpr (PM == 0) {
+#pragma unroll
+                        for (int j = 0; j < FR; ++j) pre[j] = v[ch][j];
+                    } else {
+                        const FRing rg = rs.pre[ch];
+                        // (the line lives in the zero-initialised ring area: no first-lap check)
+                        aesf_read<FR, 0>(rings + rg.off, pa, ((rg.lag + 3) & ~3) - rg.lag, rg.len, pre);
+                    }
                     aes_static_for<0, NC>([&](auto icc) {
                         constexpr int cc = decltype(icc)::value;
                         const float ex = __shfl_up_sync(0xffffffffu, e[ch][cc], 1);
@@ -639,7 +643,7 @@ __device__ void aes_rv_body(const FastArgs &a)
                             const float ua = fmaf(h, u, y[ch][cc][j]);
                             u = fmaf(h, ua, y[ch][cc][j + 1]);
                             const float2 n2 = aes_fma2(make_float2(gs, gs), make_float2(ua, u),
-                                                       make_float2(pre[ch][j], pre[ch][j + 1]));   // buf[n] = x + g*(1-h)*u
+                                                       make_float2(pre[j], pre[j + 1]));   // buf[n] = x + g*(1-h)*u
                             nb[j] = n2.x; nb[j + 1] = n2.y;
                             if (cc == 0) { sum[ch][j] = y[ch][0][j]; sum[ch][j + 1] = y[ch][0][j + 1]; }   // reverb.py:235-241: sum starts at 0
                             else {
@@ -683,22 +687,23 @@ __device__ void aes_rv_body(const FastArgs &a)
             }                                               // have to be ordered before the next tile's reads
             yp += 2 * T;
             if (has_cur) {
+                if constexpr (PM != 0) {
+                    // the dry frames come back from the pre-delay line, where phase 1 put them (this thread's own
+                    // stores, the slot has not moved yet): they need no registers across phases 2 and 3
 #pragma unroll
-                for (int ch = 0; ch < 2; ++ch)
+                    for (int ch = 0; ch < 2; ++ch) aes_ldv_sp<FR, 0>(rings + rs.pre[ch].off + pw, vprev[ch]);
+                } else {
 #pragma unroll
-                    for (int j = 0; j < FR; ++j) vprev[ch][j] = v[ch][j];
+                    for (int ch = 0; ch < 2; ++ch)
+#pragma unroll
+                        for (int j = 0; j < FR; ++j) vprev[ch][j] = v[ch][j];
+                }
                 aes_static_for<0, 2 * NC>([&](auto ic) {
                     constexpr int ch = decltype(ic)::value / NC, cc = decltype(ic)::value % NC;
                     using CR = AesrvComb<aesf_topo_comb(TOPO, ch, cc)>;
                     wb[ch][cc] = aesf_adv(wb[ch][cc], CR::TINC, CR::WRAP);
                 });
-                if constexpr (PM != 0) {
-#pragma unroll
-                    for (int ch = 0; ch < 2; ++ch) {
-                        pw[ch] = aesf_adv(pw[ch], rs.pre[ch].tinc, rs.pre[ch].len);
-                        pa[ch] = aesf_adv(pa[ch], rs.pre[ch].tinc, rs.pre[ch].len);
-                    }
-                }
+                if constexpr (PM != 0) pw = aesf_adv(pw, rs.pre[0].tinc, rs.pre[0].len);
                 if constexpr (PRE == AESRV_PRE_DELAY) {
 #pragma unroll
                     for (int ch = 0; ch < 2; ++ch) {
