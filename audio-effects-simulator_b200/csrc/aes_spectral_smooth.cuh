@@ -276,7 +276,7 @@ __device__ __forceinline__ float aesm_sample(const SmoothArgs &a, int fr, int n,
 }
 
 // ---- K1: column FFTs ---------------------------------------------------------------------------------
-template <int SHAPE>
+template <int SHAPE, int NT = AESM_NTC>
 __device__ void aesm_cols_fwd_body(const SmoothArgs &a)
 {
     AES_DYN_SMEM(cpx, s);                                   // [n1][C]
@@ -298,7 +298,7 @@ __device__ void aesm_cols_fwd_body(const SmoothArgs &a)
             s[e] = z;
         }
         __syncthreads();
-        if (SHAPE == AESM_SHAPE_960x1000) aesm_fft_c<false, 960, AESM_C, 1, AESM_C, AESM_NTC, 8, 8, 3, 5>(s, a.tw1);
+        if (SHAPE == AESM_SHAPE_960x1000) aesm_fft_c<false, 960, AESM_C, 1, AESM_C, NT, 8, 8, 3, 5>(s, a.tw1);
         else aesm_fft<false>(s, AESM_C, divC, 1, AESM_C, a.f1, a.tw1);
         cpx *dst = a.buf + (long long)p * a.M;
         for (int e = threadIdx.x; e < n1 * AESM_C; e += blockDim.x) {
