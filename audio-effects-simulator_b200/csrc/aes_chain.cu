@@ -46,8 +46,10 @@ static thread_local SlotCache t_cache;
 typedef void (*fast_kernel_t)(const FastArgs);
 struct FastShape { int c[AESF_MAX_STAGES]; int topo; fast_kernel_t fn; };
 #define X(c0, c1, c2, c3, mp) { { c0, c1, c2, c3 }, mp, aes_fast_kernel<4, c0, c1, c2, c3, mp> },
-static const FastShape g_fast_shapes[] = { AESF_SHAPES(X) };
+#define X3(c0, c1, c2, c3, mp) { { c0, c1, c2, c3 }, mp, aes_fast_kernel<4, c0, c1, c2, c3, mp, 3> },
+static const FastShape g_fast_shapes[] = { AESF_SHAPES(X) AESF_SHAPES_3CTA(X3) };
 #undef X
+#undef X3
 
 // ---- pipelined reverb-chain kernels (aes_rv_kernel.cuh): launch table ------------------------
 struct RvShape { int topo, pre, pm; fast_kernel_t fn; };

@@ -1112,8 +1112,8 @@ __device__ void aes_fast_body(const FastArgs &a)
 #define AESF_MIN_CTAS 2
 #endif
 #ifndef AES_CPU_EMU
-template <int FR, int C0, int C1, int C2, int C3, int TOPO>
-__global__ void __launch_bounds__(AES_NT, AESF_MIN_CTAS) aes_fast_kernel(const __grid_constant__ FastArgs a)
+template <int FR, int C0, int C1, int C2, int C3, int TOPO, int MIN_CTAS = AESF_MIN_CTAS>
+__global__ void __launch_bounds__(AES_NT, MIN_CTAS) aes_fast_kernel(const __grid_constant__ FastArgs a)
 {
     aes_fast_body<FR, C0, C1, C2, C3, TOPO>(a);
 }

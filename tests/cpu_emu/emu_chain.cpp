@@ -22,7 +22,7 @@ template <int C0, int C1, int C2, int C3, int MP> static void fentry(void *p)
 }
 struct FastShape { int c[4]; int topo; void (*fn)(void *); };
 #define X(c0, c1, c2, c3, mp) { { c0, c1, c2, c3 }, mp, fentry<c0, c1, c2, c3, mp> },
-static const FastShape g_shapes[] = { AESF_SHAPES(X) };
+static const FastShape g_shapes[] = { AESF_SHAPES(X) AESF_SHAPES_3CTA(X) };
 #undef X
 template <int TOPO, int PRE, int PM> static void rventry(void *p) { aes_rv_body<TOPO, PRE, PM>(*reinterpret_cast<FastArgs *>(p)); }
 struct RvShape { int topo, pre, pm; void (*fn)(void *); };
