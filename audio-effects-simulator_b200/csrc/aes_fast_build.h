@@ -38,15 +38,16 @@
     X(AESF_DIST, AESF_OCTAVER, AESF_DELAY_PF, 0, AESF_TOPO_NONE)    /* BASELINE configs[2]            */ \
     X(AESF_BIQUAD, 0, 0, 0, AESF_TOPO_NONE)                                                              \
     X(AESF_BIQUAD, AESF_BIQUAD, AESF_BIQUAD, AESF_BIQUAD, AESF_TOPO_NONE)   /* BASELINE configs[1]    */ \
-    X(AESF_GATE, 0, 0, 0, AESF_TOPO_NONE)                                                                \
     X(AESF_DIST, 0, 0, 0, AESF_TOPO_NONE)
 
 // Shapes built for THREE resident CTAs per SM (launch bounds 256 x 3: 80 registers, which they fit without a spill;
 // their rings leave room for three).  Measured (r2at, 8192 clips): Robot Voice 204 -> 224 Gsamples/s, the octaver
-// alone 327 -> 378 on 1184; on exactly 4 x 296 clips Robot Voice loses 3 % (1184 clips are 2.67 waves of 444 CTAs).
+// alone 327 -> 378 on 1184, the gate alone 3.48 -> 3.04 ms per 2048 clips (Clean Noise Removal's second stage);
+// on exactly 4 x 296 clips Robot Voice loses 3 % (1184 clips are 2.67 waves of 444 CTAs).
 // Not for distortion > octaver > delay: 231 -> 217 on 1184 clips.
 #define AESF_SHAPES_3CTA(X)                                                                             \
     X(AESF_GATE, AESF_OCTAVER, AESF_DELAY_PF, 0, AESF_TOPO_NONE)    /* Robot Voice                    */ \
+    X(AESF_GATE, 0, 0, 0, AESF_TOPO_NONE)                                                                \
     X(AESF_OCTAVER, 0, 0, 0, AESF_TOPO_NONE)
 
 // compile-time topology (aes_fast_kernel.cuh) matching the plan's single reverb stage, or 0
